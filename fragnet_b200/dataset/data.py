@@ -1,0 +1,79 @@
+"""Batch assembly for the GAT2 hot path: ``collate_fn`` / ``collate_fn_pt``.
+
+Drop-in for the reference's ``fragnet/dataset/data.py:877-948`` (``collate_fn``)
+and ``:951-1032`` (``collate_fn_pt``): same input (a list of per-molecule
+records carrying the attribute names of ``data.py:437-482``), same output keys,
+dtypes and values.  The reference concatenates per-molecule tensors and adds
+per-molecule node-count prefixes to the five index tensors with Python loops
+over the molecule list (``get_incr_*``, ``data.py:11-113``), routing the offsets
+through float32 (exact below 2**24 nodes per index space).  Here the offsets are
+one exclusive prefix sum per index space and one ``repeat_interleave`` per index
+tensor, kept in int64 throughout, so the result is the same integers with no
+2**24 ceiling.
+
+RDKit-dependent graph *construction* (``CreateData``) is preprocessing and out
+of scope for this package.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+
+def _prefix(counts: torch.Tensor) -> torch.Tensor:
+    """Exclusive prefix sum of per-molecule counts (int64)."""
+    out = torch.zeros_like(counts)
+    if counts.numel() > 1:
+        torch.cumsum(counts[:-1], 0, out=out[1:])
+    return out
+
+
+def _offset_columns(parts: List[torch.Tensor], node_counts: torch.Tensor, dim: int) -> torch.Tensor:
+    """Concatenate per-molecule index tensors along ``dim`` and shift molecule ``i``'s entries by
+    the number of nodes in molecules ``0..i-1`` (what ``get_incr_*`` + add does, data.py:11-113)."""
+    cat = torch.cat([p.to(torch.long) for p in parts], dim=dim)
+    widths = torch.tensor([p.shape[dim] for p in parts], dtype=torch.long)
+    shift = torch.repeat_interleave(_prefix(node_counts), widths)
+    return cat + shift
+
+
+def _collate(data_list, pretrain: bool) -> Dict[str, torch.Tensor]:
+    n_atoms = torch.tensor([d.x_atoms.shape[0] for d in data_list], dtype=torch.long)
+    n_frags = torch.tensor([int(d.n_frags.item()) for d in data_list], dtype=torch.long)
+    n_bnodes = torch.tensor([d.node_features_bonds.shape[0] for d in data_list], dtype=torch.long)
+    n_fbnodes = torch.tensor([d.node_feautures_fbondg.shape[0] for d in data_list], dtype=torch.long)
+    mol_ids = torch.arange(len(data_list), dtype=torch.long)
+    out = {
+        "x_atoms": torch.cat([d.x_atoms for d in data_list], dim=0),
+        "edge_index": _offset_columns([d.edge_index for d in data_list], n_atoms, 1),
+        "frag_index": _offset_columns([d.frag_index for d in data_list], n_frags, 1),
+        "x_frags": torch.cat([d.x_frags for d in data_list], dim=0),
+        "edge_attr": torch.cat([d.edge_attr for d in data_list], dim=0),
+        "cnx_attr": torch.cat([d.cnx_attr for d in data_list], dim=0),
+        "batch": torch.repeat_interleave(mol_ids, n_atoms),
+        "frag_batch": torch.repeat_interleave(mol_ids, n_frags),
+        "atom_to_frag_ids": _offset_columns([d.atom_id_frag_id for d in data_list], n_frags, 0),
+        "node_features_bonds": torch.cat([d.node_features_bonds for d in data_list], dim=0),
+        "edge_index_bonds_graph": _offset_columns([d.edge_index_bonds for d in data_list], n_bnodes, 1),
+        "edge_attr_bonds": torch.cat([d.edge_attr_bonds for d in data_list], dim=0),
+        "node_features_fbonds": torch.cat([d.node_feautures_fbondg for d in data_list], dim=0),
+        "edge_index_fbonds": _offset_columns([d.edge_index_fbondg for d in data_list], n_fbnodes, 1),
+        "edge_attr_fbonds": torch.cat([d.edge_attr_fbondg for d in data_list], dim=0),
+    }
+    if pretrain:
+        out["bnd_lngth"] = torch.cat([d.bnd_lngth for d in data_list], dim=0)
+        out["bnd_angl"] = torch.cat([d.bnd_angl for d in data_list], dim=0)
+        out["dh_angl"] = torch.cat([d.dh_angl for d in data_list], dim=0)
+    out["y"] = torch.cat([d.y for d in data_list], dim=0).type(torch.float)
+    return out
+
+
+def collate_fn(data_list):
+    """Finetune batches: 16 keys (reference ``data.py:931-948``)."""
+    return _collate(data_list, pretrain=False)
+
+
+def collate_fn_pt(data_list):
+    """Pretraining batches: adds ``bnd_lngth``, ``bnd_angl``, ``dh_angl`` (reference ``data.py:1012-1032``)."""
+    return _collate(data_list, pretrain=True)
