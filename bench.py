@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the FragNet GAT2 hot path (BASELINE.json: molecules/s, fwd+bwd GAT2 message passing).
+
+Workload (``config.workload``): the reference's pretraining step -- ``FragNetPreTrain`` per
+``exps/pt/unimol_exp1s4/config.yaml`` (4 layers, 4 heads, emb 128, drop 0.2, Adam lr 1e-4, loss of
+``train/pretrain/pretrain_utils.py``) on UniMol-shaped synthetic molecules, per-GPU batch ``--batch``
+(default 1024, the per-GPU batch of BASELINE configs[3]; weak scaling).  A step = forward + backward +
+gradient all-reduce (N > 1) + Adam step on one batch; ``--rotate`` distinct pre-collated batches are cycled so
+the working set exceeds the 126 MB L2.
+
+  python bench.py --gpus N --steps K --warmup W             (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference ...                      CPU oracle port on the host cores, same metric
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PT_KW = dict(num_layer=4, drop_ratio=0.2, num_heads=4, emb_dim=128, atom_features=167, frag_features=167,
+             edge_features=17, fedge_in=6, fbond_edge_in=6)
+LR = 1e-4
+METRIC = "molecules/s fwd+bwd GAT2 msg-passing (FragNetPreTrain step)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="molecules per GPU per step")
+    ap.add_argument("--shape", default="unimol", choices=["esol", "unimol", "stress"])
+    ap.add_argument("--rotate", type=int, default=4, help="distinct batches cycled through")
+    ap.add_argument("--pool", type=int, default=512, help="distinct synthetic molecules generated")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def make_batches(shape, batch, rotate, pool, seed):
+    """``rotate`` collated batches of ``batch`` molecules drawn (with replacement) from a pool of distinct
+    synthetic molecules; deterministic per seed."""
+    import random
+
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    mols = synth.make_dataset(shape, min(pool, batch * rotate), seed=seed)
+    rng = random.Random(seed)
+    return [collate_fn_pt([mols[rng.randrange(len(mols))] for _ in range(batch)]) for _ in range(rotate)]
+
+
+def batch_counts(b):
+    return dict(G=int(b["y"].shape[0]), Na=b["x_atoms"].shape[0], Ea=b["edge_index"].shape[1],
+                Eb=b["edge_index_bonds_graph"].shape[1], Nf=b["x_frags"].shape[0], Ef=b["frag_index"].shape[1],
+                Efb=b["edge_index_fbonds"].shape[1])
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def attention_bytes(N, E, X, saved_p=True):
+    """B_att_fwd = 2*N*D*4 + X + E*4 + (N+1)*4 + E*H*4."""
+    return 2 * N * 128 * 4 + X + E * 4 + (N + 1) * 4 + (E * 4 * 4 if saved_p else 0)
+
+
+def roofline_bond_fwd(batch_dev, peaks, iters=20):
+    """Live CUDA-event timing of the dominant message-passing kernel (bond-graph fused attention forward,
+    ~6.5 edges per node) on the bench batch, L2 flushed before every launch."""
+    from fragnet_b200 import ops
+    b = batch_dev
+    dev = b["x_atoms"].device
+    Nb, Eb = b["node_features_bonds"].shape[0], b["edge_index_bonds_graph"].shape[1]
+    eb = b["edge_index_bonds_graph"]
+    g = ops.csr_build(eb[0].contiguous(), eb[1].contiguous(), Nb)
+    cos = ops.gather_rows(b["edge_attr_bonds"].reshape(-1, 1), g.eid, Eb)
+    h = torch.randn(Nb, 128, device=dev)
+    alpha = torch.randn(4, 96, device=dev) * 0.1
+    S = ops.node_scalars(h, alpha, 96, 0, 64)
+    coef = torch.randn(8, device=dev) * 0.1
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    times = []
+    for i in range(iters + 3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        ops.gat_fwd(g, h, S, ops.EDGE_AFFINE1, cos, coef, True)
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = statistics.mean(times)
+    nbytes = attention_bytes(Nb, Eb, Eb * 4)
+    peak = peaks.get("hbm_gbs")
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_gat_fwd<AFFINE1> (bond graph)", "achieved": round(achieved, 1),
+            "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if peak else None, "traffic": None,
+            "bytes_per_launch": nbytes, "us_per_launch": round(ms * 1e3, 2), "nodes": Nb, "edges": Eb,
+            "peak_source": peaks.get("source")}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(shape, n_mols, steps, warmup, seed=0):
+    """Reference algorithm (oracle port) fwd+bwd+Adam on the host cores: molecules/s."""
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from oracle import gat2_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(seed)
+    m = FragNetPreTrain(**PT_KW)
+    P = O.params_from_module(m)
+    live = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(live, lr=LR)
+    batches = make_batches(shape, n_mols, 2, 256, seed + 1)
+    times = []
+    for i in range(warmup + steps):
+        b = batches[i % len(batches)]
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = O.pretrain_loss(O.pretrain_forward(P, b, drop_ratio=PT_KW["drop_ratio"], training=True), b)
+        loss.backward()
+        loss.item()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return n_mols / statistics.mean(times), statistics.mean(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0 / max(1, args.steps + args.warmup)            # seconds per step
+    n_mols = int(max(32, min(512, 150 * budget)))
+    rate, sec = cpu_oracle_rate(args.shape, n_mols, args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    sample = f"{n_mols} {args.shape}-shaped molecules per step (fwd+bwd+Adam, train mode, drop 0.2)"
+    line = {"metric": METRIC, "value": round(rate, 2), "unit": "molecules/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": f"FragNetPreTrain unimol_exp1s4 step, {args.shape}-shaped molecules",
+                       "per_gpu_batch": args.batch, "sample_batch": n_mols},
+            "cpu_baseline": {"value": round(rate, 2), "unit": "molecules/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": round(rate, 2), "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet_b200 import _abi
+    from fragnet_b200.dist import FlatGradSync
+    from fragnet_b200.train.pretrain_utils import pretrain_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _abi.load()
+
+    torch.manual_seed(1234)                      # identical initial weights on every rank
+    model = FragNetPreTrain(**PT_KW).to(dev).train()
+    loss_fn = torch.nn.MSELoss()
+    host_batches = make_batches(args.shape, args.batch, args.rotate, args.pool, seed=100 + rank)
+    for b in host_batches:
+        for k in b:
+            b[k] = b[k].pin_memory()
+    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
+    sync = FlatGradSync(model.parameters())
+    opt = None
+
+    def step(batch):
+        nonlocal opt
+        sync.zero()
+        loss = pretrain_loss(loss_fn, model(batch), batch)
+        loss.backward()
+        sync.sync()
+        if opt is None:          # Adam over the live parameters (grad-less ones are skipped by Adam anyway)
+            opt = torch.optim.Adam(sync.live_parameters(), lr=LR, fused=True)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step, n_steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        l0 = lib.fnb_launch_count()
+        e0.record()
+        for i in range(n_steps):
+            run_step(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), lib.fnb_launch_count() - l0
+
+    # ---- kernel-resident throughput: inputs already in HBM
+    for i in range(args.warmup):
+        step(dev_batches[i % args.rotate])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(lambda i: step(dev_batches[i % args.rotate]), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    mols = args.batch * world * args.steps
+    value = mols / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with HOST (pinned) batches: H2D + step + loss read back
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+        def e2e_step(i):
+            hb = host_batches[i % args.rotate]
+            b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+            step(b).item()
+
+        for i in range(min(3, args.warmup)):
+            e2e_step(i)
+        ms_e2e, _ = timed(e2e_step, args.steps)
+        e2e = {"value": round(mols / (ms_e2e * 1e-3), 1), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)}
+
+    roofline = cpu = None
+    if rank == 0:
+        peaks = load_peaks()
+        if not args.no_roofline:
+            roofline = roofline_bond_fwd(dev_batches[0], peaks)
+        if not args.no_cpu_baseline and world == 1:
+            with contextlib.redirect_stdout(io.StringIO()):
+                rate, _ = cpu_oracle_rate(args.shape, 128, 3, 1)
+            cpu = {"value": round(rate, 2), "unit": "molecules/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"128 {args.shape}-shaped molecules per step, 1 warm-up + 3 timed steps "
+                             "(fwd+bwd+Adam, train mode)"}
+        counts = batch_counts(host_batches[0])
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "molecules/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"FragNetPreTrain exps/pt/unimol_exp1s4 step (4 layers, 4 heads, emb 128, "
+                                       f"drop 0.2, Adam), {args.shape}-shaped molecules",
+                           "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+                           "parallelism": f"dp{world}", "batch0_counts": counts,
+                           "cache": f"{args.rotate} distinct batches rotated; fwd+bwd working set > 126 MB L2"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,330 @@
+// Node/edge linear projections of the GAT2 blocks, fp32 (strict-parity path).
+//
+// Reference: nn.Linear projection_a / projection_b / projection_fb (fragnet/model/gat/gat2.py:142,
+// 189, 247) followed by .view(N, H, d) and, per edge, two 32-wide dot products of the gathered rows
+// with the head vector (gat2.py:148-150, 204-208, 252-254).  Here the projection kernel also emits the
+// per-NODE halves of those dot products (S[n,0:4] target half, S[n,4:8] source half) from its
+// epilogue while the output tile is still in registers, so the attention kernels never re-read
+// 128-wide rows to form a logit.
+//
+// This file is the fp32 SIMT implementation used for exact (<=1e-5) parity with the reference;
+// FFMA-bound, not HBM-bound -- see DESIGN.md "projection" for the tensor-core plan.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 128, BK = 32;
+constexpr int kGemmThreads = 256;
+
+struct GemmArgs {
+  const float *A; int lda;      // [M, Kd]
+  const float *B; int ldb;      // TRANS_B: [Nc, Kd] (nn.Linear weight), else [Kd, Nc]
+  float *C; int ldc;            // [M, Nc]
+  int64_t M; int Kd; int Nc;
+  const float *bias;            // [Nc] or NULL
+  const float *alpha; int alpha_stride, off_t, off_s;  // epilogue scalars (EPI only)
+  float *S;                     // [M, 8] or NULL
+};
+
+template <bool TRANS_B, bool EPI>
+__global__ void __launch_bounds__(kGemmThreads) k_gemm(GemmArgs g) {
+  __shared__ float As[BM][BK + 1];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.Kd; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / kGemmThreads; ++i) {
+      const int idx = tid + i * kGemmThreads;
+      const int k = idx & (BK - 1), r = idx / BK;
+      const int64_t row = m0 + r;
+      As[r][k] = (row < g.M && k0 + k < g.Kd) ? __ldg(g.A + row * g.lda + k0 + k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < (BK * BN) / kGemmThreads; ++i) {
+      const int idx = tid + i * kGemmThreads;
+      const int n = idx & (BN - 1), k = idx / BN;
+      float v = 0.f;
+      if (n0 + n < g.Nc && k0 + k < g.Kd)
+        v = TRANS_B ? __ldg(g.B + (int64_t)(n0 + n) * g.ldb + k0 + k) : __ldg(g.B + (int64_t)(k0 + k) * g.ldb + n0 + n);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][k];
+      const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 8 + 4]);
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int c0 = n0 + tx * 8;
+  if (g.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bj = (c0 + j < g.Nc) ? __ldg(g.bias + c0 + j) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][j] += bj;
+    }
+  }
+  const bool vec_ok = ((g.ldc & 3) == 0) && (c0 + 8 <= g.Nc) && fnb_is_aligned16_dev(g.C);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = m0 + ty * 4 + i;
+    if (row >= g.M) continue;
+    float *cp = g.C + row * g.ldc + c0;
+    if (vec_ok) {
+      st4(cp, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      st4(cp + 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < g.Nc) cp[j] = acc[i][j];
+    }
+  }
+  if (EPI && g.S) {
+    // columns c0..c0+7 lie in head c0/32; the 4 threads tx&~3 .. tx|3 cover that head's 32 columns
+    const int head = tx >> 2, within = (tx & 3) * 8;
+    float at[8], as[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      at[j] = __ldg(g.alpha + head * g.alpha_stride + g.off_t + within + j);
+      as[j] = __ldg(g.alpha + head * g.alpha_stride + g.off_s + within + j);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float st = 0.f, ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        st = fmaf(acc[i][j], at[j], st);
+        ss = fmaf(acc[i][j], as[j], ss);
+      }
+      st += __shfl_xor_sync(kFull, st, 1); st += __shfl_xor_sync(kFull, st, 2);
+      ss += __shfl_xor_sync(kFull, ss, 1); ss += __shfl_xor_sync(kFull, ss, 2);
+      const int64_t row = m0 + ty * 4 + i;
+      if ((tx & 3) == 0 && row < g.M) {
+        g.S[row * 8 + head] = st;
+        g.S[row * 8 + 4 + head] = ss;
+      }
+    }
+  }
+}
+
+// dW[o,k] = sum_n dh[n,o] x[n,k], db[o] = sum_n dh[n,o]; per-CTA partial over a contiguous row range.
+constexpr int kDwRows = 32;
+__global__ void __launch_bounds__(256) k_proj_dw(const float *__restrict__ dh, const float *__restrict__ x, int64_t n_rows,
+                                                 int K, int64_t rows_per_block, float *__restrict__ partials,
+                                                 int64_t rec_stride) {
+  __shared__ __align__(16) float dhs[kDwRows][128];
+  __shared__ __align__(16) float xs[kDwRows][128];
+  const int tid = threadIdx.x, tk = tid & 15, to = tid >> 4;
+  const int kt0 = blockIdx.y * 128;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(n_rows, r_begin + rows_per_block);
+  float acc[8][8], dbacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dbacc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  }
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += kDwRows) {
+#pragma unroll
+    for (int i = 0; i < (kDwRows * 128) / 256; ++i) {
+      const int idx = tid + i * 256;
+      const int c = idx & 127, r = idx >> 7;
+      const int64_t row = r0 + r;
+      const bool in = row < r_end;
+      dhs[r][c] = in ? __ldg(dh + row * 128 + c) : 0.f;
+      xs[r][c] = (in && kt0 + c < K) ? __ldg(x + row * K + kt0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < kDwRows; ++r) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(&dhs[r][to * 8]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&dhs[r][to * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4 *>(&xs[r][tk * 8]);
+      const float4 b1 = *reinterpret_cast<const float4 *>(&xs[r][tk * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dbacc[i] += a[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  float *rec = partials + (int64_t)blockIdx.x * rec_stride;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = to * 8 + i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kt0 + tk * 8 + j;
+      if (k < K) rec[(int64_t)o * K + k] = acc[i][j];
+    }
+    if (tk == 0 && blockIdx.y == 0) rec[(int64_t)128 * K + o] = dbacc[i];
+  }
+}
+
+// S for un-projected features: one warp per row.
+__global__ void __launch_bounds__(256) k_node_scalars(const float *__restrict__ h, int64_t n_rows,
+                                                      const float *__restrict__ alpha, int alpha_stride, int off_t,
+                                                      int off_s, float *__restrict__ S) {
+  const int lane = threadIdx.x & 31, head = lane >> 3;
+  const float4 at = ldg4(alpha + (int64_t)head * alpha_stride + off_t + (lane & 7) * 4);
+  const float4 as = ldg4(alpha + (int64_t)head * alpha_stride + off_s + (lane & 7) * 4);
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = w0; n < n_rows; n += wstride) {
+    const float4 v = ldg4(h + n * kD + lane * 4);
+    const float st = head_sum(dot4(v, at)), ss = head_sum(dot4(v, as));
+    if ((lane & 7) == 0) {
+      S[n * 8 + head] = st;
+      S[n * 8 + 4 + head] = ss;
+    }
+  }
+}
+
+// coef[h*in + k] = sum_j We[j,k] alpha_e[h,j];  coef[4*in + h] = sum_j be[j] alpha_e[h,j]
+__global__ void k_edge_coef_fwd(const float *__restrict__ We, const float *__restrict__ be, int in_dim,
+                                const float *__restrict__ alpha, int alpha_stride, int off_e,
+                                float *__restrict__ coef) {
+  const int o = threadIdx.x;
+  if (o >= 4 * in_dim + 4) return;
+  float s = 0.f;
+  if (o < 4 * in_dim) {
+    const int hh = o / in_dim, k = o % in_dim;
+    for (int j = 0; j < kHd; ++j) s = fmaf(We[j * in_dim + k], alpha[hh * alpha_stride + off_e + j], s);
+  } else {
+    const int hh = o - 4 * in_dim;
+    for (int j = 0; j < kHd; ++j) s = fmaf(be[j], alpha[hh * alpha_stride + off_e + j], s);
+  }
+  coef[o] = s;
+}
+
+__global__ void k_edge_coef_bwd(const float *__restrict__ We, const float *__restrict__ be, int in_dim,
+                                const float *__restrict__ alpha, int alpha_stride, int off_e,
+                                const float *__restrict__ d_coef, float *__restrict__ dWe, float *__restrict__ dbe,
+                                float *__restrict__ d_alpha) {
+  const int tid = threadIdx.x;
+  const int n_w = kHd * in_dim;
+  if (tid < n_w) {  // dWe[j,k] = sum_h d_coef[h*in+k] alpha_e[h,j]
+    const int j = tid / in_dim, k = tid % in_dim;
+    float s = 0.f;
+    for (int hh = 0; hh < kH; ++hh) s = fmaf(d_coef[hh * in_dim + k], alpha[hh * alpha_stride + off_e + j], s);
+    dWe[tid] = s;
+  } else if (tid < n_w + kHd) {  // dbe[j] = sum_h d_coef[4in+h] alpha_e[h,j]
+    const int j = tid - n_w;
+    float s = 0.f;
+    for (int hh = 0; hh < kH; ++hh) s = fmaf(d_coef[4 * in_dim + hh], alpha[hh * alpha_stride + off_e + j], s);
+    dbe[j] = s;
+  } else if (tid < n_w + kHd + kH * kHd) {  // d alpha_e[h,j] = sum_k d_coef[h*in+k] We[j,k] + d_coef[4in+h] be[j]
+    const int r = tid - n_w - kHd;
+    const int hh = r / kHd, j = r % kHd;
+    float s = d_coef[4 * in_dim + hh] * be[j];
+    for (int k = 0; k < in_dim; ++k) s = fmaf(d_coef[hh * in_dim + k], We[j * in_dim + k], s);
+    d_alpha[hh * alpha_stride + off_e + j] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int64_t n_rows, int K, const float *alpha,
+                            int alpha_stride, int off_t, int off_s, float *h, float *S, void *stream) {
+  if (n_rows < 0 || K <= 0) return FNB_ERR_SIZE;
+  if (n_rows == 0) return 0;
+  if (!x || !W || !h) return FNB_ERR_NULL;
+  if (S && !alpha) return FNB_ERR_NULL;
+  if (!fnb_aligned16(h)) return FNB_ERR_ALIGN;
+  GemmArgs g;
+  g.A = x; g.lda = K; g.B = W; g.ldb = K; g.C = h; g.ldc = kD; g.M = n_rows; g.Kd = K; g.Nc = kD; g.bias = b;
+  g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s; g.S = S;
+  dim3 grid((unsigned)((n_rows + BM - 1) / BM), 1);
+  k_gemm<true, true><<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(g);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int64_t n_rows, int K, float *dx,
+                            float *dW, float *db, void *scratch, void *stream_) {
+  if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
+  if (!x || !W || !dh || !dW || !scratch) return FNB_ERR_NULL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (dx && n_rows > 0) {
+    GemmArgs g;
+    g.A = dh; g.lda = kD; g.B = W; g.ldb = K; g.C = dx; g.ldc = K; g.M = n_rows; g.Kd = kD; g.Nc = K; g.bias = nullptr;
+    g.alpha = nullptr; g.alpha_stride = 0; g.off_t = 0; g.off_s = 0; g.S = nullptr;
+    dim3 grid((unsigned)((n_rows + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
+    k_gemm<false, false><<<grid, kGemmThreads, 0, stream>>>(g);
+    FNB_CHECK_LAUNCH();
+  }
+  int64_t nb = (n_rows + 255) / 256;
+  if (nb > kNumSMs) nb = kNumSMs;
+  if (nb < 1) nb = 1;
+  int64_t rows_per_block = (n_rows + nb - 1) / nb;
+  rows_per_block = ((rows_per_block + kDwRows - 1) / kDwRows) * kDwRows;
+  if (rows_per_block < kDwRows) rows_per_block = kDwRows;
+  const int64_t rec_stride = (int64_t)128 * K + 128;
+  dim3 grid((unsigned)nb, (unsigned)((K + 127) / 128));
+  k_proj_dw<<<grid, 256, 0, stream>>>(dh, x, n_rows, K, rows_per_block, (float *)scratch, rec_stride);
+  FNB_CHECK_LAUNCH();
+  int rc = fnb_launch_reduce_partials((const float *)scratch, (int)nb, (int)rec_stride, 128 * K, dW, 128 * K, 128 * K, 0,
+                                      stream);
+  if (rc) return rc;
+  if (db)
+    rc = fnb_launch_reduce_partials((const float *)scratch + (int64_t)128 * K, (int)nb, (int)rec_stride, 128, db, 128,
+                                    128, 0, stream);
+  return rc;
+}
+
+extern "C" int fnb_node_scalars(const float *h, int64_t n_rows, const float *alpha, int alpha_stride, int off_t,
+                                int off_s, float *S, void *stream) {
+  if (n_rows < 0) return FNB_ERR_SIZE;
+  if (n_rows == 0) return 0;
+  if (!h || !alpha || !S) return FNB_ERR_NULL;
+  if ((alpha_stride & 3) || (off_t & 3) || (off_s & 3) || !fnb_aligned16(alpha) || !fnb_aligned16(h))
+    return FNB_ERR_ALIGN;
+  int64_t blocks = (n_rows + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  k_node_scalars<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(h, n_rows, alpha, alpha_stride, off_t, off_s, S);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fnb_edge_coef_fwd(const float *We, const float *be, int in_dim, const float *alpha, int alpha_stride,
+                                 int off_e, float *coef, void *stream) {
+  if (in_dim != 1 && in_dim != 6) return FNB_ERR_MODE;
+  if (!We || !be || !alpha || !coef) return FNB_ERR_NULL;
+  k_edge_coef_fwd<<<1, 32, 0, (cudaStream_t)stream>>>(We, be, in_dim, alpha, alpha_stride, off_e, coef);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fnb_edge_coef_bwd(const float *We, const float *be, int in_dim, const float *alpha, int alpha_stride,
+                                 int off_e, const float *d_coef, float *dWe, float *dbe, float *d_alpha,
+                                 void *stream) {
+  if (in_dim != 1 && in_dim != 6) return FNB_ERR_MODE;
+  if (!We || !be || !alpha || !d_coef || !dWe || !dbe || !d_alpha) return FNB_ERR_NULL;
+  k_edge_coef_bwd<<<1, 512, 0, (cudaStream_t)stream>>>(We, be, in_dim, alpha, alpha_stride, off_e, d_coef, dWe, dbe,
+                                                       d_alpha);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,354 @@
+"""Thin host wrappers over the C ABI: tensor -> pointer plumbing, CSR plans, scratch buffers.
+
+PyTorch is used here only for device memory and streams; every computation is a call into
+``libfragnet_b200.so``.  All wrappers launch on ``torch.cuda.current_stream()`` and never
+synchronise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._abi import EDGE_AFFINE1, EDGE_AFFINE6, EDGE_NONE, EDGE_TABLE  # noqa: F401  (re-exported)
+
+D, H = 128, 4
+
+
+def _lib():
+    return _abi.load()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous view of ``t`` (copy only if needed)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def require_cuda(device=None) -> torch.device:
+    """The device kernels run on.  There is no CPU fallback."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("fragnet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is not None and torch.device(device).type == "cuda":
+        return torch.device(device)
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+_scratch_cache = {}
+
+
+def scratch(device: torch.device) -> torch.Tensor:
+    """Per (device, stream) scratch of ``fnb_scratch_bytes()`` for partial sums."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch_cache.get(key)
+    if buf is None:
+        buf = torch.empty(_lib().fnb_scratch_bytes(), dtype=torch.uint8, device=device)
+        _scratch_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# (a) CSR plans
+@dataclass
+class GraphCSR:
+    """Destination-sorted CSR + reverse CSR of one batched graph (all int32, on device)."""
+    n_nodes: int
+    n_edges: int          # including appended self loops
+    n_real: int           # edges present in the input edge list
+    rowptr: torch.Tensor
+    col: Optional[torch.Tensor]
+    eid: Optional[torch.Tensor]
+    slot_of_eid: Optional[torch.Tensor]
+    rrowptr: Optional[torch.Tensor] = None
+    rslot: Optional[torch.Tensor] = None
+    rdst: Optional[torch.Tensor] = None
+    status: Optional[torch.Tensor] = None   # int32[1], non-zero if an index was out of range
+    attr: Optional[torch.Tensor] = None     # per-edge attributes permuted into slot order
+
+
+def csr_build(dst: torch.Tensor, src: Optional[torch.Tensor], n_nodes: int, self_loops: bool = False,
+              reverse: bool = True) -> GraphCSR:
+    """``fnb_csr_build`` on int64 index vectors that live on a CUDA device."""
+    assert dst.dtype == torch.int64 and dst.is_cuda and dst.is_contiguous()
+    if src is not None:
+        assert src.dtype == torch.int64 and src.is_contiguous() and src.shape == dst.shape
+    dev = dst.device
+    E = dst.numel()
+    total = E + (n_nodes if self_loops else 0)
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n_nodes + 1, **i32)
+    col = torch.empty(total, **i32)
+    eid = torch.empty(total, **i32)
+    slot_of_eid = torch.empty(total, **i32)
+    rrowptr = rslot = rdst = None
+    if reverse:
+        rrowptr = torch.empty(n_nodes + 1, **i32)
+        rslot = torch.empty(total, **i32)
+        rdst = torch.empty(total, **i32)
+    lib = _lib()
+    ws_bytes = lib.fnb_csr_workspace_bytes(n_nodes, total)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, **i32)
+    rc = lib.fnb_csr_build(_p(dst), _p(src), E, n_nodes, int(self_loops), _p(rowptr), _p(col), _p(eid),
+                           _p(slot_of_eid), _p(rrowptr), _p(rslot), _p(rdst), _p(ws), ws_bytes, _p(status), _stream())
+    _abi.check(rc, "csr_build")
+    return GraphCSR(n_nodes, total, E, rowptr, col, eid, slot_of_eid, rrowptr, rslot, rdst, status)
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, n_rows: int) -> torch.Tensor:
+    src = _f32c(src)
+    width = src.shape[1] if src.dim() == 2 else 1
+    out = torch.empty((n_rows, width), dtype=torch.float32, device=src.device)
+    _abi.check(_lib().fnb_gather_rows(_p(src), _p(index), n_rows, width, _p(out), _stream()), "gather_rows")
+    return out
+
+
+def segment_offsets(sorted_ids: torch.Tensor, n_segments: int) -> torch.Tensor:
+    out = torch.empty(n_segments + 1, dtype=torch.int32, device=sorted_ids.device)
+    _abi.check(_lib().fnb_segment_offsets(_p(sorted_ids), sorted_ids.numel(), n_segments, _p(out), _stream()),
+               "segment_offsets")
+    return out
+
+
+def narrow_index(ids: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
+    _abi.check(_lib().fnb_narrow_index(_p(ids), ids.numel(), _p(out), _stream()), "narrow_index")
+    return out
+
+
+@dataclass
+class LayerPlan:
+    """Everything index-shaped that the four GAT2 blocks of a batch share across layers, forward
+    and backward: CSR / reverse CSR of the four graphs, the atom->fragment membership CSR and the
+    edge attributes permuted into slot order."""
+    bond: GraphCSR
+    atom: GraphCSR
+    fbond: GraphCSR
+    frag: GraphCSR
+    pool: GraphCSR                 # fragment -> member atoms
+    a2f32: torch.Tensor            # int32 copy of atom_to_frag_ids (pool backward gather)
+    n_atoms: int
+    n_frags: int
+    refs: tuple = field(default=(), repr=False)
+
+
+def _idx(t: torch.Tensor, dev) -> torch.Tensor:
+    t = t.to(device=dev, dtype=torch.int64)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def build_layer_plan(edge_index, frag_index, atom_to_frag_ids, edge_index_bonds_graph, edge_attr_bonds,
+                     edge_index_fbonds, edge_attr_fbonds, n_atoms: int, n_frags: int, n_bond_nodes: int,
+                     n_fbond_nodes: int, device) -> LayerPlan:
+    """On-device collate (north-star kernel a) for one batch.
+
+    Row conventions: bond / fragment-connection graphs use row 0 as the softmax
+    segment (reference gat2.py:138, :239); atom / fragment graphs use row 1 (gat2.py:187, :283), and
+    the atom graph gets its self loops appended (gat2.py:179)."""
+    dev = require_cuda(device)
+    ei, fi = _idx(edge_index, dev), _idx(frag_index, dev)
+    eb, efb = _idx(edge_index_bonds_graph, dev), _idx(edge_index_fbonds, dev)
+    a2f = _idx(atom_to_frag_ids, dev)
+    bond = csr_build(eb[0], eb[1], n_bond_nodes)
+    atom = csr_build(ei[1], ei[0], n_atoms, self_loops=True)
+    fbond = csr_build(efb[0], efb[1], n_fbond_nodes)
+    frag = csr_build(fi[1], fi[0], n_frags)
+    pool = csr_build(a2f, None, n_frags, reverse=False)
+    bond.attr = gather_rows(edge_attr_bonds.to(dev).reshape(-1, 1), bond.eid, bond.n_edges)
+    fbond.attr = gather_rows(edge_attr_fbonds.to(dev), fbond.eid, fbond.n_edges)
+    return LayerPlan(bond, atom, fbond, frag, pool, narrow_index(a2f), n_atoms, n_frags)
+
+
+_plan_cache = []          # [(weakrefs, versions, sizes, plan)], most recent first
+_PLAN_CACHE_SIZE = 4
+
+
+def layer_plan_for(index_tensors: tuple, sizes: tuple, device) -> LayerPlan:
+    """Plan cache keyed by the IDENTITY of the caller's index tensors (weak references + version
+    counters), so the 4 layers of one forward share one plan and a new batch never hits a stale one."""
+    for refs, versions, szs, dev, plan in _plan_cache:
+        if szs == sizes and dev == device and all(r() is t for r, t in zip(refs, index_tensors)) and \
+                versions == tuple(t._version for t in index_tensors):
+            return plan
+    plan = build_layer_plan(*index_tensors, *sizes, device)
+    refs = tuple(weakref.ref(t) for t in index_tensors)
+    _plan_cache.insert(0, (refs, tuple(t._version for t in index_tensors), sizes, device, plan))
+    del _plan_cache[_PLAN_CACHE_SIZE:]
+    return plan
+
+
+@dataclass
+class ReadoutPlan:
+    n_graphs: int
+    atom_ptr: torch.Tensor     # int32 [G+1]
+    frag_ptr: torch.Tensor
+    batch32: torch.Tensor      # int32 [Na]
+    frag_batch32: torch.Tensor
+
+
+_readout_cache = []
+
+
+def readout_plan_for(batch_vec: torch.Tensor, frag_batch_vec: torch.Tensor, device) -> ReadoutPlan:
+    """Molecule boundaries of the sorted ``batch`` / ``frag_batch`` vectors.  The number of molecules
+    is data dependent in the reference (scatter_add sizes its output ``index.max()+1``,
+    gat2.py:820-821); reading it is the one host sync per batch, done on the CPU copy when the
+    vectors still live on the host."""
+    for refs, plan in _readout_cache:
+        if refs[0]() is batch_vec and refs[1]() is frag_batch_vec:
+            return plan
+    dev = require_cuda(device)
+    n_graphs = 0
+    for v in (batch_vec, frag_batch_vec):
+        if v.numel():
+            n_graphs = max(n_graphs, int(v[-1]) + 1)
+    b, fb = _idx(batch_vec, dev), _idx(frag_batch_vec, dev)
+    plan = ReadoutPlan(n_graphs, segment_offsets(b, n_graphs), segment_offsets(fb, n_graphs),
+                       narrow_index(b), narrow_index(fb))
+    _readout_cache.insert(0, ((weakref.ref(batch_vec), weakref.ref(frag_batch_vec)), plan))
+    del _readout_cache[_PLAN_CACHE_SIZE:]
+    return plan
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel wrappers (no autograd here; see autograd.py)
+def proj_fwd(x, W, b, alpha=None, alpha_stride=0, off_t=0, off_s=0, want_S=True):
+    n, K = x.shape
+    h = torch.empty((n, D), dtype=torch.float32, device=x.device)
+    S = torch.empty((n, 8), dtype=torch.float32, device=x.device) if want_S else None
+    _abi.check(_lib().fnb_proj_fwd(_p(x), _p(W), _p(b), n, K, _p(alpha), alpha_stride, off_t, off_s, _p(h), _p(S),
+                                   _stream()), "proj_fwd")
+    return h, S
+
+
+def proj_bwd(x, W, dh, need_dx: bool):
+    n, K = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dW = torch.empty_like(W)
+    db = torch.empty(D, dtype=torch.float32, device=x.device)
+    _abi.check(_lib().fnb_proj_bwd(_p(x), _p(W), _p(dh), n, K, _p(dx), _p(dW), _p(db), _p(scratch(x.device)),
+                                   _stream()), "proj_bwd")
+    return dx, dW, db
+
+
+def node_scalars(h, alpha, alpha_stride, off_t, off_s):
+    S = torch.empty((h.shape[0], 8), dtype=torch.float32, device=h.device)
+    _abi.check(_lib().fnb_node_scalars(_p(h), h.shape[0], _p(alpha), alpha_stride, off_t, off_s, _p(S), _stream()),
+               "node_scalars")
+    return S
+
+
+def edge_coef_fwd(We, be, in_dim, alpha, alpha_stride, off_e):
+    coef = torch.empty(4 * in_dim + 4, dtype=torch.float32, device=We.device)
+    _abi.check(_lib().fnb_edge_coef_fwd(_p(We), _p(be), in_dim, _p(alpha), alpha_stride, off_e, _p(coef), _stream()),
+               "edge_coef_fwd")
+    return coef
+
+
+def edge_coef_bwd(We, be, in_dim, alpha, alpha_stride, off_e, d_coef, d_alpha):
+    dWe, dbe = torch.empty_like(We), torch.empty_like(be)
+    _abi.check(_lib().fnb_edge_coef_bwd(_p(We), _p(be), in_dim, _p(alpha), alpha_stride, off_e, _p(d_coef), _p(dWe),
+                                        _p(dbe), _p(d_alpha), _stream()), "edge_coef_bwd")
+    return dWe, dbe
+
+
+def gat_fwd(g: GraphCSR, h, S, mode, edge_attr=None, coef=None, save_p=True, mask=(-1, -1),
+            next_alpha=None, next_alpha_stride=0):
+    """Returns (out [N,128], p_saved [E,4] or None, next_Se [N,4] or None)."""
+    out = torch.empty((g.n_nodes, D), dtype=torch.float32, device=h.device)
+    p = torch.empty((g.n_edges, H), dtype=torch.float32, device=h.device) if save_p else None
+    nse = torch.empty((g.n_nodes, H), dtype=torch.float32, device=h.device) if next_alpha is not None else None
+    _abi.check(_lib().fnb_gat_fwd(_p(g.rowptr), _p(g.col), g.n_nodes, g.n_edges, _p(h), _p(S), mode, _p(edge_attr),
+                                  _p(coef), _p(g.eid), g.n_real, _p(out), _p(p), mask[0], mask[1], _p(next_alpha),
+                                  next_alpha_stride, _p(nse), _stream()), "gat_fwd")
+    return out, p, nse
+
+
+def attn_by_source(g: GraphCSR, p):
+    w = torch.empty((g.n_nodes, H), dtype=torch.float32, device=p.device)
+    _abi.check(_lib().fnb_attn_by_source(_p(g.rrowptr), _p(g.rslot), _p(p), g.n_nodes, _p(w), _stream()),
+               "attn_by_source")
+    return w
+
+
+def gat_bwd_dst(g: GraphCSR, h, dout, p, mode=EDGE_NONE, edge_attr=None, want_coef=False):
+    dz = torch.empty((g.n_edges, H), dtype=torch.float32, device=h.device)
+    dSt = torch.empty((g.n_nodes, H), dtype=torch.float32, device=h.device)
+    d_coef = None
+    if want_coef:
+        d_coef = torch.empty(8 if mode == EDGE_AFFINE1 else 28, dtype=torch.float32, device=h.device)
+    _abi.check(_lib().fnb_gat_bwd_dst(_p(g.rowptr), _p(g.col), g.n_nodes, g.n_edges, _p(h), _p(dout), _p(p), mode,
+                                      _p(edge_attr), _p(dz), _p(dSt), _p(d_coef), _p(scratch(h.device)), _stream()),
+               "gat_bwd_dst")
+    return dz, dSt, d_coef
+
+
+def gat_bwd_src(g: GraphCSR, h, dout, p, dz, dSt, alpha, alpha_stride, off_t, off_s, d_alpha):
+    dh = torch.empty((g.n_nodes, D), dtype=torch.float32, device=h.device)
+    _abi.check(_lib().fnb_gat_bwd_src(_p(g.rrowptr), _p(g.rslot), _p(g.rdst), g.n_nodes, _p(h), _p(dout), _p(p),
+                                      _p(dz), _p(dSt), _p(alpha), alpha_stride, off_t, off_s, _p(dh), _p(d_alpha),
+                                      _p(scratch(h.device)), _stream()), "gat_bwd_src")
+    return dh
+
+
+def edge_table_bwd(g: GraphCSR, dz, feat, alpha, alpha_stride, off_e, g_base, d_alpha):
+    g_feat = torch.empty((g.n_real, D), dtype=torch.float32, device=feat.device)
+    _abi.check(_lib().fnb_edge_table_bwd(_p(dz), _p(g.slot_of_eid), g.n_real, _p(feat), _p(alpha), alpha_stride,
+                                         off_e, _p(g_base), _p(g_feat), _p(d_alpha), _p(scratch(feat.device)),
+                                         _stream()), "edge_table_bwd")
+    return g_feat
+
+
+def segment_sum(rowptr, col, n_segments, x, out=None, out_stride=D, alpha=None, alpha_stride=0, off_t=0, off_s=0):
+    if out is None:
+        out = torch.empty((n_segments, D), dtype=torch.float32, device=x.device)
+    S = torch.empty((n_segments, 8), dtype=torch.float32, device=x.device) if alpha is not None else None
+    _abi.check(_lib().fnb_segment_sum(_p(rowptr), _p(col), n_segments, _p(x), _p(out), out_stride, _p(alpha),
+                                      alpha_stride, off_t, off_s, _p(S), _stream()), "segment_sum")
+    return out, S
+
+
+def segment_gather(g, g_stride, seg_of, n_rows, base=None):
+    dx = torch.empty((n_rows, D), dtype=torch.float32, device=g.device)
+    _abi.check(_lib().fnb_segment_gather(_p(g), g_stride, _p(seg_of), n_rows, _p(base), _p(dx), _stream()),
+               "segment_gather")
+    return dx
+
+
+_philox_offset = 0
+
+
+def next_philox(n_elems: int):
+    """(seed, offset) for one dropout call; the offset stream advances by the number of Philox
+    counters the call consumes, so no two calls of a run share random numbers."""
+    global _philox_offset
+    off = _philox_offset
+    _philox_offset += (n_elems + 3) // 4
+    return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, off
+
+
+def dropout_relu_fwd(x, p: float, training: bool, relu: bool, seed: int, offset: int):
+    y = torch.empty_like(x)
+    _abi.check(_lib().fnb_dropout_relu_fwd(_p(x), _p(y), x.numel(), float(p), int(training), int(relu), seed, offset,
+                                           _stream()), "dropout_relu_fwd")
+    return y
+
+
+def dropout_relu_bwd(dy, y, p: float, training: bool):
+    dx = torch.empty_like(y)
+    _abi.check(_lib().fnb_dropout_relu_bwd(_p(dy), _p(y), _p(dx), y.numel(), float(p), int(training), _stream()),
+               "dropout_relu_bwd")
+    return dx

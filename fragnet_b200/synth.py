@@ -32,6 +32,7 @@ connection columns (fragnet/dataset/features.py:43-139).
 from __future__ import annotations
 
 import random
+import zlib
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import List, Sequence
@@ -342,7 +343,7 @@ def handmade(kind: str) -> SimpleNamespace:
     two-atom component (``[Cl-].CC``-like).  ``single_frag``: a 4-atom chain, one fragment.
     ``two_frag``: a 4-atom chain cut in the middle.
     """
-    rng = random.Random(hash(kind) & 0xFFFF)
+    rng = random.Random(zlib.crc32(kind.encode()))
     if kind == "two_atom":
         bonds, n_atoms, cut = [(0, 1)], 2, []
     elif kind == "ion_pair":

@@ -1,0 +1,171 @@
+/*
+ * fragnet_b200 -- C ABI of the B200 (sm_100a) kernels behind FragNet's GAT2 hot path.
+ *
+ * The reference (pnnl/FragNet) is pure Python; on this path it calls three third-party
+ * native ops through their Python bindings:
+ *     torch_scatter.scatter_add / scatter_softmax    fragnet/model/gat/gat2.py:153-165,210-219,
+ *                                                    234,257-268,303-312,820-821
+ *     torch_geometric.utils.add_self_loops           fragnet/model/gat/gat2.py:179
+ *     torch.index_select / nn.Linear (ATen)          fragnet/model/gat/gat2.py:139-147,189-201,...
+ * The entry points below are what a binding for that boundary links against.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors); the library never
+ *     allocates, frees or synchronises; outputs and workspaces are caller-allocated;
+ *   - the last argument is the cudaStream_t to launch on (passed as void*);
+ *   - return value: 0 = ok, negative = argument validation error (see fnb_error_string),
+ *     positive = cudaError_t of a failed launch;
+ *   - re-entrant, no global state;  all feature matrices are row-major fp32 with D = 128
+ *     columns, H = 4 heads of d = 32 (the only geometry FragNet's gat2 uses with emb_dim 128);
+ *   - graph indices handed in are int64 (as produced by the reference's collate_fn,
+ *     fragnet/dataset/data.py:931-948); the CSR arrays produced and consumed are int32.
+ */
+#ifndef FRAGNET_B200_H
+#define FRAGNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNB_D 128 /* embedding width  */
+#define FNB_H 4   /* attention heads  */
+#define FNB_ABI_VERSION 1
+
+/* edge-term modes of the fused attention kernels */
+#define FNB_EDGE_NONE 0   /* no edge term                                              */
+#define FNB_EDGE_AFFINE1 1 /* bond graph: S_e[h] = attr[slot]*coef[h] + coef[4+h]       */
+#define FNB_EDGE_AFFINE6 2 /* fragment-connection graph: attr[slot,0:6] . coef[h,0:6] + coef[24+h] */
+#define FNB_EDGE_TABLE 3  /* atom / fragment graph: S_e = table[eid[slot], 0:4]; eid >= n_real -> 0 (self loop) */
+
+int fnb_version(void);
+const char *fnb_error_string(int code);
+/* Diagnostic: number of kernels this library has launched in this process (monotonic). */
+uint64_t fnb_launch_count(void);
+
+/* Scratch bytes every backward / reduction entry point may use (constant, independent of sizes). */
+size_t fnb_scratch_bytes(void);
+
+/* ---- (a) on-device collate: destination-sorted CSR + reverse (source-sorted) CSR ------------
+ * Replaces the implicit grouping done by scatter_softmax/scatter_add (gat2.py:153-165 etc.) and
+ * add_self_loops (gat2.py:179).  Edges are (dst[e], src[e]), e < n_edges; with
+ * append_self_loops != 0, n_nodes extra edges (i,i) with ids n_edges+i follow them.
+ * Slots of one destination are ordered by edge id (== stable sort by destination):
+ *   rowptr[n_nodes+1], col[slot] = source node, eid[slot] = edge id, slot_of_eid[e] = slot
+ * Reverse CSR groups the same edges by source, again ordered by edge id:
+ *   rrowptr[n_nodes+1], rslot[r] = forward slot of that edge, rdst[r] = its destination node.
+ * src == NULL means src[e] = e (membership lists such as atom_to_frag_ids, gat2.py:234).
+ * status[0] is set non-zero on the device if an index is out of [0, n_nodes).
+ */
+size_t fnb_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges_total);
+int fnb_csr_build(const int64_t *dst, const int64_t *src, int64_t n_edges, int64_t n_nodes,
+                  int append_self_loops, int32_t *rowptr, int32_t *col, int32_t *eid,
+                  int32_t *slot_of_eid, int32_t *rrowptr, int32_t *rslot, int32_t *rdst,
+                  void *workspace, size_t workspace_bytes, int32_t *status, void *stream);
+
+/* out[r, 0:width] = in[index[r], 0:width]  -- puts per-edge attributes into CSR slot order. */
+int fnb_gather_rows(const float *in, const int32_t *index, int64_t n_rows, int width, float *out,
+                    void *stream);
+
+/* offsets[g] = first position i with sorted_ids[i] >= g, g = 0..n_segments (molecule boundaries
+ * of the sorted `batch` / `frag_batch` vectors, data.py:896-901). */
+int fnb_segment_offsets(const int64_t *sorted_ids, int64_t n, int64_t n_segments, int32_t *offsets,
+                        void *stream);
+
+/* int64 -> int32 narrowing of an index vector (atom_to_frag_ids, batch). */
+int fnb_narrow_index(const int64_t *in, int64_t n, int32_t *out, void *stream);
+
+/* ---- dense projection with the per-node logit scalars fused into the epilogue ---------------
+ * h[n,:] = x[n,:] @ W^T + b          (nn.Linear; projection_{a,b,fb}, gat2.py:142,189,247)
+ * S[n,h]   = <h[n,h,:], alpha[h, off_t : off_t+32]>    (target half of the head vector)
+ * S[n,4+h] = <h[n,h,:], alpha[h, off_s : off_s+32]>    (source half)
+ * x [n_rows,K], W [128,K], b [128], alpha [4,alpha_stride].  S may be NULL.
+ */
+int fnb_proj_fwd(const float *x, const float *W, const float *b, int64_t n_rows, int K,
+                 const float *alpha, int alpha_stride, int off_t, int off_s, float *h, float *S,
+                 void *stream);
+/* dx = dh @ W (dx may be NULL); dW = dh^T @ x; db = column sums of dh.  scratch: fnb_scratch_bytes(). */
+int fnb_proj_bwd(const float *x, const float *W, const float *dh, int64_t n_rows, int K, float *dx,
+                 float *dW, float *db, void *scratch, void *stream);
+/* S for features that are not projected (fragment graph: hf = pooled atoms, gat2.py:285). */
+int fnb_node_scalars(const float *h, int64_t n_rows, const float *alpha, int alpha_stride,
+                     int off_t, int off_s, float *S, void *stream);
+
+/* Constants of the affine edge term from the tiny edge-attribute embedding (App. A.5):
+ * coef[h, 0:in] = We^T alpha_e[h], coef[4*in + h] = <be, alpha_e[h]>,
+ * We [32,in] = edge_attr_{bond,fbond}_embed.weight, alpha_e = alpha[h, off_e : off_e+32]. */
+int fnb_edge_coef_fwd(const float *We, const float *be, int in_dim, const float *alpha,
+                      int alpha_stride, int off_e, float *coef, void *stream);
+/* d_coef [4*in+4] -> dWe [32,in], dbe [32], d_alpha[h, off_e:off_e+32] (written, not accumulated). */
+int fnb_edge_coef_bwd(const float *We, const float *be, int in_dim, const float *alpha,
+                      int alpha_stride, int off_e, const float *d_coef, float *dWe, float *dbe,
+                      float *d_alpha, void *stream);
+
+/* ---- (b) fused gather -> edge logit -> LeakyReLU(0.2) -> segment softmax -> aggregate -------
+ * One warp per destination node (gat2.py:146-169, 196-224, 250-272, 286-316 in one pass):
+ *   z[e,h] = S[t,h] + S_e[e,h] + S[s,4+h];  p = softmax over the slots of t;  out[t] = sum p*h[s]
+ * p_saved [n_edges,4] (slot order; sign bit carries z>0 for the LeakyReLU derivative) may be
+ * NULL for inference.  Rows [mask_lo, mask_hi) of out are zeroed (bond / frag-bond / atom masks,
+ * gat2.py:173-176,227-231,275-278); pass mask_lo = mask_hi = -1 for none.
+ * If next_alpha_e != NULL, also emits next_Se[t,h] = <out[t,:], next_alpha_e[h, 0:128]>, the edge
+ * term of the graph whose edges are this graph's nodes (bond -> atom, fbond -> fragment).
+ */
+int fnb_gat_fwd(const int32_t *rowptr, const int32_t *col, int64_t n_nodes, int64_t n_edges,
+                const float *h, const float *S, int edge_mode, const float *edge_attr,
+                const float *edge_coef, const int32_t *eid, int64_t n_real_edges, float *out,
+                float *p_saved, int64_t mask_lo, int64_t mask_hi, const float *next_alpha_e,
+                int next_alpha_stride, float *next_Se, void *stream);
+
+/* w[n,h] = sum of p over the edges whose SOURCE is n (gat2.py:165,219,268,312), atomics-free over
+ * the reverse CSR. */
+int fnb_attn_by_source(const int32_t *rrowptr, const int32_t *rslot, const float *p_saved,
+                       int64_t n_nodes, float *w, void *stream);
+
+/* ---- (c) atomics-free backward --------------------------------------------------------------
+ * Pass 1, destination segments: dz[slot,h] (gradient of the pre-LeakyReLU logit), dSt[t,h], and
+ * the gradient of the affine edge-term constants d_coef (same layout as coef; NULL unless the
+ * mode is AFFINE1/AFFINE6).  With extra_g/extra_index, dout[t] += extra_g[extra_index[t]] is
+ * applied on the fly and the combined rows are written to dout_combined (atom->fragment pooling
+ * backward, gat2.py:234).  scratch: fnb_scratch_bytes().
+ */
+int fnb_gat_bwd_dst(const int32_t *rowptr, const int32_t *col, int64_t n_nodes, int64_t n_edges,
+                    const float *h, const float *dout, const float *p_saved, int edge_mode,
+                    const float *edge_attr, float *dz, float *dSt, float *d_coef, void *scratch,
+                    void *stream);
+/* Pass 2, source segments over the reverse CSR: dh[s] = sum p*dout[t] + dSt[s]*alpha_t + dSs[s]*alpha_s,
+ * and d_alpha[h, off_t:+32], d_alpha[h, off_s:+32] (written). */
+int fnb_gat_bwd_src(const int32_t *rrowptr, const int32_t *rslot, const int32_t *rdst,
+                    int64_t n_nodes, const float *h, const float *dout, const float *p_saved,
+                    const float *dz, const float *dSt, const float *alpha, int alpha_stride,
+                    int off_t, int off_s, float *dh, float *d_alpha, void *scratch, void *stream);
+/* Edge-term backward for TABLE mode: for every real edge e with feature row feat[e,:]:
+ *   g_feat[e,:] = g_base[e,:] + sum_h dz[slot_of_eid[e],h] * alpha_e[h,:]   (g_base NULL = 0; may alias g_feat)
+ *   d_alpha[h, off_e:off_e+128] = sum_e dz[slot_of_eid[e],h] * feat[e,:] */
+int fnb_edge_table_bwd(const float *dz, const int32_t *slot_of_eid, int64_t n_real_edges,
+                       const float *feat, const float *alpha, int alpha_stride, int off_e,
+                       const float *g_base, float *g_feat, float *d_alpha, void *scratch, void *stream);
+
+/* ---- (d) segment-sum pooling ----------------------------------------------------------------
+ * out[seg,:] = sum over members (gat2.py:234 atom->fragment via a membership CSR; gat2.py:820-821
+ * readout via contiguous offsets: pass col == NULL).  out rows have stride out_stride floats so
+ * the readout can write both halves of the [G,256] concatenation in place.  Optional fused S. */
+int fnb_segment_sum(const int32_t *rowptr, const int32_t *col, int64_t n_segments, const float *x,
+                    float *out, int64_t out_stride, const float *alpha, int alpha_stride, int off_t,
+                    int off_s, float *S, void *stream);
+/* dx[i,:] = base[i,:] + g[seg_of[i], 0:128] with g row stride g_stride (base NULL = 0; may alias dx). */
+int fnb_segment_gather(const float *g, int64_t g_stride, const int32_t *seg_of, int64_t n_rows,
+                       const float *base, float *dx, void *stream);
+
+/* ---- fused ReLU(Dropout(x)) (gat2.py:414-418,436-440) ----------------------------------------
+ * y = relu(keep(i) ? x/(1-p) : 0), keep from Philox4x32-10(seed, offset + i/4).  p = 0 or
+ * training == 0 gives plain ReLU.  relu == 0 gives plain dropout (input features, gat2.py:396). */
+int fnb_dropout_relu_fwd(const float *x, float *y, int64_t n, float p, int training, int relu,
+                         uint64_t seed, uint64_t offset, void *stream);
+/* dx = dy * (y > 0) / (1-p)   (valid for the fused ReLU form; y is the forward output) */
+int fnb_dropout_relu_bwd(const float *dy, const float *y, float *dx, int64_t n, float p,
+                         int training, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRAGNET_B200_H */

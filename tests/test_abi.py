@@ -1,0 +1,50 @@
+"""The C-ABI library builds, loads, and exports exactly what include/fragnet_b200.h declares (CPU only:
+no kernel is launched here)."""
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "fragnet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fnb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from fragnet_b200 import _abi
+    assert _declared() == sorted(_abi.SIGNATURES)
+
+
+def test_library_exports_every_symbol():
+    from fragnet_b200 import _abi
+    lib = _abi.load()
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert lib.fnb_version() == 1
+    assert lib.fnb_scratch_bytes() >= 148 * (128 * 256 + 128) * 4
+    assert lib.fnb_csr_workspace_bytes(1000, 5000) > 2 * 1000 * 4 + 2 * 5000 * 4
+    assert lib.fnb_error_string(0) == b"ok"
+    assert b"NULL" in lib.fnb_error_string(-1)
+
+
+def test_argument_validation_needs_no_gpu():
+    """Negative return codes come from host-side checks before any launch."""
+    from fragnet_b200 import _abi
+    lib = _abi.load()
+    assert lib.fnb_csr_build(None, None, -1, 4, 0, None, None, None, None, None, None, None, None, 0, None, None) == -2
+    assert lib.fnb_csr_build(None, None, 0, 4, 0, None, None, None, None, None, None, None, None, 0, None, None) == -1
+    assert lib.fnb_proj_fwd(None, None, None, 8, 128, None, 0, 0, 0, None, None, None) == -1
+    assert lib.fnb_edge_coef_fwd(None, None, 3, None, 96, 32, None, None) == -3
+    assert lib.fnb_dropout_relu_fwd(None, None, 4, 1.5, 1, 1, 0, 0, None) == -2
+
+
+def test_no_cpu_fallback_in_product_path():
+    """The product package never imports the oracle."""
+    pkg = os.path.join(ROOT, "fragnet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), os.path.join(dirpath, f)
