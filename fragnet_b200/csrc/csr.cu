@@ -241,7 +241,7 @@ extern "C" int fnb_csr_build(const int64_t *dst, const int64_t *src, int64_t n_e
   if (workspace_bytes < fnb_csr_workspace_bytes(n_nodes, n_total)) return FNB_ERR_WORKSPACE;
   // With src == NULL the "source" index space is the edge list itself (membership lists); a reverse
   // CSR makes no sense there.
-  if (!src && reverse) return FNB_ERR_MODE;
+  if (!src && reverse && n_edges > 0) return FNB_ERR_MODE;
   const int64_t n_src_nodes = src ? n_nodes : n_total;
 
   char *ws = (char *)workspace;

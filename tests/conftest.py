@@ -35,6 +35,23 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+def grad_errs(pairs, floor=1e-4):
+    """Gradient parity metric: per tensor, max|a-b| / max(max|b|, floor * largest gradient entry of the model).
+
+    Some GAT2 gradients are sums that cancel to rounding noise (softmax is shift invariant, so e.g. the bias of the
+    edge-attribute embedding only gets the LeakyReLU slope residual: entries ~1e-9 next to ~1e-2 elsewhere); for
+    those tensors a pure per-tensor relative error compares noise with noise, hence the floor tied to the model's
+    overall gradient scale.  ``pairs``: iterable of (name, got, want).  Returns {name: err}."""
+    pairs = [(k, a.detach().double().cpu(), b.detach().double().cpu()) for k, a, b in pairs]
+    scale = max((float(b.abs().max()) for _, _, b in pairs if b.numel()), default=0.0)
+    out = {}
+    for k, a, b in pairs:
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        den = max(float(b.abs().max()) if b.numel() else 0.0, floor * scale, 1e-30)
+        out[k] = float((a - b).abs().max()) / den if b.numel() else 0.0
+    return out
+
+
 @pytest.fixture(scope="session")
 def golden():
     return torch.load(GOLDEN)
