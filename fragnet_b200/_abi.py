@@ -23,8 +23,8 @@ SIGNATURES = {
     "fnb_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "fnb_segment_offsets": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "fnb_narrow_index": (C.c_int, [_vp, _i64, _vp, _vp]),
-    "fnb_proj_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "fnb_proj_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fnb_proj_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "fnb_proj_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fnb_node_scalars": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp]),
     "fnb_edge_coef_fwd": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "fnb_edge_coef_bwd": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -42,6 +42,7 @@ SIGNATURES = {
 }
 
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
+PRECISION_FP32, PRECISION_TF32 = 0, 1
 
 _lib = None
 

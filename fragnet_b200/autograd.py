@@ -29,6 +29,7 @@ class LayerOptions:
     atom_mask: object = None          # int, sequence or tensor of atom rows to zero (gat2.py:227-231)
     want_attention: bool = False
     want_frag_block: bool = True      # False elides the fragment-graph block (dead for non-final layers)
+    precision: int = 0                # ops.PRECISION_FP32 / PRECISION_TF32 for the dense projections
 
 
 def _range_mask(start, width):
@@ -55,11 +56,11 @@ class FragNetLayerFn(torch.autograd.Function):
 
         # bond graph (gat2.py:138-169); epilogue emits the atom graph's edge term <new_bond[e], a_e[h]>
         coef_b = ops.edge_coef_fwd(We_b, be_b, 1, a_b, AB_STRIDE, AB_E)
-        hb, Sb = ops.proj_fwd(x_bond, Wb, bb, a_b, AB_STRIDE, AB_T, AB_S)
+        hb, Sb = ops.proj_fwd(x_bond, Wb, bb, a_b, AB_STRIDE, AB_T, AB_S, precision=opts.precision)
         new_bond, p_b, se_atom = ops.gat_fwd(plan.bond, hb, Sb, EDGE_AFFINE1, plan.bond.attr, coef_b, save_p,
                                              _range_mask(opts.bond_mask, 2), a[:, A_E:], A_STRIDE)
         # atom graph with self loops (gat2.py:179-224)
-        ha, Sa = ops.proj_fwd(x_atoms, Wa, ba, a, A_STRIDE, A_T, A_S)
+        ha, Sa = ops.proj_fwd(x_atoms, Wa, ba, a, A_STRIDE, A_T, A_S, precision=opts.precision)
         am = opts.atom_mask
         am_int = isinstance(am, int)
         x_atoms_new, p_a, _ = ops.gat_fwd(plan.atom, ha, Sa, EDGE_TABLE, se_atom, None, save_p,
@@ -71,7 +72,7 @@ class FragNetLayerFn(torch.autograd.Function):
                                  alpha=f, alpha_stride=A_STRIDE, off_t=A_T, off_s=A_S)
         # fragment-connection graph (gat2.py:239-272); epilogue emits the fragment graph's edge term
         coef_fb = ops.edge_coef_fwd(We_fb, be_fb, 6, f_a_b, AB_STRIDE, AB_E)
-        hfb, Sfb = ops.proj_fwd(x_fbond, Wfb, bfb, f_a_b, AB_STRIDE, AB_T, AB_S)
+        hfb, Sfb = ops.proj_fwd(x_fbond, Wfb, bfb, f_a_b, AB_STRIDE, AB_T, AB_S, precision=opts.precision)
         fmask = (-1, -1) if opts.frag_bond_mask is None else (2 * int(opts.frag_bond_mask), 2 * int(opts.frag_bond_mask) + 2)
         new_fbond, p_fb, se_frag = ops.gat_fwd(plan.fbond, hfb, Sfb, EDGE_AFFINE6, plan.fbond.attr, coef_fb, save_p,
                                                fmask, f[:, A_E:] if opts.want_frag_block else None, A_STRIDE)
@@ -118,7 +119,7 @@ class FragNetLayerFn(torch.autograd.Function):
             dz, dSt, d_coef = ops.gat_bwd_dst(plan.fbond, hfb, g_fbond, p_fb, EDGE_AFFINE6, plan.fbond.attr, True)
             d_hfb = ops.gat_bwd_src(plan.fbond, hfb, g_fbond, p_fb, dz, dSt, f_a_b, AB_STRIDE, AB_T, AB_S, d_fab)
             dWe_fb, dbe_fb = ops.edge_coef_bwd(We_fb, be_fb, 6, f_a_b, AB_STRIDE, AB_E, d_coef, d_fab)
-            dx_fbond, dWfb, dbfb = ops.proj_bwd(x_fbond, Wfb, d_hfb, needs[4])
+            dx_fbond, dWfb, dbfb = ops.proj_bwd(x_fbond, Wfb, d_hfb, needs[4], opts.precision)
         # ---- pooling backward folded into the atom block's incoming gradient
         if d_hf is not None:
             g_atoms = ops.segment_gather(d_hf, ops.D, plan.a2f32, plan.n_atoms, g_atoms)
@@ -129,7 +130,7 @@ class FragNetLayerFn(torch.autograd.Function):
             dz, dSt, _ = ops.gat_bwd_dst(plan.atom, ha, g_atoms, p_a)
             d_ha = ops.gat_bwd_src(plan.atom, ha, g_atoms, p_a, dz, dSt, a, A_STRIDE, A_T, A_S, d_a)
             g_bond = ops.edge_table_bwd(plan.atom, dz, new_bond, a, A_STRIDE, A_E, g_bond, d_a)
-            dx_atoms, dWa, dba = ops.proj_bwd(x_atoms, Wa, d_ha, needs[2])
+            dx_atoms, dWa, dba = ops.proj_bwd(x_atoms, Wa, d_ha, needs[2], opts.precision)
         # ---- bond graph block
         d_ab = dWb = dbb = dWe_b = dbe_b = dx_bond = None
         if g_bond is not None:
@@ -137,7 +138,7 @@ class FragNetLayerFn(torch.autograd.Function):
             dz, dSt, d_coef = ops.gat_bwd_dst(plan.bond, hb, g_bond, p_b, EDGE_AFFINE1, plan.bond.attr, True)
             d_hb = ops.gat_bwd_src(plan.bond, hb, g_bond, p_b, dz, dSt, a_b, AB_STRIDE, AB_T, AB_S, d_ab)
             dWe_b, dbe_b = ops.edge_coef_bwd(We_b, be_b, 1, a_b, AB_STRIDE, AB_E, d_coef, d_ab)
-            dx_bond, dWb, dbb = ops.proj_bwd(x_bond, Wb, d_hb, needs[3])
+            dx_bond, dWb, dbb = ops.proj_bwd(x_bond, Wb, d_hb, needs[3], opts.precision)
         return (None, None, dx_atoms, dx_bond, dx_fbond, dWb, dbb, dWfb, dbfb, dWe_b, dbe_b, dWe_fb, dbe_fb,
                 dWa, dba, d_ab, d_a, d_f, d_fab)
 

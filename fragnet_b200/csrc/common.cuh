@@ -69,3 +69,8 @@ __device__ __forceinline__ float leaky(float z) { return z > 0.f ? z : kNegSlope
 //   out[(j / row_len) * out_stride + j % row_len] (+)= sum_b partials[b * pstride + j],  j < width.
 int fnb_launch_reduce_partials(const float *partials, int n_blocks, int pstride, int width, float *out, int row_len,
                                int out_stride, int accumulate, cudaStream_t stream);
+
+// Tensor-core (tcgen05, TF32) projection path, tc_gemm.cu.  Returns FNB_ERR_MODE when the shape cannot use TMA.
+int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
+                       int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream);
+int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream);

@@ -248,12 +248,19 @@ __global__ void k_edge_coef_bwd(const float *__restrict__ We, const float *__res
 }  // namespace
 
 extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int64_t n_rows, int K, const float *alpha,
-                            int alpha_stride, int off_t, int off_s, float *h, float *S, void *stream) {
+                            int alpha_stride, int off_t, int off_s, float *h, float *S, int precision, void *stream) {
   if (n_rows < 0 || K <= 0) return FNB_ERR_SIZE;
   if (n_rows == 0) return 0;
   if (!x || !W || !h) return FNB_ERR_NULL;
   if (S && !alpha) return FNB_ERR_NULL;
   if (!fnb_aligned16(h)) return FNB_ERR_ALIGN;
+  if (precision == FNB_PRECISION_TF32) {
+    const int rc = fnb_tc_proj_launch(x, W, b, n_rows, K, S ? alpha : nullptr, alpha_stride, off_t, off_s, h, S,
+                                      (cudaStream_t)stream);
+    if (rc != FNB_ERR_MODE) return rc;   // shapes TMA cannot address (K*4 % 16 != 0) take the SIMT kernel below
+  } else if (precision != FNB_PRECISION_FP32) {
+    return FNB_ERR_MODE;
+  }
   GemmArgs g;
   g.A = x; g.lda = K; g.B = W; g.ldb = K; g.C = h; g.ldc = kD; g.M = n_rows; g.Kd = K; g.Nc = kD; g.bias = b;
   g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s; g.S = S;
@@ -264,11 +271,23 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
 }
 
 extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int64_t n_rows, int K, float *dx,
-                            float *dW, float *db, void *scratch, void *stream_) {
+                            float *dW, float *db, int precision, void *scratch, void *stream_) {
   if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
   if (!x || !W || !dh || !dW || !scratch) return FNB_ERR_NULL;
+  if (precision != FNB_PRECISION_FP32 && precision != FNB_PRECISION_TF32) return FNB_ERR_MODE;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (dx && n_rows > 0) {
+  bool dx_done = false;
+  if (dx && n_rows > 0 && precision == FNB_PRECISION_TF32 && K == kD) {
+    // dx = dh @ W as the same tensor-core kernel with B = W^T (staged in the head of the scratch buffer; the
+    // weight-gradient partials below are written after this kernel on the same stream)
+    float *Wt = (float *)scratch;
+    int rc = fnb_tc_transpose128_launch(W, Wt, stream);
+    if (rc) return rc;
+    rc = fnb_tc_proj_launch(dh, Wt, nullptr, n_rows, kD, nullptr, 0, 0, 0, dx, nullptr, stream);
+    if (rc == 0) dx_done = true;
+    else if (rc != FNB_ERR_MODE) return rc;
+  }
+  if (dx && n_rows > 0 && !dx_done) {
     GemmArgs g;
     g.A = dh; g.lda = kD; g.B = W; g.ldb = K; g.C = dx; g.ldc = K; g.M = n_rows; g.Kd = kD; g.Nc = K; g.bias = nullptr;
     g.alpha = nullptr; g.alpha_stride = 0; g.off_t = 0; g.off_s = 0; g.S = nullptr;

@@ -1,0 +1,335 @@
+// Tensor-core projection GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma (TF32 in, FP32 accumulate in
+// TMEM) -> tcgen05.ld epilogue with the per-node logit scalars fused.
+//
+//   C[M,128] = A[M,K] @ B[128,K]^T (+ bias),  S[m, h] = <C[m, 32h:32h+32], alpha_t[h]>,  S[m, 4+h] likewise with alpha_s
+//
+// Reference op: nn.Linear projection_{a,b,fb} (fragnet/model/gat/gat2.py:142,189,247) and, through the same
+// kernel with B = W^T, the input gradient dX = dH @ W of its backward.  The shapes are M = nodes of one batched
+// graph (1e4..1e6), N = 128, K = 128: ~32 flop/byte, i.e. HBM-bound on B200 even at TF32 rate, so the design goal
+// is simply "one pass over A and C at memory speed": persistent CTAs (one per SM), the weight matrix resident in
+// shared memory for the CTA's lifetime, A streamed through a 6-deep TMA ring of 128x32 K-blocks (128-byte swizzle,
+// K-major), two 128-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter w -> rows 32w..32w+31 of the tile, one row per
+// thread, so the per-head dot products of the fused epilogue need no shuffles), warp 4 TMA producer (one lane),
+// warp 5 TMEM allocator + MMA issuer (one lane).
+//
+// Numerics: TF32 operands (10-bit mantissa) with FP32 accumulation -- more accurate than the bf16-in/fp32-acc the
+// north star allows for the projections; the strict-FP32 path (proj.cu) remains the parity reference.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 128;
+constexpr int TC_BK = 32;                                  // fp32 elements = 128 bytes = one swizzle row
+constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB per 128x32 K-block
+constexpr int TC_STAGES = 6;
+constexpr int TC_MAX_KB = 8;                               // K <= 256
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;                          // two 128-column FP32 accumulators
+constexpr int UMMA_K = 8;                                  // K per tcgen05.mma for kind::tf32 (32 bytes)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (tile row), register j = column j.
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows are 128 bytes apart, 8-row groups are
+// 1024 bytes apart (SBO); LBO is not used by swizzled K-major layouts (canonical value 1); bits 46-47 = 0b01 is the
+// sm_100 descriptor version; layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc_sw128_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128.
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+
+struct TcArgs {
+  float *C;             // [M,128]
+  const float *bias;    // [128] or NULL
+  const float *alpha;   // [4, alpha_stride] or NULL (no S)
+  int alpha_stride, off_t, off_s;
+  float *S;             // [M,8] or NULL
+  int64_t M;
+  int n_kb;             // K-blocks of 32
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 1 + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[128], s_at[128], s_as[128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dynamic smem: [W: n_kb x 16 KiB][A ring: TC_STAGES x 16 KiB], 1024-byte aligned for the 128B swizzle
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_w = smem_base;
+  const uint32_t smem_a = smem_base + (uint32_t)g.n_kb * TC_STAGE_BYTES;
+  const uint32_t bar_full = smem_u32(&bars[0]);                    // [TC_STAGES]
+  const uint32_t bar_empty = smem_u32(&bars[TC_STAGES]);           // [TC_STAGES]
+  const uint32_t bar_w = smem_u32(&bars[2 * TC_STAGES]);
+  const uint32_t bar_acc_full = smem_u32(&bars[2 * TC_STAGES + 1]);   // [2]
+  const uint32_t bar_acc_empty = smem_u32(&bars[2 * TC_STAGES + 3]);  // [2]
+
+  for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
+    s_bias[i] = g.bias ? g.bias[i] : 0.f;
+    const int hh = i >> 5, j = i & 31;
+    s_at[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_t + j] : 0.f;
+    s_as[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_s + j] : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_w, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int64_t n_tiles = (g.M + TC_BM - 1) / TC_BM;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, (uint32_t)g.n_kb * TC_STAGE_BYTES);
+      for (int kb = 0; kb < g.n_kb; ++kb) tma_load_2d(smem_w + kb * TC_STAGE_BYTES, &tm_b, bar_w, kb * TC_BK, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+          tma_load_2d(smem_a + stage * TC_STAGE_BYTES, &tm_a, bar_full + 8 * stage, kb * TC_BK, (int)(tile * TC_BM));
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(bar_w, 0);
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * TC_BN;
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_a + stage * TC_STAGE_BYTES;
+          const uint32_t b_addr = smem_w + kb * TC_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+            const uint64_t da = make_desc_sw128_kmajor(a_addr + k * UMMA_K * 4);
+            const uint64_t db = make_desc_sw128_kmajor(b_addr + k * UMMA_K * 4);
+            tc_mma_tf32(tmem_d, da, db, kIdescTf32, (kb | k) != 0);
+          }
+          tc_commit(bar_empty + 8 * stage);                     // frees the A slot once these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_acc_full + 8 * acc);                      // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 0..3: TMEM -> registers -> (bias, logit scalars) -> global =====
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t row = tile * TC_BM + warp * 32 + lane;
+      const bool in = row < g.M;
+      float st[4], ss[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        uint32_t r[32];
+        tc_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * TC_BN + hh * 32, r);
+        float a_t = 0.f, a_s = 0.f;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r[j]) + s_bias[hh * 32 + j];
+          a_t = fmaf(v[j], s_at[hh * 32 + j], a_t);
+          a_s = fmaf(v[j], s_as[hh * 32 + j], a_s);
+        }
+        st[hh] = a_t;
+        ss[hh] = a_s;
+        if (in) {
+          float *cp = g.C + row * TC_BN + hh * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) st4(cp + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * acc);
+      if (in && g.S) {
+        st4(g.S + row * 8, make_float4(st[0], st[1], st[2], st[3]));
+        st4(g.S + row * 8 + 4, make_float4(ss[0], ss[1], ss[2], ss[3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// B^T for the input-gradient GEMM: Wt[i, o] = W[o, i] (128 x 128).
+__global__ void k_transpose_128(const float *__restrict__ W, float *__restrict__ Wt) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) tile[j][threadIdx.x] = W[(by + j) * 128 + bx + threadIdx.x];
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) Wt[(bx + j) * 128 + by + threadIdx.x] = tile[threadIdx.x][j];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;   // resolved once; the driver entry point is process-wide and immutable
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box = 32 columns (128 bytes) x box_rows, 128-byte swizzle, zero OOB fill.
+int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return FNB_ERR_MODE;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : FNB_ERR_MODE;
+}
+
+}  // namespace
+
+// C[M,128] = A[M,K] @ B[128,K]^T (+bias) with optional fused S; returns FNB_ERR_MODE if the shape cannot take the
+// TMA path (K*4 not a multiple of 16 bytes, K > 256, unaligned pointers) so the caller can fall back to proj.cu.
+int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
+                       int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if ((K & 3) || K > TC_MAX_KB * TC_BK || !fnb_aligned16(A) || !fnb_aligned16(B) || !fnb_aligned16(C) ||
+      (S && !fnb_aligned16(S)) || M >= (int64_t)INT32_MAX)
+    return FNB_ERR_MODE;
+  CUtensorMap tm_a, tm_b;
+  int rc = make_map(&tm_a, A, M, K, TC_BM);
+  if (rc) return rc;
+  rc = make_map(&tm_b, B, TC_BN, K, TC_BN);
+  if (rc) return rc;
+  TcArgs g;
+  g.C = C; g.bias = bias; g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s;
+  g.S = alpha ? S : nullptr; g.M = M; g.n_kb = (K + TC_BK - 1) / TC_BK;
+  const size_t smem = (size_t)(g.n_kb + TC_STAGES) * TC_STAGE_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_tc_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t n_tiles = (M + TC_BM - 1) / TC_BM;
+  const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  k_tc_proj<<<grid, TC_THREADS, smem, stream>>>(tm_a, tm_b, g);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream) {
+  k_transpose_128<<<dim3(4, 4), dim3(32, 8), 0, stream>>>(W, Wt);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}

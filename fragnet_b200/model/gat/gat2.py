@@ -20,7 +20,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import config, ops
 from ...autograd import DropoutReluFn, FragNetLayerFn, LayerOptions, ReadoutFn
 
 _ACTIVATIONS = {
@@ -103,7 +103,8 @@ class FragNetLayerA(nn.Module):
         sizes = (x_atoms.size(0), int(n_frags), x_bond_nodes.size(0), x_fbond_nodes.size(0))
         plan = ops.layer_plan_for(index_tensors, sizes, dev)
         opts = LayerOptions(_as_int_or_none(self.bond_mask), _as_int_or_none(self.frag_bond_mask),
-                            _as_int_or_none(self.atom_mask_individual), want_attention, want_frag_block)
+                            _as_int_or_none(self.atom_mask_individual), want_attention, want_frag_block,
+                            config.precision_id())
         on = lambda t: t if t.device == dev else t.to(dev)
         params = [on(p) for p in self._live_parameters()]
         return FragNetLayerFn.apply(plan, opts, on(x_atoms), on(x_bond_nodes), on(x_fbond_nodes), *params)

@@ -14,7 +14,8 @@ from typing import Optional
 import torch
 
 from . import _abi
-from ._abi import EDGE_AFFINE1, EDGE_AFFINE6, EDGE_NONE, EDGE_TABLE  # noqa: F401  (re-exported)
+from ._abi import (EDGE_AFFINE1, EDGE_AFFINE6, EDGE_NONE, EDGE_TABLE,  # noqa: F401  (re-exported)
+                   PRECISION_FP32, PRECISION_TF32)
 
 D, H = 128, 4
 
@@ -225,22 +226,22 @@ def readout_plan_for(batch_vec: torch.Tensor, frag_batch_vec: torch.Tensor, devi
 
 # ------------------------------------------------------------------------------------------------
 # kernel wrappers (no autograd here; see autograd.py)
-def proj_fwd(x, W, b, alpha=None, alpha_stride=0, off_t=0, off_s=0, want_S=True):
+def proj_fwd(x, W, b, alpha=None, alpha_stride=0, off_t=0, off_s=0, want_S=True, precision=0):
     n, K = x.shape
     h = torch.empty((n, D), dtype=torch.float32, device=x.device)
     S = torch.empty((n, 8), dtype=torch.float32, device=x.device) if want_S else None
     _abi.check(_lib().fnb_proj_fwd(_p(x), _p(W), _p(b), n, K, _p(alpha), alpha_stride, off_t, off_s, _p(h), _p(S),
-                                   _stream()), "proj_fwd")
+                                   precision, _stream()), "proj_fwd")
     return h, S
 
 
-def proj_bwd(x, W, dh, need_dx: bool):
+def proj_bwd(x, W, dh, need_dx: bool, precision=0):
     n, K = x.shape
     dx = torch.empty_like(x) if need_dx else None
     dW = torch.empty_like(W)
     db = torch.empty(D, dtype=torch.float32, device=x.device)
-    _abi.check(_lib().fnb_proj_bwd(_p(x), _p(W), _p(dh), n, K, _p(dx), _p(dW), _p(db), _p(scratch(x.device)),
-                                   _stream()), "proj_bwd")
+    _abi.check(_lib().fnb_proj_bwd(_p(x), _p(W), _p(dh), n, K, _p(dx), _p(dW), _p(db), precision,
+                                   _p(scratch(x.device)), _stream()), "proj_bwd")
     return dx, dW, db
 
 

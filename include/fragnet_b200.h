@@ -33,6 +33,10 @@ extern "C" {
 #define FNB_ABI_VERSION 1
 
 /* edge-term modes of the fused attention kernels */
+/* arithmetic of the dense projections */
+#define FNB_PRECISION_FP32 0 /* FP32 FFMA: bit-for-bit comparable with the reference within 1e-5            */
+#define FNB_PRECISION_TF32 1 /* tcgen05 tensor cores, TF32 operands, FP32 accumulate (stated tolerance 2e-3) */
+
 #define FNB_EDGE_NONE 0   /* no edge term                                              */
 #define FNB_EDGE_AFFINE1 1 /* bond graph: S_e[h] = attr[slot]*coef[h] + coef[4+h]       */
 #define FNB_EDGE_AFFINE6 2 /* fragment-connection graph: attr[slot,0:6] . coef[h,0:6] + coef[24+h] */
@@ -83,10 +87,10 @@ int fnb_narrow_index(const int64_t *in, int64_t n, int32_t *out, void *stream);
  */
 int fnb_proj_fwd(const float *x, const float *W, const float *b, int64_t n_rows, int K,
                  const float *alpha, int alpha_stride, int off_t, int off_s, float *h, float *S,
-                 void *stream);
+                 int precision, void *stream);
 /* dx = dh @ W (dx may be NULL); dW = dh^T @ x; db = column sums of dh.  scratch: fnb_scratch_bytes(). */
 int fnb_proj_bwd(const float *x, const float *W, const float *dh, int64_t n_rows, int K, float *dx,
-                 float *dW, float *db, void *scratch, void *stream);
+                 float *dW, float *db, int precision, void *scratch, void *stream);
 /* S for features that are not projected (fragment graph: hf = pooled atoms, gat2.py:285). */
 int fnb_node_scalars(const float *h, int64_t n_rows, const float *alpha, int alpha_stride,
                      int off_t, int off_s, float *S, void *stream);

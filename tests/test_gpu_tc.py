@@ -1,0 +1,101 @@
+"""Tensor-core (tcgen05 / TF32) projection path: parity within the stated TF32 tolerance against fp32 torch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 2e-3      # stated tolerance of the tensor-core mode: TF32 operands (10-bit mantissa), FP32 accumulate
+
+
+@pytest.mark.parametrize("n,K", [(1, 128), (127, 128), (128, 128), (129, 128), (1000, 128), (54001, 128),
+                                 (300, 32), (300, 64), (300, 256), (40000, 128)])
+def test_tc_projection_forward(n, K):
+    from fragnet_b200 import ops
+    g = torch.Generator().manual_seed(n + K)
+    x = torch.randn(n, K, generator=g)
+    W = torch.randn(128, K, generator=g) * 0.2
+    b = torch.randn(128, generator=g)
+    alpha = torch.randn(4, 192, generator=g)
+    h, S = ops.proj_fwd(x.cuda(), W.cuda(), b.cuda(), alpha.cuda(), 192, 0, 160, precision=ops.PRECISION_TF32)
+    torch.cuda.synchronize()
+    href = F.linear(x, W, b)
+    assert rel_err(h, href) <= TF32_TOL
+    hv = href.view(n, 4, 32)
+    Sref = torch.cat([(hv * alpha[:, 0:32]).sum(-1), (hv * alpha[:, 160:192]).sum(-1)], dim=1)
+    assert rel_err(S, Sref) <= TF32_TOL
+    # exactness of the data path: integer-valued operands are exact in TF32
+    xi = torch.randint(-4, 5, (n, K), generator=g).float()
+    Wi = torch.randint(-4, 5, (128, K), generator=g).float()
+    hi, _ = ops.proj_fwd(xi.cuda(), Wi.cuda(), None, None, want_S=False, precision=ops.PRECISION_TF32)
+    assert torch.equal(hi.cpu(), xi @ Wi.t())
+
+
+def test_tc_projection_backward_dx():
+    from fragnet_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n = 5000
+    x = torch.randn(n, 128, generator=g)
+    W = torch.randn(128, 128, generator=g) * 0.2
+    dh = torch.randn(n, 128, generator=g)
+    dx, dW, db = ops.proj_bwd(x.cuda(), W.cuda(), dh.cuda(), True, ops.PRECISION_TF32)
+    assert rel_err(dx, dh @ W) <= TF32_TOL
+    assert rel_err(dW, dh.t() @ x) <= TF32_TOL
+    assert rel_err(db, dh.sum(0)) <= 1e-5
+
+
+def test_unaligned_k_falls_back_to_fp32_kernel():
+    from fragnet_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(300, 167, generator=g)
+    W = torch.randn(128, 167, generator=g) * 0.2
+    h, _ = ops.proj_fwd(x.cuda(), W.cuda(), None, None, want_S=False, precision=ops.PRECISION_TF32)
+    assert rel_err(h, x @ W.t()) <= 1e-5
+
+
+def test_model_in_tf32_mode_within_stated_tolerance():
+    from fragnet.model.gat.gat2 import FragNetFineTune
+    from fragnet_b200 import config, synth
+    from fragnet_b200.dataset.data import collate_fn
+    from oracle import gat2_oracle as O
+    b = collate_fn(synth.make_dataset("unimol", 48, seed=6))
+    torch.manual_seed(5)
+    m = FragNetFineTune(num_layer=4, drop_ratio=0.0, h1=128, h2=256, h3=256, h4=128, act="relu").eval()
+    P = O.params_from_module(m)
+    m = m.cuda()
+    config.set_precision("tf32")
+    try:
+        pred = m({k: v.cuda() for k, v in b.items()})
+        pred.sum().backward()
+    finally:
+        config.set_precision("fp32")
+    ref = O.finetune_forward(P, b)
+    ref.sum().backward()
+    assert rel_err(pred, ref) <= 5e-3
+    g = dict(m.named_parameters())["pretrain.layers.1.projection_b.weight"].grad
+    assert rel_err(g, P["pretrain.layers.1.projection_b.weight"].grad) <= 2e-2
+
+
+def test_tc_projection_speed_report(capsys):
+    from fragnet_b200 import ops
+    n = 54000
+    x = torch.randn(n, 128, device="cuda")
+    W = torch.randn(128, 128, device="cuda")
+    b = torch.randn(128, device="cuda")
+    a = torch.randn(4, 96, device="cuda")
+    out = {}
+    for name, prec in (("fp32", 0), ("tf32", 1)):
+        for _ in range(3):
+            ops.proj_fwd(x, W, b, a, 96, 0, 64, precision=prec)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(20):
+            ops.proj_fwd(x, W, b, a, 96, 0, 64, precision=prec)
+        e1.record()
+        e1.synchronize()
+        out[name] = e0.elapsed_time(e1) / 20 * 1e3
+    with capsys.disabled():
+        gb = n * 1024 / 1e9
+        print(f"\n[proj_fwd 54000x128x128] fp32 {out['fp32']:.1f} us, tf32 {out['tf32']:.1f} us "
+              f"({gb / (out['tf32'] * 1e-6):.0f} GB/s algorithmic, L2-warm)")
