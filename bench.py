@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--shape", default="unimol", choices=["esol", "unimol", "stress"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct batches cycled through")
     ap.add_argument("--pool", type=int, default=512, help="distinct synthetic molecules generated")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="arithmetic of the dense projections (everything else is fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -231,6 +233,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _abi.load()
+    from fragnet_b200 import config
+    config.set_precision(args.precision)
 
     torch.manual_seed(1234)                      # identical initial weights on every rank
     model = FragNetPreTrain(**PT_KW).to(dev).train()
@@ -314,7 +318,8 @@ def run_ours(args):
         counts = batch_counts(host_batches[0])
         line = {"metric": METRIC, "value": round(value, 1), "unit": "molecules/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.precision == "fp32" else "f32 (tf32-in/f32-acc tensor-core projections)",
                 "data": "synthetic",
                 "config": {"workload": f"FragNetPreTrain exps/pt/unimol_exp1s4 step (4 layers, 4 heads, emb 128, "
                                        f"drop 0.2, Adam), {args.shape}-shaped molecules",

@@ -47,7 +47,7 @@ class FragNetLayerFn(torch.autograd.Function):
         x_atoms, x_bond, x_fbond = f32(x_atoms), f32(x_bond), f32(x_fbond)
         params = [f32(t) for t in (Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b)]
         Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b = params
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         if need_grad and (opts.bond_mask is not None or opts.frag_bond_mask is not None or opts.atom_mask is not None):
             raise NotImplementedError(
                 "fragnet_b200: bond/atom/fragment-bond masks are inference-only (the reference applies them "
@@ -103,7 +103,8 @@ class FragNetLayerFn(torch.autograd.Function):
         c = lambda t: None if t is None else ops._f32c(t)
         g_atoms, g_frags, g_bond, g_fbond = c(g_atoms), c(g_frags), c(g_bond), c(g_fbond)
         dev = x_atoms.device
-        zeros = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        # every slice of the head-vector gradients is written by exactly one kernel below: no zero fill needed
+        zeros = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
 
         # ---- fragment graph block
         d_f = d_hf = None
@@ -117,9 +118,10 @@ class FragNetLayerFn(torch.autograd.Function):
         if g_fbond is not None:
             d_fab = zeros(4, AB_STRIDE)
             dz, dSt, d_coef = ops.gat_bwd_dst(plan.fbond, hfb, g_fbond, p_fb, EDGE_AFFINE6, plan.fbond.attr, True)
-            d_hfb = ops.gat_bwd_src(plan.fbond, hfb, g_fbond, p_fb, dz, dSt, f_a_b, AB_STRIDE, AB_T, AB_S, d_fab)
+            d_hfb, dbfb = ops.gat_bwd_src(plan.fbond, hfb, g_fbond, p_fb, dz, dSt, f_a_b, AB_STRIDE, AB_T, AB_S, d_fab,
+                                          want_bias_grad=True)
             dWe_fb, dbe_fb = ops.edge_coef_bwd(We_fb, be_fb, 6, f_a_b, AB_STRIDE, AB_E, d_coef, d_fab)
-            dx_fbond, dWfb, dbfb = ops.proj_bwd(x_fbond, Wfb, d_hfb, needs[4], opts.precision)
+            dx_fbond, dWfb, _ = ops.proj_bwd(x_fbond, Wfb, d_hfb, needs[4], opts.precision, want_db=False)
         # ---- pooling backward folded into the atom block's incoming gradient
         if d_hf is not None:
             g_atoms = ops.segment_gather(d_hf, ops.D, plan.a2f32, plan.n_atoms, g_atoms)
@@ -128,17 +130,19 @@ class FragNetLayerFn(torch.autograd.Function):
         if g_atoms is not None:
             d_a = zeros(4, A_STRIDE)
             dz, dSt, _ = ops.gat_bwd_dst(plan.atom, ha, g_atoms, p_a)
-            d_ha = ops.gat_bwd_src(plan.atom, ha, g_atoms, p_a, dz, dSt, a, A_STRIDE, A_T, A_S, d_a)
+            d_ha, dba = ops.gat_bwd_src(plan.atom, ha, g_atoms, p_a, dz, dSt, a, A_STRIDE, A_T, A_S, d_a,
+                                        want_bias_grad=True)
             g_bond = ops.edge_table_bwd(plan.atom, dz, new_bond, a, A_STRIDE, A_E, g_bond, d_a)
-            dx_atoms, dWa, dba = ops.proj_bwd(x_atoms, Wa, d_ha, needs[2], opts.precision)
+            dx_atoms, dWa, _ = ops.proj_bwd(x_atoms, Wa, d_ha, needs[2], opts.precision, want_db=False)
         # ---- bond graph block
         d_ab = dWb = dbb = dWe_b = dbe_b = dx_bond = None
         if g_bond is not None:
             d_ab = zeros(4, AB_STRIDE)
             dz, dSt, d_coef = ops.gat_bwd_dst(plan.bond, hb, g_bond, p_b, EDGE_AFFINE1, plan.bond.attr, True)
-            d_hb = ops.gat_bwd_src(plan.bond, hb, g_bond, p_b, dz, dSt, a_b, AB_STRIDE, AB_T, AB_S, d_ab)
+            d_hb, dbb = ops.gat_bwd_src(plan.bond, hb, g_bond, p_b, dz, dSt, a_b, AB_STRIDE, AB_T, AB_S, d_ab,
+                                        want_bias_grad=True)
             dWe_b, dbe_b = ops.edge_coef_bwd(We_b, be_b, 1, a_b, AB_STRIDE, AB_E, d_coef, d_ab)
-            dx_bond, dWb, dbb = ops.proj_bwd(x_bond, Wb, d_hb, needs[3], opts.precision)
+            dx_bond, dWb, _ = ops.proj_bwd(x_bond, Wb, d_hb, needs[3], opts.precision, want_db=False)
         return (None, None, dx_atoms, dx_bond, dx_fbond, dWb, dbb, dWfb, dbfb, dWe_b, dbe_b, dWe_fb, dbe_fb,
                 dWa, dba, d_ab, d_a, d_f, d_fab)
 

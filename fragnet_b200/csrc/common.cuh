@@ -65,6 +65,19 @@ __device__ __forceinline__ float pick(const float4 &v, int i) {
 }
 __device__ __forceinline__ float leaky(float z) { return z > 0.f ? z : kNegSlope * z; }
 
+// Up to 4 output segments of one partial record, reduced by a single launch (gat_bwd.cu).
+struct ReduceSegments {
+  int n;
+  int rec_off[4];       // float offset of the segment inside a record
+  int width[4];         // number of columns
+  int padded_width[4];  // filled by the launcher
+  float *out[4];
+  int row_len[4];       // out index = (j / row_len) * out_stride + j % row_len
+  int out_stride[4];
+};
+int fnb_launch_reduce_segments(const float *partials, int n_blocks, int pstride, ReduceSegments segs,
+                               cudaStream_t stream);
+
 // Deterministic second stage for per-CTA partial sums (gat_bwd.cu):
 //   out[(j / row_len) * out_stride + j % row_len] (+)= sum_b partials[b * pstride + j],  j < width.
 int fnb_launch_reduce_partials(const float *partials, int n_blocks, int pstride, int width, float *out, int row_len,
@@ -74,3 +87,4 @@ int fnb_launch_reduce_partials(const float *partials, int n_blocks, int pstride,
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
                        int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream);
 int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream);
+int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, float *dW, float *scratch, cudaStream_t stream);

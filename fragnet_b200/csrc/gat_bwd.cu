@@ -21,24 +21,36 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
 // ------------------------------------------------------------------------------------------------
-// second stage: out[(j / row_len) * out_stride + j % row_len] (+)= sum_b partials[b * pstride + j]
+// Second stage of every parameter-gradient reduction: per-CTA partial records -> final tensors, in a fixed
+// order (deterministic).  One launch handles up to 4 output segments of the record:
+//   out_s[(j / row_len_s) * out_stride_s + j % row_len_s] = sum_b partials[b * pstride + rec_off_s + j],  j < width_s
+// Block = 32 partial-row lanes x 8 columns: each thread sums every 32nd record, then a fixed-order smem tree.
 __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict__ partials, int n_blocks, int pstride,
-                                                         int width, float *__restrict__ out, int row_len,
-                                                         int out_stride, int accumulate) {
-  __shared__ float sm[8][32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + tx;
+                                                         ReduceSegments segs) {
+  __shared__ float sm[32][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  int col = blockIdx.x * 8 + tx;          // column in the concatenation of the (8-padded) segments
+  int seg = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (seg == i && i + 1 < segs.n && col >= segs.padded_width[i]) {
+      col -= segs.padded_width[i];
+      seg = i + 1;
+    }
+  const bool valid = col < segs.width[seg];
   float acc = 0.f;
-  if (j < width)
-    for (int b = ty; b < n_blocks; b += 8) acc += partials[(int64_t)b * pstride + j];
+  if (valid) {
+    const float *src = partials + segs.rec_off[seg] + col;
+    for (int b = ty; b < n_blocks; b += 32) acc += src[(int64_t)b * pstride];
+  }
   sm[ty][tx] = acc;
   __syncthreads();
-  if (ty == 0 && j < width) {
+  if (ty == 0 && valid) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += sm[k][tx];
-    const int o = (j / row_len) * out_stride + (j % row_len);
-    out[o] = accumulate ? out[o] + s : s;
+    for (int k = 0; k < 32; ++k) s += sm[k][tx];
+    const int rl = segs.row_len[seg];
+    segs.out[seg][(col / rl) * segs.out_stride[seg] + (col % rl)] = s;
   }
 }
 
@@ -200,14 +212,14 @@ struct SrcArgs {
   const float *alpha;
   int alpha_stride, off_t, off_s;
   float *dh;
-  float *partials;  // [gridDim.x][256]: d alpha_t [4,32] then d alpha_s [4,32]
+  float *partials;  // [gridDim.x][384]: d alpha_t [4,32], d alpha_s [4,32], column sums of dh [128]
   int64_t n_nodes;
 };
 
 __global__ void __launch_bounds__(kThreads) k_gat_bwd_src(SrcArgs a) {
   __shared__ float s_p[kWarpsPerBlock][32 * 4];
   __shared__ int s_t[kWarpsPerBlock][32];
-  __shared__ float s_acc[kWarpsPerBlock * 256];
+  __shared__ float s_acc[kWarpsPerBlock * 384];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int head = lane >> 3;
   float *wp = s_p[warp];
@@ -215,6 +227,7 @@ __global__ void __launch_bounds__(kThreads) k_gat_bwd_src(SrcArgs a) {
   const float4 at = ldg4(a.alpha + (int64_t)head * a.alpha_stride + a.off_t + (lane & 7) * 4);
   const float4 as = ldg4(a.alpha + (int64_t)head * a.alpha_stride + a.off_s + (lane & 7) * 4);
   float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // d alpha_t (4) | d alpha_s (4) for this lane's columns
+  float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);          // sum of dh rows = bias gradient of the projection
 
   const int64_t warp_global = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   const int64_t warp_stride = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -271,22 +284,24 @@ __global__ void __launch_bounds__(kThreads) k_gat_bwd_src(SrcArgs a) {
     acc.z += gt * at.z + gs * as.z;
     acc.w += gt * at.w + gs * as.w;
     st4(a.dh + s * kD + lane * 4, acc);
+    colsum.x += acc.x; colsum.y += acc.y; colsum.z += acc.z; colsum.w += acc.w;
     pa[0] = fmaf(gt, hr.x, pa[0]); pa[1] = fmaf(gt, hr.y, pa[1]); pa[2] = fmaf(gt, hr.z, pa[2]); pa[3] = fmaf(gt, hr.w, pa[3]);
     pa[4] = fmaf(gs, hr.x, pa[4]); pa[5] = fmaf(gs, hr.y, pa[5]); pa[6] = fmaf(gs, hr.z, pa[6]); pa[7] = fmaf(gs, hr.w, pa[7]);
   }
-  // CTA partial record: [0,128) = d alpha_t[4,32] (index head*32 + col = lane*4 + i), [128,256) = d alpha_s
+  // CTA partial record: [0,128) = d alpha_t[4,32] (index head*32 + col = lane*4 + i), [128,256) = d alpha_s,
+  // [256,384) = column sums of dh
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    s_acc[warp * 256 + lane * 4 + i] = pa[i];
-    s_acc[warp * 256 + 128 + lane * 4 + i] = pa[4 + i];
+    s_acc[warp * 384 + lane * 4 + i] = pa[i];
+    s_acc[warp * 384 + 128 + lane * 4 + i] = pa[4 + i];
   }
+  st4(s_acc + warp * 384 + 256 + lane * 4, colsum);
   __syncthreads();
-  {
-    const int j = threadIdx.x;  // kThreads == 256 == record width
+  for (int j = threadIdx.x; j < 384; j += kThreads) {
     float sum = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_acc[w * 256 + j];
-    a.partials[(int64_t)blockIdx.x * 256 + j] = sum;
+    for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_acc[w * 384 + j];
+    a.partials[(int64_t)blockIdx.x * 384 + j] = sum;
   }
 }
 
@@ -360,12 +375,27 @@ inline int warp_grid(int64_t n_items) {
 
 }  // namespace
 
-int fnb_launch_reduce_partials(const float *partials, int n_blocks, int pstride, int width, float *out, int row_len,
-                               int out_stride, int accumulate, cudaStream_t stream) {
-  k_reduce_partials<<<(width + 31) / 32, 256, 0, stream>>>(partials, n_blocks, pstride, width, out, row_len,
-                                                          out_stride, accumulate);
+int fnb_launch_reduce_segments(const float *partials, int n_blocks, int pstride, ReduceSegments segs,
+                               cudaStream_t stream) {
+  int cols = 0;
+  for (int i = 0; i < segs.n; ++i) {
+    segs.padded_width[i] = (segs.width[i] + 7) & ~7;
+    cols += segs.padded_width[i];
+  }
+  if (cols == 0) return 0;
+  k_reduce_partials<<<cols / 8, 256, 0, stream>>>(partials, n_blocks, pstride, segs);
   FNB_CHECK_LAUNCH();
   return 0;
+}
+
+int fnb_launch_reduce_partials(const float *partials, int n_blocks, int pstride, int width, float *out, int row_len,
+                               int out_stride, int accumulate, cudaStream_t stream) {
+  (void)accumulate;
+  ReduceSegments segs;
+  segs.n = 1;
+  segs.rec_off[0] = 0; segs.width[0] = width; segs.out[0] = out; segs.row_len[0] = row_len;
+  segs.out_stride[0] = out_stride;
+  return fnb_launch_reduce_segments(partials, n_blocks, pstride, segs, stream);
 }
 
 extern "C" size_t fnb_scratch_bytes(void) { return (size_t)kScratchFloats * sizeof(float); }
@@ -407,7 +437,7 @@ extern "C" int fnb_gat_bwd_dst(const int32_t *rowptr, const int32_t *col, int64_
 extern "C" int fnb_gat_bwd_src(const int32_t *rrowptr, const int32_t *rslot, const int32_t *rdst, int64_t n_nodes,
                                const float *h, const float *dout, const float *p_saved, const float *dz,
                                const float *dSt, const float *alpha, int alpha_stride, int off_t, int off_s,
-                               float *dh, float *d_alpha, void *scratch, void *stream_) {
+                               float *dh, float *d_alpha, float *d_bias, void *scratch, void *stream_) {
   if (n_nodes < 0) return FNB_ERR_SIZE;
   if (n_nodes == 0) return 0;
   if (!rrowptr || !rslot || !rdst || !h || !dout || !p_saved || !dz || !dSt || !alpha || !dh || !d_alpha || !scratch)
@@ -424,9 +454,12 @@ extern "C" int fnb_gat_bwd_src(const int32_t *rrowptr, const int32_t *rslot, con
   const int blocks = warp_grid(n_nodes);
   k_gat_bwd_src<<<blocks, kThreads, 0, stream>>>(a);
   FNB_CHECK_LAUNCH();
-  int rc = fnb_launch_reduce_partials(a.partials, blocks, 256, 128, d_alpha + off_t, kHd, alpha_stride, 0, stream);
-  if (rc) return rc;
-  return fnb_launch_reduce_partials(a.partials + 128, blocks, 256, 128, d_alpha + off_s, kHd, alpha_stride, 0, stream);
+  ReduceSegments segs;
+  segs.n = d_bias ? 3 : 2;
+  segs.rec_off[0] = 0;   segs.width[0] = 128; segs.out[0] = d_alpha + off_t; segs.row_len[0] = kHd; segs.out_stride[0] = alpha_stride;
+  segs.rec_off[1] = 128; segs.width[1] = 128; segs.out[1] = d_alpha + off_s; segs.row_len[1] = kHd; segs.out_stride[1] = alpha_stride;
+  segs.rec_off[2] = 256; segs.width[2] = 128; segs.out[2] = d_bias;          segs.row_len[2] = 128; segs.out_stride[2] = 128;
+  return fnb_launch_reduce_segments(a.partials, blocks, 384, segs, stream);
 }
 
 extern "C" int fnb_edge_table_bwd(const float *dz, const int32_t *slot_of_eid, int64_t n_real_edges,

@@ -295,6 +295,10 @@ extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int
     k_gemm<false, false><<<grid, kGemmThreads, 0, stream>>>(g);
     FNB_CHECK_LAUNCH();
   }
+  if (precision == FNB_PRECISION_TF32 && K == kD && n_rows > 0 && !db) {
+    const int rc = fnb_tc_dw_launch(dh, x, n_rows, dW, (float *)scratch, stream);
+    if (rc != FNB_ERR_MODE) return rc;
+  }
   int64_t nb = (n_rows + 255) / 256;
   if (nb > kNumSMs) nb = kNumSMs;
   if (nb < 1) nb = 1;
@@ -305,13 +309,11 @@ extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int
   dim3 grid((unsigned)nb, (unsigned)((K + 127) / 128));
   k_proj_dw<<<grid, 256, 0, stream>>>(dh, x, n_rows, K, rows_per_block, (float *)scratch, rec_stride);
   FNB_CHECK_LAUNCH();
-  int rc = fnb_launch_reduce_partials((const float *)scratch, (int)nb, (int)rec_stride, 128 * K, dW, 128 * K, 128 * K, 0,
-                                      stream);
-  if (rc) return rc;
-  if (db)
-    rc = fnb_launch_reduce_partials((const float *)scratch + (int64_t)128 * K, (int)nb, (int)rec_stride, 128, db, 128,
-                                    128, 0, stream);
-  return rc;
+  ReduceSegments segs;
+  segs.n = db ? 2 : 1;
+  segs.rec_off[0] = 0;       segs.width[0] = 128 * K; segs.out[0] = dW; segs.row_len[0] = 128 * K; segs.out_stride[0] = 128 * K;
+  segs.rec_off[1] = 128 * K; segs.width[1] = 128;     segs.out[1] = db; segs.row_len[1] = 128;     segs.out_stride[1] = 128;
+  return fnb_launch_reduce_segments((const float *)scratch, (int)nb, (int)rec_stride, segs, stream);
 }
 
 extern "C" int fnb_node_scalars(const float *h, int64_t n_rows, const float *alpha, int alpha_stride, int off_t,

@@ -261,6 +261,115 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient dW[o,i] = sum_n dH[n,o] X[n,i] on the tensor cores.  Both operands are "MN-major" for the MMA
+// (the reduction index n is the slow index of the row-major inputs).  MN-major TF32 operands have exactly one legal
+// shared-memory layout, SWIZZLE_128B_BASE32B (128-byte rows swizzled at 32-byte granularity, atoms of 4 rows), which
+// TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Each 32-row block of dH / X is fetched as four 32x32 boxes:
+// box c holds columns 32c..32c+31, rows 128 bytes apart => LBO = 4096 bytes between column chunks, SBO = 512 bytes
+// between 4-row atoms; one tcgen05.mma (K = 8 rows) consumes 1024 bytes of every chunk.  Every CTA reduces a contiguous range of
+// row blocks into one TMEM accumulator and writes a 128x128 partial; a fixed-order second stage sums the partials.
+constexpr int DW_STAGE_BYTES = 2 * TC_STAGE_BYTES;   // dH block (16 KiB) + X block (16 KiB)
+constexpr int DW_STAGES = 6;
+
+__device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;   // LBO: next 32-element chunk along M/N
+  d |= (uint64_t)(512 >> 4) << 32;    // SBO: next atom of 4 rows along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;             // SWIZZLE_128B_BASE32B
+  return d;
+}
+constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);   // A and B MN-major
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUtensorMap tm_x, float *partials,
+        int64_t n_row_blocks, int64_t blocks_per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * DW_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[DW_STAGES]);
+  const uint32_t bar_done = smem_u32(&bars[2 * DW_STAGES]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DW_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(128)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int64_t rb_begin = (int64_t)blockIdx.x * blocks_per_cta;
+  const int64_t rb_end = min(n_row_blocks, rb_begin + blocks_per_cta);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t rb = rb_begin; rb < rb_end; ++rb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        mbar_arrive_expect_tx(bar_full + 8 * stage, DW_STAGE_BYTES);
+        const uint32_t a_addr = smem_base + stage * DW_STAGE_BYTES, b_addr = a_addr + TC_STAGE_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tma_load_2d(a_addr + c * 4096, &tm_dh, bar_full + 8 * stage, c * 32, (int)(rb * 32));
+          tma_load_2d(b_addr + c * 4096, &tm_x, bar_full + 8 * stage, c * 32, (int)(rb * 32));
+        }
+        if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t rb = rb_begin; rb < rb_end; ++rb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * DW_STAGE_BYTES, b_addr = a_addr + TC_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_tf32(tmem_base, make_desc_sw128_mnmajor(a_addr + k * 1024), make_desc_sw128_mnmajor(b_addr + k * 1024),
+                      kIdescTf32MN, (rb != rb_begin) || (k != 0));
+        tc_commit(bar_empty + 8 * stage);
+        if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(bar_done);
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    float *rec = partials + ((int64_t)blockIdx.x * 128 + warp * 32 + lane) * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tc_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, r);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        st4(rec + c * 32 + 4 * q, make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                              __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+  }
+}
+
 // B^T for the input-gradient GEMM: Wt[i, o] = W[o, i] (128 x 128).
 __global__ void k_transpose_128(const float *__restrict__ W, float *__restrict__ Wt) {
   __shared__ float tile[32][33];
@@ -287,7 +396,8 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 row-major [rows, cols] tensor, box = 32 columns (128 bytes) x box_rows, 128-byte swizzle, zero OOB fill.
-int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int cols, int box_rows) {
+int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int cols, int box_rows,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return FNB_ERR_MODE;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -295,7 +405,7 @@ int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int cols, int box
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), gdim, gstride, box, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : FNB_ERR_MODE;
 }
@@ -332,4 +442,24 @@ int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream) {
   k_transpose_128<<<dim3(4, 4), dim3(32, 8), 0, stream>>>(W, Wt);
   FNB_CHECK_LAUNCH();
   return 0;
+}
+
+// dW[128,128] = dH[n,128]^T @ X[n,128] (TF32).  scratch must hold kNumSMs * 128 * 128 floats of partials.
+int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, float *dW, float *scratch,
+                     cudaStream_t stream) {
+  if (n_rows <= 0 || !fnb_aligned16(dh) || !fnb_aligned16(x) || n_rows >= (int64_t)INT32_MAX) return FNB_ERR_MODE;
+  CUtensorMap tm_dh, tm_x;
+  int rc = make_map(&tm_dh, dh, n_rows, 128, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = make_map(&tm_x, x, n_rows, 128, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const int64_t n_rb = (n_rows + 31) / 32;
+  const int64_t per = (n_rb + kNumSMs - 1) / kNumSMs;
+  const int grid = (int)((n_rb + per - 1) / per);
+  const size_t smem = (size_t)DW_STAGES * DW_STAGE_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_tc_dw<<<grid, TC_THREADS, smem, stream>>>(tm_dh, tm_x, scratch, n_rb, per);
+  FNB_CHECK_LAUNCH();
+  return fnb_launch_reduce_partials(scratch, grid, 128 * 128, 128 * 128, dW, 128 * 128, 128 * 128, 0, stream);
 }

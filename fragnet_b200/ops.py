@@ -235,11 +235,11 @@ def proj_fwd(x, W, b, alpha=None, alpha_stride=0, off_t=0, off_s=0, want_S=True,
     return h, S
 
 
-def proj_bwd(x, W, dh, need_dx: bool, precision=0):
+def proj_bwd(x, W, dh, need_dx: bool, precision=0, want_db=True):
     n, K = x.shape
     dx = torch.empty_like(x) if need_dx else None
     dW = torch.empty_like(W)
-    db = torch.empty(D, dtype=torch.float32, device=x.device)
+    db = torch.empty(D, dtype=torch.float32, device=x.device) if want_db else None
     _abi.check(_lib().fnb_proj_bwd(_p(x), _p(W), _p(dh), n, K, _p(dx), _p(dW), _p(db), precision,
                                    _p(scratch(x.device)), _stream()), "proj_bwd")
     return dx, dW, db
@@ -297,12 +297,14 @@ def gat_bwd_dst(g: GraphCSR, h, dout, p, mode=EDGE_NONE, edge_attr=None, want_co
     return dz, dSt, d_coef
 
 
-def gat_bwd_src(g: GraphCSR, h, dout, p, dz, dSt, alpha, alpha_stride, off_t, off_s, d_alpha):
+def gat_bwd_src(g: GraphCSR, h, dout, p, dz, dSt, alpha, alpha_stride, off_t, off_s, d_alpha, want_bias_grad=False):
+    """Returns dh, or (dh, d_bias) with ``want_bias_grad`` (d_bias = column sums of dh)."""
     dh = torch.empty((g.n_nodes, D), dtype=torch.float32, device=h.device)
+    db = torch.empty(D, dtype=torch.float32, device=h.device) if want_bias_grad else None
     _abi.check(_lib().fnb_gat_bwd_src(_p(g.rrowptr), _p(g.rslot), _p(g.rdst), g.n_nodes, _p(h), _p(dout), _p(p),
                                       _p(dz), _p(dSt), _p(alpha), alpha_stride, off_t, off_s, _p(dh), _p(d_alpha),
-                                      _p(scratch(h.device)), _stream()), "gat_bwd_src")
-    return dh
+                                      _p(db), _p(scratch(h.device)), _stream()), "gat_bwd_src")
+    return (dh, db) if want_bias_grad else dh
 
 
 def edge_table_bwd(g: GraphCSR, dz, feat, alpha, alpha_stride, off_e, g_base, d_alpha):

@@ -88,7 +88,8 @@ int fnb_narrow_index(const int64_t *in, int64_t n, int32_t *out, void *stream);
 int fnb_proj_fwd(const float *x, const float *W, const float *b, int64_t n_rows, int K,
                  const float *alpha, int alpha_stride, int off_t, int off_s, float *h, float *S,
                  int precision, void *stream);
-/* dx = dh @ W (dx may be NULL); dW = dh^T @ x; db = column sums of dh.  scratch: fnb_scratch_bytes(). */
+/* dx = dh @ W (dx may be NULL); dW = dh^T @ x; db = column sums of dh (may be NULL: fnb_gat_bwd_src can emit
+ * it for free).  scratch: fnb_scratch_bytes(). */
 int fnb_proj_bwd(const float *x, const float *W, const float *dh, int64_t n_rows, int K, float *dx,
                  float *dW, float *db, int precision, void *scratch, void *stream);
 /* S for features that are not projected (fragment graph: hf = pooled atoms, gat2.py:285). */
@@ -137,11 +138,13 @@ int fnb_gat_bwd_dst(const int32_t *rowptr, const int32_t *col, int64_t n_nodes, 
                     const float *edge_attr, float *dz, float *dSt, float *d_coef, void *scratch,
                     void *stream);
 /* Pass 2, source segments over the reverse CSR: dh[s] = sum p*dout[t] + dSt[s]*alpha_t + dSs[s]*alpha_s,
- * and d_alpha[h, off_t:+32], d_alpha[h, off_s:+32] (written). */
+ * d_alpha[h, off_t:+32], d_alpha[h, off_s:+32] (written), and optionally d_bias[128] = column sums of dh
+ * (the bias gradient of the projection that produced h; NULL to skip). */
 int fnb_gat_bwd_src(const int32_t *rrowptr, const int32_t *rslot, const int32_t *rdst,
                     int64_t n_nodes, const float *h, const float *dout, const float *p_saved,
                     const float *dz, const float *dSt, const float *alpha, int alpha_stride,
-                    int off_t, int off_s, float *dh, float *d_alpha, void *scratch, void *stream);
+                    int off_t, int off_s, float *dh, float *d_alpha, float *d_bias, void *scratch,
+                    void *stream);
 /* Edge-term backward for TABLE mode: for every real edge e with feature row feat[e,:]:
  *   g_feat[e,:] = g_base[e,:] + sum_h dz[slot_of_eid[e],h] * alpha_e[h,:]   (g_base NULL = 0; may alias g_feat)
  *   d_alpha[h, off_e:off_e+128] = sum_e dz[slot_of_eid[e],h] * feat[e,:] */

@@ -5,15 +5,16 @@ set -u
 mkdir -p gpurun_out
 tag=${1:-run}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
-for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_model.py; do
+for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_model.py tests/test_gpu_tc.py; do
   timeout 600 python -m pytest $f -q --no-header -p no:cacheprovider -m gpu 2>&1 | tail -120 > gpurun_out/${tag}_$(basename $f .py).log
 done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 --precision fp32 --no-cpu-baseline > gpurun_out/${tag}_bench_fp32.log 2>&1
 if [ "${2:-}" = "ncu" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
     --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-roofline \
     > gpurun_out/${tag}_ncu_bench.log 2>&1
 fi
-tail -5 gpurun_out/${tag}_test_gpu_csr.log gpurun_out/${tag}_test_gpu_kernels.log gpurun_out/${tag}_test_gpu_model.log gpurun_out/${tag}_smoke.log
-tail -2 gpurun_out/${tag}_bench.log
+for f in gpurun_out/${tag}_test_gpu_*.log gpurun_out/${tag}_smoke.log; do echo "== $f"; tail -n 4 $f; done
+tail -n 2 gpurun_out/${tag}_bench.log gpurun_out/${tag}_bench_fp32.log

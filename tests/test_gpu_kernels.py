@@ -93,7 +93,8 @@ def test_attention_block_forward_backward(mode, n_nodes, n_edges, hub):
                                       kw.get("edge_attr") if mode.startswith("affine") else None,
                                       mode.startswith("affine"))
     d_alpha = torch.zeros(4, stride, device="cuda")
-    dh = ops.gat_bwd_src(graph, hc, go, p, dz, dSt, ac, stride, off_t, off_s, d_alpha)
+    dh, dbias = ops.gat_bwd_src(graph, hc, go, p, dz, dSt, ac, stride, off_t, off_s, d_alpha, want_bias_grad=True)
+    assert rel_err(dbias, h.grad.sum(0)) <= 2e-4
     gtol = 2e-5      # gradients: sums of O(100) fp32 products, two independent summation orders
     assert rel_err(dh, h.grad) <= gtol
     if mode.startswith("affine"):

@@ -43,6 +43,15 @@ def test_tc_projection_backward_dx():
     assert rel_err(dx, dh @ W) <= TF32_TOL
     assert rel_err(dW, dh.t() @ x) <= TF32_TOL
     assert rel_err(db, dh.sum(0)) <= 1e-5
+    for n2 in (1, 31, 32, 33, 4800, 54001):       # tensor-core weight gradient (no db): ragged row counts
+        _, dW2, _ = ops.proj_bwd(x[:n2].cuda().contiguous(), W.cuda(), dh[:n2].cuda().contiguous(), False,
+                                 ops.PRECISION_TF32, want_db=False) if n2 <= n else (None, None, None)
+        if n2 <= n:
+            assert rel_err(dW2, dh[:n2].t() @ x[:n2]) <= TF32_TOL, n2
+    xi = torch.randint(-3, 4, (777, 128), generator=g).float()
+    di = torch.randint(-3, 4, (777, 128), generator=g).float()
+    _, dWi, _ = ops.proj_bwd(xi.cuda(), W.cuda(), di.cuda(), False, ops.PRECISION_TF32, want_db=False)
+    assert torch.equal(dWi.cpu(), di.t() @ xi)
 
 
 def test_unaligned_k_falls_back_to_fp32_kernel():
