@@ -30,6 +30,7 @@ class LayerOptions:
     want_attention: bool = False
     want_frag_block: bool = True      # False elides the fragment-graph block (dead for non-final layers)
     precision: int = 0                # ops.PRECISION_FP32 / PRECISION_TF32 for the dense projections
+    grad_enabled: bool = True         # torch.is_grad_enabled() at the call site
 
 
 def _range_mask(start, width):
@@ -47,7 +48,8 @@ class FragNetLayerFn(torch.autograd.Function):
         x_atoms, x_bond, x_fbond = f32(x_atoms), f32(x_bond), f32(x_fbond)
         params = [f32(t) for t in (Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b)]
         Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b = params
-        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        # grad mode is always off INSIDE Function.forward and needs_input_grad ignores torch.no_grad(): the caller samples it
+        need_grad = opts.grad_enabled and any(ctx.needs_input_grad)
         if need_grad and (opts.bond_mask is not None or opts.frag_bond_mask is not None or opts.atom_mask is not None):
             raise NotImplementedError(
                 "fragnet_b200: bond/atom/fragment-bond masks are inference-only (the reference applies them "

@@ -104,7 +104,7 @@ class FragNetLayerA(nn.Module):
         plan = ops.layer_plan_for(index_tensors, sizes, dev)
         opts = LayerOptions(_as_int_or_none(self.bond_mask), _as_int_or_none(self.frag_bond_mask),
                             _as_int_or_none(self.atom_mask_individual), want_attention, want_frag_block,
-                            config.precision_id())
+                            config.precision_id(), torch.is_grad_enabled())
         on = lambda t: t if t.device == dev else t.to(dev)
         params = [on(p) for p in self._live_parameters()]
         return FragNetLayerFn.apply(plan, opts, on(x_atoms), on(x_bond_nodes), on(x_fbond_nodes), *params)

@@ -18,3 +18,11 @@ if [ "${2:-}" = "ncu" ]; then
 fi
 for f in gpurun_out/${tag}_test_gpu_*.log gpurun_out/${tag}_smoke.log; do echo "== $f"; tail -n 4 $f; done
 tail -n 2 gpurun_out/${tag}_bench.log gpurun_out/${tag}_bench_fp32.log
+if [ "${3:-}" = "full" ]; then
+  # one `ncu --set full` capture of the message-passing kernels (bond-graph launches of layer >= 1)
+  for k in k_gat_fwd k_gat_bwd_dst k_gat_bwd_src; do
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 2 -f \
+      -o gpurun_out/${tag}_full_$k python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-roofline \
+      > gpurun_out/${tag}_full_$k.log 2>&1
+  done
+fi
