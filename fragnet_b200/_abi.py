@@ -19,7 +19,7 @@ SIGNATURES = {
     "fnb_launch_count": (_u64, []),
     "fnb_scratch_bytes": (_sz, []),
     "fnb_csr_workspace_bytes": (_sz, [_i64, _i64]),
-    "fnb_csr_build": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "fnb_csr_build": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "fnb_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "fnb_segment_offsets": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "fnb_narrow_index": (C.c_int, [_vp, _i64, _vp, _vp]),
@@ -39,8 +39,42 @@ SIGNATURES = {
     "fnb_segment_gather": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "fnb_dropout_relu_fwd": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _i32, _u64, _u64, _vp]),
     "fnb_dropout_relu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _i32, _vp]),
+    "fnb_gat_fwd_tiled": (C.c_int, [_vp, _vp, _vp]),
+    "fnb_gat_bwd_tiled": (C.c_int, [_vp, _vp, _vp]),
+    "fnb_edge_table_bwd_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "fnb_encoder_workspace_bytes": (_sz, [_vp, _vp, _vp]),
+    "fnb_encoder_bwd_workspace_bytes": (_sz, [_vp, _vp, _vp]),
+    "fnb_encoder_philox_span": (_u64, [_vp, _vp, _vp]),
+    "fnb_encoder_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "fnb_encoder_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
 }
 
+
+# C structs of include/fragnet_b200.h (native alignment, same field order)
+class CGraph(C.Structure):
+    _fields_ = [("n_nodes", _i64), ("n_edges", _i64), ("n_real_edges", _i64),
+                ("rowptr", _vp), ("col", _vp), ("row", _vp), ("eid", _vp), ("slot_of_eid", _vp),
+                ("rrowptr", _vp), ("rslot", _vp), ("rdst", _vp), ("edge_attr", _vp)]
+
+
+class CPostAct(C.Structure):
+    _fields_ = [("p", _f32), ("training", _i32), ("relu", _i32), ("seed", _u64), ("offset", _u64)]
+
+
+class CGatFwdArgs(C.Structure):
+    _fields_ = [("h", _vp), ("S", _vp), ("edge_mode", _i32), ("edge_table", _vp), ("We", _vp), ("be", _vp),
+                ("alpha_e", _vp), ("alpha_stride", _i32), ("out", _vp), ("y", _vp), ("post", CPostAct),
+                ("p_saved", _vp), ("mask_lo", _i64), ("mask_hi", _i64), ("next_alpha_e", _vp),
+                ("next_alpha_stride", _i32), ("next_Se", _vp)]
+
+
+class CGatBwdArgs(C.Structure):
+    _fields_ = [("h", _vp), ("dout", _vp), ("p_saved", _vp), ("edge_mode", _i32), ("We", _vp), ("be", _vp),
+                ("alpha", _vp), ("alpha_stride", _i32), ("off_t", _i32), ("off_e", _i32), ("off_s", _i32),
+                ("dz", _vp), ("dSt", _vp), ("dh", _vp), ("d_alpha", _vp), ("d_bias", _vp), ("dWe", _vp), ("dbe", _vp),
+                ("scratch", _vp)]
+
+ABI_VERSION = 2
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_TF32 = 0, 1
 
@@ -67,8 +101,8 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == ABI / header mismatch: fail loudly
         fn.restype, fn.argtypes = res, args
-    if lib.fnb_version() != 1:
-        raise RuntimeError(f"fragnet_b200: ABI version mismatch ({lib.fnb_version()} != 1)")
+    if lib.fnb_version() != ABI_VERSION:
+        raise RuntimeError(f"fragnet_b200: ABI version mismatch ({lib.fnb_version()} != {ABI_VERSION})")
     _lib = lib
     return lib
 
@@ -77,3 +111,34 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().fnb_error_string(rc).decode()
         raise RuntimeError(f"fragnet_b200.{what} failed: {msg} (code {rc})")
+
+
+PARAM_FIELDS = ("Wb", "bb", "Wfb", "bfb", "We_b", "be_b", "We_fb", "be_fb", "Wa", "ba", "a_b", "a", "f", "f_a_b")
+
+
+class CLayerParams(C.Structure):
+    _fields_ = [(n, _vp) for n in PARAM_FIELDS] + [
+        ("K_atom", _i32), ("K_bond", _i32), ("K_fbond", _i32), ("run_frag_block", _i32), ("want_attention", _i32),
+        ("bond_mask", _i64), ("frag_bond_mask", _i64), ("atom_mask", _i64), ("atom_mask_list", _vp),
+        ("n_atom_mask", _i64)]
+
+
+class CLayerGrads(C.Structure):
+    _fields_ = [(n, _vp) for n in PARAM_FIELDS]
+
+
+class CBatchPlan(C.Structure):
+    _fields_ = [("bond", CGraph), ("atom", CGraph), ("fbond", CGraph), ("frag", CGraph),
+                ("pool_rowptr", _vp), ("pool_col", _vp), ("a2f", _vp), ("n_atoms", _i64), ("n_frags", _i64)]
+
+
+class CEncoderOpts(C.Structure):
+    _fields_ = [("n_layers", _i32), ("post_act", _i32), ("drop_p", _f32), ("training", _i32), ("seed", _u64),
+                ("offset", _u64), ("precision", _i32), ("save_for_backward", _i32), ("need_dx_atoms", _i32),
+                ("need_dx_bond", _i32), ("need_dx_fbond", _i32)]
+
+
+class CEncoderIO(C.Structure):
+    _fields_ = [(n, _vp) for n in ("x_atoms", "x_bond", "x_fbond", "out_atoms", "out_frags", "out_bond", "out_fbond",
+                                   "attn_atoms", "attn_frags", "attn_bonds", "attn_fbonds", "g_atoms", "g_frags",
+                                   "g_bond", "g_fbond", "dx_atoms", "dx_bond", "dx_fbond")]

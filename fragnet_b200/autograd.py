@@ -1,157 +1,175 @@
-"""``torch.autograd.Function`` wrappers that sequence the kernels of one GAT2 layer.
+"""``torch.autograd.Function`` wrappers over the library's encoder programs.
 
-One Function per ``FragNetLayerA.forward`` (reference fragnet/model/gat/gat2.py:121-330) rather than
-one per op: the blocks exchange by-products that only make sense fused (the bond block's epilogue
-emits the atom block's edge term, the pooling epilogue emits the fragment block's node scalars, the
-atom block's backward folds the pooling backward into its incoming gradient), and a single Function
-keeps exactly the tensors the hand-written backward needs.
+One Function for the WHOLE encoder (all layers of ``FragNet.forward``, reference fragnet/model/gat/gat2.py:381-442,
+or one bare ``FragNetLayerA.forward``, gat2.py:121-330) rather than one per op or per layer: the forward is a single
+``fnb_encoder_forward`` call and the backward a single ``fnb_encoder_backward`` call (encoder.cu sequences every
+launch in C++), so a training step crosses the Python boundary twice for the message passing instead of ~190 times,
+and autograd keeps exactly one workspace tensor alive for the backward.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Optional
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
 
 import torch
 
-from . import ops
-from .ops import EDGE_AFFINE1, EDGE_AFFINE6, EDGE_NONE, EDGE_TABLE, LayerPlan
+from . import _abi, ops
+from .ops import LayerPlan
 
-# head-vector layouts (reference gat2.py:98-109): a_b / f_a_b = [target 32 | edge 32 | source 32],
-# a / f = [target 32 | edge 128 | source 32]
-AB_STRIDE, AB_T, AB_E, AB_S = 96, 0, 32, 64
-A_STRIDE, A_T, A_E, A_S = 192, 0, 32, 160
+N_PARAMS = len(_abi.PARAM_FIELDS)     # live tensors per layer, in ``FragNetLayerA._live_parameters`` order
+_F_INDEX = _abi.PARAM_FIELDS.index("f")
 
 
 @dataclass
-class LayerOptions:
+class LayerSwitches:
+    """Per-layer switches that are not tensors (mirrors the non-pointer tail of ``fnb_layer_params``)."""
+    run_frag_block: bool = True
+    want_attention: bool = False
     bond_mask: Optional[int] = None
     frag_bond_mask: Optional[int] = None
-    atom_mask: object = None          # int, sequence or tensor of atom rows to zero (gat2.py:227-231)
-    want_attention: bool = False
-    want_frag_block: bool = True      # False elides the fragment-graph block (dead for non-final layers)
-    precision: int = 0                # ops.PRECISION_FP32 / PRECISION_TF32 for the dense projections
-    grad_enabled: bool = True         # torch.is_grad_enabled() at the call site
+    atom_mask: object = None            # int, or a sequence / tensor of atom rows (gat2.py:227-231)
 
 
-def _range_mask(start, width):
-    return (-1, -1) if start is None else (int(start), int(start) + width)
+@dataclass
+class EncoderConfig:
+    layers: List[LayerSwitches]
+    post_act: bool                      # True: FragNet.forward (ReLU(Dropout) everywhere); False: one bare layer
+    drop_p: float = 0.0
+    training: bool = False
+    precision: int = 0
+    grad_enabled: bool = True           # torch.is_grad_enabled() at the call site (it is always off inside forward)
+    _keep: list = field(default_factory=list, repr=False)   # tensors the C structs point into
 
 
-class FragNetLayerFn(torch.autograd.Function):
-    """inputs: plan, opts, x_atoms, x_bond, x_fbond, then the 14 live parameter tensors.
-    outputs: x_atoms_new, x_frags_new, new_bond, new_fbond [, attn_atoms, attn_frags, attn_bonds, attn_fbonds]"""
+def _has_mask(cfg: EncoderConfig) -> bool:
+    return any(s.bond_mask is not None or s.frag_bond_mask is not None or s.atom_mask is not None for s in cfg.layers)
+
+
+def _layer_structs(cfg: EncoderConfig, params, dev):
+    n = len(cfg.layers)
+    arr = (_abi.CLayerParams * n)()
+    for l, sw in enumerate(cfg.layers):
+        ps = params[l * N_PARAMS:(l + 1) * N_PARAMS]
+        for name, t in zip(_abi.PARAM_FIELDS, ps):
+            setattr(arr[l], name, t.data_ptr())
+        arr[l].K_bond, arr[l].K_fbond, arr[l].K_atom = ps[0].shape[1], ps[2].shape[1], ps[8].shape[1]
+        arr[l].run_frag_block, arr[l].want_attention = int(sw.run_frag_block), int(sw.want_attention)
+        arr[l].bond_mask = -1 if sw.bond_mask is None else int(sw.bond_mask)
+        arr[l].frag_bond_mask = -1 if sw.frag_bond_mask is None else int(sw.frag_bond_mask)
+        arr[l].atom_mask, arr[l].atom_mask_list, arr[l].n_atom_mask = -1, None, 0
+        am = sw.atom_mask
+        if am is not None:
+            if isinstance(am, int):
+                arr[l].atom_mask = am
+            else:
+                idx = torch.as_tensor(am, device=dev).reshape(-1).to(torch.int32).contiguous()
+                cfg._keep.append(idx)
+                arr[l].atom_mask_list, arr[l].n_atom_mask = idx.data_ptr(), idx.numel()
+    return arr
+
+
+class EncoderFn(torch.autograd.Function):
+    """inputs: plan, cfg, x_atoms, x_bond, x_fbond, then 14 live parameter tensors per layer.
+    outputs: atoms, frags, bond, fbond [, attn_atoms, attn_frags, attn_bonds, attn_fbonds of the attention layer]."""
 
     @staticmethod
-    def forward(ctx, plan: LayerPlan, opts: LayerOptions, x_atoms, x_bond, x_fbond,
-                Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b):
+    def forward(ctx, plan: LayerPlan, cfg: EncoderConfig, x_atoms, x_bond, x_fbond, *params):
         f32 = ops._f32c
         x_atoms, x_bond, x_fbond = f32(x_atoms), f32(x_bond), f32(x_fbond)
-        params = [f32(t) for t in (Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b)]
-        Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b = params
-        # grad mode is always off INSIDE Function.forward and needs_input_grad ignores torch.no_grad(): the caller samples it
-        need_grad = opts.grad_enabled and any(ctx.needs_input_grad)
-        if need_grad and (opts.bond_mask is not None or opts.frag_bond_mask is not None or opts.atom_mask is not None):
+        params = [f32(t) for t in params]
+        dev = x_atoms.device
+        n_layers = len(cfg.layers)
+        assert len(params) == n_layers * N_PARAMS
+        need_grad = cfg.grad_enabled and any(ctx.needs_input_grad)
+        if need_grad and _has_mask(cfg):
             raise NotImplementedError(
                 "fragnet_b200: bond/atom/fragment-bond masks are inference-only (the reference applies them "
                 "in-place under no_grad, gat2.py:173-176,227-231,275-278); run under torch.no_grad()")
-        save_p = need_grad or opts.want_attention
-
-        # bond graph (gat2.py:138-169); epilogue emits the atom graph's edge term <new_bond[e], a_e[h]>
-        coef_b = ops.edge_coef_fwd(We_b, be_b, 1, a_b, AB_STRIDE, AB_E)
-        hb, Sb = ops.proj_fwd(x_bond, Wb, bb, a_b, AB_STRIDE, AB_T, AB_S, precision=opts.precision)
-        new_bond, p_b, se_atom = ops.gat_fwd(plan.bond, hb, Sb, EDGE_AFFINE1, plan.bond.attr, coef_b, save_p,
-                                             _range_mask(opts.bond_mask, 2), a[:, A_E:], A_STRIDE)
-        # atom graph with self loops (gat2.py:179-224)
-        ha, Sa = ops.proj_fwd(x_atoms, Wa, ba, a, A_STRIDE, A_T, A_S, precision=opts.precision)
-        am = opts.atom_mask
-        am_int = isinstance(am, int)
-        x_atoms_new, p_a, _ = ops.gat_fwd(plan.atom, ha, Sa, EDGE_TABLE, se_atom, None, save_p,
-                                          _range_mask(am if am_int else None, 1))
-        if am is not None and not am_int:
-            x_atoms_new[torch.as_tensor(am, device=x_atoms_new.device)] = 0.0
-        # atom -> fragment pooling (gat2.py:234); epilogue emits the fragment graph's node scalars
-        hf, Sf = ops.segment_sum(plan.pool.rowptr, plan.pool.col, plan.n_frags, x_atoms_new,
-                                 alpha=f, alpha_stride=A_STRIDE, off_t=A_T, off_s=A_S)
-        # fragment-connection graph (gat2.py:239-272); epilogue emits the fragment graph's edge term
-        coef_fb = ops.edge_coef_fwd(We_fb, be_fb, 6, f_a_b, AB_STRIDE, AB_E)
-        hfb, Sfb = ops.proj_fwd(x_fbond, Wfb, bfb, f_a_b, AB_STRIDE, AB_T, AB_S, precision=opts.precision)
-        fmask = (-1, -1) if opts.frag_bond_mask is None else (2 * int(opts.frag_bond_mask), 2 * int(opts.frag_bond_mask) + 2)
-        new_fbond, p_fb, se_frag = ops.gat_fwd(plan.fbond, hfb, Sfb, EDGE_AFFINE6, plan.fbond.attr, coef_fb, save_p,
-                                               fmask, f[:, A_E:] if opts.want_frag_block else None, A_STRIDE)
-        # fragment graph: no projection, no self loops (gat2.py:283-316)
-        if opts.want_frag_block:
-            x_frags_new, p_f, _ = ops.gat_fwd(plan.frag, hf, Sf, EDGE_TABLE, se_frag, None, save_p)
-        else:
-            x_frags_new, p_f = hf, None      # placeholder; the caller ignores it
-        outs = [x_atoms_new, x_frags_new, new_bond, new_fbond]
-        if opts.want_attention:
-            attn = [ops.attn_by_source(plan.atom, p_a),
-                    ops.attn_by_source(plan.frag, p_f) if p_f is not None else None,
-                    ops.attn_by_source(plan.bond, p_b), ops.attn_by_source(plan.fbond, p_fb)]
+        lib = ops._lib()
+        layers = _layer_structs(cfg, params, dev)
+        dropping = cfg.post_act and cfg.training and cfg.drop_p > 0
+        opts = _abi.CEncoderOpts(n_layers, int(cfg.post_act), float(cfg.drop_p), int(cfg.training),
+                                 torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, 0, cfg.precision, int(need_grad),
+                                 0, 0, 0)
+        cplan = plan.cstruct()
+        if dropping:
+            opts.offset = ops.reserve_philox(lib.fnb_encoder_philox_span(C.byref(cplan), C.byref(opts), layers))
+        new = lambda rows, cols=ops.D: torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        run_frag_last = cfg.layers[-1].run_frag_block
+        out_atoms, out_bond, out_fbond = new(plan.n_atoms), new(plan.bond.n_nodes), new(plan.fbond.n_nodes)
+        out_frags = new(plan.n_frags) if run_frag_last else None
+        attn_layer = next((l for l, s in enumerate(cfg.layers) if s.want_attention), None)
+        attn = [None] * 4
+        if attn_layer is not None:
+            attn = [new(plan.n_atoms, ops.H), new(plan.n_frags, ops.H) if cfg.layers[attn_layer].run_frag_block else None,
+                    new(plan.bond.n_nodes, ops.H), new(plan.fbond.n_nodes, ops.H)]
+        ws_bytes = lib.fnb_encoder_workspace_bytes(C.byref(cplan), C.byref(opts), layers)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        pt = ops._ptr
+        io = _abi.CEncoderIO(pt(x_atoms), pt(x_bond), pt(x_fbond), pt(out_atoms), pt(out_frags), pt(out_bond),
+                             pt(out_fbond), pt(attn[0]), pt(attn[1]), pt(attn[2]), pt(attn[3]))
+        _abi.check(lib.fnb_encoder_forward(C.byref(cplan), C.byref(opts), layers, C.byref(io), pt(ws), ws_bytes,
+                                           pt(ops.scratch(dev)), ops._stream()), "encoder_forward")
+        if out_frags is None:
+            out_frags = out_atoms.new_zeros((plan.n_frags, ops.D))     # placeholder nobody reads
+        outs = [out_atoms, out_frags, out_bond, out_fbond]
+        if attn_layer is not None:
+            if attn[1] is None:
+                attn[1] = out_atoms.new_zeros((plan.n_frags, ops.H))
             outs += attn
-            ctx.mark_non_differentiable(*[t for t in attn if t is not None])
+            ctx.mark_non_differentiable(*attn)
         if need_grad:
-            ctx.plan, ctx.opts = plan, opts
-            ctx.save_for_backward(x_atoms, x_bond, x_fbond, *params, hb, ha, hf, hfb, p_b, p_a, p_f, p_fb,
-                                  new_bond, new_fbond)
+            ctx.set_materialize_grads(False)
+            ctx.plan, ctx.cfg, ctx.opts, ctx.ws = plan, cfg, opts, ws
+            ctx.save_for_backward(x_atoms, x_bond, x_fbond, *params, out_atoms, out_frags, out_bond, out_fbond)
         return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_atoms, g_frags, g_bond, g_fbond, *_unused):
-        plan, opts = ctx.plan, ctx.opts
-        (x_atoms, x_bond, x_fbond, Wb, bb, Wfb, bfb, We_b, be_b, We_fb, be_fb, Wa, ba, a_b, a, f, f_a_b,
-         hb, ha, hf, hfb, p_b, p_a, p_f, p_fb, new_bond, new_fbond) = ctx.saved_tensors
-        needs = ctx.needs_input_grad          # indices: 2 x_atoms, 3 x_bond, 4 x_fbond
+    def backward(ctx, g_atoms, g_frags, g_bond, g_fbond, *_attn_grads):
+        plan, cfg, opts, ws = ctx.plan, ctx.cfg, ctx.opts, ctx.ws
+        saved = ctx.saved_tensors
+        x_atoms, x_bond, x_fbond = saved[:3]
+        params = list(saved[3:-4])
+        out_atoms, out_frags, out_bond, out_fbond = saved[-4:]
+        dev = x_atoms.device
+        needs = ctx.needs_input_grad          # 2 x_atoms, 3 x_bond, 4 x_fbond, 5.. parameters
+        lib = ops._lib()
         c = lambda t: None if t is None else ops._f32c(t)
         g_atoms, g_frags, g_bond, g_fbond = c(g_atoms), c(g_frags), c(g_bond), c(g_fbond)
-        dev = x_atoms.device
-        # every slice of the head-vector gradients is written by exactly one kernel below: no zero fill needed
-        zeros = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-
-        # ---- fragment graph block
-        d_f = d_hf = None
-        if opts.want_frag_block and g_frags is not None:
-            d_f = zeros(4, A_STRIDE)
-            dz, dSt, _ = ops.gat_bwd_dst(plan.frag, hf, g_frags, p_f)
-            d_hf = ops.gat_bwd_src(plan.frag, hf, g_frags, p_f, dz, dSt, f, A_STRIDE, A_T, A_S, d_f)
-            g_fbond = ops.edge_table_bwd(plan.frag, dz, new_fbond, f, A_STRIDE, A_E, g_fbond, d_f)
-        # ---- fragment-connection graph block
-        d_fab = dWfb = dbfb = dWe_fb = dbe_fb = dx_fbond = None
-        if g_fbond is not None:
-            d_fab = zeros(4, AB_STRIDE)
-            dz, dSt, d_coef = ops.gat_bwd_dst(plan.fbond, hfb, g_fbond, p_fb, EDGE_AFFINE6, plan.fbond.attr, True)
-            d_hfb, dbfb = ops.gat_bwd_src(plan.fbond, hfb, g_fbond, p_fb, dz, dSt, f_a_b, AB_STRIDE, AB_T, AB_S, d_fab,
-                                          want_bias_grad=True)
-            dWe_fb, dbe_fb = ops.edge_coef_bwd(We_fb, be_fb, 6, f_a_b, AB_STRIDE, AB_E, d_coef, d_fab)
-            dx_fbond, dWfb, _ = ops.proj_bwd(x_fbond, Wfb, d_hfb, needs[4], opts.precision, want_db=False)
-        # ---- pooling backward folded into the atom block's incoming gradient
-        if d_hf is not None:
-            g_atoms = ops.segment_gather(d_hf, ops.D, plan.a2f32, plan.n_atoms, g_atoms)
-        # ---- atom graph block
-        d_a = dWa = dba = dx_atoms = None
-        if g_atoms is not None:
-            d_a = zeros(4, A_STRIDE)
-            dz, dSt, _ = ops.gat_bwd_dst(plan.atom, ha, g_atoms, p_a)
-            d_ha, dba = ops.gat_bwd_src(plan.atom, ha, g_atoms, p_a, dz, dSt, a, A_STRIDE, A_T, A_S, d_a,
-                                        want_bias_grad=True)
-            g_bond = ops.edge_table_bwd(plan.atom, dz, new_bond, a, A_STRIDE, A_E, g_bond, d_a)
-            dx_atoms, dWa, _ = ops.proj_bwd(x_atoms, Wa, d_ha, needs[2], opts.precision, want_db=False)
-        # ---- bond graph block
-        d_ab = dWb = dbb = dWe_b = dbe_b = dx_bond = None
-        if g_bond is not None:
-            d_ab = zeros(4, AB_STRIDE)
-            dz, dSt, d_coef = ops.gat_bwd_dst(plan.bond, hb, g_bond, p_b, EDGE_AFFINE1, plan.bond.attr, True)
-            d_hb, dbb = ops.gat_bwd_src(plan.bond, hb, g_bond, p_b, dz, dSt, a_b, AB_STRIDE, AB_T, AB_S, d_ab,
-                                        want_bias_grad=True)
-            dWe_b, dbe_b = ops.edge_coef_bwd(We_b, be_b, 1, a_b, AB_STRIDE, AB_E, d_coef, d_ab)
-            dx_bond, dWb, _ = ops.proj_bwd(x_bond, Wb, d_hb, needs[3], opts.precision, want_db=False)
-        return (None, None, dx_atoms, dx_bond, dx_fbond, dWb, dbb, dWfb, dbfb, dWe_b, dbe_b, dWe_fb, dbe_fb,
-                dWa, dba, d_ab, d_a, d_f, d_fab)
+        layers = _layer_structs(cfg, params, dev)
+        # every parameter gradient of the pass lives in ONE flat buffer (views are handed to autograd)
+        sizes = [p.numel() for p in params]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        views = [v.view_as(p) for v, p in zip(flat.split(sizes), params)]
+        grads = (_abi.CLayerGrads * len(cfg.layers))()
+        for l in range(len(cfg.layers)):
+            for name, v in zip(_abi.PARAM_FIELDS, views[l * N_PARAMS:(l + 1) * N_PARAMS]):
+                setattr(grads[l], name, v.data_ptr())
+        opts.need_dx_atoms, opts.need_dx_bond, opts.need_dx_fbond = int(needs[2]), int(needs[3]), int(needs[4])
+        dx = [torch.empty_like(x) if n else None for x, n in zip((x_atoms, x_bond, x_fbond), needs[2:5])]
+        cplan = plan.cstruct()
+        bws_bytes = lib.fnb_encoder_bwd_workspace_bytes(C.byref(cplan), C.byref(opts), layers)
+        bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
+        pt = ops._ptr
+        run_frag_last = cfg.layers[-1].run_frag_block
+        io = _abi.CEncoderIO(pt(x_atoms), pt(x_bond), pt(x_fbond), pt(out_atoms), pt(out_frags) if run_frag_last else None,
+                             pt(out_bond), pt(out_fbond), None, None, None, None, pt(g_atoms),
+                             pt(g_frags) if run_frag_last else None, pt(g_bond), pt(g_fbond), pt(dx[0]), pt(dx[1]), pt(dx[2]))
+        _abi.check(lib.fnb_encoder_backward(C.byref(cplan), C.byref(opts), layers, grads, C.byref(io), pt(ws), ws.numel(),
+                                            pt(bws), bws_bytes, pt(ops.scratch(dev)), ops._stream()), "encoder_backward")
+        out = []
+        for l, sw in enumerate(cfg.layers):
+            for j in range(N_PARAMS):
+                k = l * N_PARAMS + j
+                dead = j == _F_INDEX and not (sw.run_frag_block and g_frags is not None and l == len(cfg.layers) - 1)
+                out.append(views[k] if needs[5 + k] and not dead else None)
+        return (None, None, dx[0], dx[1], dx[2], *out)
 
 
 class DropoutReluFn(torch.autograd.Function):
     """y = ReLU(Dropout_p(x)) (reference gat2.py:414-418) or plain Dropout_p(x) with ``relu=False``
-    (gat2.py:396).  Nothing but y is kept for backward."""
+    (gat2.py:396) as a standalone op.  Nothing but y is kept for backward."""
 
     @staticmethod
     def forward(ctx, x, p: float, training: bool, relu: bool):

@@ -149,7 +149,8 @@ __global__ void k_claim(const int64_t *__restrict__ dst, const int64_t *__restri
 // One thread per claimed slot: rank of its edge id among the ids of its segment -> final slot.
 __global__ void k_rank_forward(const int64_t *__restrict__ dst, const int64_t *__restrict__ src, int64_t n_real,
                                int64_t n_total, const int *__restrict__ rowptr, const int *__restrict__ tmp_eid,
-                               int *__restrict__ col, int *__restrict__ eid, int *__restrict__ slot_of_eid) {
+                               int *__restrict__ col, int *__restrict__ row, int *__restrict__ eid,
+                               int *__restrict__ slot_of_eid) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
     const int e = tmp_eid[i];
     if (e < 0 || e >= n_total) continue;  // only reachable after an out-of-range index (status != 0)
@@ -160,6 +161,7 @@ __global__ void k_rank_forward(const int64_t *__restrict__ dst, const int64_t *_
     for (int j = beg; j < end; ++j) rank += (tmp_eid[j] < e);
     const int slot = beg + rank;
     if (col) col[slot] = (int)s;
+    if (row) row[slot] = (int)d;
     if (eid) eid[slot] = e;
     if (slot_of_eid) slot_of_eid[e] = slot;
   }
@@ -228,7 +230,7 @@ extern "C" size_t fnb_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges_total
 }
 
 extern "C" int fnb_csr_build(const int64_t *dst, const int64_t *src, int64_t n_edges, int64_t n_nodes,
-                             int append_self_loops, int32_t *rowptr, int32_t *col, int32_t *eid,
+                             int append_self_loops, int32_t *rowptr, int32_t *col, int32_t *row, int32_t *eid,
                              int32_t *slot_of_eid, int32_t *rrowptr, int32_t *rslot, int32_t *rdst, void *workspace,
                              size_t workspace_bytes, int32_t *status, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -286,7 +288,7 @@ extern "C" int fnb_csr_build(const int64_t *dst, const int64_t *src, int64_t n_e
                                                         rrowptr, cnt_dst, reverse ? cnt_src : nullptr, tmp_eid,
                                                         tmp_reid);
     FNB_CHECK_LAUNCH();
-    k_rank_forward<<<grid_for(n_total, 256), 256, 0, stream>>>(dst, src, n_edges, n_total, rowptr, tmp_eid, col, eid,
+    k_rank_forward<<<grid_for(n_total, 256), 256, 0, stream>>>(dst, src, n_edges, n_total, rowptr, tmp_eid, col, row, eid,
                                                                slot_of_eid);
     FNB_CHECK_LAUNCH();
     if (reverse) {

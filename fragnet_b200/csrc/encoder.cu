@@ -1,0 +1,515 @@
+// Whole-encoder programs: FragNet.forward / its backward as ONE library call each.
+//
+// Reference: FragNet.forward (fragnet/model/gat/gat2.py:381-442) runs num_layer x FragNetLayerA.forward
+// (gat2.py:121-330: bond graph -> atom graph -> atom->fragment pooling -> fragment-connection graph -> fragment
+// graph) with ReLU(Dropout(.)) on the four outputs of every layer (gat2.py:414-418, 436-440).  Upstream that is a few
+// hundred eager torch ops per step; the first version of this library still paid ~190 Python->C calls and ~300
+// allocator calls per training step and was host-bound.  Here the host side of the sequence is
+// C++: one call issues every launch of the pass back to back on the caller's stream, all intermediates come out of
+// one caller-allocated workspace whose layout is a pure function of the sizes, and nothing synchronises.
+//
+// Per layer, forward: 3 projections (tcgen05 TF32 or FP32), 3 tiled attention kernels (4 in the layer that runs
+// the fragment block, plus the pooling).  Folded into those launches: edge-embedding constants, output masks,
+// ReLU(Dropout), the consumer graph's edge term, the fragment graph's node scalars.
+// Backward: per graph one destination pass + one source pass (parameter-gradient reductions inside), the edge-table
+// backward with the ReLU(Dropout) backward folded in, and the projection backward (dX, dW).
+#include "common.cuh"
+
+namespace {
+
+constexpr int AB_STRIDE = 96, AB_T = 0, AB_E = 32, AB_S = 64;    // a_b / f_a_b = [target 32 | edge 32 | source 32]
+constexpr int A_STRIDE = 192, A_T = 0, A_E = 32, A_S = 160;      // a / f     = [target 32 | edge 128 | source 32]
+
+struct Arena {
+  char *base;
+  size_t off;
+  template <class T>
+  T *take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct LayerBufs {
+  float *xa0;                                                   // layer 0: Dropout(x_atoms) (training only)
+  float *hb, *Sb, *pre_bond, *y_bond, *p_b, *se_atom;
+  float *ha, *Sa, *pre_atom, *y_atom, *p_a;
+  float *hfb, *Sfb, *pre_fbond, *y_fbond, *p_fb, *se_frag;
+  float *hf, *Sf, *pre_frag, *y_frag, *p_f;
+};
+
+struct Sizes {
+  int64_t Na, Nb, Nfb, Nf, Ea, Eb, Efb, Ef;   // E* include appended self loops (atom graph)
+};
+
+Sizes sizes_of(const fnb_batch_plan *p) {
+  Sizes s;
+  s.Na = p->atom.n_nodes; s.Nb = p->bond.n_nodes; s.Nfb = p->fbond.n_nodes; s.Nf = p->frag.n_nodes;
+  s.Ea = p->atom.n_edges; s.Eb = p->bond.n_edges; s.Efb = p->fbond.n_edges; s.Ef = p->frag.n_edges;
+  return s;
+}
+
+bool input_dropout(const fnb_encoder_opts *o) { return o->post_act && o->training && o->drop_p > 0.f; }
+
+// Forward workspace layout (identical in fnb_encoder_forward / _backward / _workspace_bytes).
+size_t layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L, char *base,
+              LayerBufs *bufs) {
+  const Sizes z = sizes_of(plan);
+  Arena a{base, 0};
+  for (int l = 0; l < o->n_layers; ++l) {
+    LayerBufs b{};
+    const bool last = l == o->n_layers - 1;
+    const bool keep = o->save_for_backward != 0;
+    const bool want_p = keep || L[l].want_attention;
+    const bool frag = L[l].run_frag_block != 0;
+    if (l == 0 && input_dropout(o)) b.xa0 = a.take<float>(z.Na * L[0].K_atom);
+    b.hb = a.take<float>(z.Nb * kD);
+    b.Sb = a.take<float>(z.Nb * 8);
+    b.se_atom = a.take<float>(z.Nb * 4);
+    b.ha = a.take<float>(z.Na * kD);
+    b.Sa = a.take<float>(z.Na * 8);
+    b.hfb = a.take<float>(z.Nfb * kD);
+    b.Sfb = a.take<float>(z.Nfb * 8);
+    if (want_p) {
+      b.p_b = a.take<float>(z.Eb * 4);
+      b.p_a = a.take<float>(z.Ea * 4);
+      b.p_fb = a.take<float>(z.Efb * 4);
+    }
+    if (o->post_act) {
+      // pre-activations only where something downstream reads them: the bond features feed d alpha_e of the atom
+      // block's backward; the atom features feed the pooling; the fragment-connection features feed d alpha_e of
+      // the fragment block.  Post-activations of the last layer go straight to the caller's outputs.
+      if (keep) b.pre_bond = a.take<float>(z.Nb * kD);
+      if (frag) b.pre_atom = a.take<float>(z.Na * kD);
+      if (frag && keep) b.pre_fbond = a.take<float>(z.Nfb * kD);
+      if (!last) {
+        b.y_bond = a.take<float>(z.Nb * kD);
+        b.y_atom = a.take<float>(z.Na * kD);
+        b.y_fbond = a.take<float>(z.Nfb * kD);
+      }
+    }
+    if (frag) {
+      b.hf = a.take<float>(z.Nf * kD);
+      b.Sf = a.take<float>(z.Nf * 8);
+      b.se_frag = a.take<float>(z.Nfb * 4);
+      if (want_p) b.p_f = a.take<float>(z.Ef * 4);
+      if (o->post_act && !last) b.y_frag = a.take<float>(z.Nf * kD);   // dead output of a non-final layer
+    }
+    if (bufs) bufs[l] = b;
+  }
+  return (a.off + 255) & ~(size_t)255;
+}
+
+struct BwdBufs {
+  float *g_bond, *dz_b, *dSt_b, *dh_b, *dx_bond;
+  float *g_atom, *dz_a, *dSt_a, *dh_a, *dx_atom;
+  float *g_fbond, *dz_fb, *dSt_fb, *dh_fb, *dx_fbond;
+  float *g_frag, *dz_f, *dSt_f, *d_hf;
+  float *Wt;   // [n_layers][3][128*128] transposed K=128 projection weights
+};
+
+size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *base, BwdBufs *out) {
+  const Sizes z = sizes_of(plan);
+  Arena a{base, 0};
+  BwdBufs b{};
+  b.g_bond = a.take<float>(z.Nb * kD); b.dz_b = a.take<float>(z.Eb * 4); b.dSt_b = a.take<float>(z.Nb * 4);
+  b.dh_b = a.take<float>(z.Nb * kD); b.dx_bond = a.take<float>(z.Nb * kD);
+  b.g_atom = a.take<float>(z.Na * kD); b.dz_a = a.take<float>(z.Ea * 4); b.dSt_a = a.take<float>(z.Na * 4);
+  b.dh_a = a.take<float>(z.Na * kD); b.dx_atom = a.take<float>(z.Na * kD);
+  b.g_fbond = a.take<float>(z.Nfb * kD); b.dz_fb = a.take<float>(z.Efb * 4); b.dSt_fb = a.take<float>(z.Nfb * 4);
+  b.dh_fb = a.take<float>(z.Nfb * kD); b.dx_fbond = a.take<float>(z.Nfb * kD);
+  b.g_frag = a.take<float>(z.Nf * kD); b.dz_f = a.take<float>(z.Ef * 4); b.dSt_f = a.take<float>(z.Nf * 4);
+  b.d_hf = a.take<float>(z.Nf * kD);
+  b.Wt = a.take<float>((size_t)o->n_layers * 3 * kD * kD);
+  if (out) *out = b;
+  return (a.off + 255) & ~(size_t)255;
+}
+
+// Philox counters consumed by one dropout site over n elements.
+uint64_t span(int64_t n) { return (uint64_t)((n + 3) / 4); }
+
+// Counter bases of the dropout sites, in a fixed order: input, then per layer bond, atom, fbond, frag.
+struct PhiloxPlan {
+  uint64_t input;
+  uint64_t bond[16], atom[16], fbond[16], frag[16];
+  uint64_t total;
+};
+
+PhiloxPlan philox_plan(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L) {
+  const Sizes z = sizes_of(plan);
+  PhiloxPlan p{};
+  uint64_t c = o->offset;
+  p.input = c;
+  c += span(z.Na * (int64_t)L[0].K_atom);
+  for (int l = 0; l < o->n_layers && l < 16; ++l) {
+    p.bond[l] = c;  c += span(z.Nb * kD);
+    p.atom[l] = c;  c += span(z.Na * kD);
+    p.fbond[l] = c; c += span(z.Nfb * kD);
+    p.frag[l] = c;  c += span(z.Nf * kD);
+  }
+  p.total = c - o->offset;
+  return p;
+}
+
+fnb_post_act post_of(const fnb_encoder_opts *o, uint64_t counter) {
+  fnb_post_act pa;
+  pa.p = o->drop_p; pa.training = o->training; pa.relu = 1; pa.seed = o->seed; pa.offset = counter;
+  return pa;
+}
+
+// g[i,:] = (dy ? dy[i,:] * (y[i,:] > 0) * scale : 0) + (base ? base[i,:] : 0) + (pooled ? pooled[seg_of[i],:] : 0)
+// -- the ReLU(Dropout) backward (gat2.py:414-418), an additive gradient and the atom->fragment pooling backward
+// (gat2.py:234) in one pass.  With y == NULL, dy is taken as is (bare-layer mode).
+__global__ void __launch_bounds__(256) k_grad_combine(const float *__restrict__ dy, const float *__restrict__ y,
+                                                      float scale, const float *__restrict__ pooled,
+                                                      const int *__restrict__ seg_of, int64_t n_rows,
+                                                      float *__restrict__ g) {
+  const int64_t total = n_rows * 32;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i >> 5;
+    const int c = (int)(i & 31) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dy) {
+      v = ldg4(dy + r * kD + c);
+      if (y) {
+        const float4 o = ldg4(y + r * kD + c);
+        v.x = o.x > 0.f ? v.x * scale : 0.f;
+        v.y = o.y > 0.f ? v.y * scale : 0.f;
+        v.z = o.z > 0.f ? v.z * scale : 0.f;
+        v.w = o.w > 0.f ? v.w * scale : 0.f;
+      }
+    }
+    if (pooled) {
+      const float4 q = ldg4(pooled + (int64_t)__ldg(seg_of + r) * kD + c);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    st4(g + r * kD + c, v);
+  }
+}
+
+__global__ void k_zero_rows(float *__restrict__ a, float *__restrict__ b, const int *__restrict__ rows, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * 32; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = __ldg(rows + (i >> 5));
+    const int c = (int)(i & 31) * 4;
+    if (a) st4(a + r * kD + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (b) st4(b + r * kD + c, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
+int grad_combine(const float *dy, const float *y, float scale, const float *pooled, const int *seg_of, int64_t n_rows,
+                 float *g, cudaStream_t stream) {
+  if (n_rows == 0) return 0;
+  int64_t blocks = (n_rows * 32 + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  k_grad_combine<<<(int)blocks, 256, 0, stream>>>(dy, y, scale, pooled, seg_of, n_rows, g);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+#define RC(expr)            \
+  do {                      \
+    const int rc__ = (expr); \
+    if (rc__) return rc__;   \
+  } while (0)
+
+int check_common(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
+                 const fnb_encoder_io *io) {
+  if (!plan || !o || !L || !io) return FNB_ERR_NULL;
+  if (o->n_layers < 1 || o->n_layers > 16) return FNB_ERR_SIZE;
+  if (!o->post_act && o->n_layers != 1) return FNB_ERR_MODE;
+  if (!(o->drop_p >= 0.f && o->drop_p < 1.f)) return FNB_ERR_SIZE;
+  if (!io->x_atoms || !io->x_bond || !io->x_fbond || !io->out_atoms || !io->out_bond || !io->out_fbond)
+    return FNB_ERR_NULL;
+  const Sizes z = sizes_of(plan);
+  if (z.Na != plan->n_atoms || z.Nf != plan->n_frags) return FNB_ERR_SIZE;
+  // the atom graph's edges are the bond graph's nodes, the fragment graph's edges the fragment-connection nodes
+  if (plan->atom.n_real_edges != z.Nb || plan->frag.n_real_edges != z.Nfb) return FNB_ERR_SIZE;
+  for (int l = 0; l < o->n_layers; ++l) {
+    if (l > 0 && (L[l].K_atom != kD || L[l].K_bond != kD || L[l].K_fbond != kD)) return FNB_ERR_SIZE;
+    if (L[l].run_frag_block && !io->out_frags && l == o->n_layers - 1) return FNB_ERR_NULL;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t fnb_encoder_workspace_bytes(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+                                              const fnb_layer_params *layers) {
+  if (!plan || !opts || !layers || opts->n_layers < 1 || opts->n_layers > 16) return 0;
+  return layout(plan, opts, layers, nullptr, nullptr);
+}
+
+extern "C" size_t fnb_encoder_bwd_workspace_bytes(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+                                                  const fnb_layer_params *layers) {
+  (void)layers;
+  if (!plan || !opts || opts->n_layers < 1 || opts->n_layers > 16) return 0;
+  return bwd_layout(plan, opts, nullptr, nullptr);
+}
+
+extern "C" uint64_t fnb_encoder_philox_span(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+                                            const fnb_layer_params *layers) {
+  if (!plan || !opts || !layers || opts->n_layers < 1 || opts->n_layers > 16) return 0;
+  return philox_plan(plan, opts, layers).total;
+}
+
+extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
+                                   const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
+                                   void *stream_) {
+  RC(check_common(plan, o, L, io));
+  if (!workspace || !scratch) return FNB_ERR_NULL;
+  LayerBufs B[16];
+  if (layout(plan, o, L, (char *)workspace, B) > workspace_bytes) return FNB_ERR_WORKSPACE;
+  const Sizes z = sizes_of(plan);
+  const PhiloxPlan ph = philox_plan(plan, o, L);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool keep = o->save_for_backward != 0;
+
+  const float *xa = io->x_atoms, *xb = io->x_bond, *xfb = io->x_fbond;
+  if (input_dropout(o)) {  // nn.Dropout on the raw atom features, gat2.py:396
+    RC(fnb_dropout_relu_fwd(xa, B[0].xa0, z.Na * (int64_t)L[0].K_atom, o->drop_p, 1, 0, o->seed, ph.input, stream_));
+    xa = B[0].xa0;
+  }
+  for (int l = 0; l < o->n_layers; ++l) {
+    const fnb_layer_params &P = L[l];
+    LayerBufs &b = B[l];
+    const bool last = l == o->n_layers - 1;
+    const bool frag = P.run_frag_block != 0;
+    const bool want_p = keep || P.want_attention;
+    // where the four results of this layer go
+    float *pre_bond = o->post_act ? b.pre_bond : io->out_bond;
+    float *pre_atom = o->post_act ? b.pre_atom : io->out_atoms;
+    float *pre_fbond = o->post_act ? b.pre_fbond : io->out_fbond;
+    float *pre_frag = o->post_act ? nullptr : io->out_frags;
+    float *y_bond = o->post_act ? (last ? io->out_bond : b.y_bond) : nullptr;
+    float *y_atom = o->post_act ? (last ? io->out_atoms : b.y_atom) : nullptr;
+    float *y_fbond = o->post_act ? (last ? io->out_fbond : b.y_fbond) : nullptr;
+    float *y_frag = o->post_act ? (last ? io->out_frags : b.y_frag) : nullptr;
+
+    // ---- bond graph (gat2.py:138-176); epilogue emits the atom graph's edge term <new_bond[e], a_e[h]>
+    RC(fnb_proj_fwd(xb, P.Wb, P.bb, z.Nb, P.K_bond, P.a_b, AB_STRIDE, AB_T, AB_S, b.hb, b.Sb, o->precision, stream_));
+    {
+      fnb_gat_fwd_args f{};
+      f.h = b.hb; f.S = b.Sb; f.edge_mode = FNB_EDGE_AFFINE1; f.We = P.We_b; f.be = P.be_b;
+      f.alpha_e = P.a_b + AB_E; f.alpha_stride = AB_STRIDE; f.out = pre_bond; f.y = y_bond;
+      f.post = post_of(o, ph.bond[l]); f.p_saved = want_p ? b.p_b : nullptr;
+      f.mask_lo = P.bond_mask >= 0 ? P.bond_mask : -1; f.mask_hi = P.bond_mask >= 0 ? P.bond_mask + 2 : -1;
+      f.next_alpha_e = P.a + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_atom;
+      RC(fnb_gat_fwd_tiled(&plan->bond, &f, stream_));
+    }
+    // ---- atom graph with self loops (gat2.py:179-231)
+    RC(fnb_proj_fwd(xa, P.Wa, P.ba, z.Na, P.K_atom, P.a, A_STRIDE, A_T, A_S, b.ha, b.Sa, o->precision, stream_));
+    {
+      fnb_gat_fwd_args f{};
+      f.h = b.ha; f.S = b.Sa; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = b.se_atom; f.out = pre_atom; f.y = y_atom;
+      f.post = post_of(o, ph.atom[l]); f.p_saved = want_p ? b.p_a : nullptr;
+      f.mask_lo = P.atom_mask >= 0 ? P.atom_mask : -1; f.mask_hi = P.atom_mask >= 0 ? P.atom_mask + 1 : -1;
+      RC(fnb_gat_fwd_tiled(&plan->atom, &f, stream_));
+      if (P.atom_mask_list && P.n_atom_mask > 0) {
+        k_zero_rows<<<(int)((P.n_atom_mask * 32 + 255) / 256), 256, 0, stream>>>(pre_atom, y_atom, P.atom_mask_list,
+                                                                               P.n_atom_mask);
+        FNB_CHECK_LAUNCH();
+      }
+    }
+    // ---- fragment-connection graph (gat2.py:239-278); epilogue emits the fragment graph's edge term
+    RC(fnb_proj_fwd(xfb, P.Wfb, P.bfb, z.Nfb, P.K_fbond, P.f_a_b, AB_STRIDE, AB_T, AB_S, b.hfb, b.Sfb, o->precision,
+                    stream_));
+    {
+      fnb_gat_fwd_args f{};
+      f.h = b.hfb; f.S = b.Sfb; f.edge_mode = FNB_EDGE_AFFINE6; f.We = P.We_fb; f.be = P.be_fb;
+      f.alpha_e = P.f_a_b + AB_E; f.alpha_stride = AB_STRIDE; f.out = pre_fbond; f.y = y_fbond;
+      f.post = post_of(o, ph.fbond[l]); f.p_saved = want_p ? b.p_fb : nullptr;
+      f.mask_lo = P.frag_bond_mask >= 0 ? 2 * P.frag_bond_mask : -1;
+      f.mask_hi = P.frag_bond_mask >= 0 ? 2 * P.frag_bond_mask + 2 : -1;
+      if (frag) { f.next_alpha_e = P.f + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_frag; }
+      RC(fnb_gat_fwd_tiled(&plan->fbond, &f, stream_));
+    }
+    // ---- atom -> fragment pooling (gat2.py:234) and the fragment graph (gat2.py:283-316): only where its output lives
+    if (frag) {
+      RC(fnb_segment_sum(plan->pool_rowptr, plan->pool_col, z.Nf, pre_atom, b.hf, kD, P.f, A_STRIDE, A_T, A_S, b.Sf,
+                         stream_));
+      fnb_gat_fwd_args f{};
+      f.h = b.hf; f.S = b.Sf; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = b.se_frag; f.out = pre_frag; f.y = y_frag;
+      f.post = post_of(o, ph.frag[l]); f.p_saved = want_p ? b.p_f : nullptr; f.mask_lo = f.mask_hi = -1;
+      RC(fnb_gat_fwd_tiled(&plan->frag, &f, stream_));
+    }
+    if (P.want_attention) {  // by-source attention sums (gat2.py:165,219,268,312)
+      if (io->attn_bonds) RC(fnb_attn_by_source(plan->bond.rrowptr, plan->bond.rslot, b.p_b, z.Nb, io->attn_bonds, stream_));
+      if (io->attn_atoms) RC(fnb_attn_by_source(plan->atom.rrowptr, plan->atom.rslot, b.p_a, z.Na, io->attn_atoms, stream_));
+      if (io->attn_fbonds)
+        RC(fnb_attn_by_source(plan->fbond.rrowptr, plan->fbond.rslot, b.p_fb, z.Nfb, io->attn_fbonds, stream_));
+      if (io->attn_frags && frag)
+        RC(fnb_attn_by_source(plan->frag.rrowptr, plan->frag.rslot, b.p_f, z.Nf, io->attn_frags, stream_));
+    }
+    xa = y_atom; xb = y_bond; xfb = y_fbond;   // inputs of the next layer (post_act mode only has further layers)
+  }
+  return 0;
+}
+
+extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
+                                    const fnb_layer_grads *G, const fnb_encoder_io *io, void *workspace,
+                                    size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
+                                    void *scratch, void *stream_) {
+  RC(check_common(plan, o, L, io));
+  if (!G || !workspace || !bwd_workspace || !scratch) return FNB_ERR_NULL;
+  if (!o->save_for_backward) return FNB_ERR_MODE;
+  LayerBufs B[16];
+  BwdBufs W;
+  if (layout(plan, o, L, (char *)workspace, B) > workspace_bytes) return FNB_ERR_WORKSPACE;
+  if (bwd_layout(plan, o, (char *)bwd_workspace, &W) > bwd_workspace_bytes) return FNB_ERR_WORKSPACE;
+  const Sizes z = sizes_of(plan);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const float scale = (o->post_act && o->training && o->drop_p > 0.f) ? 1.f / (1.f - o->drop_p) : 1.f;
+  const bool tf32 = o->precision == FNB_PRECISION_TF32;
+
+  // W^T of every K = 128 projection in one launch per 16 matrices (used by the tensor-core dX GEMMs)
+  int wt_slot[16][3];
+  {
+    const float *mats[48];
+    int nm = 0;
+    for (int l = 0; l < o->n_layers; ++l) {
+      const float *ws[3] = {L[l].Wb, L[l].Wa, L[l].Wfb};
+      const int ks[3] = {L[l].K_bond, L[l].K_atom, L[l].K_fbond};
+      for (int j = 0; j < 3; ++j) {
+        wt_slot[l][j] = -1;
+        if (tf32 && ks[j] == kD && (l > 0 || (j == 0 ? o->need_dx_bond : (j == 1 ? o->need_dx_atoms : o->need_dx_fbond)))) {
+          wt_slot[l][j] = nm;
+          mats[nm++] = ws[j];
+        }
+      }
+    }
+    for (int c = 0; c < nm; c += 16) {
+      TransposeBatch tb{};
+      tb.count = nm - c < 16 ? nm - c : 16;
+      for (int i = 0; i < tb.count; ++i) tb.W[i] = mats[c + i];
+      RC(fnb_tc_transpose128_batched(tb, W.Wt + (size_t)c * kD * kD, stream));
+    }
+  }
+  auto wt_of = [&](int layer, int j) -> const float * {
+    return wt_slot[layer][j] >= 0 ? W.Wt + (size_t)wt_slot[layer][j] * kD * kD : nullptr;
+  };
+
+  // gradients arriving at the four outputs of the current layer (post-activation copies in post_act mode)
+  const float *dy_atom = io->g_atoms, *dy_bond = io->g_bond, *dy_fbond = io->g_fbond, *dy_frag = io->g_frags;
+  for (int l = o->n_layers - 1; l >= 0; --l) {
+    const fnb_layer_params &P = L[l];
+    const fnb_layer_grads &D = G[l];
+    LayerBufs &b = B[l];
+    const bool last = l == o->n_layers - 1;
+    const bool frag = P.run_frag_block != 0;
+    const float *xa = l == 0 ? (b.xa0 ? b.xa0 : io->x_atoms) : B[l - 1].y_atom;
+    const float *xb = l == 0 ? io->x_bond : B[l - 1].y_bond;
+    const float *xfb = l == 0 ? io->x_fbond : B[l - 1].y_fbond;
+    const float *y_bond = o->post_act ? (last ? io->out_bond : b.y_bond) : nullptr;
+    const float *y_atom = o->post_act ? (last ? io->out_atoms : b.y_atom) : nullptr;
+    const float *y_fbond = o->post_act ? (last ? io->out_fbond : b.y_fbond) : nullptr;
+    const float *y_frag = o->post_act ? (last ? io->out_frags : b.y_frag) : nullptr;
+    const float *pre_bond = o->post_act ? b.pre_bond : io->out_bond;
+    const float *pre_fbond = o->post_act ? b.pre_fbond : io->out_fbond;
+    const bool need_dx = l > 0;
+
+    // ---- fragment graph block (only where it ran and a gradient arrives)
+    const float *d_hf = nullptr;
+    bool frag_bwd = frag && dy_frag != nullptr;
+    if (frag_bwd) {
+      if (!D.f) return FNB_ERR_NULL;
+      RC(grad_combine(dy_frag, y_frag, scale, nullptr, nullptr, z.Nf, W.g_frag, stream));
+      fnb_gat_bwd_args a{};
+      a.h = b.hf; a.dout = W.g_frag; a.p_saved = b.p_f; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.f;
+      a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_f; a.dSt = W.dSt_f;
+      a.dh = W.d_hf; a.d_alpha = D.f; a.d_bias = nullptr; a.scratch = scratch;
+      RC(fnb_gat_bwd_tiled(&plan->frag, &a, stream_));
+      d_hf = W.d_hf;
+    }
+    // ---- fragment-connection graph block
+    {
+      bool have = true;
+      if (frag_bwd) {  // g = ReLU(Dropout) backward of dy + sum_h dz_f alpha_e; also d f[:, edge slice]
+        RC(fnb_edge_table_bwd_fused(&plan->frag, W.dz_f, pre_fbond, P.f, A_STRIDE, A_E, y_fbond ? nullptr : dy_fbond,
+                                    y_fbond ? dy_fbond : nullptr, y_fbond && dy_fbond ? y_fbond : nullptr, scale,
+                                    W.g_fbond, D.f, scratch, stream_));
+      } else if (dy_fbond) {
+        RC(grad_combine(dy_fbond, y_fbond, scale, nullptr, nullptr, z.Nfb, W.g_fbond, stream));
+      } else {
+        have = false;
+      }
+      if (have) {
+        fnb_gat_bwd_args a{};
+        a.h = b.hfb; a.dout = W.g_fbond; a.p_saved = b.p_fb; a.edge_mode = FNB_EDGE_AFFINE6; a.We = P.We_fb;
+        a.be = P.be_fb; a.alpha = P.f_a_b; a.alpha_stride = AB_STRIDE; a.off_t = AB_T; a.off_e = AB_E; a.off_s = AB_S;
+        a.dz = W.dz_fb; a.dSt = W.dSt_fb; a.dh = W.dh_fb; a.d_alpha = D.f_a_b; a.d_bias = D.bfb; a.dWe = D.We_fb;
+        a.dbe = D.be_fb; a.scratch = scratch;
+        RC(fnb_gat_bwd_tiled(&plan->fbond, &a, stream_));
+        float *dx = need_dx ? W.dx_fbond : (o->need_dx_fbond ? io->dx_fbond : nullptr);
+        RC(fnb_proj_bwd_impl(xfb, P.Wfb, wt_of(l, 2), W.dh_fb, z.Nfb, P.K_fbond, dx, D.Wfb, nullptr, o->precision,
+                             scratch, stream_));
+        dy_fbond = need_dx ? W.dx_fbond : nullptr;
+      } else {
+        dy_fbond = nullptr;
+      }
+      if (!have) {  // no gradient reaches this block: its parameters get zeros
+        RC((int)cudaMemsetAsync(D.f_a_b, 0, 4 * AB_STRIDE * 4, stream));
+        RC((int)cudaMemsetAsync(D.bfb, 0, kD * 4, stream));
+        RC((int)cudaMemsetAsync(D.We_fb, 0, 32 * 6 * 4, stream));
+        RC((int)cudaMemsetAsync(D.be_fb, 0, 32 * 4, stream));
+        RC((int)cudaMemsetAsync(D.Wfb, 0, (size_t)kD * P.K_fbond * 4, stream));
+      }
+    }
+    // ---- atom graph block: incoming gradient = activation backward + pooling backward
+    {
+      const bool have = dy_atom != nullptr || d_hf != nullptr;
+      if (have) {
+        RC(grad_combine(dy_atom, y_atom, scale, d_hf, plan->a2f, z.Na, W.g_atom, stream));
+        fnb_gat_bwd_args a{};
+        a.h = b.ha; a.dout = W.g_atom; a.p_saved = b.p_a; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.a;
+        a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_a; a.dSt = W.dSt_a;
+        a.dh = W.dh_a; a.d_alpha = D.a; a.d_bias = D.ba; a.scratch = scratch;
+        RC(fnb_gat_bwd_tiled(&plan->atom, &a, stream_));
+        // bond features were this graph's edge vectors: their gradient, plus the activation backward of dy_bond
+        RC(fnb_edge_table_bwd_fused(&plan->atom, W.dz_a, pre_bond, P.a, A_STRIDE, A_E, y_bond ? nullptr : dy_bond,
+                                    y_bond ? dy_bond : nullptr, y_bond && dy_bond ? y_bond : nullptr, scale, W.g_bond,
+                                    D.a, scratch, stream_));
+        float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);
+        RC(fnb_proj_bwd_impl(xa, P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, D.Wa, nullptr, o->precision, scratch,
+                             stream_));
+        dy_atom = need_dx ? W.dx_atom : nullptr;
+      } else {
+        RC((int)cudaMemsetAsync(D.a, 0, 4 * A_STRIDE * 4, stream));
+        RC((int)cudaMemsetAsync(D.ba, 0, kD * 4, stream));
+        RC((int)cudaMemsetAsync(D.Wa, 0, (size_t)kD * P.K_atom * 4, stream));
+        if (dy_bond) RC(grad_combine(dy_bond, y_bond, scale, nullptr, nullptr, z.Nb, W.g_bond, stream));
+        dy_atom = nullptr;
+      }
+      // ---- bond graph block
+      if (have || dy_bond) {
+        fnb_gat_bwd_args a{};
+        a.h = b.hb; a.dout = W.g_bond; a.p_saved = b.p_b; a.edge_mode = FNB_EDGE_AFFINE1; a.We = P.We_b; a.be = P.be_b;
+        a.alpha = P.a_b; a.alpha_stride = AB_STRIDE; a.off_t = AB_T; a.off_e = AB_E; a.off_s = AB_S; a.dz = W.dz_b;
+        a.dSt = W.dSt_b; a.dh = W.dh_b; a.d_alpha = D.a_b; a.d_bias = D.bb; a.dWe = D.We_b; a.dbe = D.be_b;
+        a.scratch = scratch;
+        RC(fnb_gat_bwd_tiled(&plan->bond, &a, stream_));
+        float *dx = need_dx ? W.dx_bond : (o->need_dx_bond ? io->dx_bond : nullptr);
+        RC(fnb_proj_bwd_impl(xb, P.Wb, wt_of(l, 0), W.dh_b, z.Nb, P.K_bond, dx, D.Wb, nullptr, o->precision, scratch,
+                             stream_));
+        dy_bond = need_dx ? W.dx_bond : nullptr;
+      } else {
+        RC((int)cudaMemsetAsync(D.a_b, 0, 4 * AB_STRIDE * 4, stream));
+        RC((int)cudaMemsetAsync(D.bb, 0, kD * 4, stream));
+        RC((int)cudaMemsetAsync(D.We_b, 0, 32 * 4, stream));
+        RC((int)cudaMemsetAsync(D.be_b, 0, 32 * 4, stream));
+        RC((int)cudaMemsetAsync(D.Wb, 0, (size_t)kD * P.K_bond * 4, stream));
+        dy_bond = nullptr;
+      }
+    }
+    if (!frag_bwd && D.f) RC((int)cudaMemsetAsync(D.f, 0, 4 * A_STRIDE * 4, stream));
+    dy_frag = nullptr;   // the fragment output of a lower layer is dead (overwritten unread, gat2.py:234)
+  }
+  // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same Philox stream as the forward
+  if (o->need_dx_atoms && io->dx_atoms && input_dropout(o)) {
+    const PhiloxPlan ph = philox_plan(plan, o, L);
+    RC(fnb_dropout_relu_fwd(io->dx_atoms, io->dx_atoms, z.Na * (int64_t)L[0].K_atom, o->drop_p, 1, 0, o->seed, ph.input,
+                            stream_));
+  }
+  return 0;
+}

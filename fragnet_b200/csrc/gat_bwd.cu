@@ -413,7 +413,7 @@ extern "C" int fnb_gat_bwd_dst(const int32_t *rowptr, const int32_t *col, int64_
   cudaStream_t stream = (cudaStream_t)stream_;
   DstArgs a;
   a.rowptr = rowptr; a.col = col; a.h = h; a.dout = dout; a.p_saved = p_saved; a.edge_attr = edge_attr; a.dz = dz;
-  a.dSt = dSt; a.partials = (float *)scratch; a.n_nodes = n_nodes;
+  a.dSt = dSt; a.partials = scratch_body(scratch); a.n_nodes = n_nodes;
   const int blocks = warp_grid(n_nodes);
   const bool want_coef = d_coef != nullptr;
   if (want_coef && (!scratch || !edge_attr)) return FNB_ERR_NULL;
@@ -450,7 +450,7 @@ extern "C" int fnb_gat_bwd_src(const int32_t *rrowptr, const int32_t *rslot, con
   SrcArgs a;
   a.rrowptr = rrowptr; a.rslot = rslot; a.rdst = rdst; a.h = h; a.dout = dout; a.p_saved = p_saved; a.dz = dz;
   a.dSt = dSt; a.alpha = alpha; a.alpha_stride = alpha_stride; a.off_t = off_t; a.off_s = off_s; a.dh = dh;
-  a.partials = (float *)scratch; a.n_nodes = n_nodes;
+  a.partials = scratch_body(scratch); a.n_nodes = n_nodes;
   const int blocks = warp_grid(n_nodes);
   k_gat_bwd_src<<<blocks, kThreads, 0, stream>>>(a);
   FNB_CHECK_LAUNCH();
@@ -474,7 +474,7 @@ extern "C" int fnb_edge_table_bwd(const float *dz, const int32_t *slot_of_eid, i
   cudaStream_t stream = (cudaStream_t)stream_;
   TableArgs a;
   a.dz = dz; a.slot_of_eid = slot_of_eid; a.feat = feat; a.alpha = alpha; a.alpha_stride = alpha_stride;
-  a.off_e = off_e; a.g_base = g_base; a.g_feat = g_feat; a.partials = (float *)scratch;
+  a.off_e = off_e; a.g_base = g_base; a.g_feat = g_feat; a.partials = scratch_body(scratch);
   a.n_real = n_real_edges;
   const int blocks = warp_grid(n_real_edges);
   k_edge_table_bwd<<<blocks, kThreads, 0, stream>>>(a);

@@ -272,6 +272,13 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
 
 extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int64_t n_rows, int K, float *dx,
                             float *dW, float *db, int precision, void *scratch, void *stream_) {
+  return fnb_proj_bwd_impl(x, W, nullptr, dh, n_rows, K, dx, dW, db, precision, scratch, stream_);
+}
+
+// Wt_pre: optional W^T [K=128,128] already transposed by the caller (the encoder program transposes every layer's
+// weights in one launch at the start of its backward pass).
+int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K,
+                      float *dx, float *dW, float *db, int precision, void *scratch, void *stream_) {
   if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
   if (!x || !W || !dh || !dW || !scratch) return FNB_ERR_NULL;
   if (precision != FNB_PRECISION_FP32 && precision != FNB_PRECISION_TF32) return FNB_ERR_MODE;
@@ -280,9 +287,13 @@ extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int
   if (dx && n_rows > 0 && precision == FNB_PRECISION_TF32 && K == kD) {
     // dx = dh @ W as the same tensor-core kernel with B = W^T (staged in the head of the scratch buffer; the
     // weight-gradient partials below are written after this kernel on the same stream)
-    float *Wt = (float *)scratch;
-    int rc = fnb_tc_transpose128_launch(W, Wt, stream);
-    if (rc) return rc;
+    const float *Wt = Wt_pre;
+    int rc = 0;
+    if (!Wt) {
+      rc = fnb_tc_transpose128_launch(W, scratch_body(scratch), stream);
+      if (rc) return rc;
+      Wt = scratch_body(scratch);
+    }
     rc = fnb_tc_proj_launch(dh, Wt, nullptr, n_rows, kD, nullptr, 0, 0, 0, dx, nullptr, stream);
     if (rc == 0) dx_done = true;
     else if (rc != FNB_ERR_MODE) return rc;
@@ -296,7 +307,7 @@ extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int
     FNB_CHECK_LAUNCH();
   }
   if (precision == FNB_PRECISION_TF32 && K == kD && n_rows > 0 && !db) {
-    const int rc = fnb_tc_dw_launch(dh, x, n_rows, dW, (float *)scratch, stream);
+    const int rc = fnb_tc_dw_launch(dh, x, n_rows, dW, scratch_body(scratch), stream);
     if (rc != FNB_ERR_MODE) return rc;
   }
   int64_t nb = (n_rows + 255) / 256;
@@ -307,13 +318,13 @@ extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int
   if (rows_per_block < kDwRows) rows_per_block = kDwRows;
   const int64_t rec_stride = (int64_t)128 * K + 128;
   dim3 grid((unsigned)nb, (unsigned)((K + 127) / 128));
-  k_proj_dw<<<grid, 256, 0, stream>>>(dh, x, n_rows, K, rows_per_block, (float *)scratch, rec_stride);
+  k_proj_dw<<<grid, 256, 0, stream>>>(dh, x, n_rows, K, rows_per_block, scratch_body(scratch), rec_stride);
   FNB_CHECK_LAUNCH();
   ReduceSegments segs;
   segs.n = db ? 2 : 1;
   segs.rec_off[0] = 0;       segs.width[0] = 128 * K; segs.out[0] = dW; segs.row_len[0] = 128 * K; segs.out_stride[0] = 128 * K;
   segs.rec_off[1] = 128 * K; segs.width[1] = 128;     segs.out[1] = db; segs.row_len[1] = 128;     segs.out_stride[1] = 128;
-  return fnb_launch_reduce_segments((const float *)scratch, (int)nb, (int)rec_stride, segs, stream);
+  return fnb_launch_reduce_segments(scratch_body(scratch), (int)nb, (int)rec_stride, segs, stream);
 }
 
 extern "C" int fnb_node_scalars(const float *h, int64_t n_rows, const float *alpha, int alpha_stride, int off_t,

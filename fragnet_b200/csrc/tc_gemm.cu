@@ -379,6 +379,16 @@ __global__ void k_transpose_128(const float *__restrict__ W, float *__restrict__
   for (int j = threadIdx.y; j < 32; j += blockDim.y) Wt[(bx + j) * 128 + by + threadIdx.x] = tile[threadIdx.x][j];
 }
 
+__global__ void k_transpose_128_batched(TransposeBatch b, float *__restrict__ Wt_base) {
+  __shared__ float tile[32][33];
+  const float *W = b.W[blockIdx.z];
+  float *Wt = Wt_base + (size_t)blockIdx.z * 128 * 128;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) tile[j][threadIdx.x] = W[(by + j) * 128 + bx + threadIdx.x];
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) Wt[(bx + j) * 128 + by + threadIdx.x] = tile[threadIdx.x][j];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -440,6 +450,13 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
 
 int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream) {
   k_transpose_128<<<dim3(4, 4), dim3(32, 8), 0, stream>>>(W, Wt);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+int fnb_tc_transpose128_batched(const TransposeBatch &b, float *Wt_base, cudaStream_t stream) {
+  if (b.count <= 0) return 0;
+  k_transpose_128_batched<<<dim3(4, 4, b.count), dim3(32, 8), 0, stream>>>(b, Wt_base);
   FNB_CHECK_LAUNCH();
   return 0;
 }

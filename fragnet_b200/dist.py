@@ -6,8 +6,11 @@ batches, fragnet/dataset/data.py:877-948) so the forward/backward needs no commu
 exchange is the gradient of the LIVE parameters (87 of FragNet's tensors never receive a gradient,
 SURVEY.md fact 7, and are skipped exactly as DDP/Adam skip ``grad is None``).
 
-Gradients of live parameters are views into one flat fp32 buffer, so the exchange is a single
-``all_reduce`` (NCCL over NVLink/NVSwitch; gloo in the CPU tests) with no pack/unpack copies.
+Per step: ``zero()`` drops the gradients (``grad = None``: the next backward then hands its freshly written
+gradient tensors straight to the parameters, no accumulate kernels), ``sync()`` packs the live gradients
+into one flat fp32 buffer (one multi-tensor copy), all-reduces it once (NCCL over NVLink/NVSwitch; gloo in
+the CPU tests), scales by 1/world and rebinds every ``.grad`` to its slice of the buffer.  With one rank
+``sync()`` does nothing.
 """
 from __future__ import annotations
 
@@ -18,21 +21,20 @@ import torch.distributed as dist
 
 
 class FlatGradSync:
-    """Call ``prepare()`` once after the first backward, then per step: ``zero()``, backward, ``sync()``."""
-
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
         self.all_params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.live: List[torch.nn.Parameter] = []
         self.flat = None
+        self._views: List[torch.Tensor] = []
 
     @property
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def prepare(self) -> None:
-        """Find the parameters that received a gradient and rebind their ``.grad`` into one flat buffer.
-        The live set must agree across ranks (it is a property of the model, not the batch)."""
+        """Find the parameters that received a gradient (a property of the model, not of the batch; checked to
+        agree across ranks) and lay out the flat buffer."""
         self.live = [p for p in self.all_params if p.grad is not None]
         if self.world_size > 1:
             n = torch.tensor([len(self.live), sum(p.numel() for p in self.live)], dtype=torch.int64,
@@ -42,22 +44,14 @@ class FlatGradSync:
             dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
             if not torch.equal(lo, hi):
                 raise RuntimeError("FlatGradSync: ranks disagree on the set of live parameters")
-        total = sum(p.numel() for p in self.live)
         ref = self.live[0]
-        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.live:
-            view = self.flat[off:off + p.numel()].view_as(p)
-            view.copy_(p.grad)
-            p.grad = view
-            off += p.numel()
+        sizes = [p.numel() for p in self.live]
+        self.flat = torch.zeros(sum(sizes), dtype=ref.dtype, device=ref.device)
+        self._views = [v.view_as(p) for v, p in zip(self.flat.split(sizes), self.live)]
 
     def zero(self) -> None:
-        if self.flat is None:
-            for p in self.all_params:
-                p.grad = None
-        else:
-            self.flat.zero_()
+        for p in self.all_params:
+            p.grad = None
 
     def sync(self) -> None:
         """Mean of the per-rank gradients (DDP semantics)."""
@@ -66,8 +60,11 @@ class FlatGradSync:
         w = self.world_size
         if w == 1:
             return
+        torch._foreach_copy_(self._views, [p.grad for p in self.live])
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.div_(w)
+        for p, v in zip(self.live, self._views):
+            p.grad = v
 
     def live_parameters(self) -> List[torch.nn.Parameter]:
         return self.live

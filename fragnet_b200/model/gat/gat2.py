@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from ... import config, ops
-from ...autograd import DropoutReluFn, FragNetLayerFn, LayerOptions, ReadoutFn
+from ...autograd import EncoderConfig, EncoderFn, LayerSwitches, ReadoutFn
 
 _ACTIVATIONS = {
     "relu": nn.ReLU, "silu": nn.SiLU, "gelu": nn.GELU, "celu": nn.CELU, "selu": nn.SELU,
@@ -35,6 +35,14 @@ def _as_int_or_none(v):
     if hasattr(v, "ndim") and v.ndim == 0:
         return int(v)
     return v
+
+
+def _plan_for(dev, n_atoms, n_frags, n_bond_nodes, n_fbond_nodes, edge_index, frag_index, atom_to_frag_ids,
+              edge_index_bonds_graph, edge_attr_bonds, edge_index_fbonds, edge_attr_fbonds):
+    """CSR plan of a batch (built on the device once, cached on the identity of the caller's index tensors)."""
+    index_tensors = (edge_index, frag_index, atom_to_frag_ids, edge_index_bonds_graph, edge_attr_bonds,
+                     edge_index_fbonds, edge_attr_fbonds)
+    return ops.layer_plan_for(index_tensors, (n_atoms, n_frags, n_bond_nodes, n_fbond_nodes), dev)
 
 
 class FragNetLayerA(nn.Module):
@@ -93,21 +101,23 @@ class FragNetLayerA(nn.Module):
                 self.edge_attr_fbond_embed.weight, self.edge_attr_fbond_embed.bias,
                 self.projection_a.weight, self.projection_a.bias, self.a_b, self.a, self.f, self.f_a_b)
 
+    def _switches(self, run_frag_block=True, want_attention=False) -> LayerSwitches:
+        return LayerSwitches(run_frag_block, want_attention, _as_int_or_none(self.bond_mask),
+                             _as_int_or_none(self.frag_bond_mask), _as_int_or_none(self.atom_mask_individual))
+
     def _run(self, x_atoms, edge_index, frag_index, n_frags, atom_to_frag_ids, x_bond_nodes, edge_index_bonds_graph,
-             edge_attr_bond_graph, x_fbond_nodes, edge_index_fbond_graph, edge_attr_fbond_graph,
-             want_frag_block=True, want_attention=False):
+             edge_attr_bond_graph, x_fbond_nodes, edge_index_fbond_graph, edge_attr_fbond_graph, want_attention=False):
+        """The bare layer: one ``fnb_encoder_forward`` call in pre-activation mode."""
         self._check_geometry()
         dev = ops.require_cuda(x_atoms.device if x_atoms.is_cuda else self.a.device)
-        index_tensors = (edge_index, frag_index, atom_to_frag_ids, edge_index_bonds_graph, edge_attr_bond_graph,
+        plan = _plan_for(dev, x_atoms.size(0), int(n_frags), x_bond_nodes.size(0), x_fbond_nodes.size(0), edge_index,
+                         frag_index, atom_to_frag_ids, edge_index_bonds_graph, edge_attr_bond_graph,
                          edge_index_fbond_graph, edge_attr_fbond_graph)
-        sizes = (x_atoms.size(0), int(n_frags), x_bond_nodes.size(0), x_fbond_nodes.size(0))
-        plan = ops.layer_plan_for(index_tensors, sizes, dev)
-        opts = LayerOptions(_as_int_or_none(self.bond_mask), _as_int_or_none(self.frag_bond_mask),
-                            _as_int_or_none(self.atom_mask_individual), want_attention, want_frag_block,
-                            config.precision_id(), torch.is_grad_enabled())
+        cfg = EncoderConfig([self._switches(True, want_attention)], post_act=False, precision=config.precision_id(),
+                            grad_enabled=torch.is_grad_enabled())
         on = lambda t: t if t.device == dev else t.to(dev)
         params = [on(p) for p in self._live_parameters()]
-        return FragNetLayerFn.apply(plan, opts, on(x_atoms), on(x_bond_nodes), on(x_fbond_nodes), *params)
+        return EncoderFn.apply(plan, cfg, on(x_atoms), on(x_bond_nodes), on(x_fbond_nodes), *params)
 
     def forward(self, x_atoms, edge_index, edge_attr, frag_index, x_frags, atom_to_frag_ids,
                 node_feautures_bond_graph, edge_index_bonds_graph, edge_attr_bond_graph,
@@ -119,7 +129,7 @@ class FragNetLayerA(nn.Module):
         outs = self._run(x_atoms, edge_index, frag_index, x_frags.size(0), atom_to_frag_ids,
                          node_feautures_bond_graph, edge_index_bonds_graph, edge_attr_bond_graph,
                          node_feautures_fbond_graph, edge_index_fbond_graph, edge_attr_fbond_graph,
-                         want_frag_block=True, want_attention=self.return_attentions)
+                         want_attention=self.return_attentions)
         if home.type != "cuda":
             outs = tuple(o.to(home) for o in outs)
         return outs
@@ -143,36 +153,31 @@ class FragNet(nn.Module):
                                              edge_in=emb_dim, edge_out=emb_dim, fedge_in=emb_dim,
                                              fbond_edge_in=fbond_edge_in, num_heads=num_heads))
 
-    def _post(self, t):
-        """``act(dropout(t))`` (gat2.py:414-418) as one fused kernel."""
-        return DropoutReluFn.apply(t, self.dropout.p, self.training, True)
-
     def _encode(self, batch, attention_from_last: bool):
+        """All layers in one ``fnb_encoder_forward`` call (and one ``fnb_encoder_backward`` call under autograd)."""
         x_atoms = batch["x_atoms"]
         home = x_atoms.device
-        n_frags = batch["x_frags"].size(0)
         dev = ops.require_cuda(home if home.type == "cuda" else self.layers[0].a.device)
-        x_atoms = x_atoms.to(dev)
-        if self.training and self.dropout.p > 0:                 # input dropout, gat2.py:396
-            x_atoms = DropoutReluFn.apply(x_atoms, self.dropout.p, True, False)
-        bond_nodes = batch["node_features_bonds"].to(dev)
-        fbond_nodes = batch["node_features_fbonds"].to(dev)
+        for layer in self.layers:
+            layer._check_geometry()
+        bond_nodes, fbond_nodes = batch["node_features_bonds"], batch["node_features_fbonds"]
+        plan = _plan_for(dev, x_atoms.size(0), batch["x_frags"].size(0), bond_nodes.size(0), fbond_nodes.size(0),
+                         batch["edge_index"], batch["frag_index"], batch["atom_to_frag_ids"],
+                         batch["edge_index_bonds_graph"], batch["edge_attr_bonds"], batch["edge_index_fbonds"],
+                         batch["edge_attr_fbonds"])
         last = len(self.layers) - 1
-        attn = ()
-        for li, layer in enumerate(self.layers):
-            is_last = li == last
-            outs = layer._run(x_atoms, batch["edge_index"], batch["frag_index"], n_frags, batch["atom_to_frag_ids"],
-                              bond_nodes, batch["edge_index_bonds_graph"], batch["edge_attr_bonds"],
-                              fbond_nodes, batch["edge_index_fbonds"], batch["edge_attr_fbonds"],
-                              want_frag_block=is_last,
-                              want_attention=(attention_from_last and is_last) or layer.return_attentions)
-            x_atoms = self._post(outs[0])
-            x_frags = self._post(outs[1]) if is_last else None
-            bond_nodes = self._post(outs[2])
-            fbond_nodes = self._post(outs[3])
-            if len(outs) > 4:
-                attn = outs[4:]
-        result = (x_atoms, x_frags, bond_nodes, fbond_nodes) + tuple(attn if attention_from_last else ())
+        # the fragment-graph block of every layer but the last is skipped: its output is overwritten unread by the
+        # next layer (gat2.py:234), so nothing observable changes (SURVEY.md fact 6)
+        switches = [layer._switches(run_frag_block=li == last,
+                                    want_attention=(attention_from_last and li == last) or
+                                                   (layer.return_attentions and li == last))
+                    for li, layer in enumerate(self.layers)]
+        cfg = EncoderConfig(switches, post_act=True, drop_p=float(self.dropout.p), training=self.training,
+                            precision=config.precision_id(), grad_enabled=torch.is_grad_enabled())
+        on = lambda t: t if t.device == dev else t.to(dev)
+        params = [on(p) for layer in self.layers for p in layer._live_parameters()]
+        outs = EncoderFn.apply(plan, cfg, on(x_atoms), on(bond_nodes), on(fbond_nodes), *params)
+        result = tuple(outs[:4]) + (tuple(outs[4:]) if attention_from_last else ())
         if home.type != "cuda":
             result = tuple(t.to(home) for t in result)
         return result

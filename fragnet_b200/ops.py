@@ -56,7 +56,7 @@ def scratch(device: torch.device) -> torch.Tensor:
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch_cache.get(key)
     if buf is None:
-        buf = torch.empty(_lib().fnb_scratch_bytes(), dtype=torch.uint8, device=device)
+        buf = torch.zeros(_lib().fnb_scratch_bytes(), dtype=torch.uint8, device=device)   # arrival counters start at 0
         _scratch_cache[key] = buf
     return buf
 
@@ -71,6 +71,7 @@ class GraphCSR:
     n_real: int           # edges present in the input edge list
     rowptr: torch.Tensor
     col: Optional[torch.Tensor]
+    row: Optional[torch.Tensor]     # destination node of every slot
     eid: Optional[torch.Tensor]
     slot_of_eid: Optional[torch.Tensor]
     rrowptr: Optional[torch.Tensor] = None
@@ -78,6 +79,16 @@ class GraphCSR:
     rdst: Optional[torch.Tensor] = None
     status: Optional[torch.Tensor] = None   # int32[1], non-zero if an index was out of range
     attr: Optional[torch.Tensor] = None     # per-edge attributes permuted into slot order
+    _c: Optional[_abi.CGraph] = field(default=None, repr=False)
+
+    def cstruct(self) -> _abi.CGraph:
+        """``fnb_graph`` view of this plan (built on first use; set ``attr`` before that)."""
+        if self._c is None:
+            a = lambda t: None if t is None else t.data_ptr()
+            self._c = _abi.CGraph(self.n_nodes, self.n_edges, self.n_real, a(self.rowptr), a(self.col), a(self.row),
+                                  a(self.eid), a(self.slot_of_eid), a(self.rrowptr), a(self.rslot), a(self.rdst),
+                                  a(self.attr))
+        return self._c
 
 
 def csr_build(dst: torch.Tensor, src: Optional[torch.Tensor], n_nodes: int, self_loops: bool = False,
@@ -92,6 +103,7 @@ def csr_build(dst: torch.Tensor, src: Optional[torch.Tensor], n_nodes: int, self
     i32 = dict(dtype=torch.int32, device=dev)
     rowptr = torch.empty(n_nodes + 1, **i32)
     col = torch.empty(total, **i32)
+    row = torch.empty(total, **i32)
     eid = torch.empty(total, **i32)
     slot_of_eid = torch.empty(total, **i32)
     rrowptr = rslot = rdst = None
@@ -103,10 +115,10 @@ def csr_build(dst: torch.Tensor, src: Optional[torch.Tensor], n_nodes: int, self
     ws_bytes = lib.fnb_csr_workspace_bytes(n_nodes, total)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     status = torch.zeros(1, **i32)
-    rc = lib.fnb_csr_build(_p(dst), _p(src), E, n_nodes, int(self_loops), _p(rowptr), _p(col), _p(eid),
+    rc = lib.fnb_csr_build(_p(dst), _p(src), E, n_nodes, int(self_loops), _p(rowptr), _p(col), _p(row), _p(eid),
                            _p(slot_of_eid), _p(rrowptr), _p(rslot), _p(rdst), _p(ws), ws_bytes, _p(status), _stream())
     _abi.check(rc, "csr_build")
-    return GraphCSR(n_nodes, total, E, rowptr, col, eid, slot_of_eid, rrowptr, rslot, rdst, status)
+    return GraphCSR(n_nodes, total, E, rowptr, col, row, eid, slot_of_eid, rrowptr, rslot, rdst, status)
 
 
 def gather_rows(src: torch.Tensor, index: torch.Tensor, n_rows: int) -> torch.Tensor:
@@ -144,6 +156,15 @@ class LayerPlan:
     n_atoms: int
     n_frags: int
     refs: tuple = field(default=(), repr=False)
+    _c: Optional[_abi.CBatchPlan] = field(default=None, repr=False)
+
+    def cstruct(self) -> _abi.CBatchPlan:
+        """``fnb_batch_plan`` view (built once; the ctypes struct keeps raw pointers, the dataclass keeps the tensors)."""
+        if self._c is None:
+            self._c = _abi.CBatchPlan(self.bond.cstruct(), self.atom.cstruct(), self.fbond.cstruct(),
+                                      self.frag.cstruct(), self.pool.rowptr.data_ptr(), self.pool.col.data_ptr(),
+                                      self.a2f32.data_ptr(), self.n_atoms, self.n_frags)
+        return self._c
 
 
 def _idx(t: torch.Tensor, dev) -> torch.Tensor:
@@ -315,6 +336,58 @@ def edge_table_bwd(g: GraphCSR, dz, feat, alpha, alpha_stride, off_e, g_base, d_
     return g_feat
 
 
+# ---- node-tiled attention kernels (gat_tiled.cu) ------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gat_fwd_tiled(g: GraphCSR, h, S, mode, *, table=None, We=None, be=None, alpha_e=None, alpha_stride=0,
+                  save_p=True, want_out=True, post=None, mask=(-1, -1), next_alpha=None, next_alpha_stride=0):
+    """``fnb_gat_fwd_tiled``.  ``post`` = (p, training, relu, seed, offset) additionally returns
+    y = ReLU(Dropout(out)).  Returns (out | None, y | None, p_saved | None, next_Se | None)."""
+    dev = h.device
+    out = torch.empty((g.n_nodes, D), dtype=torch.float32, device=dev) if want_out else None
+    y = torch.empty((g.n_nodes, D), dtype=torch.float32, device=dev) if post is not None else None
+    p = torch.empty((g.n_edges, H), dtype=torch.float32, device=dev) if save_p else None
+    nse = torch.empty((g.n_nodes, H), dtype=torch.float32, device=dev) if next_alpha is not None else None
+    pa = _abi.CPostAct(*(post if post is not None else (0.0, 0, 0, 0, 0)))
+    args = _abi.CGatFwdArgs(_ptr(h), _ptr(S), mode, _ptr(table), _ptr(We), _ptr(be), _ptr(alpha_e), alpha_stride,
+                            _ptr(out), _ptr(y), pa, _ptr(p), mask[0], mask[1], _ptr(next_alpha), next_alpha_stride,
+                            _ptr(nse))
+    _abi.check(_lib().fnb_gat_fwd_tiled(C.byref(g.cstruct()), C.byref(args), _stream()), "gat_fwd_tiled")
+    return out, y, p, nse
+
+
+def gat_bwd_tiled(g: GraphCSR, h, dout, p, mode, alpha, alpha_stride, off_t, off_e, off_s, d_alpha, *, We=None,
+                  be=None, want_bias_grad=False):
+    """``fnb_gat_bwd_tiled`` (destination pass + source pass).  Writes the off_t / off_s (and, for the affine modes,
+    off_e) slices of ``d_alpha``.  Returns (dh, dz, d_bias | None, dWe | None, dbe | None)."""
+    dev = h.device
+    dz = torch.empty((g.n_edges, H), dtype=torch.float32, device=dev)
+    dSt = torch.empty((g.n_nodes, H), dtype=torch.float32, device=dev)
+    dh = torch.empty((g.n_nodes, D), dtype=torch.float32, device=dev)
+    db = torch.empty(D, dtype=torch.float32, device=dev) if want_bias_grad else None
+    affine = mode in (EDGE_AFFINE1, EDGE_AFFINE6)
+    dWe = torch.empty_like(We) if affine else None
+    dbe = torch.empty_like(be) if affine else None
+    args = _abi.CGatBwdArgs(_ptr(h), _ptr(dout), _ptr(p), mode, _ptr(We), _ptr(be), _ptr(alpha), alpha_stride, off_t,
+                            off_e, off_s, _ptr(dz), _ptr(dSt), _ptr(dh), _ptr(d_alpha), _ptr(db), _ptr(dWe), _ptr(dbe),
+                            _ptr(scratch(dev)))
+    _abi.check(_lib().fnb_gat_bwd_tiled(C.byref(g.cstruct()), C.byref(args), _stream()), "gat_bwd_tiled")
+    return dh, dz, db, dWe, dbe
+
+
+def edge_table_bwd_fused(g: GraphCSR, dz, feat, alpha, alpha_stride, off_e, d_alpha, *, g_base=None, dy=None, y=None,
+                         post_scale=1.0):
+    """``fnb_edge_table_bwd_fused``: edge-term backward of a TABLE graph with the ReLU(Dropout) backward of the
+    gradient arriving at the post-activation copy of ``feat`` folded in."""
+    g_feat = torch.empty((g.n_real, D), dtype=torch.float32, device=feat.device)
+    _abi.check(_lib().fnb_edge_table_bwd_fused(C.byref(g.cstruct()), _p(dz), _p(feat), _p(alpha), alpha_stride, off_e,
+                                               _p(g_base), _p(dy), _p(y), float(post_scale), _p(g_feat), _p(d_alpha),
+                                               _p(scratch(feat.device)), _stream()), "edge_table_bwd_fused")
+    return g_feat
+
+
 def segment_sum(rowptr, col, n_segments, x, out=None, out_stride=D, alpha=None, alpha_stride=0, off_t=0, off_s=0):
     if out is None:
         out = torch.empty((n_segments, D), dtype=torch.float32, device=x.device)
@@ -341,6 +414,15 @@ def next_philox(n_elems: int):
     off = _philox_offset
     _philox_offset += (n_elems + 3) // 4
     return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, off
+
+
+def reserve_philox(n_counters: int) -> int:
+    """First counter of a block of ``n_counters`` Philox counters (whole-encoder calls reserve all their dropout sites
+    at once: ``fnb_encoder_philox_span``)."""
+    global _philox_offset
+    off = _philox_offset
+    _philox_offset += int(n_counters)
+    return off
 
 
 def dropout_relu_fwd(x, p: float, training: bool, relu: bool, seed: int, offset: int):

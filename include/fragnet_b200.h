@@ -30,7 +30,7 @@ extern "C" {
 
 #define FNB_D 128 /* embedding width  */
 #define FNB_H 4   /* attention heads  */
-#define FNB_ABI_VERSION 1
+#define FNB_ABI_VERSION 2
 
 /* edge-term modes of the fused attention kernels */
 /* arithmetic of the dense projections */
@@ -55,7 +55,8 @@ size_t fnb_scratch_bytes(void);
  * add_self_loops (gat2.py:179).  Edges are (dst[e], src[e]), e < n_edges; with
  * append_self_loops != 0, n_nodes extra edges (i,i) with ids n_edges+i follow them.
  * Slots of one destination are ordered by edge id (== stable sort by destination):
- *   rowptr[n_nodes+1], col[slot] = source node, eid[slot] = edge id, slot_of_eid[e] = slot
+ *   rowptr[n_nodes+1], col[slot] = source node, row[slot] = destination node (may be NULL),
+ *   eid[slot] = edge id, slot_of_eid[e] = slot
  * Reverse CSR groups the same edges by source, again ordered by edge id:
  *   rrowptr[n_nodes+1], rslot[r] = forward slot of that edge, rdst[r] = its destination node.
  * src == NULL means src[e] = e (membership lists such as atom_to_frag_ids, gat2.py:234).
@@ -63,7 +64,7 @@ size_t fnb_scratch_bytes(void);
  */
 size_t fnb_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges_total);
 int fnb_csr_build(const int64_t *dst, const int64_t *src, int64_t n_edges, int64_t n_nodes,
-                  int append_self_loops, int32_t *rowptr, int32_t *col, int32_t *eid,
+                  int append_self_loops, int32_t *rowptr, int32_t *col, int32_t *row, int32_t *eid,
                   int32_t *slot_of_eid, int32_t *rrowptr, int32_t *rslot, int32_t *rdst,
                   void *workspace, size_t workspace_bytes, int32_t *status, void *stream);
 
@@ -151,6 +152,142 @@ int fnb_gat_bwd_src(const int32_t *rrowptr, const int32_t *rslot, const int32_t 
 int fnb_edge_table_bwd(const float *dz, const int32_t *slot_of_eid, int64_t n_real_edges,
                        const float *feat, const float *alpha, int alpha_stride, int off_e,
                        const float *g_base, float *g_feat, float *d_alpha, void *scratch, void *stream);
+
+/* ---- node-tiled attention kernels (gat_tiled.cu): the production path ------------------------
+ * Same math as fnb_gat_fwd / fnb_gat_bwd_dst / fnb_gat_bwd_src / fnb_edge_table_bwd above, restructured after
+ * profiling: a CTA owns 64 consecutive destination nodes, logits are computed one thread per
+ * edge slot, the softmax one thread per (node, head) in shared memory, the row aggregation one warp per node.
+ * Folded in: the edge-embedding constants (fnb_edge_coef_fwd/bwd), the inter-layer ReLU(Dropout(.)) of
+ * gat2.py:414-418 (forward epilogue / edge-table backward), and the cross-CTA reduction of every parameter
+ * gradient (last CTA to finish; deterministic, no atomics on floats, no second launch).
+ * scratch: fnb_scratch_bytes() bytes whose first 256 bytes are ZERO before the first call and are left zero by
+ * every call (arrival counters). */
+typedef struct fnb_graph {
+  int64_t n_nodes, n_edges, n_real_edges; /* n_edges includes appended self loops */
+  const int32_t *rowptr, *col, *row, *eid, *slot_of_eid; /* destination-sorted CSR (fnb_csr_build) */
+  const int32_t *rrowptr, *rslot, *rdst;                 /* reverse (source-sorted) CSR             */
+  const float *edge_attr; /* slot-ordered attributes: [E] (bond graph), [E,6] (fragment-connection graph), else NULL */
+} fnb_graph;
+
+typedef struct fnb_post_act { /* y = ReLU(Dropout_p(out)); Philox counter of element i is offset + i/4 */
+  float p;
+  int training, relu;
+  uint64_t seed, offset;
+} fnb_post_act;
+
+typedef struct fnb_gat_fwd_args {
+  const float *h, *S;      /* [N,128] projected features, [N,8] logit scalars */
+  int edge_mode;           /* FNB_EDGE_* */
+  const float *edge_table; /* TABLE: [n_real_edges,4] */
+  const float *We, *be;    /* AFFINE1/6: edge_attr_{bond,fbond}_embed weight [32,in] and bias [32] (gat2.py:91-92) */
+  const float *alpha_e;    /* AFFINE1/6: head vector at its edge slice, rows alpha_stride apart */
+  int alpha_stride;
+  float *out;              /* [N,128] pre-activation output, may be NULL when only y is wanted */
+  float *y;                /* [N,128] ReLU(Dropout(out)) or NULL */
+  fnb_post_act post;
+  float *p_saved;          /* [E,4] or NULL (inference) */
+  int64_t mask_lo, mask_hi;
+  const float *next_alpha_e; /* consumer graph's edge slice [4, next_alpha_stride] or NULL */
+  int next_alpha_stride;
+  float *next_Se;          /* [N,4] */
+} fnb_gat_fwd_args;
+
+typedef struct fnb_gat_bwd_args {
+  const float *h, *dout, *p_saved;
+  int edge_mode;
+  const float *We, *be;    /* AFFINE1/6 */
+  const float *alpha;      /* full head vector [4, alpha_stride] */
+  int alpha_stride, off_t, off_e, off_s;
+  float *dz, *dSt;         /* [E,4], [N,4]: outputs of the destination pass, inputs of the source pass */
+  float *dh;               /* [N,128] */
+  float *d_alpha;          /* [4, alpha_stride]: slices off_t, off_s (and off_e for AFFINE modes) are written */
+  float *d_bias;           /* [128] column sums of dh, or NULL */
+  float *dWe, *dbe;        /* AFFINE1/6 */
+  void *scratch;
+} fnb_gat_bwd_args;
+
+int fnb_gat_fwd_tiled(const fnb_graph *g, const fnb_gat_fwd_args *args, void *stream);
+/* destination pass then source pass (two launches) */
+int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *args, void *stream);
+/* g_feat[e,:] = g_base[e,:] (if given) + dy[e,:]*(y[e,:]>0)*post_scale (if given) + sum_h dz[slot_of_eid[e],h]*alpha_e[h,:];
+ * d_alpha[h, off_e:off_e+128] = sum_e dz[slot_of_eid[e],h] * feat[e,:] */
+int fnb_edge_table_bwd_fused(const fnb_graph *g, const float *dz, const float *feat, const float *alpha,
+                             int alpha_stride, int off_e, const float *g_base, const float *dy, const float *y,
+                             float post_scale, float *g_feat, float *d_alpha, void *scratch, void *stream);
+
+/* ---- whole-encoder programs (encoder.cu) -------------------------------------------------------
+ * FragNet.forward (gat2.py:381-442) = n_layers x FragNetLayerA.forward (gat2.py:121-330) with ReLU(Dropout(.)) on the
+ * four outputs of every layer, sequenced on the host side of the library so that a forward (backward) pass is ONE
+ * call issuing ~7 (~20) launches per layer back to back.  Activations that the backward needs live in a caller
+ * allocated workspace whose layout is a pure function of (plan sizes, options).
+ *
+ * Modes.  post_act = 1: outputs are y = ReLU(Dropout_p(.)) of the last layer (FragNet.forward); the fragment-graph
+ * block runs only where run_frag_block says so (its output is dead in all but the last layer, gat2.py:234).
+ * post_act = 0 with n_layers = 1: the bare FragNetLayerA.forward -- outputs are the pre-activation tensors.
+ */
+typedef struct fnb_layer_params {
+  const float *Wb, *bb;       /* projection_b  [128,K_bond], [128]   gat2.py:88  */
+  const float *Wfb, *bfb;     /* projection_fb [128,K_fbond]         gat2.py:89  */
+  const float *We_b, *be_b;   /* edge_attr_bond_embed  [32,1], [32]  gat2.py:91  */
+  const float *We_fb, *be_fb; /* edge_attr_fbond_embed [32,6], [32]  gat2.py:92  */
+  const float *Wa, *ba;       /* projection_a  [128,K_atom]          gat2.py:95  */
+  const float *a_b, *a, *f, *f_a_b; /* head vectors [4,96] [4,192] [4,192] [4,96]  gat2.py:98-107 */
+  int K_atom, K_bond, K_fbond;
+  /* per-layer switches */
+  int run_frag_block;                 /* fragment-graph block (gat2.py:283-316) */
+  int want_attention;                 /* emit the four by-source attention sums of this layer */
+  int64_t bond_mask, frag_bond_mask;  /* -1 = none; rows [m,m+2) / [2k,2k+2) zeroed (gat2.py:173-176, 275-278) */
+  int64_t atom_mask;                  /* -1 = none; row zeroed (gat2.py:227-231) */
+  const int32_t *atom_mask_list;      /* optional device list of rows to zero, n_atom_mask entries */
+  int64_t n_atom_mask;
+} fnb_layer_params;
+
+typedef struct fnb_layer_grads { /* same shapes as the parameters; every tensor is written (not accumulated) */
+  float *Wb, *bb, *Wfb, *bfb, *We_b, *be_b, *We_fb, *be_fb, *Wa, *ba, *a_b, *a, *f, *f_a_b;
+} fnb_layer_grads;
+
+typedef struct fnb_batch_plan {
+  fnb_graph bond, atom, fbond, frag;
+  const int32_t *pool_rowptr, *pool_col; /* fragment -> member atoms (membership CSR of atom_to_frag_ids) */
+  const int32_t *a2f;                    /* int32 atom_to_frag_ids */
+  int64_t n_atoms, n_frags;
+} fnb_batch_plan;
+
+typedef struct fnb_encoder_opts {
+  int n_layers;
+  int post_act;          /* 1: ReLU(Dropout) between layers and on the outputs; 0: bare layer (n_layers must be 1) */
+  float drop_p;
+  int training;
+  uint64_t seed, offset; /* Philox key / first counter; the call consumes fnb_encoder_philox_span() counters */
+  int precision;         /* FNB_PRECISION_* for the dense projections */
+  int save_for_backward; /* keep what fnb_encoder_backward needs */
+  int need_dx_atoms, need_dx_bond, need_dx_fbond; /* backward: gradients of the layer-0 inputs */
+} fnb_encoder_opts;
+
+typedef struct fnb_encoder_io {
+  const float *x_atoms, *x_bond, *x_fbond; /* layer-0 inputs [Na,K_atom] [Nb,K_bond] [Nfb,K_fbond] */
+  float *out_atoms, *out_frags, *out_bond, *out_fbond; /* [.,128] outputs of the last layer (out_frags may be NULL
+                                                          when no layer runs the fragment block) */
+  float *attn_atoms, *attn_frags, *attn_bonds, *attn_fbonds; /* [N,4] of the layer with want_attention, or NULL */
+  /* backward only */
+  const float *g_atoms, *g_frags, *g_bond, *g_fbond; /* gradients of the four outputs; NULL = zero */
+  float *dx_atoms, *dx_bond, *dx_fbond;              /* gradients of the layer-0 inputs (see need_dx_*) */
+} fnb_encoder_io;
+
+size_t fnb_encoder_workspace_bytes(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+                                   const fnb_layer_params *layers);
+size_t fnb_encoder_bwd_workspace_bytes(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+                                       const fnb_layer_params *layers);
+uint64_t fnb_encoder_philox_span(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+                                 const fnb_layer_params *layers);
+int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder_opts *opts, const fnb_layer_params *layers,
+                        const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
+                        void *stream);
+/* workspace = the forward call's workspace (unchanged since), bwd_workspace = fnb_encoder_bwd_workspace_bytes(). */
+int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encoder_opts *opts, const fnb_layer_params *layers,
+                         const fnb_layer_grads *grads, const fnb_encoder_io *io, void *workspace,
+                         size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes, void *scratch,
+                         void *stream);
 
 /* ---- (d) segment-sum pooling ----------------------------------------------------------------
  * out[seg,:] = sum over members (gat2.py:234 atom->fragment via a membership CSR; gat2.py:820-821

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 tag=${1:-run}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
-for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_model.py tests/test_gpu_tc.py; do
+for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_tiled.py tests/test_gpu_model.py tests/test_gpu_tc.py; do
   timeout 600 python -m pytest $f -q --no-header -p no:cacheprovider -m gpu 2>&1 | tail -120 > gpurun_out/${tag}_$(basename $f .py).log
 done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1
@@ -20,8 +20,8 @@ for f in gpurun_out/${tag}_test_gpu_*.log gpurun_out/${tag}_smoke.log; do echo "
 tail -n 2 gpurun_out/${tag}_bench.log gpurun_out/${tag}_bench_fp32.log
 if [ "${3:-}" = "full" ]; then
   # one `ncu --set full` capture of the message-passing kernels (bond-graph launches of layer >= 1)
-  for k in k_gat_fwd k_gat_bwd_dst k_gat_bwd_src; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 2 -f \
+  for k in k_gat_fwd_tiled k_gat_bwd_dst_tiled k_gat_bwd_src_tiled; do
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 0 -c 3 -f \
       -o gpurun_out/${tag}_full_$k python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-roofline \
       > gpurun_out/${tag}_full_$k.log 2>&1
   done

@@ -22,7 +22,7 @@ def test_library_exports_every_symbol():
     lib = _abi.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.fnb_version() == 1
+    assert lib.fnb_version() == _abi.ABI_VERSION
     assert lib.fnb_scratch_bytes() >= 148 * (128 * 256 + 128) * 4
     assert lib.fnb_csr_workspace_bytes(1000, 5000) > 2 * 1000 * 4 + 2 * 5000 * 4
     assert lib.fnb_error_string(0) == b"ok"
@@ -33,11 +33,13 @@ def test_argument_validation_needs_no_gpu():
     """Negative return codes come from host-side checks before any launch."""
     from fragnet_b200 import _abi
     lib = _abi.load()
-    assert lib.fnb_csr_build(None, None, -1, 4, 0, None, None, None, None, None, None, None, None, 0, None, None) == -2
-    assert lib.fnb_csr_build(None, None, 0, 4, 0, None, None, None, None, None, None, None, None, 0, None, None) == -1
+    assert lib.fnb_csr_build(None, None, -1, 4, 0, None, None, None, None, None, None, None, None, None, 0, None, None) == -2
+    assert lib.fnb_csr_build(None, None, 0, 4, 0, None, None, None, None, None, None, None, None, None, 0, None, None) == -1
     assert lib.fnb_proj_fwd(None, None, None, 8, 128, None, 0, 0, 0, None, None, 0, None) == -1
     assert lib.fnb_edge_coef_fwd(None, None, 3, None, 96, 32, None, None) == -3
     assert lib.fnb_dropout_relu_fwd(None, None, 4, 1.5, 1, 1, 0, 0, None) == -2
+    assert lib.fnb_gat_fwd_tiled(None, None, None) == -1
+    assert lib.fnb_gat_bwd_tiled(None, None, None) == -1
 
 
 def test_no_cpu_fallback_in_product_path():
@@ -48,3 +50,31 @@ def test_no_cpu_fallback_in_product_path():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), os.path.join(dirpath, f)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct in include/fragnet_b200.h, compiled with gcc, equal the ctypes mirrors."""
+    import ctypes as C
+    import subprocess
+
+    from fragnet_b200 import _abi as A
+    pairs = [("fnb_graph", A.CGraph), ("fnb_post_act", A.CPostAct), ("fnb_gat_fwd_args", A.CGatFwdArgs),
+             ("fnb_gat_bwd_args", A.CGatBwdArgs), ("fnb_layer_params", A.CLayerParams),
+             ("fnb_layer_grads", A.CLayerGrads), ("fnb_batch_plan", A.CBatchPlan),
+             ("fnb_encoder_opts", A.CEncoderOpts), ("fnb_encoder_io", A.CEncoderIO)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fragnet_b200.h"', 'int main(void){']
+    for cname, cls in pairs:
+        lines.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('printf("\\n");')
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for (cname, cls), line in zip(pairs, out):
+        got = [int(x) for x in line.split()[1:]]
+        want = [C.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert got == want, cname

@@ -34,7 +34,7 @@ def _to(batch, dev):
 def test_native_library_is_loaded():
     from fragnet_b200 import _abi
     lib = _abi.load()
-    assert lib.fnb_version() == 1
+    assert lib.fnb_version() == _abi.ABI_VERSION
     maps = open("/proc/self/maps").read()
     assert "libfragnet_b200.so" in maps
 
