@@ -42,6 +42,8 @@ SIGNATURES = {
     "fnb_gat_fwd_tiled": (C.c_int, [_vp, _vp, _vp]),
     "fnb_gat_bwd_tiled": (C.c_int, [_vp, _vp, _vp]),
     "fnb_edge_table_bwd_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "fnb_batch_plan_bytes": (_sz, [_vp]),
+    "fnb_batch_plan_build": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "fnb_encoder_workspace_bytes": (_sz, [_vp, _vp, _vp]),
     "fnb_encoder_bwd_workspace_bytes": (_sz, [_vp, _vp, _vp]),
     "fnb_encoder_philox_span": (_u64, [_vp, _vp, _vp]),
@@ -129,7 +131,17 @@ class CLayerGrads(C.Structure):
 
 class CBatchPlan(C.Structure):
     _fields_ = [("bond", CGraph), ("atom", CGraph), ("fbond", CGraph), ("frag", CGraph),
-                ("pool_rowptr", _vp), ("pool_col", _vp), ("a2f", _vp), ("n_atoms", _i64), ("n_frags", _i64)]
+                ("pool_rowptr", _vp), ("pool_col", _vp), ("a2f", _vp), ("n_atoms", _i64), ("n_frags", _i64),
+                ("mol_atom_ptr", _vp), ("mol_frag_ptr", _vp), ("batch32", _vp), ("frag_batch32", _vp),
+                ("n_graphs", _i64), ("status", _vp)]
+
+
+class CBatchInputs(C.Structure):
+    _fields_ = [(n, _vp) for n in ("edge_index", "frag_index", "atom_to_frag_ids", "edge_index_bonds_graph",
+                                   "edge_index_fbonds", "batch", "frag_batch", "edge_attr_bonds",
+                                   "edge_attr_fbonds")] + \
+               [(n, _i64) for n in ("n_atoms", "n_frags", "n_bonds", "n_bond_edges", "n_fbond_nodes", "n_fbond_edges",
+                                    "n_graphs")]
 
 
 class CEncoderOpts(C.Structure):

@@ -18,11 +18,13 @@
 // The tiny edge-embedding algebra (App. A.5), the inter-layer ReLU(Dropout(.)) (gat2.py:414-418), the output masks
 // (gat2.py:173-176) and the consumer graph's edge term ride in the prologue/epilogue, and parameter-gradient partials
 // are reduced by the last CTA to finish (common.cuh: cta_finish) -- no floating-point atomics, no extra launches.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int T_NPC = 64;        // destination (or source) nodes per tile
+constexpr int T_NPC = 64;        // max destination (or source) nodes per tile; the launcher picks npc <= T_NPC
 constexpr int T_THREADS = 256;
 constexpr int T_WARPS = T_THREADS / 32;
 constexpr int FWD_CAP = 1024;    // edge slots staged per sub-tile (forward)
@@ -51,6 +53,7 @@ struct FwdT {
   const float *next_alpha;
   int next_stride;
   float *next_Se;
+  int npc;
 };
 
 template <int MODE>
@@ -185,9 +188,9 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_fwd_tiled(FwdT a) {
   if (a.next_alpha)  // consumer graph's edge slice, 4 heads x 128 columns
     for (int i = tid; i < 4 * kD; i += T_THREADS) s_na[i] = __ldg(a.next_alpha + (int64_t)(i >> 7) * a.next_stride + (i & 127));
 
-  const int n_tiles = (a.n_nodes + T_NPC - 1) / T_NPC;
+  const int n_tiles = (a.n_nodes + a.npc - 1) / a.npc;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int n0 = tile * T_NPC, nn = min(T_NPC, a.n_nodes - n0);
+    const int n0 = tile * a.npc, nn = min(a.npc, a.n_nodes - n0);
     __syncthreads();  // readers of the previous tile are done; also publishes s_coef
     if (tid <= nn) s_rowptr[tid] = __ldg(a.rowptr + n0 + tid);
     __syncthreads();
@@ -274,6 +277,7 @@ struct DstT {
   const float *We, *be, *alpha_e;
   int alpha_e_stride;
   float *dWe, *dbe, *d_alpha_e;
+  int npc;
 };
 
 template <int MODE> struct CoefT { static constexpr int NC = 1, PARTS = 1, IN = 1; };
@@ -326,9 +330,9 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
   const int c_k = (NC == 8) ? (c < 4 ? 0 : -1) : (c < 24 ? c % 6 : -1);  // -1: bias term (attribute = 1)
   float cacc = 0.f;
 
-  const int n_tiles = (a.n_nodes + T_NPC - 1) / T_NPC;
+  const int n_tiles = (a.n_nodes + a.npc - 1) / a.npc;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int n0 = tile * T_NPC, nn = min(T_NPC, a.n_nodes - n0);
+    const int n0 = tile * a.npc, nn = min(a.npc, a.n_nodes - n0);
     __syncthreads();
     if (tid <= nn) s_rowptr[tid] = __ldg(a.rowptr + n0 + tid);
     __syncthreads();
@@ -452,6 +456,7 @@ struct SrcT {
   float *dh, *d_alpha, *d_bias;
   float *scratch;
   int n_nodes;
+  int npc;
 };
 
 __global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
@@ -480,9 +485,9 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
     pa[4] = fmaf(gs, hr.x, pa[4]); pa[5] = fmaf(gs, hr.y, pa[5]); pa[6] = fmaf(gs, hr.z, pa[6]); pa[7] = fmaf(gs, hr.w, pa[7]);
   };
 
-  const int n_tiles = (a.n_nodes + T_NPC - 1) / T_NPC;
+  const int n_tiles = (a.n_nodes + a.npc - 1) / a.npc;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int n0 = tile * T_NPC, nn = min(T_NPC, a.n_nodes - n0);
+    const int n0 = tile * a.npc, nn = min(a.npc, a.n_nodes - n0);
     __syncthreads();
     if (tid <= nn) s_rowptr[tid] = __ldg(a.rrowptr + n0 + tid);
     __syncthreads();
@@ -662,8 +667,19 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_edge_table_bwd_tiled(TableT a)
   for (int j = threadIdx.x; j < 512; j += T_THREADS) a.d_alpha[(j >> 7) * a.alpha_stride + a.off_e + (j & 127)] = s_fin[j];
 }
 
-inline int tile_grid(int64_t n_nodes, int ctas_per_sm) {
-  int64_t tiles = (n_nodes + T_NPC - 1) / T_NPC;
+// Nodes per tile: 64 when that still yields >= 2 tiles per SM, otherwise halve (down to 8 = one node per warp) so that
+// small graphs (fragment / fragment-connection graphs have 5-10x fewer nodes than the bond graph) fill the machine
+// (measured sweep: profiles/r1f_kbench_npc*.log).
+inline int pick_npc(int64_t n_nodes) {
+  static const int forced = [] { const char *e = getenv("FNB_NPC"); return e ? atoi(e) : 0; }();
+  if (forced == 8 || forced == 16 || forced == 32 || forced == 64) return forced;
+  for (int npc = T_NPC; npc > 8; npc >>= 1)
+    if ((n_nodes + npc - 1) / npc >= (int64_t)kNumSMs * 2) return npc;
+  return 8;
+}
+
+inline int tile_grid(int64_t n_nodes, int npc, int ctas_per_sm) {
+  int64_t tiles = (n_nodes + npc - 1) / npc;
   const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
@@ -696,7 +712,8 @@ extern "C" int fnb_gat_fwd_tiled(const fnb_graph *g, const fnb_gat_fwd_args *f, 
   a.post.relu = f->post.relu; a.post.seed = f->post.seed; a.post.offset = f->post.offset;
   a.mask_lo = (int)f->mask_lo; a.mask_hi = (int)f->mask_hi;
   a.next_alpha = f->next_alpha_e; a.next_stride = f->next_alpha_stride; a.next_Se = f->next_Se;
-  const int grid = tile_grid(g->n_nodes, 6);
+  a.npc = pick_npc(g->n_nodes);
+  const int grid = tile_grid(g->n_nodes, a.npc, 6);
   cudaStream_t stream = (cudaStream_t)stream_;
   switch (f->edge_mode) {
     case FNB_EDGE_NONE:
@@ -742,7 +759,8 @@ extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, 
   d.edge_attr = g->edge_attr; d.dz = b->dz; d.dSt = b->dSt; d.n_nodes = (int)g->n_nodes; d.scratch = (float *)b->scratch;
   d.We = b->We; d.be = b->be; d.alpha_e = b->alpha + b->off_e; d.alpha_e_stride = b->alpha_stride;
   d.dWe = b->dWe; d.dbe = b->dbe; d.d_alpha_e = b->d_alpha + b->off_e;
-  const int grid = tile_grid(g->n_nodes, 6);
+  d.npc = pick_npc(g->n_nodes);
+  const int grid = tile_grid(g->n_nodes, d.npc, 6);
   const bool affine = b->edge_mode == FNB_EDGE_AFFINE1 || b->edge_mode == FNB_EDGE_AFFINE6;
   if (affine && (!g->edge_attr || !b->We || !b->be || !b->dWe || !b->dbe)) return FNB_ERR_NULL;
   if (b->edge_mode == FNB_EDGE_AFFINE1) {
@@ -761,6 +779,7 @@ extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, 
   s.dz = b->dz; s.dSt = b->dSt; s.alpha = b->alpha; s.alpha_stride = b->alpha_stride; s.off_t = b->off_t;
   s.off_s = b->off_s; s.dh = b->dh; s.d_alpha = b->d_alpha; s.d_bias = b->d_bias; s.scratch = (float *)b->scratch;
   s.n_nodes = (int)g->n_nodes;
+  s.npc = d.npc;
   k_gat_bwd_src_tiled<<<grid, T_THREADS, 0, stream>>>(s);
   FNB_CHECK_LAUNCH();
   return 0;

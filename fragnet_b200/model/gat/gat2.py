@@ -38,11 +38,13 @@ def _as_int_or_none(v):
 
 
 def _plan_for(dev, n_atoms, n_frags, n_bond_nodes, n_fbond_nodes, edge_index, frag_index, atom_to_frag_ids,
-              edge_index_bonds_graph, edge_attr_bonds, edge_index_fbonds, edge_attr_fbonds):
+              edge_index_bonds_graph, edge_attr_bonds, edge_index_fbonds, edge_attr_fbonds, batch_vec=None,
+              frag_batch_vec=None):
     """CSR plan of a batch (built on the device once, cached on the identity of the caller's index tensors)."""
     index_tensors = (edge_index, frag_index, atom_to_frag_ids, edge_index_bonds_graph, edge_attr_bonds,
                      edge_index_fbonds, edge_attr_fbonds)
-    return ops.layer_plan_for(index_tensors, (n_atoms, n_frags, n_bond_nodes, n_fbond_nodes), dev)
+    return ops.layer_plan_for(index_tensors, (n_atoms, n_frags, n_bond_nodes, n_fbond_nodes), dev, batch_vec,
+                              frag_batch_vec)
 
 
 class FragNetLayerA(nn.Module):
@@ -164,7 +166,7 @@ class FragNet(nn.Module):
         plan = _plan_for(dev, x_atoms.size(0), batch["x_frags"].size(0), bond_nodes.size(0), fbond_nodes.size(0),
                          batch["edge_index"], batch["frag_index"], batch["atom_to_frag_ids"],
                          batch["edge_index_bonds_graph"], batch["edge_attr_bonds"], batch["edge_index_fbonds"],
-                         batch["edge_attr_fbonds"])
+                         batch["edge_attr_fbonds"], batch.get("batch"), batch.get("frag_batch"))
         last = len(self.layers) - 1
         # the fragment-graph block of every layer but the last is skipped: its output is overwritten unread by the
         # next layer (gat2.py:234), so nothing observable changes

@@ -28,6 +28,10 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -142,29 +146,104 @@ def narrow_index(ids: torch.Tensor) -> torch.Tensor:
     return out
 
 
-@dataclass
+class MoleculeCount:
+    """Number of molecules of a batch = last entry of the sorted ``batch`` / ``frag_batch`` vectors + 1.  It is data
+    dependent in the reference (scatter_add sizes its output ``index.max()+1``, gat2.py:820-821) and is the one
+    value the host needs from the device per batch.  For device-resident vectors the 16-byte read-back is queued
+    FIRST on the stream (before the collate and encoder launches) into pinned memory and only waited for when the
+    readout needs it, by which time it has long completed -- the launch pipeline is never drained."""
+
+    def __init__(self, batch_vec, frag_batch_vec):
+        self._value, self._event, self._pinned = None, None, None
+        vecs = [v for v in (batch_vec, frag_batch_vec) if v is not None and v.numel()]
+        if not vecs:
+            self._value = 0
+        elif all(not v.is_cuda for v in vecs):
+            self._value = max(int(v[-1]) for v in vecs) + 1
+        else:
+            self._pinned = torch.zeros(2, dtype=torch.int64).pin_memory()
+            for i, v in enumerate(vecs):
+                self._pinned[i:i + 1].copy_(v[-1:], non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()
+
+    def get(self) -> int:
+        if self._value is None:
+            self._event.synchronize()
+            self._value = int(self._pinned.max()) + 1
+        return self._value
+
+
+class ReadoutPlan:
+    def __init__(self, count, atom_ptr, frag_ptr, batch32, frag_batch32):
+        self._count = count
+        self.atom_ptr, self.frag_ptr = atom_ptr, frag_ptr          # int32 [>= G+1] molecule boundaries
+        self.batch32, self.frag_batch32 = batch32, frag_batch32    # int32 [Na], [Nf]
+
+    @property
+    def n_graphs(self) -> int:
+        return self._count.get() if isinstance(self._count, MoleculeCount) else int(self._count)
+
+
 class LayerPlan:
-    """Everything index-shaped that the four GAT2 blocks of a batch share across layers, forward
-    and backward: CSR / reverse CSR of the four graphs, the atom->fragment membership CSR and the
-    edge attributes permuted into slot order."""
-    bond: GraphCSR
-    atom: GraphCSR
-    fbond: GraphCSR
-    frag: GraphCSR
-    pool: GraphCSR                 # fragment -> member atoms
-    a2f32: torch.Tensor            # int32 copy of atom_to_frag_ids (pool backward gather)
-    n_atoms: int
-    n_frags: int
-    refs: tuple = field(default=(), repr=False)
-    _c: Optional[_abi.CBatchPlan] = field(default=None, repr=False)
+    """Everything index-shaped that the GAT2 blocks of one batch share across layers, forward and backward, built by
+    ONE ``fnb_batch_plan_build`` call into one arena: CSR / reverse CSR of the four graphs, the atom->fragment
+    membership CSR, edge attributes permuted into slot order, int32 index copies and the readout offsets.
+    ``bond / atom / fbond / frag / pool`` expose the same data as ``GraphCSR`` tensor views (tests, tools)."""
+
+    def __init__(self, arena: torch.Tensor, c: _abi.CBatchPlan, keep: tuple, count: Optional[MoleculeCount] = None):
+        self.arena, self.c, self.keep, self.count = arena, c, keep, count
+        self.n_atoms, self.n_frags = int(c.n_atoms), int(c.n_frags)
+        self._views = {}
 
     def cstruct(self) -> _abi.CBatchPlan:
-        """``fnb_batch_plan`` view (built once; the ctypes struct keeps raw pointers, the dataclass keeps the tensors)."""
-        if self._c is None:
-            self._c = _abi.CBatchPlan(self.bond.cstruct(), self.atom.cstruct(), self.fbond.cstruct(),
-                                      self.frag.cstruct(), self.pool.rowptr.data_ptr(), self.pool.col.data_ptr(),
-                                      self.a2f32.data_ptr(), self.n_atoms, self.n_frags)
-        return self._c
+        return self.c
+
+    def _view(self, ptr, n, dtype=torch.int32):
+        if not ptr:
+            return None
+        off = ptr - self.arena.data_ptr()
+        return self.arena[off:off + 4 * n].view(dtype)
+
+    def _graph(self, name) -> GraphCSR:
+        if name not in self._views:
+            if name == "pool":
+                g = GraphCSR(self.n_frags, self.n_atoms, self.n_atoms, self._view(self.c.pool_rowptr, self.n_frags + 1),
+                             self._view(self.c.pool_col, self.n_atoms), None, None, None)
+            else:
+                cg = getattr(self.c, name)
+                n, e = int(cg.n_nodes), int(cg.n_edges)
+                aw = {"bond": 1, "fbond": 6}.get(name, 0)
+                attr = self._view(cg.edge_attr, e * aw, torch.float32) if aw else None
+                g = GraphCSR(n, e, int(cg.n_real_edges), self._view(cg.rowptr, n + 1), self._view(cg.col, e),
+                             self._view(cg.row, e), self._view(cg.eid, e), self._view(cg.slot_of_eid, e),
+                             self._view(cg.rrowptr, n + 1), self._view(cg.rslot, e), self._view(cg.rdst, e),
+                             self._view(self.c.status, 1), attr.view(e, aw) if aw > 1 else attr)
+                g._c = cg
+            self._views[name] = g
+        return self._views[name]
+
+    bond = property(lambda self: self._graph("bond"))
+    atom = property(lambda self: self._graph("atom"))
+    fbond = property(lambda self: self._graph("fbond"))
+    frag = property(lambda self: self._graph("frag"))
+    pool = property(lambda self: self._graph("pool"))
+
+    @property
+    def a2f32(self):
+        return self._view(self.c.a2f, self.n_atoms)
+
+    @property
+    def status(self):
+        return self._view(self.c.status, 1)
+
+    @property
+    def readout(self) -> Optional[ReadoutPlan]:
+        if not self.c.mol_atom_ptr:
+            return None
+        cap = int(self.c.n_graphs)      # capacity of the offset arrays (an upper bound on the molecule count)
+        return ReadoutPlan(self.count, self._view(self.c.mol_atom_ptr, cap + 1), self._view(self.c.mol_frag_ptr, cap + 1),
+                           self._view(self.c.batch32, self.n_atoms), self._view(self.c.frag_batch32, self.n_frags))
 
 
 def _idx(t: torch.Tensor, dev) -> torch.Tensor:
@@ -174,69 +253,83 @@ def _idx(t: torch.Tensor, dev) -> torch.Tensor:
 
 def build_layer_plan(edge_index, frag_index, atom_to_frag_ids, edge_index_bonds_graph, edge_attr_bonds,
                      edge_index_fbonds, edge_attr_fbonds, n_atoms: int, n_frags: int, n_bond_nodes: int,
-                     n_fbond_nodes: int, device) -> LayerPlan:
-    """On-device collate (north-star kernel a) for one batch.
+                     n_fbond_nodes: int, device, batch_vec=None, frag_batch_vec=None) -> LayerPlan:
+    """On-device collate (north-star kernel a) for one batch: one library call, 9 launches.
 
     Row conventions: bond / fragment-connection graphs use row 0 as the softmax
     segment (reference gat2.py:138, :239); atom / fragment graphs use row 1 (gat2.py:187, :283), and
     the atom graph gets its self loops appended (gat2.py:179)."""
     dev = require_cuda(device)
+    if edge_index.shape[1] != n_bond_nodes or frag_index.shape[1] != n_fbond_nodes:
+        raise ValueError("fragnet_b200: the bond graph needs one node per column of edge_index and the "
+                         "fragment-connection graph one node per column of frag_index (gat2.py:179-185, 293-295); got "
+                         f"{n_bond_nodes} vs {edge_index.shape[1]} and {n_fbond_nodes} vs {frag_index.shape[1]}")
+    # molecule count: read back lazily (MoleculeCount); the offset arrays are sized by the upper bound n_frags
+    # (every molecule owns at least one fragment, fragments.py:230-234)
+    have_batch = batch_vec is not None and frag_batch_vec is not None
+    count = MoleculeCount(batch_vec, frag_batch_vec) if have_batch else None
+    n_graphs = n_frags if have_batch else 0
     ei, fi = _idx(edge_index, dev), _idx(frag_index, dev)
     eb, efb = _idx(edge_index_bonds_graph, dev), _idx(edge_index_fbonds, dev)
     a2f = _idx(atom_to_frag_ids, dev)
-    bond = csr_build(eb[0], eb[1], n_bond_nodes)
-    atom = csr_build(ei[1], ei[0], n_atoms, self_loops=True)
-    fbond = csr_build(efb[0], efb[1], n_fbond_nodes)
-    frag = csr_build(fi[1], fi[0], n_frags)
-    pool = csr_build(a2f, None, n_frags, reverse=False)
-    bond.attr = gather_rows(edge_attr_bonds.to(dev).reshape(-1, 1), bond.eid, bond.n_edges)
-    fbond.attr = gather_rows(edge_attr_fbonds.to(dev), fbond.eid, fbond.n_edges)
-    return LayerPlan(bond, atom, fbond, frag, pool, narrow_index(a2f), n_atoms, n_frags)
+    cos = _f32c(edge_attr_bonds.to(dev)).reshape(-1)
+    a6 = _f32c(edge_attr_fbonds.to(dev))
+    bv = fbv = None
+    if have_batch:
+        bv, fbv = _idx(batch_vec, dev), _idx(frag_batch_vec, dev)
+    keep = (ei, fi, eb, efb, a2f, cos, a6, bv, fbv)
+    inp = _abi.CBatchInputs(_ptr(ei), _ptr(fi), _ptr(a2f), _ptr(eb), _ptr(efb), _ptr(bv), _ptr(fbv), _ptr(cos), _ptr(a6),
+                            n_atoms, n_frags, n_bond_nodes, eb.shape[1], n_fbond_nodes, efb.shape[1], n_graphs)
+    lib = _lib()
+    nbytes = lib.fnb_batch_plan_bytes(C.byref(inp))
+    arena = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+    c = _abi.CBatchPlan()
+    _abi.check(lib.fnb_batch_plan_build(C.byref(inp), _ptr(arena), arena.numel(), C.byref(c), _stream()),
+               "batch_plan_build")
+    return LayerPlan(arena, c, keep, count)
 
 
-_plan_cache = []          # [(weakrefs, versions, sizes, plan)], most recent first
+_plan_cache = []          # [(weakrefs, versions, sizes, device, plan)], most recent first
 _PLAN_CACHE_SIZE = 4
 
 
-def layer_plan_for(index_tensors: tuple, sizes: tuple, device) -> LayerPlan:
+def clear_plan_cache() -> None:
+    """Forget cached plans (benchmarks call this every step so that the on-device collate is always timed)."""
+    del _plan_cache[:]
+    del _readout_cache[:]
+
+
+def layer_plan_for(index_tensors: tuple, sizes: tuple, device, batch_vec=None, frag_batch_vec=None) -> LayerPlan:
     """Plan cache keyed by the IDENTITY of the caller's index tensors (weak references + version
-    counters), so the 4 layers of one forward share one plan and a new batch never hits a stale one."""
+    counters): the separate layer calls of the visualisation code share one plan, a new batch never hits a stale one."""
+    key_tensors = tuple(index_tensors) + tuple(t for t in (batch_vec, frag_batch_vec) if t is not None)
     for refs, versions, szs, dev, plan in _plan_cache:
-        if szs == sizes and dev == device and all(r() is t for r, t in zip(refs, index_tensors)) and \
-                versions == tuple(t._version for t in index_tensors):
+        if szs == sizes and dev == device and len(refs) == len(key_tensors) and \
+                all(r() is t for r, t in zip(refs, key_tensors)) and \
+                versions == tuple(t._version for t in key_tensors):
             return plan
-    plan = build_layer_plan(*index_tensors, *sizes, device)
-    refs = tuple(weakref.ref(t) for t in index_tensors)
-    _plan_cache.insert(0, (refs, tuple(t._version for t in index_tensors), sizes, device, plan))
+    plan = build_layer_plan(*index_tensors, *sizes, device, batch_vec, frag_batch_vec)
+    refs = tuple(weakref.ref(t) for t in key_tensors)
+    _plan_cache.insert(0, (refs, tuple(t._version for t in key_tensors), sizes, device, plan))
     del _plan_cache[_PLAN_CACHE_SIZE:]
     return plan
-
-
-@dataclass
-class ReadoutPlan:
-    n_graphs: int
-    atom_ptr: torch.Tensor     # int32 [G+1]
-    frag_ptr: torch.Tensor
-    batch32: torch.Tensor      # int32 [Na]
-    frag_batch32: torch.Tensor
 
 
 _readout_cache = []
 
 
 def readout_plan_for(batch_vec: torch.Tensor, frag_batch_vec: torch.Tensor, device) -> ReadoutPlan:
-    """Molecule boundaries of the sorted ``batch`` / ``frag_batch`` vectors.  The number of molecules
-    is data dependent in the reference (scatter_add sizes its output ``index.max()+1``,
-    gat2.py:820-821); reading it is the one host sync per batch, done on the CPU copy when the
-    vectors still live on the host."""
+    """Molecule boundaries of the sorted ``batch`` / ``frag_batch`` vectors: taken from the batch plan the encoder
+    built for the same tensors, else computed standalone."""
+    for refs, _, _, dev, plan in _plan_cache:
+        if dev == device and len(refs) >= 2 and refs[-2]() is batch_vec and refs[-1]() is frag_batch_vec and \
+                plan.readout is not None:
+            return plan.readout
     for refs, plan in _readout_cache:
         if refs[0]() is batch_vec and refs[1]() is frag_batch_vec:
             return plan
     dev = require_cuda(device)
-    n_graphs = 0
-    for v in (batch_vec, frag_batch_vec):
-        if v.numel():
-            n_graphs = max(n_graphs, int(v[-1]) + 1)
+    n_graphs = MoleculeCount(batch_vec, frag_batch_vec).get()
     b, fb = _idx(batch_vec, dev), _idx(frag_batch_vec, dev)
     plan = ReadoutPlan(n_graphs, segment_offsets(b, n_graphs), segment_offsets(fb, n_graphs),
                        narrow_index(b), narrow_index(fb))
@@ -337,10 +430,6 @@ def edge_table_bwd(g: GraphCSR, dz, feat, alpha, alpha_stride, off_e, g_base, d_
 
 
 # ---- node-tiled attention kernels (gat_tiled.cu) ------------------------------------------------
-def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
-
-
 def gat_fwd_tiled(g: GraphCSR, h, S, mode, *, table=None, We=None, be=None, alpha_e=None, alpha_stride=0,
                   save_p=True, want_out=True, post=None, mask=(-1, -1), next_alpha=None, next_alpha_stride=0):
     """``fnb_gat_fwd_tiled``.  ``post`` = (p, training, relu, seed, offset) additionally returns

@@ -251,7 +251,33 @@ typedef struct fnb_batch_plan {
   const int32_t *pool_rowptr, *pool_col; /* fragment -> member atoms (membership CSR of atom_to_frag_ids) */
   const int32_t *a2f;                    /* int32 atom_to_frag_ids */
   int64_t n_atoms, n_frags;
+  /* readout (gat2.py:820-821): molecule boundaries of the sorted batch / frag_batch vectors, or NULL */
+  const int32_t *mol_atom_ptr, *mol_frag_ptr; /* [n_graphs + 1] */
+  const int32_t *batch32, *frag_batch32;      /* int32 copies of batch [Na], frag_batch [Nf] */
+  int64_t n_graphs;
+  const int32_t *status; /* device word, non-zero if any index was out of range */
 } fnb_batch_plan;
+
+/* The batch dict of the reference's collate_fn (fragnet/dataset/data.py:931-948), device pointers.  Edge lists are
+ * contiguous int64 [2, E]: row 0 at the pointer, row 1 at pointer + E. */
+typedef struct fnb_batch_inputs {
+  const int64_t *edge_index;             /* [2, n_bonds]        atom graph: row 0 = source, row 1 = target (gat2.py:187) */
+  const int64_t *frag_index;             /* [2, n_fbond_nodes]  fragment graph: row 0 = source, row 1 = target (:283)   */
+  const int64_t *atom_to_frag_ids;       /* [n_atoms]                                                              */
+  const int64_t *edge_index_bonds_graph; /* [2, n_bond_edges]   bond graph: row 0 = target, row 1 = source (:138)       */
+  const int64_t *edge_index_fbonds;      /* [2, n_fbond_edges]  fragment-connection graph: row 0 = target (:239)        */
+  const int64_t *batch, *frag_batch;     /* sorted molecule ids of atoms / fragments, or both NULL                     */
+  const float *edge_attr_bonds;          /* [n_bond_edges]      cos(theta)                                             */
+  const float *edge_attr_fbonds;         /* [n_fbond_edges, 6]                                                         */
+  int64_t n_atoms, n_frags, n_bonds, n_bond_edges, n_fbond_nodes, n_fbond_edges, n_graphs;
+} fnb_batch_inputs;
+
+/* One call builds everything index-shaped a batch needs (9 launches): the four CSR + reverse CSR plans, the
+ * membership CSR, slot-ordered edge attributes, int32 copies and readout offsets.  arena: caller-allocated,
+ * 256-byte aligned, fnb_batch_plan_bytes() bytes; the pointers written to *out point into it. */
+size_t fnb_batch_plan_bytes(const fnb_batch_inputs *in);
+int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out,
+                         void *stream);
 
 typedef struct fnb_encoder_opts {
   int n_layers;

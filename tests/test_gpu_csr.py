@@ -81,3 +81,60 @@ def test_out_of_range_index_sets_status():
     src = torch.tensor([1, 0, 1], dtype=torch.int64).cuda()
     g = ops.csr_build(dst, src, 3)
     assert int(g.status.item()) == 1
+
+
+@pytest.mark.parametrize("shape,n", [("unimol", 40), ("stress", 3), ("esol", 300)])
+def test_batch_plan_one_call_equals_stable_sort(shape, n):
+    """fnb_batch_plan_build (all five CSRs, attributes, offsets in one call) against the CPU stable sort, bit-exact."""
+    from fragnet_b200 import ops, synth
+    from fragnet_b200.dataset.data import collate_fn
+    b = collate_fn(synth.make_dataset(shape, n, seed=4)
+                   + [synth.handmade(k) for k in ("two_atom", "ion_pair", "single_frag", "two_frag")])
+    na, nb, nfb, nf = b["x_atoms"].shape[0], b["node_features_bonds"].shape[0], b["node_features_fbonds"].shape[0], \
+        b["x_frags"].shape[0]
+    bc = {k: v.cuda() for k, v in b.items()}
+    plan = ops.build_layer_plan(bc["edge_index"], bc["frag_index"], bc["atom_to_frag_ids"],
+                                bc["edge_index_bonds_graph"], bc["edge_attr_bonds"], bc["edge_index_fbonds"],
+                                bc["edge_attr_fbonds"], na, nf, nb, nfb, "cuda", bc["batch"], bc["frag_batch"])
+    assert int(plan.status.item()) == 0
+    specs = [("bond", b["edge_index_bonds_graph"][0], b["edge_index_bonds_graph"][1], nb, False),
+             ("atom", b["edge_index"][1], b["edge_index"][0], na, True),
+             ("fbond", b["edge_index_fbonds"][0], b["edge_index_fbonds"][1], nfb, False),
+             ("frag", b["frag_index"][1], b["frag_index"][0], nf, False)]
+    for name, dst, src, nn, loops in specs:
+        g = getattr(plan, name)
+        want = _cpu_csr(dst, src, nn, loops)
+        for k, w in want.items():
+            assert torch.equal(getattr(g, k).cpu().to(torch.int64), w), (name, k)
+        dst_full = torch.cat([dst, torch.arange(nn)]) if loops else dst
+        assert torch.equal(g.row.cpu().long(), dst_full[want["eid"]]), name
+    # slot-ordered edge attributes
+    assert torch.equal(plan.bond.attr.cpu().view(-1), b["edge_attr_bonds"].view(-1)[plan.bond.eid.cpu().long()])
+    assert torch.equal(plan.fbond.attr.cpu(), b["edge_attr_fbonds"][plan.fbond.eid.cpu().long()])
+    # membership CSR, narrowing, readout offsets
+    a2f = b["atom_to_frag_ids"]
+    order = torch.sort(a2f, stable=True).indices
+    assert torch.equal(plan.pool.col.cpu().long(), order)
+    assert torch.equal(plan.pool.rowptr.cpu().long()[1:], torch.cumsum(torch.bincount(a2f, minlength=nf), 0))
+    assert torch.equal(plan.a2f32.cpu().long(), a2f)
+    ro = plan.readout
+    G = int(b["batch"][-1]) + 1
+    assert ro.n_graphs == G
+    # the offset arrays are sized by the upper bound n_frags; entries past the last molecule equal the totals
+    assert torch.equal(ro.atom_ptr.cpu().long(), torch.searchsorted(b["batch"], torch.arange(nf + 1)))
+    assert torch.equal(ro.frag_ptr.cpu().long(), torch.searchsorted(b["frag_batch"], torch.arange(nf + 1)))
+    assert torch.equal(ro.batch32.cpu().long(), b["batch"]) and torch.equal(ro.frag_batch32.cpu().long(), b["frag_batch"])
+
+
+def test_batch_plan_flags_out_of_range_indices():
+    from fragnet_b200 import ops, synth
+    from fragnet_b200.dataset.data import collate_fn
+    b = collate_fn(synth.make_dataset("unimol", 4, seed=1))
+    bc = {k: v.cuda() for k, v in b.items()}
+    bad = bc["edge_index_bonds_graph"].clone()
+    bad[0, 3] = 10 ** 6
+    na, nb, nfb, nf = b["x_atoms"].shape[0], b["node_features_bonds"].shape[0], b["node_features_fbonds"].shape[0], \
+        b["x_frags"].shape[0]
+    plan = ops.build_layer_plan(bc["edge_index"], bc["frag_index"], bc["atom_to_frag_ids"], bad, bc["edge_attr_bonds"],
+                                bc["edge_index_fbonds"], bc["edge_attr_fbonds"], na, nf, nb, nfb, "cuda")
+    assert int(plan.status.item()) == 1

@@ -65,8 +65,17 @@ def test_layer_forward_backward_matches_oracle():
                           xfb_o, b["edge_index_fbonds"], b["edge_attr_fbonds"])
     assert len(outs) == 8
     names = ("x_atoms", "x_frags", "bond", "fbond", "attn_atoms", "attn_frags", "attn_bonds", "attn_fbonds")
-    for n, a, r in zip(names, outs, ref):
-        assert rel_err(a, r) <= FP32_REL_TOL, n
+    # Unit-variance 128-d inputs drive the logits to |z| ~ 10, where the reference's OWN fp32 rounding (order of the
+    # 96/192-term dot products) moves the softmax by ~1e-5; measure that noise against a float64 run of the same
+    # oracle and allow for it (realistic activations, tested below on whole models, stay at ~1e-7).
+    P64 = {k: v.detach().double() for k, v in P.items()}
+    ref64 = O.layer_forward(P64, "", 4, xa.double(), b["edge_index"], xb.double(), b["frag_index"],
+                            torch.zeros(nf, 128, dtype=torch.float64), b["atom_to_frag_ids"], xb.double(),
+                            b["edge_index_bonds_graph"], b["edge_attr_bonds"].double(), xfb.double(),
+                            b["edge_index_fbonds"], b["edge_attr_fbonds"].double())
+    for n, a, r, r64 in zip(names, outs, ref, ref64):
+        noise = rel_err(r, r64)
+        assert rel_err(a, r64) <= max(FP32_REL_TOL, 3 * noise), (n, rel_err(a, r64), noise)
     ws = [torch.randn(t.shape, generator=gen) for t in ref[:4]]
     sum((o * w.cuda()).sum() for o, w in zip(outs[:4], ws)).backward()
     sum((o * w).sum() for o, w in zip(ref[:4], ws)).backward()
