@@ -235,6 +235,7 @@ def run_ours(args):
     from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
     from fragnet_b200 import _abi
     from fragnet_b200.dist import FlatGradSync
+    from fragnet_b200.train.optim import FlatAdam
     from fragnet_b200.train.pretrain_utils import pretrain_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,9 +275,9 @@ def run_ours(args):
         loss = pretrain_loss(loss_fn, model(batch), batch)
         loss.backward()
         sync.sync()
-        if opt is None:          # Adam over the live parameters (grad-less ones are skipped by Adam anyway)
-            opt = torch.optim.Adam(sync.live_parameters(), lr=LR, fused=True)
-        opt.step()
+        if opt is None:          # Adam over the live parameters (grad-less ones are skipped by torch's Adam too)
+            opt = FlatAdam(sync.live_parameters(), lr=LR)
+        opt.step(sync.flat if world > 1 else None)
         return loss
 
     def barrier():

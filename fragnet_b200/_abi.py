@@ -20,6 +20,7 @@ SIGNATURES = {
     "fnb_scratch_bytes": (_sz, []),
     "fnb_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "fnb_csr_build": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "fnb_tile_ranges": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fnb_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "fnb_segment_offsets": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "fnb_narrow_index": (C.c_int, [_vp, _i64, _vp, _vp]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "fnb_segment_gather": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "fnb_dropout_relu_fwd": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _i32, _u64, _u64, _vp]),
     "fnb_dropout_relu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _i32, _vp]),
+    "fnb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
     "fnb_gat_fwd_tiled": (C.c_int, [_vp, _vp, _vp]),
     "fnb_gat_bwd_tiled": (C.c_int, [_vp, _vp, _vp]),
     "fnb_edge_table_bwd_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
@@ -46,7 +48,7 @@ SIGNATURES = {
     "fnb_batch_plan_build": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "fnb_encoder_workspace_bytes": (_sz, [_vp, _vp, _vp]),
     "fnb_encoder_bwd_workspace_bytes": (_sz, [_vp, _vp, _vp]),
-    "fnb_encoder_philox_span": (_u64, [_vp, _vp, _vp]),
+    "fnb_encoder_rng_span": (_u64, [_vp, _vp, _vp]),
     "fnb_encoder_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "fnb_encoder_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
 }
@@ -56,7 +58,8 @@ SIGNATURES = {
 class CGraph(C.Structure):
     _fields_ = [("n_nodes", _i64), ("n_edges", _i64), ("n_real_edges", _i64),
                 ("rowptr", _vp), ("col", _vp), ("row", _vp), ("eid", _vp), ("slot_of_eid", _vp),
-                ("rrowptr", _vp), ("rslot", _vp), ("rdst", _vp), ("edge_attr", _vp)]
+                ("rrowptr", _vp), ("rslot", _vp), ("rdst", _vp), ("tile_range", _vp), ("rtile_range", _vp),
+                ("edge_attr", _vp)]
 
 
 class CPostAct(C.Structure):
@@ -76,7 +79,7 @@ class CGatBwdArgs(C.Structure):
                 ("dz", _vp), ("dSt", _vp), ("dh", _vp), ("d_alpha", _vp), ("d_bias", _vp), ("dWe", _vp), ("dbe", _vp),
                 ("scratch", _vp)]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_TF32 = 0, 1
 

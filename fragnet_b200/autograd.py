@@ -94,7 +94,7 @@ class EncoderFn(torch.autograd.Function):
                                  0, 0, 0)
         cplan = plan.cstruct()
         if dropping:
-            opts.offset = ops.reserve_philox(lib.fnb_encoder_philox_span(C.byref(cplan), C.byref(opts), layers))
+            opts.offset = ops.reserve_rng(lib.fnb_encoder_rng_span(C.byref(cplan), C.byref(opts), layers))
         new = lambda rows, cols=ops.D: torch.empty((rows, cols), dtype=torch.float32, device=dev)
         run_frag_last = cfg.layers[-1].run_frag_block
         out_atoms, out_bond, out_fbond = new(plan.n_atoms), new(plan.bond.n_nodes), new(plan.fbond.n_nodes)
@@ -174,7 +174,7 @@ class DropoutReluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, p: float, training: bool, relu: bool):
         x = ops._f32c(x)
-        seed, offset = ops.next_philox(x.numel()) if (training and p > 0) else (0, 0)
+        seed, offset = ops.next_rng(x.numel()) if (training and p > 0) else (0, 0)
         y = ops.dropout_relu_fwd(x, p, training, relu, seed, offset)
         ctx.cfg = (p, training, relu, seed, offset)
         if relu:
@@ -188,7 +188,7 @@ class DropoutReluFn(torch.autograd.Function):
         if relu:
             (y,) = ctx.saved_tensors
             return ops.dropout_relu_bwd(dy, y, p, training), None, None, None
-        # plain dropout: the same keep-mask applied to dy (regenerated from the Philox counters)
+        # plain dropout: the same keep-mask applied to dy (regenerated from the RNG counters)
         return ops.dropout_relu_fwd(dy, p, training, False, seed, offset), None, None, None
 
 

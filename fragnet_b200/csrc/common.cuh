@@ -69,37 +69,78 @@ __device__ __forceinline__ float pick(const float4 &v, int i) {
 }
 __device__ __forceinline__ float leaky(float z) { return z > 0.f ? z : kNegSlope * z; }
 
-// ---- Philox4x32-10 counter RNG (dropout masks are regenerated, never stored) -------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
+// ---- mbarrier + bulk asynchronous copy (TMA engine, 1-D): global -> shared memory ---------------------------------
+namespace bulk {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }  // [0,1)
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 26)) __trap();
+}
+// Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// bytes: multiple of 16; src and dst 16-byte aligned.  Completion is signalled on `bar` (complete_tx).
+__device__ __forceinline__ void copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+}  // namespace bulk
 
-// ReLU(Dropout_p(v)) of the 4 consecutive elements with flat index 4*q .. 4*q+3; Philox counter = offset + q, so a
-// fused epilogue and the standalone elementwise kernel draw the same mask for the same tensor element.
+// ---- counter-based RNG for dropout masks (regenerated from (seed, counter), never stored) ------
+// Philox4x32-10 cost ~135 instructions per group of 4 elements and made the fused forward epilogue the largest single
+// consumer of issue slots (profiles/r1e: ~190 of ~407 warp instructions per node).  Dropout only needs independent,
+// reproducible Bernoulli draws, so each group of 4 consecutive elements draws two 32-bit words from a 3-multiply
+// integer mixer ("triple32", full avalanche) keyed by (seed, counter) and uses 16 bits per element:
+// keep <=> r16 >= round(p * 65536).  ~35 instructions per group.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 17; x *= 0xed5ad4bbu;
+  x ^= x >> 11; x *= 0xac4c1b51u;
+  x ^= x >> 15; x *= 0x31848babu;
+  x ^= x >> 14;
+  return x;
+}
+
+// ReLU(Dropout_p(v)) of the 4 consecutive elements with flat index 4*q .. 4*q+3; the counter of the group is
+// offset + q, so a fused epilogue and the standalone elementwise kernel draw the same mask for the same element.
 struct PostAct {
   float p, scale;      // drop probability, 1/(1-p)
   int training, relu;
   uint64_t seed, offset;
 };
+__device__ __forceinline__ uint2 dropout_bits(uint64_t seed, uint64_t counter) {
+  const uint32_t lo = (uint32_t)counter, hi = (uint32_t)(counter >> 32);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t a = mix32(lo ^ k0) ^ (hi * 0x9E3779B1u);
+  return make_uint2(mix32(a + k1), mix32(a ^ 0x85EBCA6Bu ^ k1));
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
 __device__ __forceinline__ float4 post_act(const PostAct &pa, float4 v, uint64_t q) {
   if (pa.training && pa.p > 0.f) {
-    const uint64_t c = pa.offset + q;
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
-                                    make_uint2((uint32_t)pa.seed, (uint32_t)(pa.seed >> 32)));
-    v.x *= u01(rnd.x) >= pa.p ? pa.scale : 0.f;
-    v.y *= u01(rnd.y) >= pa.p ? pa.scale : 0.f;
-    v.z *= u01(rnd.z) >= pa.p ? pa.scale : 0.f;
-    v.w *= u01(rnd.w) >= pa.p ? pa.scale : 0.f;
+    const uint2 r = dropout_bits(pa.seed, pa.offset + q);
+    const uint32_t th = dropout_threshold(pa.p);
+    v.x *= (r.x & 0xffffu) >= th ? pa.scale : 0.f;
+    v.y *= (r.x >> 16) >= th ? pa.scale : 0.f;
+    v.z *= (r.y & 0xffffu) >= th ? pa.scale : 0.f;
+    v.w *= (r.y >> 16) >= th ? pa.scale : 0.f;
   }
   if (pa.relu) {
     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
@@ -176,6 +217,7 @@ struct ReduceSegments {
   int padded_width[4];  // filled by the launcher
   float *out[4];
   int row_len[4];       // out index = (j / row_len) * out_stride + j % row_len
+  int valid_len[4];     // columns j % row_len >= valid_len are padding and are skipped (0 = row_len)
   int out_stride[4];
 };
 int fnb_launch_reduce_segments(const float *partials, int n_blocks, int pstride, ReduceSegments segs,
@@ -186,6 +228,19 @@ int fnb_launch_reduce_segments(const float *partials, int n_blocks, int pstride,
 int fnb_launch_reduce_partials(const float *partials, int n_blocks, int pstride, int width, float *out, int row_len,
                                int out_stride, int accumulate, cudaStream_t stream);
 
+// Tile source ranges for the bulk-copy staging of gathered rows (csr.cu): up to 8 CSRs per launch.
+constexpr int kRangeTile = 64;
+struct RangeJobs {
+  const int *rowptr[8];
+  const int *col[8];
+  int n_nodes[8];
+  int *out[8];
+  int tile_base[8];   // first global tile index of job i; tile_base[n_jobs] = total
+  int n_jobs;
+  int total_tiles;
+};
+int fnb_launch_tile_ranges(const RangeJobs &jobs, cudaStream_t stream);
+
 // Tensor-core (tcgen05, TF32) projection path, tc_gemm.cu.  Returns FNB_ERR_MODE when the shape cannot use TMA.
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
                        int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream);
@@ -195,4 +250,5 @@ struct TransposeBatch { const float *W[16]; int count; };
 int fnb_tc_transpose128_batched(const TransposeBatch &b, float *Wt_base, cudaStream_t stream);
 int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K,
                       float *dx, float *dW, float *db, int precision, void *scratch, void *stream);
-int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, float *dW, float *scratch, cudaStream_t stream);
+int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols, int k_out, float *dW, float *scratch,
+                     cudaStream_t stream);

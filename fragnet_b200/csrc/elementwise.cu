@@ -3,9 +3,11 @@
 // Reference: FragNet.forward applies nn.Dropout to the raw atom features (fragnet/model/gat/gat2.py:396)
 // and ReLU(Dropout(.)) to all four outputs of every layer (gat2.py:414-418, 436-440) as separate eager
 // ops (bernoulli_ mask, mul, div, relu: ~11.5% of the reference's CPU time).  Here it is
-// one pass, the keep-mask is regenerated from a counter-based Philox4x32-10 stream (never stored),
+// one pass, the keep-mask is regenerated from a counter-based integer-hash stream (common.cuh; never stored),
 // and the backward needs only the forward OUTPUT: y > 0 implies the element was kept and positive,
 // so dx = dy * (y > 0) / (1 - p).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace {
@@ -14,25 +16,23 @@ __global__ void __launch_bounds__(256) k_dropout_relu_fwd(const float *__restric
                                                           float p, float scale, int relu, uint64_t seed,
                                                           uint64_t offset, int vec_ok) {
   const int64_t n4 = (n + 3) >> 2;
-  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  PostAct pa;
+  pa.p = p; pa.scale = scale; pa.training = 1; pa.relu = relu; pa.seed = seed; pa.offset = offset;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t c = offset + (uint64_t)q;
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
-    const float keep[4] = {u01(rnd.x) >= p ? scale : 0.f, u01(rnd.y) >= p ? scale : 0.f,
-                           u01(rnd.z) >= p ? scale : 0.f, u01(rnd.w) >= p ? scale : 0.f};
     const int64_t i = q << 2;
     if (vec_ok && i + 4 <= n) {
-      float4 v = ldg4(x + i);
-      v.x *= keep[0]; v.y *= keep[1]; v.z *= keep[2]; v.w *= keep[3];
-      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      st4(y + i, v);
+      st4(y + i, post_act(pa, ldg4(x + i), (uint64_t)q));
     } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i + u < n) {
-          float v = x[i + u] * keep[u];
-          y[i + u] = relu ? fmaxf(v, 0.f) : v;
-        }
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n) v.x = x[i];
+      if (i + 1 < n) v.y = x[i + 1];
+      if (i + 2 < n) v.z = x[i + 2];
+      if (i + 3 < n) v.w = x[i + 3];
+      v = post_act(pa, v, (uint64_t)q);
+      if (i < n) y[i] = v.x;
+      if (i + 1 < n) y[i + 1] = v.y;
+      if (i + 2 < n) y[i + 2] = v.z;
+      if (i + 3 < n) y[i + 3] = v.w;
     }
   }
 }
@@ -65,6 +65,24 @@ __global__ void __launch_bounds__(256) k_dropout_relu_bwd(const float *__restric
       for (int u = 0; u < 4; ++u)
         if (i + u < n) dx[i + u] = y[i + u] > 0.f ? dy[i + u] * scale : 0.f;
     }
+  }
+}
+
+// Adam over one flat fp32 buffer (all live parameters of the model are views into it): one launch per step instead of
+// torch's per-tensor-list bookkeeping.  Same update as torch.optim.Adam (no amsgrad, no weight decay unless given):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                              float *__restrict__ v, int64_t n, float b1, float b2, float eps,
+                                              float weight_decay, float step_size, float inv_sqrt_bc2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
   }
 }
 
@@ -108,6 +126,18 @@ extern "C" int fnb_dropout_relu_bwd(const float *dy, const float *y, float *dx, 
   const int vec_ok = fnb_aligned16(dy) && fnb_aligned16(y) && fnb_aligned16(dx);
   const float scale = (training && p > 0.f) ? 1.f / (1.f - p) : 1.f;
   k_dropout_relu_bwd<<<ew_grid((n + 3) >> 2), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n, scale, vec_ok);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fnb_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int64_t step, void *stream) {
+  if (n < 0 || step < 1) return FNB_ERR_SIZE;
+  if (n == 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return FNB_ERR_NULL;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  k_adam<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                      weight_decay, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)));
   FNB_CHECK_LAUNCH();
   return 0;
 }

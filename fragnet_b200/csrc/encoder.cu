@@ -34,6 +34,8 @@ struct Arena {
 
 struct LayerBufs {
   float *xa0;                                                   // layer 0: Dropout(x_atoms) (training only)
+  float *x_pad[3], *W_pad[3];                                   // layer 0, TF32: inputs / weights zero-padded to k_pad columns
+  int k_pad[3];                                                 // (order: bond, atom, fbond; 0 = no padding needed)
   float *hb, *Sb, *pre_bond, *y_bond, *p_b, *se_atom;
   float *ha, *Sa, *pre_atom, *y_atom, *p_a;
   float *hfb, *Sfb, *pre_fbond, *y_fbond, *p_fb, *se_frag;
@@ -53,6 +55,14 @@ Sizes sizes_of(const fnb_batch_plan *p) {
 
 bool input_dropout(const fnb_encoder_opts *o) { return o->post_act && o->training && o->drop_p > 0.f; }
 
+// Layer-0 feature widths (167 / 17 / 6) are not addressable by TMA (row pitch must be a multiple of 16 bytes) and not a
+// multiple of the 32-column K block of the tensor-core kernels: in TF32 mode the inputs and weights are zero-padded
+// once per pass to the next multiple of 32 columns and take the same tcgen05 kernels as every other layer.
+int pad_width(const fnb_encoder_opts *o, int K) {
+  if (o->precision != FNB_PRECISION_TF32 || (K & 31) == 0 || K > 224) return 0;
+  return (K + 31) & ~31;
+}
+
 // Forward workspace layout (identical in fnb_encoder_forward / _backward / _workspace_bytes).
 size_t layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L, char *base,
               LayerBufs *bufs) {
@@ -65,6 +75,17 @@ size_t layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_l
     const bool want_p = keep || L[l].want_attention;
     const bool frag = L[l].run_frag_block != 0;
     if (l == 0 && input_dropout(o)) b.xa0 = a.take<float>(z.Na * L[0].K_atom);
+    if (l == 0) {
+      const int ks[3] = {L[0].K_bond, L[0].K_atom, L[0].K_fbond};
+      const int64_t ns[3] = {z.Nb, z.Na, z.Nfb};
+      for (int j = 0; j < 3; ++j) {
+        b.k_pad[j] = pad_width(o, ks[j]);
+        if (b.k_pad[j]) {
+          b.x_pad[j] = a.take<float>(ns[j] * b.k_pad[j]);
+          b.W_pad[j] = a.take<float>((size_t)kD * b.k_pad[j]);
+        }
+      }
+    }
     b.hb = a.take<float>(z.Nb * kD);
     b.Sb = a.take<float>(z.Nb * 8);
     b.se_atom = a.take<float>(z.Nb * 4);
@@ -127,19 +148,19 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   return (a.off + 255) & ~(size_t)255;
 }
 
-// Philox counters consumed by one dropout site over n elements.
+// RNG counters consumed by one dropout site over n elements.
 uint64_t span(int64_t n) { return (uint64_t)((n + 3) / 4); }
 
 // Counter bases of the dropout sites, in a fixed order: input, then per layer bond, atom, fbond, frag.
-struct PhiloxPlan {
+struct RngPlan {
   uint64_t input;
   uint64_t bond[16], atom[16], fbond[16], frag[16];
   uint64_t total;
 };
 
-PhiloxPlan philox_plan(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L) {
+RngPlan rng_plan(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L) {
   const Sizes z = sizes_of(plan);
-  PhiloxPlan p{};
+  RngPlan p{};
   uint64_t c = o->offset;
   p.input = c;
   c += span(z.Na * (int64_t)L[0].K_atom);
@@ -186,6 +207,31 @@ __global__ void __launch_bounds__(256) k_grad_combine(const float *__restrict__ 
       v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
     st4(g + r * kD + c, v);
+  }
+}
+
+// dst[r, 0:k_pad] = [src[r, 0:K] | 0]: up to 6 matrices per launch (blockIdx.y).
+struct PadJobs {
+  const float *src[6];
+  float *dst[6];
+  int64_t rows[6];
+  int K[6], k_pad[6];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_pad_cols(PadJobs j) {
+  const int job = blockIdx.y;
+  const int K = j.K[job], kp = j.k_pad[job];
+  const int64_t total = j.rows[job] * (kp >> 2);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (kp >> 2);
+    const int c = (int)(i - r * (kp >> 2)) * 4;
+    const float *sp = j.src[job] + r * K + c;
+    float4 v;
+    v.x = c < K ? __ldg(sp) : 0.f;
+    v.y = c + 1 < K ? __ldg(sp + 1) : 0.f;
+    v.z = c + 2 < K ? __ldg(sp + 2) : 0.f;
+    v.w = c + 3 < K ? __ldg(sp + 3) : 0.f;
+    st4(j.dst[job] + r * kp + c, v);
   }
 }
 
@@ -248,10 +294,10 @@ extern "C" size_t fnb_encoder_bwd_workspace_bytes(const fnb_batch_plan *plan, co
   return bwd_layout(plan, opts, nullptr, nullptr);
 }
 
-extern "C" uint64_t fnb_encoder_philox_span(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+extern "C" uint64_t fnb_encoder_rng_span(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
                                             const fnb_layer_params *layers) {
   if (!plan || !opts || !layers || opts->n_layers < 1 || opts->n_layers > 16) return 0;
-  return philox_plan(plan, opts, layers).total;
+  return rng_plan(plan, opts, layers).total;
 }
 
 extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
@@ -262,7 +308,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
   LayerBufs B[16];
   if (layout(plan, o, L, (char *)workspace, B) > workspace_bytes) return FNB_ERR_WORKSPACE;
   const Sizes z = sizes_of(plan);
-  const PhiloxPlan ph = philox_plan(plan, o, L);
+  const RngPlan ph = rng_plan(plan, o, L);
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool keep = o->save_for_backward != 0;
 
@@ -271,12 +317,42 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     RC(fnb_dropout_relu_fwd(xa, B[0].xa0, z.Na * (int64_t)L[0].K_atom, o->drop_p, 1, 0, o->seed, ph.input, stream_));
     xa = B[0].xa0;
   }
+  {  // layer-0 operands padded for the tensor-core path (one launch for inputs and weights)
+    PadJobs pj{};
+    const float *xs[3] = {xb, xa, xfb}, *ws[3] = {L[0].Wb, L[0].Wa, L[0].Wfb};
+    const int ks[3] = {L[0].K_bond, L[0].K_atom, L[0].K_fbond};
+    const int64_t ns[3] = {z.Nb, z.Na, z.Nfb};
+    int64_t most = 0;
+    for (int j = 0; j < 3; ++j)
+      if (B[0].k_pad[j]) {
+        const int64_t rows[2] = {ns[j], kD};
+        const float *src[2] = {xs[j], ws[j]};
+        float *dst[2] = {B[0].x_pad[j], B[0].W_pad[j]};
+        for (int t = 0; t < 2; ++t) {
+          const int k = pj.n++;
+          pj.src[k] = src[t]; pj.dst[k] = dst[t]; pj.rows[k] = rows[t]; pj.K[k] = ks[j]; pj.k_pad[k] = B[0].k_pad[j];
+          if (rows[t] * (B[0].k_pad[j] >> 2) > most) most = rows[t] * (B[0].k_pad[j] >> 2);
+        }
+      }
+    if (pj.n && most > 0) {
+      int64_t blocks = (most + 255) / 256;
+      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+      k_pad_cols<<<dim3((unsigned)blocks, pj.n), 256, 0, stream>>>(pj);
+      FNB_CHECK_LAUNCH();
+    }
+  }
   for (int l = 0; l < o->n_layers; ++l) {
     const fnb_layer_params &P = L[l];
     LayerBufs &b = B[l];
     const bool last = l == o->n_layers - 1;
     const bool frag = P.run_frag_block != 0;
     const bool want_p = keep || P.want_attention;
+    // layer-0 operands may be the zero-padded copies (TF32 path)
+    const bool pb = l == 0 && b.k_pad[0], pa = l == 0 && b.k_pad[1], pf = l == 0 && b.k_pad[2];
+    const float *xb_in = pb ? b.x_pad[0] : xb, *Wb_in = pb ? b.W_pad[0] : P.Wb;
+    const float *xa_in = pa ? b.x_pad[1] : xa, *Wa_in = pa ? b.W_pad[1] : P.Wa;
+    const float *xfb_in = pf ? b.x_pad[2] : xfb, *Wfb_in = pf ? b.W_pad[2] : P.Wfb;
+    const int Kb_in = pb ? b.k_pad[0] : P.K_bond, Ka_in = pa ? b.k_pad[1] : P.K_atom, Kfb_in = pf ? b.k_pad[2] : P.K_fbond;
     // where the four results of this layer go
     float *pre_bond = o->post_act ? b.pre_bond : io->out_bond;
     float *pre_atom = o->post_act ? b.pre_atom : io->out_atoms;
@@ -288,7 +364,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     float *y_frag = o->post_act ? (last ? io->out_frags : b.y_frag) : nullptr;
 
     // ---- bond graph (gat2.py:138-176); epilogue emits the atom graph's edge term <new_bond[e], a_e[h]>
-    RC(fnb_proj_fwd(xb, P.Wb, P.bb, z.Nb, P.K_bond, P.a_b, AB_STRIDE, AB_T, AB_S, b.hb, b.Sb, o->precision, stream_));
+    RC(fnb_proj_fwd(xb_in, Wb_in, P.bb, z.Nb, Kb_in, P.a_b, AB_STRIDE, AB_T, AB_S, b.hb, b.Sb, o->precision, stream_));
     {
       fnb_gat_fwd_args f{};
       f.h = b.hb; f.S = b.Sb; f.edge_mode = FNB_EDGE_AFFINE1; f.We = P.We_b; f.be = P.be_b;
@@ -299,7 +375,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       RC(fnb_gat_fwd_tiled(&plan->bond, &f, stream_));
     }
     // ---- atom graph with self loops (gat2.py:179-231)
-    RC(fnb_proj_fwd(xa, P.Wa, P.ba, z.Na, P.K_atom, P.a, A_STRIDE, A_T, A_S, b.ha, b.Sa, o->precision, stream_));
+    RC(fnb_proj_fwd(xa_in, Wa_in, P.ba, z.Na, Ka_in, P.a, A_STRIDE, A_T, A_S, b.ha, b.Sa, o->precision, stream_));
     {
       fnb_gat_fwd_args f{};
       f.h = b.ha; f.S = b.Sa; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = b.se_atom; f.out = pre_atom; f.y = y_atom;
@@ -313,7 +389,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       }
     }
     // ---- fragment-connection graph (gat2.py:239-278); epilogue emits the fragment graph's edge term
-    RC(fnb_proj_fwd(xfb, P.Wfb, P.bfb, z.Nfb, P.K_fbond, P.f_a_b, AB_STRIDE, AB_T, AB_S, b.hfb, b.Sfb, o->precision,
+    RC(fnb_proj_fwd(xfb_in, Wfb_in, P.bfb, z.Nfb, Kfb_in, P.f_a_b, AB_STRIDE, AB_T, AB_S, b.hfb, b.Sfb, o->precision,
                     stream_));
     {
       fnb_gat_fwd_args f{};
@@ -442,8 +518,11 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         a.dbe = D.be_fb; a.scratch = scratch;
         RC(fnb_gat_bwd_tiled(&plan->fbond, &a, stream_));
         float *dx = need_dx ? W.dx_fbond : (o->need_dx_fbond ? io->dx_fbond : nullptr);
-        RC(fnb_proj_bwd_impl(xfb, P.Wfb, wt_of(l, 2), W.dh_fb, z.Nfb, P.K_fbond, dx, D.Wfb, nullptr, o->precision,
-                             scratch, stream_));
+        if (l == 0 && b.k_pad[2] && !dx)
+          RC(fnb_tc_dw_launch(W.dh_fb, b.x_pad[2], z.Nfb, b.k_pad[2], P.K_fbond, D.Wfb, scratch_body(scratch), stream));
+        else
+          RC(fnb_proj_bwd_impl(xfb, P.Wfb, wt_of(l, 2), W.dh_fb, z.Nfb, P.K_fbond, dx, D.Wfb, nullptr, o->precision,
+                               scratch, stream_));
         dy_fbond = need_dx ? W.dx_fbond : nullptr;
       } else {
         dy_fbond = nullptr;
@@ -471,8 +550,11 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
                                     y_bond ? dy_bond : nullptr, y_bond && dy_bond ? y_bond : nullptr, scale, W.g_bond,
                                     D.a, scratch, stream_));
         float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);
-        RC(fnb_proj_bwd_impl(xa, P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, D.Wa, nullptr, o->precision, scratch,
-                             stream_));
+        if (l == 0 && b.k_pad[1] && !dx)
+          RC(fnb_tc_dw_launch(W.dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratch), stream));
+        else
+          RC(fnb_proj_bwd_impl(xa, P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, D.Wa, nullptr, o->precision, scratch,
+                               stream_));
         dy_atom = need_dx ? W.dx_atom : nullptr;
       } else {
         RC((int)cudaMemsetAsync(D.a, 0, 4 * A_STRIDE * 4, stream));
@@ -490,8 +572,11 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         a.scratch = scratch;
         RC(fnb_gat_bwd_tiled(&plan->bond, &a, stream_));
         float *dx = need_dx ? W.dx_bond : (o->need_dx_bond ? io->dx_bond : nullptr);
-        RC(fnb_proj_bwd_impl(xb, P.Wb, wt_of(l, 0), W.dh_b, z.Nb, P.K_bond, dx, D.Wb, nullptr, o->precision, scratch,
-                             stream_));
+        if (l == 0 && b.k_pad[0] && !dx)
+          RC(fnb_tc_dw_launch(W.dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratch), stream));
+        else
+          RC(fnb_proj_bwd_impl(xb, P.Wb, wt_of(l, 0), W.dh_b, z.Nb, P.K_bond, dx, D.Wb, nullptr, o->precision, scratch,
+                               stream_));
         dy_bond = need_dx ? W.dx_bond : nullptr;
       } else {
         RC((int)cudaMemsetAsync(D.a_b, 0, 4 * AB_STRIDE * 4, stream));
@@ -505,9 +590,9 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     if (!frag_bwd && D.f) RC((int)cudaMemsetAsync(D.f, 0, 4 * A_STRIDE * 4, stream));
     dy_frag = nullptr;   // the fragment output of a lower layer is dead (overwritten unread, gat2.py:234)
   }
-  // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same Philox stream as the forward
+  // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same RNG stream as the forward
   if (o->need_dx_atoms && io->dx_atoms && input_dropout(o)) {
-    const PhiloxPlan ph = philox_plan(plan, o, L);
+    const RngPlan ph = rng_plan(plan, o, L);
     RC(fnb_dropout_relu_fwd(io->dx_atoms, io->dx_atoms, z.Na * (int64_t)L[0].K_atom, o->drop_p, 1, 0, o->seed, ph.input,
                             stream_));
   }

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict
       col -= segs.padded_width[i];
       seg = i + 1;
     }
-  const bool valid = col < segs.width[seg];
+  const bool valid = col < segs.width[seg] && (col % segs.row_len[seg]) < segs.valid_len[seg];
   float acc = 0.f;
   if (valid) {
     const float *src = partials + segs.rec_off[seg] + col;
@@ -380,6 +380,7 @@ int fnb_launch_reduce_segments(const float *partials, int n_blocks, int pstride,
   int cols = 0;
   for (int i = 0; i < segs.n; ++i) {
     segs.padded_width[i] = (segs.width[i] + 7) & ~7;
+    if (segs.valid_len[i] <= 0 || segs.valid_len[i] > segs.row_len[i]) segs.valid_len[i] = segs.row_len[i];
     cols += segs.padded_width[i];
   }
   if (cols == 0) return 0;
@@ -391,7 +392,7 @@ int fnb_launch_reduce_segments(const float *partials, int n_blocks, int pstride,
 int fnb_launch_reduce_partials(const float *partials, int n_blocks, int pstride, int width, float *out, int row_len,
                                int out_stride, int accumulate, cudaStream_t stream) {
   (void)accumulate;
-  ReduceSegments segs;
+  ReduceSegments segs{};
   segs.n = 1;
   segs.rec_off[0] = 0; segs.width[0] = width; segs.out[0] = out; segs.row_len[0] = row_len;
   segs.out_stride[0] = out_stride;
@@ -454,7 +455,7 @@ extern "C" int fnb_gat_bwd_src(const int32_t *rrowptr, const int32_t *rslot, con
   const int blocks = warp_grid(n_nodes);
   k_gat_bwd_src<<<blocks, kThreads, 0, stream>>>(a);
   FNB_CHECK_LAUNCH();
-  ReduceSegments segs;
+  ReduceSegments segs{};
   segs.n = d_bias ? 3 : 2;
   segs.rec_off[0] = 0;   segs.width[0] = 128; segs.out[0] = d_alpha + off_t; segs.row_len[0] = kHd; segs.out_stride[0] = alpha_stride;
   segs.rec_off[1] = 128; segs.width[1] = 128; segs.out[1] = d_alpha + off_s; segs.row_len[1] = kHd; segs.out_stride[1] = alpha_stride;

@@ -29,6 +29,14 @@ constexpr int T_THREADS = 256;
 constexpr int T_WARPS = T_THREADS / 32;
 constexpr int FWD_CAP = 1024;    // edge slots staged per sub-tile (forward)
 constexpr int BWD_CAP = 768;     // edge slots staged per sub-tile (backward kernels stage two float4 per slot)
+// Bulk-copy staging of the gathered rows.  Batched molecular graphs are block diagonal with consecutive node ids per
+// molecule, so the SOURCES of 64 consecutive destinations lie in a short contiguous id range (bond graph: ~105 rows,
+// atom graph: ~90): instead of E x 512-byte gathers through L1/L2, one cp.async.bulk (TMA) copies that row range
+// into shared memory while the logits are computed, and the aggregation reads it from there.  Tiles whose range
+// exceeds ROWS_CAP (or graphs without range hints) use the gather path.
+constexpr int ROWS_CAP = 160;
+constexpr size_t kStageRowsBytes = (size_t)ROWS_CAP * kD * 4;
+constexpr size_t kStageSBytes = (size_t)ROWS_CAP * 8 * 4;
 
 // Largest le in (lb, nn] whose slots fit `cap`; returns lb when node lb alone exceeds it (hub path).
 __device__ __forceinline__ int subtile_end(const int *s_rowptr, int lb, int nn, int cap) {
@@ -54,6 +62,7 @@ struct FwdT {
   int next_stride;
   float *next_Se;
   int npc;
+  const int *tile_range;
 };
 
 template <int MODE>
@@ -86,9 +95,10 @@ __device__ __forceinline__ float4 edge_term_t(const FwdT &a, int slot, const flo
 }
 
 template <int MODE>
-__device__ __forceinline__ float4 edge_logit(const FwdT &a, int slot, int t, int s, const float *coef) {
+__device__ __forceinline__ float4 edge_logit(const FwdT &a, int slot, int t, int s, const float *coef,
+                                             const float *s_S = nullptr, int lo = 0) {
   const float4 St = ldg4(a.S + (int64_t)t * 8);
-  const float4 Ss = ldg4(a.S + (int64_t)s * 8 + 4);
+  const float4 Ss = s_S ? ld4(s_S + (s - lo) * 8 + 4) : ldg4(a.S + (int64_t)s * 8 + 4);
   const float4 Se = edge_term_t<MODE>(a, slot, coef);
   return make_float4(leaky(St.x + Se.x + Ss.x), leaky(St.y + Se.y + Ss.y), leaky(St.z + Se.z + Ss.z),
                      leaky(St.w + Se.w + Ss.w));
@@ -175,8 +185,11 @@ __device__ void fwd_hub(const FwdT &a, int t, int beg, int end, const float *coe
   fwd_store_row(a, t, acc, s_na);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(T_THREADS, 6) k_gat_fwd_tiled(FwdT a) {
+template <int MODE, bool STAGED>
+__global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(FwdT a) {
+  extern __shared__ __align__(128) float s_dyn[];   // STAGED: [ROWS_CAP][128] rows of h, then [ROWS_CAP][8] rows of S
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ int s_stage[2];
   __shared__ int s_rowptr[T_NPC + 1];
   __shared__ int s_src[FWD_CAP];
   __shared__ __align__(16) float s_l[FWD_CAP * 4];
@@ -187,13 +200,37 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_fwd_tiled(FwdT a) {
   if (MODE == FNB_EDGE_AFFINE6) edge_coef_prologue<6>(a.We, a.be, a.alpha_e, a.alpha_e_stride, s_coef);
   if (a.next_alpha)  // consumer graph's edge slice, 4 heads x 128 columns
     for (int i = tid; i < 4 * kD; i += T_THREADS) s_na[i] = __ldg(a.next_alpha + (int64_t)(i >> 7) * a.next_stride + (i & 127));
+  float *s_rows = s_dyn, *s_S = s_dyn + ROWS_CAP * kD;
+  const uint32_t bar_rows = bulk::smem_u32(&s_bar[0]), bar_S = bulk::smem_u32(&s_bar[1]);
+  uint32_t phase = 0;
+  if (STAGED && tid == 0) {
+    bulk::mbar_init(bar_rows, 1);
+    bulk::mbar_init(bar_S, 1);
+    bulk::mbar_init_fence();
+  }
 
   const int n_tiles = (a.n_nodes + a.npc - 1) / a.npc;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int n0 = tile * a.npc, nn = min(a.npc, a.n_nodes - n0);
-    __syncthreads();  // readers of the previous tile are done; also publishes s_coef
+    __syncthreads();  // readers of the previous tile are done; also publishes s_coef and the barrier init
+    if (STAGED && tid == 0) {  // queue the bulk copies of this tile's source rows (S first: the logits need it first)
+      const int lo = __ldg(a.tile_range + 2 * tile), rows = __ldg(a.tile_range + 2 * tile + 1) - lo;
+      const int ok = rows > 0 && rows <= ROWS_CAP;
+      s_stage[0] = lo;
+      s_stage[1] = ok;
+      if (ok) {
+        bulk::fence_proxy_async();
+        bulk::mbar_expect_tx(bar_S, rows * 32);
+        bulk::copy_g2s(bulk::smem_u32(s_S), a.S + (int64_t)lo * 8, rows * 32, bar_S);
+        bulk::mbar_expect_tx(bar_rows, rows * kD * 4);
+        bulk::copy_g2s(bulk::smem_u32(s_rows), a.h + (int64_t)lo * kD, rows * kD * 4, bar_rows);
+      }
+    }
     if (tid <= nn) s_rowptr[tid] = __ldg(a.rowptr + n0 + tid);
     __syncthreads();
+    const bool staged = STAGED && s_stage[1] != 0;
+    const int lo = STAGED ? s_stage[0] : 0;
+    if (staged) bulk::mbar_wait(bar_S, phase);
     int lb = 0;
     while (lb < nn) {
       const int le = subtile_end(s_rowptr, lb, nn, FWD_CAP);
@@ -207,7 +244,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_fwd_tiled(FwdT a) {
       for (int i = tid; i < cnt; i += T_THREADS) {
         const int slot = e0 + i;
         const int s = __ldg(a.col + slot), t = __ldg(a.row + slot);
-        st4(s_l + i * 4, edge_logit<MODE>(a, slot, t, s, s_coef));
+        st4(s_l + i * 4, edge_logit<MODE>(a, slot, t, s, s_coef, staged ? s_S : nullptr, lo));
         s_src[i] = s;
       }
       __syncthreads();
@@ -218,21 +255,34 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_fwd_tiled(FwdT a) {
         float m = -INFINITY;
         for (int j = b; j < e; ++j) m = fmaxf(m, s_l[j * 4 + hh]);
         float den = 0.f;
-        for (int j = b; j < e; ++j) den += expf(s_l[j * 4 + hh] - m);
-        for (int j = b; j < e; ++j) {
+        for (int j = b; j < e; ++j) {   // one exp per edge; the sign bit keeps (z > 0) for LeakyReLU's derivative
           const float l = s_l[j * 4 + hh];
-          const float p = expf(l - m) / den;
-          s_l[j * 4 + hh] = l > 0.f ? p : -p;  // sign bit = (z > 0): LeakyReLU's derivative for the backward
+          const float ex = expf(l - m);
+          den += ex;
+          s_l[j * 4 + hh] = l > 0.f ? ex : -ex;
         }
+        const float inv = 1.f / den;
+        for (int j = b; j < e; ++j) s_l[j * 4 + hh] *= inv;
       }
       __syncthreads();
       // ---- phase 3: save p (coalesced), then one warp per node aggregates source rows
       if (a.p_saved)
         for (int i = tid; i < cnt; i += T_THREADS) st4(a.p_saved + (int64_t)(e0 + i) * 4, ld4(s_l + i * 4));
+      if (staged) bulk::mbar_wait(bar_rows, phase);
       for (int n = lb + warp; n < le; n += T_WARPS) {
         const int b = s_rowptr[n] - e0, e = s_rowptr[n + 1] - e0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int j = b;
+        if (staged) {  // rows come from the staged range in shared memory
+          for (; j < e; ++j) {
+            const float4 v = ld4(s_rows + (s_src[j] - lo) * kD + lane * 4);
+            const float pj = fabsf(s_l[j * 4 + head]);
+            acc.x = fmaf(pj, v.x, acc.x);
+            acc.y = fmaf(pj, v.y, acc.y);
+            acc.z = fmaf(pj, v.z, acc.z);
+            acc.w = fmaf(pj, v.w, acc.w);
+          }
+        }
         for (; j + 4 <= e; j += 4) {
           float4 v[4];
           float pj[4];
@@ -261,6 +311,10 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_fwd_tiled(FwdT a) {
       }
       lb = le;
       if (lb < nn) __syncthreads();  // next sub-tile overwrites the staging arrays
+    }
+    if (staged) {
+      bulk::mbar_wait(bar_rows, phase);   // (a tile made only of hub nodes never waited: consume the phase)
+      phase ^= 1;
     }
   }
 }
@@ -686,6 +740,42 @@ inline int tile_grid(int64_t n_nodes, int npc, int ctas_per_sm) {
   return (int)tiles;
 }
 
+inline bool use_staging() {
+  // measured slower than the gather path on B200 (profiles/r1h_kbench_stage*.log: 38.9 vs 32.8 us on the bond graph:
+  // the kernel is issue-bound, not L2-bound, and staging costs occupancy), hence opt-in
+  static const bool on = [] { const char *e = getenv("FNB_STAGE"); return e && e[0] == '1'; }();
+  return on;
+}
+
+// Opt in to > 48 KB of dynamic shared memory once per device.
+template <class K>
+int allow_smem(K kernel, size_t bytes, bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
+  if (!done[dev]) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    done[dev] = true;
+  }
+  return 0;
+}
+
+template <int MODE>
+int launch_fwd(const FwdT &a, bool staged, cudaStream_t stream) {
+  if (staged) {
+    static bool done[64] = {};
+    const size_t smem = kStageRowsBytes + kStageSBytes;
+    const int rc = allow_smem(k_gat_fwd_tiled<MODE, true>, smem, done);
+    if (rc) return rc;
+    k_gat_fwd_tiled<MODE, true><<<tile_grid(a.n_nodes, kRangeTile, 2), T_THREADS, smem, stream>>>(a);
+  } else {
+    k_gat_fwd_tiled<MODE, false><<<tile_grid(a.n_nodes, a.npc, 6), T_THREADS, 0, stream>>>(a);
+  }
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
 inline bool graph_ok(const fnb_graph *g) {
   return g && g->n_nodes >= 0 && g->n_edges >= 0 && g->n_nodes < INT32_MAX && g->n_edges < INT32_MAX;
 }
@@ -713,34 +803,29 @@ extern "C" int fnb_gat_fwd_tiled(const fnb_graph *g, const fnb_gat_fwd_args *f, 
   a.mask_lo = (int)f->mask_lo; a.mask_hi = (int)f->mask_hi;
   a.next_alpha = f->next_alpha_e; a.next_stride = f->next_alpha_stride; a.next_Se = f->next_Se;
   a.npc = pick_npc(g->n_nodes);
-  const int grid = tile_grid(g->n_nodes, a.npc, 6);
+  a.tile_range = g->tile_range;
+  const bool staged = use_staging() && g->tile_range != nullptr && a.npc == kRangeTile;
   cudaStream_t stream = (cudaStream_t)stream_;
   switch (f->edge_mode) {
     case FNB_EDGE_NONE:
-      k_gat_fwd_tiled<FNB_EDGE_NONE><<<grid, T_THREADS, 0, stream>>>(a);
-      break;
+      return launch_fwd<FNB_EDGE_NONE>(a, staged, stream);
     case FNB_EDGE_AFFINE1:
       if (!g->edge_attr || !f->We || !f->be || !f->alpha_e) return FNB_ERR_NULL;
       a.edge_attr = g->edge_attr;
-      k_gat_fwd_tiled<FNB_EDGE_AFFINE1><<<grid, T_THREADS, 0, stream>>>(a);
-      break;
+      return launch_fwd<FNB_EDGE_AFFINE1>(a, staged, stream);
     case FNB_EDGE_AFFINE6:
       if (!g->edge_attr || !f->We || !f->be || !f->alpha_e) return FNB_ERR_NULL;
       if (reinterpret_cast<uintptr_t>(g->edge_attr) & 7u) return FNB_ERR_ALIGN;
       a.edge_attr = g->edge_attr;
-      k_gat_fwd_tiled<FNB_EDGE_AFFINE6><<<grid, T_THREADS, 0, stream>>>(a);
-      break;
+      return launch_fwd<FNB_EDGE_AFFINE6>(a, staged, stream);
     case FNB_EDGE_TABLE:
       if (!f->edge_table || !g->eid) return FNB_ERR_NULL;
       if (!fnb_aligned16(f->edge_table)) return FNB_ERR_ALIGN;
       a.edge_attr = f->edge_table;
-      k_gat_fwd_tiled<FNB_EDGE_TABLE><<<grid, T_THREADS, 0, stream>>>(a);
-      break;
+      return launch_fwd<FNB_EDGE_TABLE>(a, staged, stream);
     default:
       return FNB_ERR_MODE;
   }
-  FNB_CHECK_LAUNCH();
-  return 0;
 }
 
 extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, void *stream_) {

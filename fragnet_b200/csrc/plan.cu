@@ -265,6 +265,7 @@ __global__ void k_plan_aux(AuxArgs a) {
 struct PlanLayout {
   // outputs
   int *rowptr[PG], *col[PG], *row[PG], *eid[PG], *slot_of_eid[PG], *rrowptr[PG], *rslot[PG], *rdst[PG];
+  int *tile_range[PG], *rtile_range[PG];
   float *attr_bond, *attr_fbond;
   int *a2f32, *batch32, *frag_batch32, *atom_ptr, *frag_ptr, *status;
   // temporaries
@@ -311,6 +312,9 @@ PlanLayout plan_layout(const fnb_batch_inputs *in, char *base) {
       L.rrowptr[i] = take<int>(base, off, (size_t)z.n_nodes[i] + 1);
       L.rslot[i] = take<int>(base, off, z.n_total[i]);
       L.rdst[i] = take<int>(base, off, z.n_total[i]);
+      const size_t nt = ((size_t)z.n_nodes[i] + kRangeTile - 1) / kRangeTile;
+      L.tile_range[i] = take<int>(base, off, 2 * nt);
+      L.rtile_range[i] = take<int>(base, off, 2 * nt);
     }
   }
   L.attr_bond = take<float>(base, off, in->n_bond_edges);
@@ -443,6 +447,27 @@ extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, siz
     k_plan_rank_reverse<<<grid_for(z.e_total), 256, 0, stream>>>(a);
     FNB_CHECK_LAUNCH();
   }
+  {  // source ranges of every 64-node tile (forward and reverse CSR of the four graphs): one launch
+    RangeJobs rj{};
+    int tiles = 0;
+    for (int i = 0; i < 4; ++i) {
+      if (z.n_nodes[i] == 0) continue;
+      const int nt = (z.n_nodes[i] + kRangeTile - 1) / kRangeTile;
+      const int *rp[2] = {L.rowptr[i], L.rrowptr[i]};
+      const int *cl[2] = {L.col[i], L.rdst[i]};
+      int *outp[2] = {L.tile_range[i], L.rtile_range[i]};
+      for (int d = 0; d < 2; ++d) {
+        const int k = rj.n_jobs++;
+        rj.rowptr[k] = rp[d]; rj.col[k] = cl[d]; rj.n_nodes[k] = z.n_nodes[i]; rj.out[k] = outp[d];
+        rj.tile_base[k] = tiles;
+        tiles += nt;
+      }
+    }
+    rj.total_tiles = tiles;
+    for (int k = rj.n_jobs; k < 8; ++k) rj.tile_base[k] = tiles;
+    const int rc = fnb_launch_tile_ranges(rj, stream);
+    if (rc) return rc;
+  }
   AuxArgs x;
   x.a2f = in->atom_to_frag_ids; x.batch = in->batch; x.frag_batch = in->frag_batch; x.a2f32 = L.a2f32;
   x.batch32 = L.batch32; x.frag_batch32 = L.frag_batch32; x.atom_ptr = L.atom_ptr; x.frag_ptr = L.frag_ptr;
@@ -456,6 +481,7 @@ extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, siz
     g.n_nodes = z.n_nodes[i]; g.n_edges = z.n_total[i]; g.n_real_edges = n_real[i];
     g.rowptr = L.rowptr[i]; g.col = L.col[i]; g.row = L.row[i]; g.eid = L.eid[i]; g.slot_of_eid = L.slot_of_eid[i];
     g.rrowptr = L.rrowptr[i]; g.rslot = L.rslot[i]; g.rdst = L.rdst[i]; g.edge_attr = nullptr;
+    g.tile_range = L.tile_range[i]; g.rtile_range = L.rtile_range[i];
   }
   out->bond.edge_attr = L.attr_bond;
   out->fbond.edge_attr = L.attr_fbond;

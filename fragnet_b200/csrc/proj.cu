@@ -184,6 +184,80 @@ __global__ void __launch_bounds__(256) k_proj_dw(const float *__restrict__ dh, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-sparse projections for the raw input features of layer 0 (K = 167 / 17 / 6: one-hot groups, a dozen non-zeros
+// per row; features.py:43-139).  K is neither a multiple of 4 (no TMA, no tensor-core path) nor worth a dense FFMA
+// sweep: a warp reads 32 feature values at a time, ballots the non-zeros and accumulates only those weight columns.
+// Lane L owns output columns L, L+32, L+64, L+96 (one per head), so the weights -- staged as W[o][K+1] in shared
+// memory, odd row stride -- are read conflict-free.  Skipping zeros is exact: fma(0, w, acc) == acc, so the result
+// equals the dense k-ascending FFMA chain bit for bit.
+constexpr int kSparseRowsPerIter = 4;
+
+__global__ void __launch_bounds__(256) k_proj_rowsparse_fwd(const float *__restrict__ x, const float *__restrict__ W,
+                                                             const float *__restrict__ bias, int64_t n_rows, int K,
+                                                             const float *__restrict__ alpha, int alpha_stride,
+                                                             int off_t, int off_s, float *__restrict__ h,
+                                                             float *__restrict__ S) {
+  extern __shared__ float s_W[];  // [128][K+1]
+  const int ld = K + 1;
+  for (int idx = threadIdx.x; idx < 128 * K; idx += blockDim.x) s_W[(idx / K) * ld + idx % K] = __ldg(W + idx);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float b4[4], at[4], as[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    b4[i] = bias ? __ldg(bias + lane + 32 * i) : 0.f;
+    at[i] = S ? __ldg(alpha + i * alpha_stride + off_t + lane) : 0.f;   // column lane + 32 i belongs to head i
+    as[i] = S ? __ldg(alpha + i * alpha_stride + off_s + lane) : 0.f;
+  }
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int n_chunks = (K + 31) >> 5;
+  for (int64_t r0 = w0 * kSparseRowsPerIter; r0 < n_rows; r0 += nw * kSparseRowsPerIter) {
+    float acc[kSparseRowsPerIter][4];
+#pragma unroll
+    for (int r = 0; r < kSparseRowsPerIter; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[r][i] = b4[i];
+    for (int c = 0; c < n_chunks; ++c) {
+      const int k = c * 32 + lane;
+      float xv[kSparseRowsPerIter];
+#pragma unroll
+      for (int r = 0; r < kSparseRowsPerIter; ++r)   // all loads of the iteration are in flight together
+        xv[r] = (k < K && r0 + r < n_rows) ? __ldg(x + (r0 + r) * K + k) : 0.f;
+#pragma unroll
+      for (int r = 0; r < kSparseRowsPerIter; ++r) {
+        unsigned m = __ballot_sync(kFull, xv[r] != 0.f);
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const float xk = __shfl_sync(kFull, xv[r], bit);
+          const float *w = s_W + lane * ld + c * 32 + bit;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[r][i] = fmaf(xk, w[32 * i * ld], acc[r][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kSparseRowsPerIter; ++r) {
+      const int64_t row = r0 + r;
+      if (row >= n_rows) break;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[row * kD + lane + 32 * i] = acc[r][i];
+      if (S) {
+        const float st = warp_sum4(acc[r][0] * at[0], acc[r][1] * at[1], acc[r][2] * at[2], acc[r][3] * at[3]);
+        const float ss = warp_sum4(acc[r][0] * as[0], acc[r][1] * as[1], acc[r][2] * as[2], acc[r][3] * as[3]);
+        if ((lane & 7) == 0) {
+          S[row * 8 + (lane >> 3)] = st;
+          S[row * 8 + 4 + (lane >> 3)] = ss;
+        }
+      }
+    }
+  }
+}
+
+inline bool rowsparse_shape(int K) { return (K & 3) != 0 || K < 32; }
+
 // S for un-projected features: one warp per row.
 __global__ void __launch_bounds__(256) k_node_scalars(const float *__restrict__ h, int64_t n_rows,
                                                       const float *__restrict__ alpha, int alpha_stride, int off_t,
@@ -261,6 +335,25 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
   } else if (precision != FNB_PRECISION_FP32) {
     return FNB_ERR_MODE;
   }
+  if (rowsparse_shape(K) && K <= kProjBwdMaxK) {
+    const size_t smem = (size_t)128 * (K + 1) * sizeof(float);
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !done[dev]) {
+      const cudaError_t e = cudaFuncSetAttribute(k_proj_rowsparse_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)((size_t)128 * (kProjBwdMaxK + 1) * sizeof(float)));
+      if (e != cudaSuccess) return (int)e;
+      done[dev] = true;
+    }
+    const int per_sm = smem > 64 * 1024 ? 2 : 4;
+    int64_t blocks = (n_rows + 8 * kSparseRowsPerIter - 1) / (8 * kSparseRowsPerIter);
+    if (blocks > kNumSMs * per_sm) blocks = kNumSMs * per_sm;
+    k_proj_rowsparse_fwd<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, W, b, n_rows, K, alpha, alpha_stride, off_t,
+                                                                          off_s, h, S);
+    FNB_CHECK_LAUNCH();
+    return 0;
+  }
   GemmArgs g;
   g.A = x; g.lda = K; g.B = W; g.ldb = K; g.C = h; g.ldc = kD; g.M = n_rows; g.Kd = K; g.Nc = kD; g.bias = b;
   g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s; g.S = S;
@@ -307,7 +400,7 @@ int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const
     FNB_CHECK_LAUNCH();
   }
   if (precision == FNB_PRECISION_TF32 && K == kD && n_rows > 0 && !db) {
-    const int rc = fnb_tc_dw_launch(dh, x, n_rows, dW, scratch_body(scratch), stream);
+    const int rc = fnb_tc_dw_launch(dh, x, n_rows, kD, kD, dW, scratch_body(scratch), stream);
     if (rc != FNB_ERR_MODE) return rc;
   }
   int64_t nb = (n_rows + 255) / 256;
@@ -320,7 +413,7 @@ int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const
   dim3 grid((unsigned)nb, (unsigned)((K + 127) / 128));
   k_proj_dw<<<grid, 256, 0, stream>>>(dh, x, n_rows, K, rows_per_block, scratch_body(scratch), rec_stride);
   FNB_CHECK_LAUNCH();
-  ReduceSegments segs;
+  ReduceSegments segs{};
   segs.n = db ? 2 : 1;
   segs.rec_off[0] = 0;       segs.width[0] = 128 * K; segs.out[0] = dW; segs.row_len[0] = 128 * K; segs.out_stride[0] = 128 * K;
   segs.rec_off[1] = 128 * K; segs.width[1] = 128;     segs.out[1] = db; segs.row_len[1] = 128;     segs.out_stride[1] = 128;

@@ -269,8 +269,12 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 // box c holds columns 32c..32c+31, rows 128 bytes apart => LBO = 4096 bytes between column chunks, SBO = 512 bytes
 // between 4-row atoms; one tcgen05.mma (K = 8 rows) consumes 1024 bytes of every chunk.  Every CTA reduces a contiguous range of
 // row blocks into one TMEM accumulator and writes a 128x128 partial; a fixed-order second stage sums the partials.
-constexpr int DW_STAGE_BYTES = 2 * TC_STAGE_BYTES;   // dH block (16 KiB) + X block (16 KiB)
-constexpr int DW_STAGES = 6;
+// The X operand may be narrower or wider than 128 columns (layer-0 inputs padded to 32 / 192 columns): n_chunks = width / 32.
+constexpr int DW_MAX_STAGES = 6;
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(int n_cols) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n_cols >> 3) << 17) |
+         ((uint32_t)(TC_BM >> 4) << 24);
+}
 
 __device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t saddr) {
   uint64_t d = 0;
@@ -281,21 +285,22 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t saddr) {
   d |= (uint64_t)1 << 61;             // SWIZZLE_128B_BASE32B
   return d;
 }
-constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);   // A and B MN-major
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUtensorMap tm_x, float *partials,
-        int64_t n_row_blocks, int64_t blocks_per_cta) {
+        int64_t n_row_blocks, int64_t blocks_per_cta, int n_chunks, int n_stages, uint32_t tmem_cols) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * DW_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * DW_MAX_STAGES + 1];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = TC_STAGE_BYTES + (uint32_t)n_chunks * 4096u;   // dH block (16 KiB) + X block
   const uint32_t bar_full = smem_u32(&bars[0]);
-  const uint32_t bar_empty = smem_u32(&bars[DW_STAGES]);
-  const uint32_t bar_done = smem_u32(&bars[2 * DW_STAGES]);
+  const uint32_t bar_empty = smem_u32(&bars[DW_MAX_STAGES]);
+  const uint32_t bar_done = smem_u32(&bars[2 * DW_MAX_STAGES]);
+  const int n_cols = n_chunks * 32;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < DW_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -304,7 +309,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
   }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                 "r"(128)
+                 "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -320,30 +325,29 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
       uint32_t stage = 0, phase = 0;
       for (int64_t rb = rb_begin; rb < rb_end; ++rb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        mbar_arrive_expect_tx(bar_full + 8 * stage, DW_STAGE_BYTES);
-        const uint32_t a_addr = smem_base + stage * DW_STAGE_BYTES, b_addr = a_addr + TC_STAGE_BYTES;
+        mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
+        const uint32_t a_addr = smem_base + stage * stage_bytes, b_addr = a_addr + TC_STAGE_BYTES;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tma_load_2d(a_addr + c * 4096, &tm_dh, bar_full + 8 * stage, c * 32, (int)(rb * 32));
-          tma_load_2d(b_addr + c * 4096, &tm_x, bar_full + 8 * stage, c * 32, (int)(rb * 32));
-        }
-        if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+        for (int c = 0; c < 4; ++c) tma_load_2d(a_addr + c * 4096, &tm_dh, bar_full + 8 * stage, c * 32, (int)(rb * 32));
+        for (int c = 0; c < n_chunks; ++c) tma_load_2d(b_addr + c * 4096, &tm_x, bar_full + 8 * stage, c * 32, (int)(rb * 32));
+        if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
     if (lane == 0) {
+      const uint32_t idesc = idesc_tf32_mn(n_cols);
       uint32_t stage = 0, phase = 0;
       for (int64_t rb = rb_begin; rb < rb_end; ++rb) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * DW_STAGE_BYTES, b_addr = a_addr + TC_STAGE_BYTES;
+        const uint32_t a_addr = smem_base + stage * stage_bytes, b_addr = a_addr + TC_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           tc_mma_tf32(tmem_base, make_desc_sw128_mnmajor(a_addr + k * 1024), make_desc_sw128_mnmajor(b_addr + k * 1024),
-                      kIdescTf32MN, (rb != rb_begin) || (k != 0));
+                      idesc, (rb != rb_begin) || (k != 0));
         tc_commit(bar_empty + 8 * stage);
-        if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
       }
       tc_commit(bar_done);
     }
@@ -351,9 +355,8 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
   } else {
     mbar_wait(bar_done, 0);
     tc_fence_after();
-    float *rec = partials + ((int64_t)blockIdx.x * 128 + warp * 32 + lane) * 128;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    float *rec = partials + ((int64_t)blockIdx.x * 128 + warp * 32 + lane) * n_cols;
+    for (int c = 0; c < n_chunks; ++c) {
       uint32_t r[32];
       tc_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, r);
 #pragma unroll
@@ -366,7 +369,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -439,8 +442,18 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
   g.C = C; g.bias = bias; g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s;
   g.S = alpha ? S : nullptr; g.M = M; g.n_kb = (K + TC_BK - 1) / TC_BK;
   const size_t smem = (size_t)(g.n_kb + TC_STAGES) * TC_STAGE_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_tc_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  {  // opt in to the largest dynamic shared memory this kernel can ask for, once per device
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
+    if (!done[dev]) {
+      const cudaError_t e = cudaFuncSetAttribute(k_tc_proj, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (TC_MAX_KB + TC_STAGES) * TC_STAGE_BYTES + 1024);
+      if (e != cudaSuccess) return (int)e;
+      done[dev] = true;
+    }
+  }
   const int64_t n_tiles = (M + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   k_tc_proj<<<grid, TC_THREADS, smem, stream>>>(tm_a, tm_b, g);
@@ -461,22 +474,45 @@ int fnb_tc_transpose128_batched(const TransposeBatch &b, float *Wt_base, cudaStr
   return 0;
 }
 
-// dW[128,128] = dH[n,128]^T @ X[n,128] (TF32).  scratch must hold kNumSMs * 128 * 128 floats of partials.
-int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, float *dW, float *scratch,
+// dW[128, k_out] = dH[n,128]^T @ X[n, x_cols] (TF32), x_cols a multiple of 32 up to 256 (columns >= k_out are padding and
+// are dropped by the second stage).  scratch must hold kNumSMs * 128 * x_cols floats of partials.
+int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols, int k_out, float *dW, float *scratch,
                      cudaStream_t stream) {
-  if (n_rows <= 0 || !fnb_aligned16(dh) || !fnb_aligned16(x) || n_rows >= (int64_t)INT32_MAX) return FNB_ERR_MODE;
+  if (n_rows <= 0 || !fnb_aligned16(dh) || !fnb_aligned16(x) || n_rows >= (int64_t)INT32_MAX || x_cols < 32 ||
+      x_cols > 256 || (x_cols & 31) || k_out > x_cols || k_out <= 0)
+    return FNB_ERR_MODE;
   CUtensorMap tm_dh, tm_x;
   int rc = make_map(&tm_dh, dh, n_rows, 128, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
-  rc = make_map(&tm_x, x, n_rows, 128, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = make_map(&tm_x, x, n_rows, x_cols, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
+  const int n_chunks = x_cols / 32;
   const int64_t n_rb = (n_rows + 31) / 32;
   const int64_t per = (n_rb + kNumSMs - 1) / kNumSMs;
   const int grid = (int)((n_rb + per - 1) / per);
-  const size_t smem = (size_t)DW_STAGES * DW_STAGE_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  k_tc_dw<<<grid, TC_THREADS, smem, stream>>>(tm_dh, tm_x, scratch, n_rb, per);
+  const size_t stage_bytes = (size_t)TC_STAGE_BYTES + (size_t)n_chunks * 4096;
+  int n_stages = (int)((200 * 1024) / stage_bytes);
+  if (n_stages > DW_MAX_STAGES) n_stages = DW_MAX_STAGES;
+  const size_t smem = (size_t)n_stages * stage_bytes + 1024;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < x_cols) tmem_cols <<= 1;
+  {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
+    if (!done[dev]) {
+      const cudaError_t e = cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024);
+      if (e != cudaSuccess) return (int)e;
+      done[dev] = true;
+    }
+  }
+  k_tc_dw<<<grid, TC_THREADS, smem, stream>>>(tm_dh, tm_x, scratch, n_rb, per, n_chunks, n_stages, tmem_cols);
   FNB_CHECK_LAUNCH();
-  return fnb_launch_reduce_partials(scratch, grid, 128 * 128, 128 * 128, dW, 128 * 128, 128 * 128, 0, stream);
+  // second stage: record [128][x_cols] -> dW [128][k_out]
+  ReduceSegments segs{};
+  segs.n = 1;
+  segs.rec_off[0] = 0; segs.width[0] = 128 * x_cols; segs.out[0] = dW; segs.row_len[0] = x_cols; segs.out_stride[0] = k_out;
+  segs.valid_len[0] = k_out;
+  return fnb_launch_reduce_segments(scratch, grid, 128 * x_cols, segs, stream);
 }

@@ -83,6 +83,8 @@ class GraphCSR:
     rdst: Optional[torch.Tensor] = None
     status: Optional[torch.Tensor] = None   # int32[1], non-zero if an index was out of range
     attr: Optional[torch.Tensor] = None     # per-edge attributes permuted into slot order
+    tile_range: Optional[torch.Tensor] = None    # [ceil(N/64), 2] source range of every 64-destination tile
+    rtile_range: Optional[torch.Tensor] = None   # same for the reverse CSR
     _c: Optional[_abi.CGraph] = field(default=None, repr=False)
 
     def cstruct(self) -> _abi.CGraph:
@@ -91,7 +93,7 @@ class GraphCSR:
             a = lambda t: None if t is None else t.data_ptr()
             self._c = _abi.CGraph(self.n_nodes, self.n_edges, self.n_real, a(self.rowptr), a(self.col), a(self.row),
                                   a(self.eid), a(self.slot_of_eid), a(self.rrowptr), a(self.rslot), a(self.rdst),
-                                  a(self.attr))
+                                  a(self.tile_range), a(self.rtile_range), a(self.attr))
         return self._c
 
 
@@ -122,7 +124,15 @@ def csr_build(dst: torch.Tensor, src: Optional[torch.Tensor], n_nodes: int, self
     rc = lib.fnb_csr_build(_p(dst), _p(src), E, n_nodes, int(self_loops), _p(rowptr), _p(col), _p(row), _p(eid),
                            _p(slot_of_eid), _p(rrowptr), _p(rslot), _p(rdst), _p(ws), ws_bytes, _p(status), _stream())
     _abi.check(rc, "csr_build")
-    return GraphCSR(n_nodes, total, E, rowptr, col, row, eid, slot_of_eid, rrowptr, rslot, rdst, status)
+    g = GraphCSR(n_nodes, total, E, rowptr, col, row, eid, slot_of_eid, rrowptr, rslot, rdst, status)
+    if n_nodes > 0 and src is not None:
+        nt = (n_nodes + 63) // 64
+        g.tile_range = torch.empty((nt, 2), **i32)
+        _abi.check(lib.fnb_tile_ranges(_p(rowptr), _p(col), n_nodes, _p(g.tile_range), _stream()), "tile_ranges")
+        if reverse:
+            g.rtile_range = torch.empty((nt, 2), **i32)
+            _abi.check(lib.fnb_tile_ranges(_p(rrowptr), _p(rdst), n_nodes, _p(g.rtile_range), _stream()), "tile_ranges")
+    return g
 
 
 def gather_rows(src: torch.Tensor, index: torch.Tensor, n_rows: int) -> torch.Tensor:
@@ -219,6 +229,9 @@ class LayerPlan:
                              self._view(cg.row, e), self._view(cg.eid, e), self._view(cg.slot_of_eid, e),
                              self._view(cg.rrowptr, n + 1), self._view(cg.rslot, e), self._view(cg.rdst, e),
                              self._view(self.c.status, 1), attr.view(e, aw) if aw > 1 else attr)
+                nt = (n + 63) // 64
+                g.tile_range = self._view(cg.tile_range, 2 * nt)
+                g.rtile_range = self._view(cg.rtile_range, 2 * nt)
                 g._c = cg
             self._views[name] = g
         return self._views[name]
@@ -493,24 +506,24 @@ def segment_gather(g, g_stride, seg_of, n_rows, base=None):
     return dx
 
 
-_philox_offset = 0
+_rng_offset = 0
 
 
-def next_philox(n_elems: int):
-    """(seed, offset) for one dropout call; the offset stream advances by the number of Philox
+def next_rng(n_elems: int):
+    """(seed, offset) for one dropout call; the offset stream advances by the number of RNG
     counters the call consumes, so no two calls of a run share random numbers."""
-    global _philox_offset
-    off = _philox_offset
-    _philox_offset += (n_elems + 3) // 4
+    global _rng_offset
+    off = _rng_offset
+    _rng_offset += (n_elems + 3) // 4
     return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, off
 
 
-def reserve_philox(n_counters: int) -> int:
-    """First counter of a block of ``n_counters`` Philox counters (whole-encoder calls reserve all their dropout sites
-    at once: ``fnb_encoder_philox_span``)."""
-    global _philox_offset
-    off = _philox_offset
-    _philox_offset += int(n_counters)
+def reserve_rng(n_counters: int) -> int:
+    """First counter of a block of ``n_counters`` RNG counters (whole-encoder calls reserve all their dropout sites
+    at once: ``fnb_encoder_rng_span``)."""
+    global _rng_offset
+    off = _rng_offset
+    _rng_offset += int(n_counters)
     return off
 
 

@@ -30,7 +30,7 @@ extern "C" {
 
 #define FNB_D 128 /* embedding width  */
 #define FNB_H 4   /* attention heads  */
-#define FNB_ABI_VERSION 2
+#define FNB_ABI_VERSION 3
 
 /* edge-term modes of the fused attention kernels */
 /* arithmetic of the dense projections */
@@ -67,6 +67,10 @@ int fnb_csr_build(const int64_t *dst, const int64_t *src, int64_t n_edges, int64
                   int append_self_loops, int32_t *rowptr, int32_t *col, int32_t *row, int32_t *eid,
                   int32_t *slot_of_eid, int32_t *rrowptr, int32_t *rslot, int32_t *rdst,
                   void *workspace, size_t workspace_bytes, int32_t *status, void *stream);
+
+/* Per tile of 64 consecutive rows of a CSR (rowptr/col), the half-open range [lo, hi) of the column indices met:
+ * ranges[2*t] = lo, ranges[2*t+1] = hi (lo = hi = 0 for a tile without edges).  n_tiles = ceil(n_nodes / 64). */
+int fnb_tile_ranges(const int32_t *rowptr, const int32_t *col, int64_t n_nodes, int32_t *ranges, void *stream);
 
 /* out[r, 0:width] = in[index[r], 0:width]  -- puts per-edge attributes into CSR slot order. */
 int fnb_gather_rows(const float *in, const int32_t *index, int64_t n_rows, int width, float *out,
@@ -166,10 +170,14 @@ typedef struct fnb_graph {
   int64_t n_nodes, n_edges, n_real_edges; /* n_edges includes appended self loops */
   const int32_t *rowptr, *col, *row, *eid, *slot_of_eid; /* destination-sorted CSR (fnb_csr_build) */
   const int32_t *rrowptr, *rslot, *rdst;                 /* reverse (source-sorted) CSR             */
+  /* Optional locality hints for the bulk-copy (TMA) staging of gathered rows: for every tile of 64 consecutive
+   * destination nodes, [lo, hi) bounds the SOURCE nodes of its edges (tile_range[2*t], tile_range[2*t+1]); rtile_range
+   * likewise bounds the DESTINATIONS met by 64 consecutive sources in the reverse CSR.  NULL = always gather. */
+  const int32_t *tile_range, *rtile_range;
   const float *edge_attr; /* slot-ordered attributes: [E] (bond graph), [E,6] (fragment-connection graph), else NULL */
 } fnb_graph;
 
-typedef struct fnb_post_act { /* y = ReLU(Dropout_p(out)); Philox counter of element i is offset + i/4 */
+typedef struct fnb_post_act { /* y = ReLU(Dropout_p(out)); RNG counter of element i is offset + i/4 */
   float p;
   int training, relu;
   uint64_t seed, offset;
@@ -284,7 +292,7 @@ typedef struct fnb_encoder_opts {
   int post_act;          /* 1: ReLU(Dropout) between layers and on the outputs; 0: bare layer (n_layers must be 1) */
   float drop_p;
   int training;
-  uint64_t seed, offset; /* Philox key / first counter; the call consumes fnb_encoder_philox_span() counters */
+  uint64_t seed, offset; /* RNG key / first counter; the call consumes fnb_encoder_rng_span() counters */
   int precision;         /* FNB_PRECISION_* for the dense projections */
   int save_for_backward; /* keep what fnb_encoder_backward needs */
   int need_dx_atoms, need_dx_bond, need_dx_fbond; /* backward: gradients of the layer-0 inputs */
@@ -304,7 +312,7 @@ size_t fnb_encoder_workspace_bytes(const fnb_batch_plan *plan, const fnb_encoder
                                    const fnb_layer_params *layers);
 size_t fnb_encoder_bwd_workspace_bytes(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
                                        const fnb_layer_params *layers);
-uint64_t fnb_encoder_philox_span(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
+uint64_t fnb_encoder_rng_span(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
                                  const fnb_layer_params *layers);
 int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder_opts *opts, const fnb_layer_params *layers,
                         const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
@@ -327,13 +335,18 @@ int fnb_segment_gather(const float *g, int64_t g_stride, const int32_t *seg_of, 
                        const float *base, float *dx, void *stream);
 
 /* ---- fused ReLU(Dropout(x)) (gat2.py:414-418,436-440) ----------------------------------------
- * y = relu(keep(i) ? x/(1-p) : 0), keep from Philox4x32-10(seed, offset + i/4).  p = 0 or
+ * y = relu(keep(i) ? x/(1-p) : 0), keep from the counter hash of common.cuh (seed, offset + i/4).  p = 0 or
  * training == 0 gives plain ReLU.  relu == 0 gives plain dropout (input features, gat2.py:396). */
 int fnb_dropout_relu_fwd(const float *x, float *y, int64_t n, float p, int training, int relu,
                          uint64_t seed, uint64_t offset, void *stream);
 /* dx = dy * (y > 0) / (1-p)   (valid for the fused ReLU form; y is the forward output) */
 int fnb_dropout_relu_bwd(const float *dy, const float *y, float *dx, int64_t n, float p,
                          int training, void *stream);
+
+/* ---- optimizer step over one flat parameter buffer (the trainer's torch.optim.Adam, pretrain_gat2.py:165) -------
+ * torch.optim.Adam's update (no amsgrad) on n contiguous fp32 elements in ONE launch; step counts from 1. */
+int fnb_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, void *stream);
 
 #ifdef __cplusplus
 }

@@ -176,3 +176,28 @@ def test_dropout_relu_statistics_and_backward():
     d = ops.dropout_relu_fwd(odd, 0.5, True, False, 9, 0)
     frac = (d != 0).float().mean().item()
     assert abs(frac - 0.5) < 0.02 and torch.allclose(d[d != 0], (odd * 2)[d != 0])
+
+
+@pytest.mark.parametrize("n,K", [(5000, 167), (9001, 17), (777, 6), (3, 167)])
+def test_rowsparse_projection_on_one_hot_features(n, K):
+    """Layer-0 inputs are one-hot groups (features.py:43-139): the row-sparse kernels must equal the dense fp32 result."""
+    from fragnet_b200 import ops
+    g = torch.Generator().manual_seed(n + K)
+    x = torch.zeros(n, K)
+    for _ in range(min(K, 9)):                       # ~9 non-zeros per row, some of them not 1.0
+        x[torch.arange(n), torch.randint(0, K, (n,), generator=g)] = 1.0
+    x[:, K - 1] = torch.randint(0, 5, (n,), generator=g).float()
+    W = torch.randn(128, K, generator=g) * 0.2
+    b = torch.randn(128, generator=g)
+    alpha = torch.randn(4, 192, generator=g)
+    h, S = ops.proj_fwd(x.cuda(), W.cuda(), b.cuda(), alpha.cuda(), 192, 0, 160)
+    href = F.linear(x, W, b)
+    assert rel_err(h, href) <= FP32_REL_TOL
+    hv = href.view(n, 4, 32)
+    Sref = torch.cat([(hv * alpha[:, 0:32]).sum(-1), (hv * alpha[:, 160:192]).sum(-1)], dim=1)
+    assert rel_err(S, Sref) <= FP32_REL_TOL
+    dh = torch.randn(n, 128, generator=g)
+    _, dW, _ = ops.proj_bwd(x.cuda(), W.cuda(), dh.cuda(), False, want_db=False)
+    assert rel_err(dW, dh.t() @ x) <= 2e-5
+    _, dW2, _ = ops.proj_bwd(x.cuda(), W.cuda(), dh.cuda(), False, want_db=False)
+    assert torch.equal(dW, dW2)                      # deterministic

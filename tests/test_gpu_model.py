@@ -207,3 +207,28 @@ def test_gradients_are_run_to_run_deterministic():
     for k in grads[0]:
         if "pretrain" in k:                # our kernels: bitwise; the torch head may use split-K atomics
             assert torch.equal(grads[0][k], grads[1][k]), k
+
+
+def test_flat_adam_equals_torch_adam():
+    """FlatAdam (one launch over a flat buffer) follows torch.optim.Adam step for step; state_dict keys survive."""
+    from fragnet.model.gat.gat2 import FragNetFineTune
+    from fragnet_b200.train.optim import FlatAdam
+    b = _to(_batch("esol", 10, 3, pretrain=False), "cuda")
+    torch.manual_seed(11)
+    m1 = FragNetFineTune(num_layer=2, drop_ratio=0.0, h1=32, h2=32, h3=32, h4=32, act="relu").cuda()
+    m2 = copy.deepcopy(m1)
+    keys = list(m1.state_dict().keys())
+    o1 = o2 = None
+    for step in range(3):
+        for m in (m1, m2):
+            for p in m.parameters():
+                p.grad = None
+            m(b).pow(2).mean().backward()
+        if o1 is None:
+            o1 = torch.optim.Adam([p for p in m1.parameters() if p.grad is not None], lr=1e-3)
+            o2 = FlatAdam([p for p in m2.parameters() if p.grad is not None], lr=1e-3)
+        o1.step()
+        o2.step()
+    assert list(m2.state_dict().keys()) == keys
+    for (k, a), (_, c) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert rel_err(c, a) <= 2e-5, k

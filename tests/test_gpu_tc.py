@@ -84,6 +84,16 @@ def test_model_in_tf32_mode_within_stated_tolerance():
     assert rel_err(pred, ref) <= 5e-3
     g = dict(m.named_parameters())["pretrain.layers.1.projection_b.weight"].grad
     assert rel_err(g, P["pretrain.layers.1.projection_b.weight"].grad) <= 2e-2
+    # every gradient, including the layer-0 weight gradients that come from the zero-padded tensor-core path
+    from conftest import grad_errs
+    named = dict(m.named_parameters())
+    errs = grad_errs([(k, named[k].grad, P[k].grad) for k in named if P[k].grad is not None])
+    assert all(k in errs for k in ("pretrain.layers.0.projection_a.weight", "pretrain.layers.0.projection_b.weight",
+                                   "pretrain.layers.0.projection_fb.weight"))
+    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    assert not bad, bad
+    for k in named:
+        assert (named[k].grad is None) == (P[k].grad is None), k
 
 
 def test_tc_projection_speed_report(capsys):

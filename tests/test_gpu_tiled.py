@@ -9,10 +9,13 @@ from conftest import FP32_REL_TOL, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _graph(n_nodes, n_edges, seed, hub_edges=0):
+def _graph(n_nodes, n_edges, seed, hub_edges=0, band=0):
     g = torch.Generator().manual_seed(seed)
     dst = torch.randint(0, n_nodes, (n_edges,), generator=g)
-    src = torch.randint(0, n_nodes, (n_edges,), generator=g)
+    if band:     # block-diagonal-like locality (sources within +-band of the destination): the bulk-copy staged path
+        src = (dst + torch.randint(-band, band + 1, (n_edges,), generator=g)).clamp_(0, n_nodes - 1)
+    else:
+        src = torch.randint(0, n_nodes, (n_edges,), generator=g)
     dst[:n_nodes] = torch.arange(n_nodes)           # every node is a target (reference requirement, App. B)
     if hub_edges:
         dst[n_nodes:n_nodes + hub_edges] = 1        # one destination segment far above the tile capacity
@@ -21,6 +24,8 @@ def _graph(n_nodes, n_edges, seed, hub_edges=0):
 
 
 CASES = [
+    (20000, 130000, -30),  # 64-node tiles with local sources: rows staged by cp.async.bulk (negative = band width)
+    (20000, 130000, -100), # ranges above the staging capacity: gather fallback inside the staged kernel
     (40, 200, 0),          # one partial tile
     (64, 3000, 0),         # one tile, several sub-tiles (3000 slots > capacity)
     (50, 6000, 2500),      # hub paths: in-degree and out-degree above the capacity of a sub-tile
@@ -34,7 +39,7 @@ CASES = [
 def test_tiled_attention_forward_backward(mode, n_nodes, n_edges, hub):
     from fragnet_b200 import ops
     from oracle import gat2_oracle as O
-    dst, src = _graph(n_nodes, n_edges, 11 + n_nodes, hub)
+    dst, src = _graph(n_nodes, n_edges, 11 + n_nodes, max(hub, 0), band=max(-hub, 0))
     gen = torch.Generator().manual_seed(n_edges)
     h = torch.randn(n_nodes, 128, generator=gen).requires_grad_()
     gout = torch.randn(n_nodes, 128, generator=gen)
