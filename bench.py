@@ -229,14 +229,51 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
-
+def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="tf32", rank=0, world=1, dev=None,
+              return_host=False):
+    """The timed unit: ``step(batch_dict)`` = on-device collate + forward + loss + backward + gradient all-reduce
+    (world > 1) + Adam on one batch.  Returns (step, device batches[, pinned host batches])."""
     from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
-    from fragnet_b200 import _abi
+    from fragnet_b200 import config, ops
     from fragnet_b200.dist import FlatGradSync
     from fragnet_b200.train.optim import FlatAdam
     from fragnet_b200.train.pretrain_utils import pretrain_loss
+    dev = dev or torch.device("cuda", torch.cuda.current_device())
+    config.set_precision(precision)
+    if precision == "tf32":      # the nn.Linear heads (library GEMMs) follow the same precision switch
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(1234)                      # identical initial weights on every rank
+    model = FragNetPreTrain(**PT_KW).to(dev).train()
+    loss_fn = torch.nn.MSELoss()
+    host_batches = make_batches(shape, batch, rotate, pool, seed=100 + rank)
+    for b in host_batches:
+        for k in b:
+            b[k] = b[k].pin_memory()
+    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
+    sync = FlatGradSync(model.parameters())
+    opt = None
+
+    def step(b):
+        nonlocal opt
+        ops.clear_plan_cache()       # every step is a new batch to the model: the on-device collate is always timed
+        sync.zero()
+        loss = pretrain_loss(loss_fn, model(b), b)
+        loss.backward()
+        sync.sync()
+        if opt is None:          # Adam over the live parameters (grad-less ones are skipped by torch's Adam too)
+            opt = FlatAdam(sync.live_parameters(), lr=LR)
+        opt.step(sync.flat if world > 1 else None)
+        return loss
+
+    return (step, dev_batches, host_batches) if return_host else (step, dev_batches)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from fragnet_b200 import _abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -249,36 +286,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _abi.load()
-    from fragnet_b200 import config
-    config.set_precision(args.precision)
-    if args.precision == "tf32":      # the nn.Linear heads (library GEMMs) follow the same precision switch
-        torch.backends.cuda.matmul.allow_tf32 = True
-        torch.backends.cudnn.allow_tf32 = True
-
-    torch.manual_seed(1234)                      # identical initial weights on every rank
-    model = FragNetPreTrain(**PT_KW).to(dev).train()
-    loss_fn = torch.nn.MSELoss()
-    host_batches = make_batches(args.shape, args.batch, args.rotate, args.pool, seed=100 + rank)
-    for b in host_batches:
-        for k in b:
-            b[k] = b[k].pin_memory()
-    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
-    sync = FlatGradSync(model.parameters())
-    opt = None
-
-    from fragnet_b200 import ops
-
-    def step(batch):
-        nonlocal opt
-        ops.clear_plan_cache()       # every step is a new batch to the model: the on-device collate is always timed
-        sync.zero()
-        loss = pretrain_loss(loss_fn, model(batch), batch)
-        loss.backward()
-        sync.sync()
-        if opt is None:          # Adam over the live parameters (grad-less ones are skipped by torch's Adam too)
-            opt = FlatAdam(sync.live_parameters(), lr=LR)
-        opt.step(sync.flat if world > 1 else None)
-        return loss
+    step, dev_batches, host_batches = make_step(args.batch, args.shape, args.rotate, args.pool, args.precision, rank,
+                                                world, dev, return_host=True)
 
     def barrier():
         if world > 1:

@@ -51,6 +51,11 @@ SIGNATURES = {
     "fnb_encoder_rng_span": (_u64, [_vp, _vp, _vp]),
     "fnb_encoder_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "fnb_encoder_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "fnb_pretrain_heads_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "fnb_pretrain_heads_bwd_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "fnb_pretrain_heads_forward": (C.c_int, [_vp, _vp, _i32, _vp, _sz, _vp, _vp]),
+    "fnb_pretrain_heads_backward": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "fnb_mse_sum_loss": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
 }
 
 
@@ -79,7 +84,7 @@ class CGatBwdArgs(C.Structure):
                 ("dz", _vp), ("dSt", _vp), ("dh", _vp), ("d_alpha", _vp), ("d_bias", _vp), ("dWe", _vp), ("dbe", _vp),
                 ("scratch", _vp)]
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_TF32 = 0, 1
 
@@ -157,3 +162,26 @@ class CEncoderIO(C.Structure):
     _fields_ = [(n, _vp) for n in ("x_atoms", "x_bond", "x_fbond", "out_atoms", "out_frags", "out_bond", "out_fbond",
                                    "attn_atoms", "attn_frags", "attn_bonds", "attn_fbonds", "g_atoms", "g_frags",
                                    "g_bond", "g_fbond", "dx_atoms", "dx_bond", "dx_fbond")]
+
+
+MLP3_FIELDS = ("W0", "b0", "W1", "b1", "W2", "b2")
+
+
+class CMlp3(C.Structure):          # fnb_mlp3_params and fnb_mlp3_grads share one layout
+    _fields_ = [(n, _vp) for n in MLP3_FIELDS]
+
+
+class CPretrainHeadParams(C.Structure):   # fnb_pretrain_head_params / fnb_pretrain_head_grads
+    _fields_ = [("Wr", _vp), ("br", _vp), ("bl", CMlp3), ("ba", CMlp3), ("da", CMlp3), ("fc", CMlp3)]
+
+
+class CPretrainHeadIO(C.Structure):
+    _fields_ = [(n, _vp) for n in ("x_atoms", "x_frags", "edge_feat", "edge_index", "mol_atom_ptr", "mol_frag_ptr",
+                                   "batch32", "frag_batch32")] + \
+               [(n, _i64) for n in ("n_atoms", "n_frags", "n_edges", "n_graphs")] + \
+               [(n, _vp) for n in ("bond_length", "bond_angle", "dihedral", "energy", "g_bond_angle", "g_dihedral",
+                                   "g_energy", "g_atoms", "g_frags", "g_edge")]
+
+
+class CMseTerm(C.Structure):
+    _fields_ = [("pred", _vp), ("target", _vp), ("n", _i64), ("weight", _f32), ("grad", _vp)]

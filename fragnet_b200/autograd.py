@@ -212,3 +212,123 @@ class ReadoutFn(torch.autograd.Function):
         ga = ops.segment_gather(g, 2 * ops.D, rp.batch32, na)
         gf = ops.segment_gather(g[:, ops.D:], 2 * ops.D, rp.frag_batch32, nf)
         return None, ga, gf
+
+
+# ------------------------------------------------------------------------------------------------
+# Pretraining heads + loss (heads.cu)
+HEAD_PARAM_COUNT = 26     # Wr, br, then (W0, b0, W1, b1, W2, b2) of bl, ba, da, fc
+
+
+def _head_struct(tensors):
+    s = _abi.CPretrainHeadParams()
+    s.Wr, s.br = tensors[0].data_ptr(), tensors[1].data_ptr()
+    for gi, group in enumerate(("bl", "ba", "da", "fc")):
+        g = getattr(s, group)
+        for fi, name in enumerate(_abi.MLP3_FIELDS):
+            setattr(g, name, tensors[2 + gi * 6 + fi].data_ptr())
+    return s
+
+
+class PretrainHeadsFn(torch.autograd.Function):
+    """``PretrainTask.forward`` (reference fragnet/model/gat/pretrain_heads.py:64-102) as one library call per
+    direction.  inputs: readout plan, edge_index [2,Ea] int64, precision id, grad_enabled, x_atoms, x_frags,
+    edge_feat, then the 26 head parameters (``HEAD_PARAM_COUNT``).  outputs: bond_length [Ea,1], bond_angle [Na,1],
+    dihedral [Ea,1], energy [G,1].  The bond-length output has no library backward (the reference's loss never uses
+    it); a gradient arriving there is handled by ``PretrainTask`` with library GEMMs instead."""
+
+    @staticmethod
+    def forward(ctx, rp, edge_index, precision: int, grad_enabled: bool, x_atoms, x_frags, edge_feat, *params):
+        f32 = ops._f32c
+        x_atoms, x_frags, edge_feat = f32(x_atoms), f32(x_frags), f32(edge_feat)
+        params = [f32(t) for t in params]
+        assert len(params) == HEAD_PARAM_COUNT
+        dev = x_atoms.device
+        lib = ops._lib()
+        na, nf, ea, g = x_atoms.shape[0], x_frags.shape[0], edge_feat.shape[0], rp.n_graphs
+        ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
+        assert ei.dtype == torch.int64 and ei.shape == (2, ea) and ei.device == dev
+        new = lambda n: torch.empty((n, 1), dtype=torch.float32, device=dev)
+        bl, ba, da, en = new(ea), new(na), new(ea), new(g)
+        ws_bytes = lib.fnb_pretrain_heads_workspace_bytes(na, ea, g)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        pt = ops._ptr
+        P = _head_struct(params)
+        io = _abi.CPretrainHeadIO(pt(x_atoms), pt(x_frags), pt(edge_feat), pt(ei), pt(rp.atom_ptr), pt(rp.frag_ptr),
+                                  pt(rp.batch32), pt(rp.frag_batch32), na, nf, ea, g, pt(bl), pt(ba), pt(da), pt(en))
+        _abi.check(lib.fnb_pretrain_heads_forward(C.byref(P), C.byref(io), precision, pt(ws), ws_bytes,
+                                                  pt(ops.scratch(dev)), ops._stream()), "pretrain_heads_forward")
+        if grad_enabled and any(ctx.needs_input_grad):
+            ctx.set_materialize_grads(False)
+            ctx.rp, ctx.ei, ctx.precision, ctx.ws, ctx.sizes = rp, ei, precision, ws, (na, nf, ea, g)
+            ctx.save_for_backward(x_atoms, x_frags, edge_feat, *params)
+        return bl, ba, da, en
+
+    @staticmethod
+    def backward(ctx, g_bl, g_ba, g_da, g_en):
+        if g_bl is not None:
+            raise NotImplementedError("PretrainHeadsFn: the bond-length output has no library backward")
+        rp, ei, ws = ctx.rp, ctx.ei, ctx.ws
+        na, nf, ea, g = ctx.sizes
+        saved = ctx.saved_tensors
+        x_atoms, x_frags, edge_feat = saved[:3]
+        params = list(saved[3:])
+        dev = x_atoms.device
+        lib = ops._lib()
+        zeros = lambda n: torch.zeros((n, 1), dtype=torch.float32, device=dev)
+        c = lambda t, n: zeros(n) if t is None else ops._f32c(t)
+        g_ba, g_da, g_en = c(g_ba, na), c(g_da, ea), c(g_en, g)
+        sizes = [p.numel() for p in params[8:]]          # ba, da, fc (the bond-length group gets no gradient)
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        views = [v.view_as(p) for v, p in zip(flat.split(sizes), params[8:])]
+        D = _head_struct(params[:8] + views)              # Wr / br / bl slots are ignored by the library
+        new = lambda n: torch.empty((n, ops.D), dtype=torch.float32, device=dev)
+        d_atoms, d_frags, d_edge = new(na), new(nf), new(ea)
+        bws_bytes = lib.fnb_pretrain_heads_bwd_workspace_bytes(na, ea, g)
+        bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
+        pt = ops._ptr
+        P = _head_struct(params)
+        io = _abi.CPretrainHeadIO(pt(x_atoms), pt(x_frags), pt(edge_feat), pt(ei), pt(rp.atom_ptr), pt(rp.frag_ptr),
+                                  pt(rp.batch32), pt(rp.frag_batch32), na, nf, ea, g, None, None, None, None,
+                                  pt(g_ba), pt(g_da), pt(g_en), pt(d_atoms), pt(d_frags), pt(d_edge))
+        _abi.check(lib.fnb_pretrain_heads_backward(C.byref(P), C.byref(D), C.byref(io), ctx.precision, pt(ws), ws.numel(),
+                                                   pt(bws), bws_bytes, pt(ops.scratch(dev)), ops._stream()),
+                   "pretrain_heads_backward")
+        needs = ctx.needs_input_grad
+        pg = [None] * 8 + [v if needs[7 + 8 + i] else None for i, v in enumerate(views)]
+        return (None, None, None, None, d_atoms if needs[4] else None, d_frags if needs[5] else None,
+                d_edge if needs[6] else None, *pg)
+
+
+class MseSumLossFn(torch.autograd.Function):
+    """``sum_t w_t * MSELoss()(pred_t, target_t)`` in one launch; the gradients of the predictions are produced by
+    the same launch and only scaled in backward.  inputs: weights tuple, then pred_0, target_0, pred_1, ..."""
+
+    @staticmethod
+    def forward(ctx, weights, *tensors):
+        preds = [ops._f32c(t) for t in tensors[0::2]]
+        targets = [ops._f32c(t) for t in tensors[1::2]]
+        n = len(preds)
+        assert n == len(weights) == len(targets) and 1 <= n <= 4
+        dev = preds[0].device
+        need = [ctx.needs_input_grad[1 + 2 * i] for i in range(n)]
+        grads = [torch.empty_like(p) if nd else None for p, nd in zip(preds, need)]
+        terms = (_abi.CMseTerm * n)()
+        for i in range(n):
+            assert preds[i].numel() == targets[i].numel() and preds[i].numel() > 0
+            terms[i] = _abi.CMseTerm(ops._ptr(preds[i]), ops._ptr(targets[i]), preds[i].numel(), float(weights[i]),
+                                     ops._ptr(grads[i]))
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _abi.check(ops._lib().fnb_mse_sum_loss(terms, n, ops._ptr(loss), ops._ptr(ops.scratch(dev)), ops._stream()),
+                   "mse_sum_loss")
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        live = [x for x in ctx.grads if x is not None]
+        if live:
+            torch._foreach_mul_(live, g)
+        out = [None]
+        for x in ctx.grads:
+            out += [x, None]
+        return tuple(out)

@@ -1,0 +1,642 @@
+// Pretraining heads and loss as library programs: one call for the four heads' forward, one for their backward,
+// one for the loss (value + gradients).
+//
+// Reference: PretrainTask.forward (fragnet/model/gat/pretrain_heads.py:64-102)
+//   bond length : cat(x_atoms[ei0], x_atoms[ei1], edge_feat) [Ea,384] -> Linear(384,128) -> (ReLU, Linear) x3 (128-64-32-1)
+//   bond angle  : x_atoms   [Na,128] -> Linear(128,64) ReLU Linear(64,32) ReLU Linear(32,1)
+//   dihedral    : edge_feat [Ea,128] -> same stack
+//   energy      : cat(scatter_add(x_atoms, batch), scatter_add(x_frags, frag_batch)) [G,256] -> 256-128-64-1
+// and the training loss of Trainer.train (fragnet/train/pretrain/pretrain_utils.py:22-26).
+// Upstream this is ~45 eager ops forward and ~90 kernels backward; the step was host-bound on them
+// (profiles/r1n_device_profile.log: ~700 us of library kernels, ~2 ms of host time per step at batch 1024).
+//
+// Decomposition.  Every head is "wide first layer + narrow tail":
+//   * the first layers are dense [N,128]x[128,64|128] contractions over tens of thousands of rows: they run on the
+//     projection kernels of this library (tcgen05 TF32 or FP32 FFMA, tc_gemm.cu / proj.cu) with the 64-row weights
+//     zero-padded to 128 rows, so forward, dX and dW reuse three tested kernels;
+//   * the 384-wide bond-length reduce layer never materialises the [Ea,384] concatenation: Linear(cat(a,b,e)) =
+//     a W_a^T + b W_b^T + e W_e^T + bias, i.e. two [Na,128] and one [Ea,128] projections followed by a gather-add;
+//   * the tails (64-32-1 or 128-64-1 per row, ~2-8 kFMA) are FP32 thread-per-row kernels with the weights broadcast
+//     from shared memory; the backward tail recomputes the hidden layer, and reduces the parameter gradients of the
+//     tail (dW1 [MID,IN], db1, dW2, db2, db0) over the rows of its tile out of shared memory into per-CTA records.
+// Parameter-gradient sums are fixed-order two-stage reductions: run-to-run deterministic, no atomics.
+#include "common.cuh"
+
+namespace {
+
+struct Arena {
+  char *base;
+  size_t off;
+  template <class T>
+  T *take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+constexpr int kPadMat = kD * kD;
+
+// ---- forward / saved workspace ------------------------------------------------------------------------------------
+struct FwdBufs {
+  // saved for backward
+  float *h0_ba, *h0_da;          // [Na,128], [Ea,128] first-layer pre-activations (columns 64.. are zero)
+  float *readout, *h0_fc;        // [G,256], [G,128]
+  float *W0pad_ba, *W0pad_da;    // [128,128] rows 64.. zero
+  float *W0padT_ba, *W0padT_da;  // transposes (B operand of the dX GEMM)
+  // transient (bond-length head and padded operands)
+  float *b0pad_ba, *b0pad_da, *b0pad_bl, *W0pad_bl, *Wr_a, *Wr_b, *Wr_e;
+  float *U, *V, *T, *h0_bl;
+};
+
+size_t fwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, FwdBufs *out) {
+  Arena a{base, 0};
+  FwdBufs b{};
+  b.h0_ba = a.take<float>(Na * kD);
+  b.h0_da = a.take<float>(Ea * kD);
+  b.readout = a.take<float>(G * 2 * kD);
+  b.h0_fc = a.take<float>(G * kD);
+  b.W0pad_ba = a.take<float>(kPadMat); b.W0pad_da = a.take<float>(kPadMat);
+  b.W0padT_ba = a.take<float>(kPadMat); b.W0padT_da = a.take<float>(kPadMat);
+  b.b0pad_ba = a.take<float>(kD); b.b0pad_da = a.take<float>(kD); b.b0pad_bl = a.take<float>(kD);
+  b.W0pad_bl = a.take<float>(kPadMat);
+  b.Wr_a = a.take<float>(kPadMat); b.Wr_b = a.take<float>(kPadMat); b.Wr_e = a.take<float>(kPadMat);
+  b.U = a.take<float>(Na * kD); b.V = a.take<float>(Na * kD);
+  b.T = a.take<float>(Ea * kD); b.h0_bl = a.take<float>(Ea * kD);
+  if (out) *out = b;
+  return (a.off + 255) & ~(size_t)255;
+}
+
+// ---- backward workspace -----------------------------------------------------------------------------------------------
+constexpr int kTailCtasMax = kNumSMs * 2;
+__host__ __device__ constexpr int rec_floats(int IN, int MID) { return (MID * IN + MID + MID + 1 + IN + 3) & ~3; }
+constexpr int kRecSmall = rec_floats(64, 32);    // 2180
+constexpr int kRecWide = rec_floats(128, 64);    // 8452
+
+struct BwdBufs {
+  float *dh0_ba, *dh0_da, *dh0_fc;   // [Na,128] [Ea,128] [G,128] gradients of the first-layer pre-activations
+  float *dx_ba;                      // [Na,128] gradient of x_atoms through the bond-angle head
+  float *d_readout;                  // [G,256]
+  float *dWpad_ba, *dWpad_da;        // [128,128] (rows 64.. are zero)
+  float *rec_ba, *rec_da, *rec_fc;   // per-CTA records of the tail gradients
+};
+
+size_t bwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, BwdBufs *out) {
+  Arena a{base, 0};
+  BwdBufs b{};
+  b.dh0_ba = a.take<float>(Na * kD); b.dh0_da = a.take<float>(Ea * kD); b.dh0_fc = a.take<float>(G * kD);
+  b.dx_ba = a.take<float>(Na * kD);
+  b.d_readout = a.take<float>(G * 2 * kD);
+  b.dWpad_ba = a.take<float>(kPadMat); b.dWpad_da = a.take<float>(kPadMat);
+  b.rec_ba = a.take<float>((size_t)kTailCtasMax * kRecSmall);
+  b.rec_da = a.take<float>((size_t)kTailCtasMax * kRecSmall);
+  b.rec_fc = a.take<float>((size_t)kTailCtasMax * kRecWide);
+  if (out) *out = b;
+  return (a.off + 255) & ~(size_t)255;
+}
+
+// ---- operand packing --------------------------------------------------------------------------------------------------
+// job j < 3: dst[j] = [W0 (64 x 128); 0 (64 x 128)], dstT[j] = its transpose (optional), bias[j] = [b0; 0]
+// job 3..5 : dst = Wr[:, 128 (j-3) : 128 (j-2)]  (the three 128-column blocks of the 384-wide reduce layer)
+struct PackJobs {
+  const float *W0[3], *b0[3];
+  float *Wpad[3], *WpadT[3], *bpad[3];
+  const float *Wr;
+  float *Wr_blk[3];
+};
+__global__ void __launch_bounds__(256) k_head_pack(PackJobs p) {
+  const int job = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kPadMat; i += gridDim.x * blockDim.x) {
+    const int r = i >> 7, c = i & 127;
+    if (job < 3) {
+      if (!p.Wpad[job]) return;
+      const float v = r < 64 ? __ldg(p.W0[job] + r * kD + c) : 0.f;
+      p.Wpad[job][i] = v;
+      if (p.WpadT[job]) p.WpadT[job][c * kD + r] = v;
+      if (i < kD) p.bpad[job][i] = i < 64 ? __ldg(p.b0[job] + i) : 0.f;
+    } else {
+      if (!p.Wr_blk[job - 3]) return;
+      p.Wr_blk[job - 3][i] = __ldg(p.Wr + r * 3 * kD + (job - 3) * kD + c);
+    }
+  }
+}
+
+// T[i,:] = ReLU(U[ei0[i],:] + V[ei1[i],:] + T[i,:])   (the activation in front of bl_layers[0], pretrain_heads.py:72-73)
+__global__ void __launch_bounds__(256) k_bl_combine(const float *__restrict__ U, const float *__restrict__ V,
+                                                    float *__restrict__ T, const int64_t *__restrict__ ei, int64_t n_edges) {
+  const int64_t total = n_edges * 32;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i >> 5;
+    const int c = (int)(i & 31) * 4;
+    const int64_t a = __ldg(ei + e), b = __ldg(ei + n_edges + e);
+    const float4 u = ldg4(U + a * kD + c), v = ldg4(V + b * kD + c), t = ld4(T + e * kD + c);
+    st4(T + e * kD + c, make_float4(fmaxf(u.x + v.x + t.x, 0.f), fmaxf(u.y + v.y + t.y, 0.f),
+                                    fmaxf(u.z + v.z + t.z, 0.f), fmaxf(u.w + v.w + t.w, 0.f)));
+  }
+}
+
+// ---- tails --------------------------------------------------------------------------------------------------------------
+// out[r] = b2 + sum_j W2[j] ReLU(b1[j] + sum_k W1[j,k] ReLU(h0[r,k])),   k < IN, j < MID, h0 rows have stride 128.
+struct TailJob {
+  const float *h0;        // [n,128] first-layer pre-activations
+  int64_t n;
+  const float *W1, *b1, *W2, *b2;
+  float *out;             // forward: [n]
+  const float *gout;      // backward: [n] gradient of out
+  float *dh0;             // backward: [n,128] gradient of h0 (columns IN.. written as zero)
+  float *rec;             // backward: per-CTA records
+};
+struct TailJobs {
+  TailJob j[3];
+  int n;
+};
+
+template <int IN, int MID>
+__device__ __forceinline__ void load_tail_weights(const TailJob &job, float *sW1t, float *sb1, float *sW2, float *sb2) {
+  for (int i = threadIdx.x; i < IN * MID; i += blockDim.x) {
+    const int k = i / MID, j = i - k * MID;
+    sW1t[i] = __ldg(job.W1 + j * IN + k);
+  }
+  for (int i = threadIdx.x; i < MID; i += blockDim.x) {
+    sb1[i] = __ldg(job.b1 + i);
+    sW2[i] = __ldg(job.W2 + i);
+  }
+  if (threadIdx.x == 0) sb2[0] = __ldg(job.b2);
+}
+
+// acc[j] = b1[j] + sum_k W1[j,k] ReLU(h0[k]) for the row at `rp`.
+template <int IN, int MID>
+__device__ __forceinline__ void tail_hidden(const float *rp, const float *sW1t, const float *sb1, float (&acc)[MID]) {
+#pragma unroll
+  for (int j = 0; j < MID; ++j) acc[j] = sb1[j];
+#pragma unroll 2
+  for (int k4 = 0; k4 < IN / 4; ++k4) {
+    const float4 a = ldg4(rp + k4 * 4);
+    const float av[4] = {fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float *w = sW1t + (k4 * 4 + u) * MID;
+#pragma unroll
+      for (int j4 = 0; j4 < MID / 4; ++j4) {
+        const float4 wv = ld4(w + j4 * 4);
+        acc[j4 * 4 + 0] = fmaf(av[u], wv.x, acc[j4 * 4 + 0]);
+        acc[j4 * 4 + 1] = fmaf(av[u], wv.y, acc[j4 * 4 + 1]);
+        acc[j4 * 4 + 2] = fmaf(av[u], wv.z, acc[j4 * 4 + 2]);
+        acc[j4 * 4 + 3] = fmaf(av[u], wv.w, acc[j4 * 4 + 3]);
+      }
+    }
+  }
+}
+
+template <int IN, int MID>
+__global__ void __launch_bounds__(128) k_mlp_tail_fwd(TailJobs J) {
+  const TailJob &job = J.j[blockIdx.y];
+  __shared__ __align__(16) float sW1t[IN * MID];
+  __shared__ float sb1[MID], sW2[MID], sb2[1];
+  if ((int64_t)blockIdx.x * 128 >= job.n) return;
+  load_tail_weights<IN, MID>(job, sW1t, sb1, sW2, sb2);
+  __syncthreads();
+  for (int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x; row < job.n; row += (int64_t)gridDim.x * 128) {
+    float acc[MID];
+    tail_hidden<IN, MID>(job.h0 + row * kD, sW1t, sb1, acc);
+    float o = sb2[0];
+#pragma unroll
+    for (int j = 0; j < MID; ++j) o = fmaf(fmaxf(acc[j], 0.f), sW2[j], o);
+    job.out[row] = o;
+  }
+}
+
+// Backward tail.  THREADS threads, ROWS <= THREADS rows per tile (thread-per-row phase), then the cross-row sums of
+// the tile: thread t owns row j = t / 4 of dW1 and, of every 16-column group, the 4 columns 4 (t % 4) .. +3 (the four
+// threads of a row read one contiguous 64-byte chunk of shared memory per step), plus one of the vector sums.
+template <int IN, int MID, int THREADS, int ROWS>
+__global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
+  constexpr int KPT = MID * IN / THREADS;      // k per thread in the dW1 phase
+  static_assert(MID * 4 == THREADS && KPT * 4 == IN, "dW1 ownership needs THREADS = 4 * MID");
+  constexpr int SA = IN + 4, SD = MID + 1;     // shared-memory row strides
+  constexpr int REC = rec_floats(IN, MID);
+  const TailJob &job = J.j[blockIdx.y];
+  extern __shared__ __align__(16) float smem[];
+  float *sW1t = smem;                          // [IN][MID]
+  float *s_a = sW1t + IN * MID;                // [ROWS][SA]   ReLU(h0)
+  float *s_dh0 = s_a + ROWS * SA;              // [ROWS][SA]
+  float *s_d1 = s_dh0 + ROWS * SA;             // [ROWS][SD]   gradient of the hidden pre-activation
+  float *s_h1g = s_d1 + ROWS * SD;             // [ROWS][SD]   gout * ReLU(hidden)
+  float *s_g = s_h1g + ROWS * SD;              // [ROWS]
+  __shared__ float sb1[MID], sW2[MID], sb2[1];
+  const int tid = threadIdx.x;
+  const int64_t n_tiles = (job.n + ROWS - 1) / ROWS;
+  if (blockIdx.x >= n_tiles && blockIdx.x > 0) return;   // CTA 0 always runs: it writes a (possibly zero) record
+  load_tail_weights<IN, MID>(job, sW1t, sb1, sW2, sb2);
+  const int oj = tid >> 2, ok0 = (tid & 3) * 4;
+  float wacc[KPT];
+#pragma unroll
+  for (int q = 0; q < KPT; ++q) wacc[q] = 0.f;
+  float vacc = 0.f;    // tid & 3 == 0: db1[oj];  == 1: dW2[oj]
+  float b0acc = 0.f;   // tid < IN: db0[tid]
+  float b2acc = 0.f;   // tid == 0: db2
+  __syncthreads();
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * ROWS;
+    const int rows = (int)min((int64_t)ROWS, job.n - r0);
+    // ---- phase 1: thread per row
+    if (tid < ROWS) {
+      float *a_row = s_a + tid * SA, *d_row = s_dh0 + tid * SA;
+      if (tid < rows) {
+        const int64_t row = r0 + tid;
+        const float *rp = job.h0 + row * kD;
+        float acc[MID];
+        tail_hidden<IN, MID>(rp, sW1t, sb1, acc);
+        const float g = __ldg(job.gout + row);
+        s_g[tid] = g;
+#pragma unroll
+        for (int j = 0; j < MID; ++j) {
+          const float h1 = fmaxf(acc[j], 0.f);
+          s_h1g[tid * SD + j] = g * h1;
+          acc[j] = acc[j] > 0.f ? g * sW2[j] : 0.f;   // d1[j]
+          s_d1[tid * SD + j] = acc[j];
+        }
+        float *dp = job.dh0 + row * kD;
+#pragma unroll 2
+        for (int k4 = 0; k4 < IN / 4; ++k4) {
+          const float4 a = ldg4(rp + k4 * 4);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+          float dv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float *w = sW1t + (k4 * 4 + u) * MID;
+            float s = 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < MID / 4; ++j4) {
+              const float4 wv = ld4(w + j4 * 4);
+              s = fmaf(acc[j4 * 4 + 0], wv.x, s);
+              s = fmaf(acc[j4 * 4 + 1], wv.y, s);
+              s = fmaf(acc[j4 * 4 + 2], wv.z, s);
+              s = fmaf(acc[j4 * 4 + 3], wv.w, s);
+            }
+            dv[u] = av[u] > 0.f ? s : 0.f;
+          }
+          st4(dp + k4 * 4, make_float4(dv[0], dv[1], dv[2], dv[3]));
+          st4(d_row + k4 * 4, make_float4(dv[0], dv[1], dv[2], dv[3]));
+          st4(a_row + k4 * 4, make_float4(fmaxf(av[0], 0.f), fmaxf(av[1], 0.f), fmaxf(av[2], 0.f), fmaxf(av[3], 0.f)));
+        }
+        if (IN < kD) {
+#pragma unroll
+          for (int k4 = IN / 4; k4 < kD / 4; ++k4) st4(dp + k4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: sums over the rows of the tile
+    for (int r = 0; r < rows; ++r) {
+      const float d = s_d1[r * SD + oj];
+      const float *ap = s_a + r * SA + ok0;
+#pragma unroll
+      for (int q4 = 0; q4 < KPT / 4; ++q4) {
+        const float4 av = ld4(ap + q4 * 16);
+        wacc[q4 * 4 + 0] = fmaf(d, av.x, wacc[q4 * 4 + 0]);
+        wacc[q4 * 4 + 1] = fmaf(d, av.y, wacc[q4 * 4 + 1]);
+        wacc[q4 * 4 + 2] = fmaf(d, av.z, wacc[q4 * 4 + 2]);
+        wacc[q4 * 4 + 3] = fmaf(d, av.w, wacc[q4 * 4 + 3]);
+      }
+      if ((tid & 3) == 0) vacc += d;
+      else if ((tid & 3) == 1) vacc += s_h1g[r * SD + oj];
+      if (tid < IN) b0acc += s_dh0[r * SA + tid];
+      if (tid == 0) b2acc += s_g[r];
+    }
+    __syncthreads();
+  }
+  // ---- CTA record: [dW1 MID*IN][db1 MID][dW2 MID][db2 1][db0 IN]
+  float *rec = job.rec + (size_t)blockIdx.x * REC;
+#pragma unroll
+  for (int q4 = 0; q4 < KPT / 4; ++q4)
+    st4(rec + oj * IN + ok0 + q4 * 16, make_float4(wacc[q4 * 4], wacc[q4 * 4 + 1], wacc[q4 * 4 + 2], wacc[q4 * 4 + 3]));
+  if ((tid & 3) == 0) rec[MID * IN + oj] = vacc;
+  if ((tid & 3) == 1) rec[MID * IN + MID + oj] = vacc;
+  if (tid == 0) rec[MID * IN + 2 * MID] = b2acc;
+  if (tid < IN) rec[MID * IN + 2 * MID + 1 + tid] = b0acc;
+}
+
+template <int IN, int MID, int ROWS>
+constexpr size_t tail_bwd_smem() {
+  return sizeof(float) * ((size_t)IN * MID + 2 * (size_t)ROWS * (IN + 4) + 2 * (size_t)ROWS * (MID + 1) + ROWS);
+}
+
+// Fixed-order sum of per-CTA records (or a plain copy with n_blocks = 1) into the gradient tensors: one launch for all
+// heads.  out[seg][i] = sum_b src[b * stride + off + i], i < width.
+struct SumJobs {
+  const float *src[20];
+  int n_blocks[20], stride[20], off[20], width[20];
+  float *out[20];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_head_sum_records(SumJobs s) {
+  const int seg = blockIdx.y;
+  const int nb = s.n_blocks[seg], stride = s.stride[seg];
+  const float *src = s.src[seg] + s.off[seg];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.width[seg]; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < nb; ++b) acc += __ldg(src + (size_t)b * stride + i);
+    s.out[seg][i] = acc;
+  }
+}
+
+struct SumBuilder {
+  SumJobs s{};
+  int max_width = 0;
+  void add(const float *src, int n_blocks, int stride, int off, int width, float *out) {
+    if (!out || width <= 0 || s.n >= 20) return;
+    const int k = s.n++;
+    s.src[k] = src; s.n_blocks[k] = n_blocks; s.stride[k] = stride; s.off[k] = off; s.width[k] = width; s.out[k] = out;
+    if (width > max_width) max_width = width;
+  }
+  // tail record of a head: [dW1][db1][dW2][db2][db0]
+  void add_tail(const float *rec, int n_ctas, int IN, int MID, float *dW1, float *db1, float *dW2, float *db2, float *db0) {
+    const int stride = rec_floats(IN, MID);
+    add(rec, n_ctas, stride, 0, MID * IN, dW1);
+    add(rec, n_ctas, stride, MID * IN, MID, db1);
+    add(rec, n_ctas, stride, MID * IN + MID, MID, dW2);
+    add(rec, n_ctas, stride, MID * IN + 2 * MID, 1, db2);
+    add(rec, n_ctas, stride, MID * IN + 2 * MID + 1, IN, db0);
+  }
+  int launch(cudaStream_t stream) {
+    if (s.n == 0) return 0;
+    int bx = (max_width + 255) / 256;
+    if (bx > 32) bx = 32;
+    k_head_sum_records<<<dim3(bx, s.n), 256, 0, stream>>>(s);
+    FNB_CHECK_LAUNCH();
+    return 0;
+  }
+};
+
+int tail_grid(int64_t n, int rows) {
+  int64_t t = (n + rows - 1) / rows;
+  if (t > kTailCtasMax) t = kTailCtasMax;
+  if (t < 1) t = 1;
+  return (int)t;
+}
+
+#define RC(expr)             \
+  do {                       \
+    const int rc__ = (expr); \
+    if (rc__) return rc__;   \
+  } while (0)
+
+int check_io(const fnb_pretrain_head_params *P, const fnb_pretrain_head_io *io) {
+  if (!P || !io) return FNB_ERR_NULL;
+  if (io->n_atoms < 0 || io->n_frags < 0 || io->n_edges < 0 || io->n_graphs < 0) return FNB_ERR_SIZE;
+  if (io->n_atoms >= INT32_MAX || io->n_edges >= INT32_MAX) return FNB_ERR_SIZE;
+  const fnb_mlp3_params *m[4] = {&P->bl, &P->ba, &P->da, &P->fc};
+  for (int i = 0; i < 4; ++i)
+    if (!m[i]->W0 || !m[i]->b0 || !m[i]->W1 || !m[i]->b1 || !m[i]->W2 || !m[i]->b2) return FNB_ERR_NULL;
+  if (!P->Wr || !P->br) return FNB_ERR_NULL;
+  if ((io->n_atoms && !io->x_atoms) || (io->n_frags && !io->x_frags) || (io->n_edges && (!io->edge_feat || !io->edge_index)))
+    return FNB_ERR_NULL;
+  if (io->n_graphs && (!io->mol_atom_ptr || !io->mol_frag_ptr)) return FNB_ERR_NULL;
+  if (!fnb_aligned16(io->x_atoms) || !fnb_aligned16(io->x_frags) || !fnb_aligned16(io->edge_feat)) return FNB_ERR_ALIGN;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t fnb_pretrain_heads_workspace_bytes(int64_t n_atoms, int64_t n_edges, int64_t n_graphs) {
+  if (n_atoms < 0 || n_edges < 0 || n_graphs < 0) return 0;
+  return fwd_layout(n_atoms, n_edges, n_graphs, nullptr, nullptr);
+}
+
+extern "C" size_t fnb_pretrain_heads_bwd_workspace_bytes(int64_t n_atoms, int64_t n_edges, int64_t n_graphs) {
+  if (n_atoms < 0 || n_edges < 0 || n_graphs < 0) return 0;
+  return bwd_layout(n_atoms, n_edges, n_graphs, nullptr, nullptr);
+}
+
+extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, const fnb_pretrain_head_io *io,
+                                          int precision, void *workspace, size_t workspace_bytes, void *scratch,
+                                          void *stream_) {
+  RC(check_io(P, io));
+  if (!workspace || !scratch) return FNB_ERR_NULL;
+  if (!io->bond_angle || !io->dihedral || !io->energy) return FNB_ERR_NULL;
+  const int64_t Na = io->n_atoms, Ea = io->n_edges, G = io->n_graphs, Nf = io->n_frags;
+  FwdBufs B;
+  if (fwd_layout(Na, Ea, G, (char *)workspace, &B) > workspace_bytes) return FNB_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool want_bl = io->bond_length != nullptr && Ea > 0;
+
+  {  // padded / split operands (one launch)
+    PackJobs p{};
+    p.W0[0] = P->ba.W0; p.b0[0] = P->ba.b0; p.Wpad[0] = B.W0pad_ba; p.WpadT[0] = B.W0padT_ba; p.bpad[0] = B.b0pad_ba;
+    p.W0[1] = P->da.W0; p.b0[1] = P->da.b0; p.Wpad[1] = B.W0pad_da; p.WpadT[1] = B.W0padT_da; p.bpad[1] = B.b0pad_da;
+    if (want_bl) {
+      p.W0[2] = P->bl.W0; p.b0[2] = P->bl.b0; p.Wpad[2] = B.W0pad_bl; p.WpadT[2] = nullptr; p.bpad[2] = B.b0pad_bl;
+      p.Wr = P->Wr; p.Wr_blk[0] = B.Wr_a; p.Wr_blk[1] = B.Wr_b; p.Wr_blk[2] = B.Wr_e;
+    }
+    k_head_pack<<<dim3(16, want_bl ? 6 : 2), 256, 0, stream>>>(p);
+    FNB_CHECK_LAUNCH();
+  }
+  // ---- first layers on the projection kernels
+  RC(fnb_proj_fwd(io->x_atoms, B.W0pad_ba, B.b0pad_ba, Na, kD, nullptr, 0, 0, 0, B.h0_ba, nullptr, precision, stream_));
+  RC(fnb_proj_fwd(io->edge_feat, B.W0pad_da, B.b0pad_da, Ea, kD, nullptr, 0, 0, 0, B.h0_da, nullptr, precision, stream_));
+  if (want_bl) {
+    RC(fnb_proj_fwd(io->x_atoms, B.Wr_a, nullptr, Na, kD, nullptr, 0, 0, 0, B.U, nullptr, precision, stream_));
+    RC(fnb_proj_fwd(io->x_atoms, B.Wr_b, nullptr, Na, kD, nullptr, 0, 0, 0, B.V, nullptr, precision, stream_));
+    RC(fnb_proj_fwd(io->edge_feat, B.Wr_e, P->br, Ea, kD, nullptr, 0, 0, 0, B.T, nullptr, precision, stream_));
+    int64_t blocks = (Ea * 32 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    k_bl_combine<<<(int)blocks, 256, 0, stream>>>(B.U, B.V, B.T, io->edge_index, Ea);
+    FNB_CHECK_LAUNCH();
+    RC(fnb_proj_fwd(B.T, B.W0pad_bl, B.b0pad_bl, Ea, kD, nullptr, 0, 0, 0, B.h0_bl, nullptr, precision, stream_));
+  }
+  // ---- graph readout (pretrain_heads.py:93-96) and the energy head's first layer
+  if (G > 0) {
+    RC(fnb_segment_sum(io->mol_atom_ptr, nullptr, G, io->x_atoms, B.readout, 2 * kD, nullptr, 0, 0, 0, nullptr, stream_));
+    RC(fnb_segment_sum(io->mol_frag_ptr, nullptr, G, io->x_frags, B.readout + kD, 2 * kD, nullptr, 0, 0, 0, nullptr,
+                       stream_));
+    RC(fnb_proj_fwd(B.readout, P->fc.W0, P->fc.b0, G, 2 * kD, nullptr, 0, 0, 0, B.h0_fc, nullptr, precision, stream_));
+  }
+  (void)Nf;
+  // ---- tails
+  {
+    TailJobs J{};
+    int64_t most = 0;
+    auto add = [&](const float *h0, int64_t n, const fnb_mlp3_params &m, float *out) {
+      if (n <= 0) return;
+      TailJob &t = J.j[J.n++];
+      t.h0 = h0; t.n = n; t.W1 = m.W1; t.b1 = m.b1; t.W2 = m.W2; t.b2 = m.b2; t.out = out;
+      if (n > most) most = n;
+    };
+    add(B.h0_ba, Na, P->ba, io->bond_angle);
+    add(B.h0_da, Ea, P->da, io->dihedral);
+    if (want_bl) add(B.h0_bl, Ea, P->bl, io->bond_length);
+    if (J.n) {
+      int64_t gx = (most + 127) / 128;
+      if (gx > kNumSMs * 8) gx = kNumSMs * 8;
+      k_mlp_tail_fwd<64, 32><<<dim3((unsigned)gx, J.n), 128, 0, stream>>>(J);
+      FNB_CHECK_LAUNCH();
+    }
+    if (G > 0) {
+      TailJobs F{};
+      F.n = 1;
+      TailJob &t = F.j[0];
+      t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.out = io->energy;
+      k_mlp_tail_fwd<128, 64><<<dim3((unsigned)((G + 127) / 128), 1), 128, 0, stream>>>(F);
+      FNB_CHECK_LAUNCH();
+    }
+  }
+  return 0;
+}
+
+extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
+                                           const fnb_pretrain_head_io *io, int precision, void *workspace,
+                                           size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
+                                           void *scratch, void *stream_) {
+  RC(check_io(P, io));
+  if (!D || !workspace || !bwd_workspace || !scratch) return FNB_ERR_NULL;
+  if (!io->g_bond_angle || !io->g_dihedral || !io->g_energy) return FNB_ERR_NULL;
+  if (!io->g_atoms || !io->g_frags || !io->g_edge) return FNB_ERR_NULL;
+  if (!io->batch32 || !io->frag_batch32) return FNB_ERR_NULL;
+  const fnb_mlp3_grads *gm[3] = {&D->ba, &D->da, &D->fc};
+  for (int i = 0; i < 3; ++i)
+    if (!gm[i]->W0 || !gm[i]->b0 || !gm[i]->W1 || !gm[i]->b1 || !gm[i]->W2 || !gm[i]->b2) return FNB_ERR_NULL;
+  const int64_t Na = io->n_atoms, Ea = io->n_edges, G = io->n_graphs, Nf = io->n_frags;
+  FwdBufs B;
+  BwdBufs W;
+  if (fwd_layout(Na, Ea, G, (char *)workspace, &B) > workspace_bytes) return FNB_ERR_WORKSPACE;
+  if (bwd_layout(Na, Ea, G, (char *)bwd_workspace, &W) > bwd_workspace_bytes) return FNB_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+
+  // ---- tails: dh0 of the three trained heads + per-CTA records of their tail gradients
+  int ctas_ba = 0, ctas_da = 0, ctas_fc = 0;
+  {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
+    constexpr size_t smem_s = tail_bwd_smem<64, 32, 128>(), smem_w = tail_bwd_smem<128, 64, 64>();
+    if (!done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(k_mlp_tail_bwd<64, 32, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_s);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(k_mlp_tail_bwd<128, 64, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+      if (e != cudaSuccess) return (int)e;
+      done[dev] = true;
+    }
+    TailJobs J{};
+    auto add = [&](const float *h0, int64_t n, const fnb_mlp3_params &m, const float *gout, float *dh0, float *rec) {
+      TailJob &t = J.j[J.n++];
+      t.h0 = h0; t.n = n; t.W1 = m.W1; t.b1 = m.b1; t.W2 = m.W2; t.b2 = m.b2; t.gout = gout; t.dh0 = dh0; t.rec = rec;
+    };
+    ctas_ba = tail_grid(Na, 128);
+    ctas_da = tail_grid(Ea, 128);
+    add(B.h0_ba, Na, P->ba, io->g_bond_angle, W.dh0_ba, W.rec_ba);
+    add(B.h0_da, Ea, P->da, io->g_dihedral, W.dh0_da, W.rec_da);
+    const int gx = ctas_ba > ctas_da ? ctas_ba : ctas_da;
+    // a job with fewer tiles than gx: its surplus CTAs return at once and write no record, so the record count of a
+    // job is min(gx, tiles of the job) = its own tail_grid
+    k_mlp_tail_bwd<64, 32, 128, 128><<<dim3(gx, 2), 128, smem_s, stream>>>(J);
+    FNB_CHECK_LAUNCH();
+    TailJobs F{};
+    F.n = 1;
+    ctas_fc = tail_grid(G, 64);
+    TailJob &t = F.j[0];
+    t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.gout = io->g_energy;
+    t.dh0 = W.dh0_fc; t.rec = W.rec_fc;
+    k_mlp_tail_bwd<128, 64, 256, 64><<<dim3(ctas_fc, 1), 256, smem_w, stream>>>(F);
+    FNB_CHECK_LAUNCH();
+  }
+  // ---- first layers: dX and dW on the projection kernels
+  if (Na > 0)
+    RC(fnb_proj_bwd_impl(io->x_atoms, B.W0pad_ba, B.W0padT_ba, W.dh0_ba, Na, kD, W.dx_ba, W.dWpad_ba, nullptr, precision,
+                         scratch, stream_));
+  else
+    RC((int)cudaMemsetAsync(W.dWpad_ba, 0, sizeof(float) * kPadMat, stream));
+  if (Ea > 0)
+    RC(fnb_proj_bwd_impl(io->edge_feat, B.W0pad_da, B.W0padT_da, W.dh0_da, Ea, kD, io->g_edge, W.dWpad_da, nullptr, precision,
+                         scratch, stream_));
+  else
+    RC((int)cudaMemsetAsync(W.dWpad_da, 0, sizeof(float) * kPadMat, stream));
+  if (G > 0) {
+    RC(fnb_proj_bwd_impl(B.readout, P->fc.W0, nullptr, W.dh0_fc, G, 2 * kD, W.d_readout, D->fc.W0, nullptr, precision,
+                         scratch, stream_));
+    // readout backward (pretrain_heads.py:93-96): every atom / fragment receives its molecule's gradient row
+    RC(fnb_segment_gather(W.d_readout, 2 * kD, io->batch32, Na, W.dx_ba, io->g_atoms, stream_));
+    RC(fnb_segment_gather(W.d_readout + kD, 2 * kD, io->frag_batch32, Nf, nullptr, io->g_frags, stream_));
+  } else {
+    RC((int)cudaMemsetAsync(D->fc.W0, 0, sizeof(float) * kD * 2 * kD, stream));
+  }
+  // ---- parameter gradients of the tails and the 64-row slices of the padded first-layer gradients
+  SumBuilder sb;
+  sb.add_tail(W.rec_ba, ctas_ba, 64, 32, D->ba.W1, D->ba.b1, D->ba.W2, D->ba.b2, D->ba.b0);
+  sb.add_tail(W.rec_da, ctas_da, 64, 32, D->da.W1, D->da.b1, D->da.W2, D->da.b2, D->da.b0);
+  sb.add_tail(W.rec_fc, ctas_fc, 128, 64, D->fc.W1, D->fc.b1, D->fc.W2, D->fc.b2, D->fc.b0);
+  sb.add(W.dWpad_ba, 1, 0, 0, 64 * kD, D->ba.W0);
+  sb.add(W.dWpad_da, 1, 0, 0, 64 * kD, D->da.W0);
+  return sb.launch(stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Loss of the pretraining loop (pretrain_utils.py:22-26): a weighted sum of mean-squared errors,
+//   loss = sum_t w_t / n_t * sum_i (pred_t[i] - target_t[i])^2,   grad_t[i] = 2 w_t / n_t (pred_t[i] - target_t[i])
+// in one launch (the reference's effective weights are dihedral 2, angle 1, energy 1 because loss_lngth is overwritten).
+namespace {
+struct MseArgs {
+  const float *pred[4], *target[4];
+  float *grad[4];
+  int64_t n[4], begin[5];
+  float w[4];
+  int n_terms;
+  float *loss;
+  float *scratch;
+};
+__global__ void __launch_bounds__(256) k_mse_sum(MseArgs a) {
+  __shared__ float s_part[8];
+  __shared__ float s_rec[4], s_fin[4];
+  const int64_t total = a.begin[a.n_terms];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (t + 1 < a.n_terms && i >= a.begin[t + 1]) ++t;
+    const int64_t k = i - a.begin[t];
+    const float d = __ldg(a.pred[t] + k) - __ldg(a.target[t] + k);
+    const float c = a.w[t] / (float)a.n[t];
+    acc = fmaf(c * d, d, acc);
+    if (a.grad[t]) a.grad[t][k] = 2.f * c * d;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    if (threadIdx.x == 0)
+      for (int w = 0; w < 8; ++w) s += s_part[w];
+    s_rec[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (!cta_finish<4>(s_rec, s_fin, a.scratch)) return;
+  if (threadIdx.x == 0) a.loss[0] = s_fin[0];
+}
+}  // namespace
+
+extern "C" int fnb_mse_sum_loss(const fnb_mse_term *terms, int n_terms, float *loss, void *scratch, void *stream) {
+  if (!terms || !loss || !scratch) return FNB_ERR_NULL;
+  if (n_terms < 1 || n_terms > 4) return FNB_ERR_SIZE;
+  MseArgs a{};
+  a.n_terms = n_terms;
+  a.loss = loss;
+  a.scratch = reinterpret_cast<float *>(scratch);
+  int64_t total = 0;
+  for (int t = 0; t < n_terms; ++t) {
+    if (terms[t].n <= 0) return FNB_ERR_SIZE;
+    if (!terms[t].pred || !terms[t].target) return FNB_ERR_NULL;
+    a.pred[t] = terms[t].pred; a.target[t] = terms[t].target; a.grad[t] = terms[t].grad; a.n[t] = terms[t].n;
+    a.w[t] = terms[t].weight;
+    a.begin[t] = total;
+    total += terms[t].n;
+  }
+  a.begin[n_terms] = total;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+  k_mse_sum<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}

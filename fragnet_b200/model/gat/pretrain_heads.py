@@ -10,6 +10,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ... import config, ops
+from ...autograd import PretrainHeadsFn
 from .gat2 import FragNet, graph_readout
 
 
@@ -40,7 +42,23 @@ class PretrainTask(nn.Module):
             x = self.activation(lin(x))
         return layers[-1](x)
 
-    def forward(self, x_atoms, x_frags, edge_attr, batch):
+    def _parameters_in_library_order(self):
+        """Wr, br, then (W0, b0, W1, b1, W2, b2) of the bond-length, bond-angle, dihedral and energy stacks
+        (``fnb_pretrain_head_params``)."""
+        out = [self.bl_reduce_layer.weight, self.bl_reduce_layer.bias]
+        for stack in (self.bl_layers, self.ba_layers, self.da_layers, self.FC_layers):
+            for lin in stack:
+                out += [lin.weight, lin.bias]
+        return out
+
+    def _library_shapes(self) -> bool:
+        """The fused programs cover the geometry the reference ships (dim_in 128, L 2, dim_out 1)."""
+        return (self.L == 2 and tuple(self.bl_reduce_layer.weight.shape) == (128, 384)
+                and tuple(self.FC_layers[0].weight.shape) == (128, 256) and self.FC_layers[2].weight.shape[0] == 1)
+
+    def _forward_linears(self, x_atoms, x_frags, edge_attr, batch):
+        """The same heads as separate library GEMMs (``nn.Linear``): used for geometries the fused programs do not
+        cover and when a gradient is requested for the bond-length output."""
         ei = batch["edge_index"].to(x_atoms.device)
         # [x_begin | x_end | bond features] per directed bond (pretrain_heads.py:67-70)
         pair = torch.cat((x_atoms.index_select(0, ei[0]), x_atoms.index_select(0, ei[1]), edge_attr), dim=1)
@@ -50,6 +68,25 @@ class PretrainTask(nn.Module):
         bond_angle = self._tail(self.ba_layers, x_atoms)
         dihedral = self._tail(self.da_layers, edge_attr)
         energy = self._tail(self.FC_layers, graph_readout(x_atoms, x_frags, batch))
+        return bond_length, bond_angle, dihedral, energy
+
+    def forward(self, x_atoms, x_frags, edge_attr, batch, bond_length_grad: bool = False):
+        """One ``fnb_pretrain_heads_forward`` call (and one backward call under autograd).  ``bond_length_grad=True``
+        keeps the bond-length output differentiable (separate GEMMs); the reference's training loss never
+        differentiates it (pretrain_utils.py:24 overwrites ``loss_lngth``)."""
+        if bond_length_grad or not self._library_shapes():
+            return self._forward_linears(x_atoms, x_frags, edge_attr, batch)
+        home = x_atoms.device
+        dev = ops.require_cuda(home if home.type == "cuda" else self.bl_reduce_layer.weight.device)
+        on = lambda t: t if t.device == dev else t.to(dev)
+        rp = ops.readout_plan_for(batch["batch"], batch["frag_batch"], dev)
+        outs = PretrainHeadsFn.apply(rp, on(batch["edge_index"]), config.precision_id(), torch.is_grad_enabled(),
+                                     on(x_atoms), on(x_frags), on(edge_attr),
+                                     *[on(p) for p in self._parameters_in_library_order()])
+        bond_length, bond_angle, dihedral, energy = outs
+        bond_length = bond_length.detach()
+        if home.type != "cuda":
+            return tuple(t.to(home) for t in (bond_length, bond_angle, dihedral, energy))
         return bond_length, bond_angle, dihedral, energy
 
 

@@ -10,9 +10,19 @@ import torch
 
 
 def pretrain_loss(loss_fn, preds, batch):
+    """``loss_fn(dihedral) + loss_fn(angle) + loss_fn(dihedral) + loss_fn(energy)`` (pretrain_utils.py:22-26).  With
+    the reference's ``nn.MSELoss()`` on CUDA tensors the four terms, their sum and the gradients of the predictions
+    come from one ``fnb_mse_sum_loss`` launch."""
     _, angle, dihedral, energy = preds
-    l_dh = loss_fn(dihedral, batch["dh_angl"])
-    return l_dh + loss_fn(angle, batch["bnd_angl"]) + l_dh + loss_fn(energy.view(-1), batch["y"])
+    t_dh, t_ba, y = batch["dh_angl"], batch["bnd_angl"], batch["y"]
+    if (isinstance(loss_fn, torch.nn.MSELoss) and loss_fn.reduction == "mean" and dihedral.is_cuda
+            and all(t.is_cuda and t.dtype == torch.float32 for t in (t_dh, t_ba, y))
+            and dihedral.shape == t_dh.shape and angle.shape == t_ba.shape and energy.numel() == y.numel()
+            and min(dihedral.numel(), angle.numel(), energy.numel()) > 0):
+        from ..autograd import MseSumLossFn
+        return MseSumLossFn.apply((2.0, 1.0, 1.0), dihedral, t_dh, angle, t_ba, energy.view(-1), y)
+    l_dh = loss_fn(dihedral, t_dh)
+    return l_dh + loss_fn(angle, t_ba) + l_dh + loss_fn(energy.view(-1), y)
 
 
 class Trainer:

@@ -30,7 +30,7 @@ extern "C" {
 
 #define FNB_D 128 /* embedding width  */
 #define FNB_H 4   /* attention heads  */
-#define FNB_ABI_VERSION 3
+#define FNB_ABI_VERSION 4
 
 /* edge-term modes of the fused attention kernels */
 /* arithmetic of the dense projections */
@@ -347,6 +347,62 @@ int fnb_dropout_relu_bwd(const float *dy, const float *y, float *dx, int64_t n, 
  * torch.optim.Adam's update (no amsgrad) on n contiguous fp32 elements in ONE launch; step counts from 1. */
 int fnb_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, void *stream);
+
+/* ---- pretraining heads + loss (heads.cu) -------------------------------------------------------------------------
+ * PretrainTask.forward (fragnet/model/gat/pretrain_heads.py:64-102) behind one call per direction: bond-length,
+ * bond-angle, dihedral heads (Linear 128-64, ReLU, 64-32, ReLU, 32-1; the bond-length head first reduces
+ * cat(x_atoms[ei0], x_atoms[ei1], edge_feat) with Linear(384,128) and applies ReLU in FRONT of every linear,
+ * pretrain_heads.py:66-74) and the energy head on the graph readout cat(scatter_add(x_atoms, batch),
+ * scatter_add(x_frags, frag_batch)) (Linear 256-128, ReLU, 128-64, ReLU, 64-1; pretrain_heads.py:93-100).
+ * The wide first layers run on the projection kernels (precision = FNB_PRECISION_*), the narrow tails in FP32. */
+typedef struct fnb_mlp3_params { /* nn.Linear weights [out,in] and biases of one three-linear stack */
+  const float *W0, *b0, *W1, *b1, *W2, *b2;
+} fnb_mlp3_params;
+typedef struct fnb_mlp3_grads {
+  float *W0, *b0, *W1, *b1, *W2, *b2;
+} fnb_mlp3_grads;
+typedef struct fnb_pretrain_head_params {
+  const float *Wr, *br;        /* bl_reduce_layer [128,384], [128]                         pretrain_heads.py:26 */
+  fnb_mlp3_params bl, ba, da;  /* bl_layers / ba_layers / da_layers: [64,128] [32,64] [1,32]   :27-47 */
+  fnb_mlp3_params fc;          /* FC_layers: [128,256] [64,128] [1,64]                         :50-55 */
+} fnb_pretrain_head_params;
+typedef struct fnb_pretrain_head_grads { /* every tensor of ba, da, fc is written; the bond-length head has no
+                                            backward here (the reference's loss never uses it: pretrain_utils.py:24
+                                            overwrites loss_lngth), Wr / br / bl are ignored */
+  float *Wr, *br;
+  fnb_mlp3_grads bl, ba, da, fc;
+} fnb_pretrain_head_grads;
+typedef struct fnb_pretrain_head_io {
+  const float *x_atoms, *x_frags, *edge_feat; /* encoder outputs [Na,128] [Nf,128] [Ea,128] */
+  const int64_t *edge_index;                  /* [2,Ea] int64 (batch["edge_index"]) */
+  const int32_t *mol_atom_ptr, *mol_frag_ptr; /* [G+1] molecule boundaries (fnb_batch_plan) */
+  const int32_t *batch32, *frag_batch32;      /* [Na], [Nf] molecule of every atom / fragment (backward only) */
+  int64_t n_atoms, n_frags, n_edges, n_graphs;
+  float *bond_length, *bond_angle, *dihedral, *energy; /* [Ea] [Na] [Ea] [G]; bond_length == NULL skips that head */
+  /* backward */
+  const float *g_bond_angle, *g_dihedral, *g_energy; /* gradients of the three trained outputs */
+  float *g_atoms, *g_frags, *g_edge;                 /* [Na,128] [Nf,128] [Ea,128], written */
+} fnb_pretrain_head_io;
+
+size_t fnb_pretrain_heads_workspace_bytes(int64_t n_atoms, int64_t n_edges, int64_t n_graphs);
+size_t fnb_pretrain_heads_bwd_workspace_bytes(int64_t n_atoms, int64_t n_edges, int64_t n_graphs);
+int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *params, const fnb_pretrain_head_io *io, int precision,
+                               void *workspace, size_t workspace_bytes, void *scratch, void *stream);
+/* workspace = the forward call's workspace (unchanged since). */
+int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *params, const fnb_pretrain_head_grads *grads,
+                                const fnb_pretrain_head_io *io, int precision, void *workspace, size_t workspace_bytes,
+                                void *bwd_workspace, size_t bwd_workspace_bytes, void *scratch, void *stream);
+
+/* loss[0] = sum_t weight_t * mean((pred_t - target_t)^2) over up to 4 terms, and (grad != NULL) its gradient
+ * grad_t[i] = 2 weight_t / n_t * (pred_t[i] - target_t[i]), in one launch.  The pretraining loop's loss
+ * (fragnet/train/pretrain/pretrain_utils.py:22-26) is dihedral x 2, bond angle x 1, energy x 1. */
+typedef struct fnb_mse_term {
+  const float *pred, *target;
+  int64_t n;
+  float weight;
+  float *grad;
+} fnb_mse_term;
+int fnb_mse_sum_loss(const fnb_mse_term *terms, int n_terms, float *loss, void *scratch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""In-situ DEVICE time of one training step: kineto (torch.profiler) kernel records of the bench step loop, warm and
+back to back -- unlike the ncu launch list, whose per-launch times are cold-cache and serialised.  Prints the summed
+kernel time per step by kernel name, the device-busy total, and the span from first launch to last completion."""
+import collections
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    step, batches = bench.make_step(batch=batch)
+    for i in range(5):
+        step(batches[i % len(batches)])
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(steps):
+            step(batches[i % len(batches)])
+        torch.cuda.synchronize()
+    by = collections.defaultdict(lambda: [0, 0.0])
+    t_first, t_last, busy = None, None, 0.0
+    for e in prof.events():
+        if e.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        dur = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        name = e.name
+        if "Memcpy" in name or "Memset" in name:
+            name = name.split("(")[0].strip()
+        by[name][0] += 1
+        by[name][1] += dur
+        busy += dur
+        t0 = e.time_range.start
+        t1 = e.time_range.end
+        t_first = t0 if t_first is None else min(t_first, t0)
+        t_last = t1 if t_last is None else max(t_last, t1)
+    rows = sorted(by.items(), key=lambda kv: -kv[1][1])
+    print(f"batch {batch}: device busy {busy / steps:.1f} us/step over {sum(v[0] for v in by.values()) / steps:.1f} "
+          f"launches/step; span {(t_last - t_first) / steps:.1f} us/step")
+    print(f"{'kernel':90s} {'n/step':>7s} {'avg us':>8s} {'us/step':>9s} {'share':>6s}")
+    for name, (n, t) in rows[:70]:
+        print(f"{name[:90]:90s} {n / steps:7.1f} {t / n:8.2f} {t / steps:9.1f} {100 * t / busy:5.1f}%")
+
+
+if __name__ == "__main__":
+    main()

@@ -61,7 +61,10 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     pairs = [("fnb_graph", A.CGraph), ("fnb_post_act", A.CPostAct), ("fnb_gat_fwd_args", A.CGatFwdArgs),
              ("fnb_gat_bwd_args", A.CGatBwdArgs), ("fnb_layer_params", A.CLayerParams),
              ("fnb_layer_grads", A.CLayerGrads), ("fnb_batch_plan", A.CBatchPlan), ("fnb_batch_inputs", A.CBatchInputs),
-             ("fnb_encoder_opts", A.CEncoderOpts), ("fnb_encoder_io", A.CEncoderIO)]
+             ("fnb_encoder_opts", A.CEncoderOpts), ("fnb_encoder_io", A.CEncoderIO), ("fnb_mlp3_params", A.CMlp3),
+             ("fnb_mlp3_grads", A.CMlp3), ("fnb_pretrain_head_params", A.CPretrainHeadParams),
+             ("fnb_pretrain_head_grads", A.CPretrainHeadParams), ("fnb_pretrain_head_io", A.CPretrainHeadIO),
+             ("fnb_mse_term", A.CMseTerm)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fragnet_b200.h"', 'int main(void){']
     for cname, cls in pairs:
         lines.append(f'printf("{cname} %zu", sizeof({cname}));')

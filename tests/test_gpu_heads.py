@@ -1,0 +1,163 @@
+"""Pretraining heads + loss programs (heads.cu) against the same heads written as separate ``nn.Linear`` calls
+(the arrangement of the reference, fragnet/model/gat/pretrain_heads.py:64-102) and against the CPU oracle."""
+import pytest
+import torch
+
+from conftest import FP32_REL_TOL, grad_errs, rel_err
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 5e-5
+
+
+def _batch(shape, n, seed):
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    mols = synth.make_dataset(shape, n, seed=seed) + [synth.handmade(k) for k in ("two_atom", "ion_pair", "two_frag")]
+    return {k: v.cuda() for k, v in collate_fn_pt(mols).items()}
+
+
+def _inputs(b, seed):
+    gen = torch.Generator().manual_seed(seed)
+    na, nf, ea = b["x_atoms"].shape[0], b["x_frags"].shape[0], b["edge_index"].shape[1]
+    mk = lambda n: torch.randn(n, 128, generator=gen).cuda().requires_grad_()
+    return mk(na), mk(nf), mk(ea)
+
+
+def _head(seed):
+    from fragnet.model.gat.pretrain_heads import PretrainTask
+    torch.manual_seed(seed)
+    return PretrainTask(128, 1).cuda()
+
+
+def _fro_errs(pairs):
+    """TF32 first layers flip the ReLU mask of pre-activations within ~1e-3 of zero, which moves single gradient
+    entries by whole weight columns: the TF32 gradient check is in the Frobenius norm, not the max norm."""
+    out = {}
+    for k, a, b in pairs:
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        out[k] = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    return out
+
+
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32", FP32_REL_TOL, GRAD_TOL), ("tf32", 2e-3, 6e-2)])
+@pytest.mark.parametrize("shape,n", [("esol", 9), ("unimol", 300)])
+def test_heads_forward_backward_match_separate_linears(precision, tol, gtol, shape, n):
+    from fragnet_b200 import config
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    config.set_precision(precision)
+    try:
+        b = _batch(shape, n, 11)
+        head = _head(5)
+        xa, xf, xe = _inputs(b, 7)
+        outs = head(xa, xf, xe, b)
+        gen = torch.Generator().manual_seed(3)
+        ws = [torch.randn(o.shape, generator=gen).cuda() for o in outs]
+        sum((o * w).sum() for o, w in zip(outs[1:], ws[1:])).backward()
+        got_in = [t.grad.clone() for t in (xa, xf, xe)]
+        got_p = {k: p.grad.clone() for k, p in head.named_parameters() if p.grad is not None}
+        for t in (xa, xf, xe):
+            t.grad = None
+        head.zero_grad(set_to_none=True)
+        ref = head._forward_linears(xa, xf, xe, b)
+        sum((o * w).sum() for o, w in zip(ref[1:], ws[1:])).backward()
+        for name, a, r in zip(("bond_length", "bond_angle", "dihedral", "energy"), outs, ref):
+            assert a.shape == r.shape, name
+            assert rel_err(a, r) <= tol, (name, rel_err(a, r))
+        pairs = [(nm, g, t.grad) for nm, g, t in zip(("x_atoms", "x_frags", "edge_feat"), got_in, (xa, xf, xe))]
+        ref_p = {k: p.grad for k, p in head.named_parameters() if p.grad is not None}
+        assert set(got_p) == set(ref_p) and not any(k.startswith("bl_") for k in got_p)
+        pairs += [(k, got_p[k], ref_p[k]) for k in ref_p]
+        errs = grad_errs(pairs) if precision == "fp32" else _fro_errs(pairs)
+        bad = {k: v for k, v in errs.items() if v > gtol}
+        assert not bad, bad
+    finally:
+        config.set_precision("fp32")
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+
+
+def test_bond_length_gradient_path_and_cpu_inputs():
+    """``bond_length_grad=True`` keeps the bond-length head differentiable; CPU inputs come back on the CPU."""
+    b = _batch("esol", 5, 2)
+    head = _head(1)
+    xa, xf, xe = _inputs(b, 4)
+    outs = head(xa, xf, xe, b, bond_length_grad=True)
+    outs[0].sum().backward()
+    assert head.bl_reduce_layer.weight.grad is not None and xa.grad is not None
+    fused = head(xa, xf, xe, b)
+    assert not fused[0].requires_grad and rel_err(fused[0], outs[0]) <= FP32_REL_TOL
+    cpu = head(xa.detach().cpu(), xf.detach().cpu(), xe.detach().cpu(), {k: v.cpu() for k, v in b.items()})
+    assert all(t.device.type == "cpu" for t in cpu) and rel_err(cpu[1], fused[1]) <= FP32_REL_TOL
+
+
+def test_heads_tiny_batch():
+    """Two three-atom ion pairs (2 directed bonds, 2 molecules): far fewer rows than one tile of any kernel."""
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    ion = synth.handmade("ion_pair")
+    b = {k: v.cuda() for k, v in collate_fn_pt([ion, ion]).items()}
+    head = _head(2)
+    xa, xf, xe = _inputs(b, 1)
+    outs = head(xa, xf, xe, b)
+    ref = head._forward_linears(xa, xf, xe, b)
+    for a, r in zip(outs, ref):
+        assert a.shape == r.shape and rel_err(a, r) <= FP32_REL_TOL
+    (outs[1].sum() + outs[3].sum() + outs[2].sum()).backward()
+    assert torch.isfinite(xa.grad).all()
+
+
+def test_fused_loss_matches_torch_and_is_deterministic():
+    from fragnet_b200.train.pretrain_utils import pretrain_loss
+    gen = torch.Generator().manual_seed(0)
+    mk = lambda *s: torch.randn(*s, generator=gen).cuda()
+    preds = [mk(700, 1), mk(333, 1).requires_grad_(), mk(700, 1).requires_grad_(), mk(40, 1).requires_grad_()]
+    batch = {"dh_angl": mk(700, 1), "bnd_angl": mk(333, 1), "y": mk(40)}
+    mse = torch.nn.MSELoss()
+    loss = pretrain_loss(mse, preds, batch)
+    (3.0 * loss).backward()
+    got = [p.grad.clone() for p in preds[1:]]
+    for p in preds[1:]:
+        p.grad = None
+    l_dh = mse(preds[2], batch["dh_angl"])
+    ref = l_dh + mse(preds[1], batch["bnd_angl"]) + l_dh + mse(preds[3].view(-1), batch["y"])
+    (3.0 * ref).backward()
+    assert rel_err(loss, ref) <= 2e-6
+    for g, p in zip(got, preds[1:]):
+        assert rel_err(g, p.grad) <= 2e-6
+    again = pretrain_loss(mse, preds, batch)
+    assert torch.equal(again, loss)
+    # any other criterion takes the generic path
+    l1 = pretrain_loss(torch.nn.L1Loss(), preds, batch)
+    assert l1.requires_grad and float(l1.detach()) > 0
+
+
+def test_pretrain_model_training_step_matches_oracle():
+    """Whole FragNetPreTrain step (encoder + fused heads + fused loss), drop_ratio 0, against the CPU oracle."""
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    from fragnet_b200.train.pretrain_utils import pretrain_loss
+    from oracle import gat2_oracle as O
+    torch.manual_seed(8)
+    hb = collate_fn_pt(synth.make_dataset("unimol", 20, seed=4) + [synth.handmade("ion_pair")])
+    gen = torch.Generator().manual_seed(5)
+    for k in ("bnd_lngth", "bnd_angl", "dh_angl"):
+        hb[k] = torch.randn(hb[k].shape, generator=gen)
+    hb["y"] = torch.randn(hb["y"].shape, generator=gen)
+    m = FragNetPreTrain(num_layer=2, drop_ratio=0.0, edge_features=17)
+    P = O.params_from_module(m)
+    m = m.cuda().train()
+    b = {k: v.cuda() for k, v in hb.items()}
+    preds = m(b)
+    loss = pretrain_loss(torch.nn.MSELoss(), preds, b)
+    loss.backward()
+    ref_preds = O.pretrain_forward(P, hb, num_layer=2)
+    ref_loss = O.pretrain_loss(ref_preds, hb)
+    ref_loss.backward()
+    for a, r in zip(preds, ref_preds):
+        assert rel_err(a, r) <= FP32_REL_TOL
+    assert rel_err(loss, ref_loss) <= FP32_REL_TOL
+    pairs = [(k, p.grad, P[k].grad) for k, p in m.named_parameters() if p.grad is not None]
+    assert {k for k, _, _ in pairs} == {k for k, v in P.items() if v.grad is not None}
+    bad = {k: v for k, v in grad_errs(pairs).items() if v > GRAD_TOL}
+    assert not bad, bad
