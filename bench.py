@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--pool", type=int, default=512, help="distinct synthetic molecules generated")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="arithmetic of the dense projections (everything else is fp32)")
+    ap.add_argument("--autograd", action="store_true",
+                    help="drive the step through nn.Module / autograd / FlatAdam instead of the one-call fused step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -230,7 +232,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="tf32", rank=0, world=1, dev=None,
-              return_host=False):
+              return_host=False, autograd_path=False):
     """The timed unit: ``step(batch_dict)`` = on-device collate + forward + loss + backward + gradient all-reduce
     (world > 1) + Adam on one batch.  Returns (step, device batches[, pinned host batches])."""
     from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
@@ -251,20 +253,26 @@ def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="tf32", 
         for k in b:
             b[k] = b[k].pin_memory()
     dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
-    sync = FlatGradSync(model.parameters())
-    opt = None
+    if autograd_path:
+        # the unchanged reference loop: model(batch) -> loss -> backward -> (all-reduce) -> Adam, through nn.Module
+        sync = FlatGradSync(model.parameters())
+        opt = None
 
-    def step(b):
-        nonlocal opt
-        ops.clear_plan_cache()       # every step is a new batch to the model: the on-device collate is always timed
-        sync.zero()
-        loss = pretrain_loss(loss_fn, model(b), b)
-        loss.backward()
-        sync.sync()
-        if opt is None:          # Adam over the live parameters (grad-less ones are skipped by torch's Adam too)
-            opt = FlatAdam(sync.live_parameters(), lr=LR)
-        opt.step(sync.flat if world > 1 else None)
-        return loss
+        def step(b):
+            nonlocal opt
+            ops.clear_plan_cache()       # every step is a new batch to the model: the on-device collate is always timed
+            sync.zero()
+            loss = pretrain_loss(loss_fn, model(b), b)
+            loss.backward()
+            sync.sync()
+            if opt is None:          # Adam over the live parameters (grad-less ones are skipped by torch's Adam too)
+                opt = FlatAdam(sync.live_parameters(), lr=LR)
+            opt.step(sync.flat if world > 1 else None)
+            return loss
+    else:
+        # the same arithmetic as ONE library call per step (+ NCCL all-reduce + one Adam launch)
+        from fragnet_b200.train.fused import FusedPretrainStep
+        step = FusedPretrainStep(model, lr=LR).step
 
     return (step, dev_batches, host_batches) if return_host else (step, dev_batches)
 
@@ -287,7 +295,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _abi.load()
     step, dev_batches, host_batches = make_step(args.batch, args.shape, args.rotate, args.pool, args.precision, rank,
-                                                world, dev, return_host=True)
+                                                world, dev, return_host=True, autograd_path=args.autograd)
 
     def barrier():
         if world > 1:
@@ -356,7 +364,9 @@ def run_ours(args):
                                        f"drop 0.2, Adam), {args.shape}-shaped molecules",
                            "per_gpu_batch": args.batch, "global_batch": args.batch * world,
                            "parallelism": f"dp{world}", "batch0_counts": counts,
-                           "cache": f"{args.rotate} distinct batches rotated; fwd+bwd working set > 126 MB L2; CSR plans rebuilt every step"},
+                           "cache": f"{args.rotate} distinct batches rotated; fwd+bwd working set > 126 MB L2; CSR plans rebuilt every step",
+                           "driver": "nn.Module + autograd + FlatAdam" if args.autograd else
+                                     "FusedPretrainStep (fnb_pretrain_step + fnb_adam_step)"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line))

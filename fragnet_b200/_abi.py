@@ -56,6 +56,9 @@ SIGNATURES = {
     "fnb_pretrain_heads_forward": (C.c_int, [_vp, _vp, _i32, _vp, _sz, _vp, _vp]),
     "fnb_pretrain_heads_backward": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _sz, _vp, _sz, _vp, _vp]),
     "fnb_mse_sum_loss": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "fnb_pretrain_step_workspace_bytes": (_sz, [_vp]),
+    "fnb_pretrain_step_rng_span": (_u64, [_vp]),
+    "fnb_pretrain_step": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
 }
 
 
@@ -185,3 +188,12 @@ class CPretrainHeadIO(C.Structure):
 
 class CMseTerm(C.Structure):
     _fields_ = [("pred", _vp), ("target", _vp), ("n", _i64), ("weight", _f32), ("grad", _vp)]
+
+
+class CPretrainStepArgs(C.Structure):
+    _fields_ = [("batch", CBatchInputs)] + \
+               [(n, _vp) for n in ("x_atoms", "x_bond", "x_fbond", "t_bond_angle", "t_dihedral", "t_energy")] + \
+               [("n_layers", _i32), ("layers", _vp), ("layer_grads", _vp), ("heads", _vp), ("head_grads", _vp),
+                ("drop_p", _f32), ("training", _i32), ("seed", _u64), ("offset", _u64), ("precision", _i32),
+                ("backward", _i32)] + \
+               [(n, _vp) for n in ("loss", "bond_length", "bond_angle", "dihedral", "energy")]

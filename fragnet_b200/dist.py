@@ -45,9 +45,8 @@ class FlatGradSync:
             if not torch.equal(lo, hi):
                 raise RuntimeError("FlatGradSync: ranks disagree on the set of live parameters")
         ref = self.live[0]
-        sizes = [p.numel() for p in self.live]
-        self.flat = torch.zeros(sum(sizes), dtype=ref.dtype, device=ref.device)
-        self._views = [v.view_as(p) for v, p in zip(self.flat.split(sizes), self.live)]
+        from .train.optim import flat_views
+        self.flat, self._views = flat_views(self.live, ref.device, ref.dtype)   # same layout as FlatAdam's buffers
 
     def zero(self) -> None:
         for p in self.all_params:

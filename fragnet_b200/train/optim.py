@@ -17,6 +17,19 @@ import torch
 from .. import _abi
 
 
+ALIGN = 64     # floats: every tensor of a flat buffer starts on a 256-byte boundary (TMA operands need 16 bytes)
+
+
+def flat_views(params, device, dtype=torch.float32):
+    """One zero-filled flat buffer with an aligned slot per tensor of ``params``; returns (flat, views)."""
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+    flat = torch.zeros(total, dtype=dtype, device=device)
+    return flat, [flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
+
+
 class FlatAdam:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0):
@@ -27,15 +40,12 @@ class FlatAdam:
         if any(p.dtype != torch.float32 or p.device != ref.device or not p.is_cuda for p in self.params):
             raise ValueError("FlatAdam needs fp32 CUDA parameters on one device")
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
-        sizes = [p.numel() for p in self.params]
-        self.flat_p = torch.empty(sum(sizes), dtype=torch.float32, device=ref.device)
-        views = [v.view_as(p) for v, p in zip(self.flat_p.split(sizes), self.params)]
+        self.flat_p, views = flat_views(self.params, ref.device)
         with torch.no_grad():
             torch._foreach_copy_(views, [p.data for p in self.params])
             for p, v in zip(self.params, views):
                 p.data = v                     # the parameter now lives in the flat buffer
-        self.flat_g = torch.zeros_like(self.flat_p)
-        self._g_views = [v.view_as(p) for v, p in zip(self.flat_g.split(sizes), self.params)]
+        self.flat_g, self._g_views = flat_views(self.params, ref.device)
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.t = 0

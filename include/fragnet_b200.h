@@ -404,6 +404,35 @@ typedef struct fnb_mse_term {
 } fnb_mse_term;
 int fnb_mse_sum_loss(const fnb_mse_term *terms, int n_terms, float *loss, void *scratch, void *stream);
 
+/* ---- one pretraining step (step.cu) ------------------------------------------------------------------------------
+ * The body of Trainer.train (fragnet/train/pretrain/pretrain_utils.py:12-30) for one batch as ONE call: on-device
+ * collate of the batch dict, FragNet.forward, PretrainTask.forward, the loss 2*MSE(dihedral) + MSE(bond angle) +
+ * MSE(energy) and, with backward != 0, every parameter gradient (written, not accumulated).  The optimizer update is
+ * fnb_adam_step on the caller's flat buffers (a gradient all-reduce can sit in between). */
+typedef struct fnb_pretrain_step_args {
+  fnb_batch_inputs batch;                         /* index tensors and sizes; n_graphs = molecules = len(y);
+                                                     batch / frag_batch are required */
+  const float *x_atoms, *x_bond, *x_fbond;        /* [Na,K_atom] [Nb,K_bond] [Nfb,K_fbond] raw features */
+  const float *t_bond_angle, *t_dihedral, *t_energy; /* targets bnd_angl [Na], dh_angl [Nb], y [G] */
+  int n_layers;
+  const fnb_layer_params *layers;                 /* run_frag_block: 1 for the last layer only (gat2.py:234) */
+  const fnb_layer_grads *layer_grads;             /* f may be NULL where the fragment block does not run */
+  const fnb_pretrain_head_params *heads;
+  const fnb_pretrain_head_grads *head_grads;
+  float drop_p;
+  int training;
+  uint64_t seed, offset;                          /* dropout RNG key / first counter (fnb_pretrain_step_rng_span) */
+  int precision;
+  int backward;                                   /* 0: forward + loss only (validation) */
+  float *loss;                                    /* device scalar */
+  float *bond_length, *bond_angle, *dihedral, *energy; /* optional prediction outputs; bond_length NULL = head skipped */
+} fnb_pretrain_step_args;
+size_t fnb_pretrain_step_workspace_bytes(const fnb_pretrain_step_args *args);
+uint64_t fnb_pretrain_step_rng_span(const fnb_pretrain_step_args *args);
+/* workspace: 256-byte aligned, fnb_pretrain_step_workspace_bytes() bytes. */
+int fnb_pretrain_step(const fnb_pretrain_step_args *args, void *workspace, size_t workspace_bytes, void *scratch,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

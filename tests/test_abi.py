@@ -64,7 +64,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
              ("fnb_encoder_opts", A.CEncoderOpts), ("fnb_encoder_io", A.CEncoderIO), ("fnb_mlp3_params", A.CMlp3),
              ("fnb_mlp3_grads", A.CMlp3), ("fnb_pretrain_head_params", A.CPretrainHeadParams),
              ("fnb_pretrain_head_grads", A.CPretrainHeadParams), ("fnb_pretrain_head_io", A.CPretrainHeadIO),
-             ("fnb_mse_term", A.CMseTerm)]
+             ("fnb_mse_term", A.CMseTerm), ("fnb_pretrain_step_args", A.CPretrainStepArgs)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fragnet_b200.h"', 'int main(void){']
     for cname, cls in pairs:
         lines.append(f'printf("{cname} %zu", sizeof({cname}));')

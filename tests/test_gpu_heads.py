@@ -161,3 +161,68 @@ def test_pretrain_model_training_step_matches_oracle():
     assert {k for k, _, _ in pairs} == {k for k, v in P.items() if v.grad is not None}
     bad = {k: v for k, v in grad_errs(pairs).items() if v > GRAD_TOL}
     assert not bad, bad
+
+
+def _pretrain_pair(seed, num_layer=2, drop=0.0):
+    """Two identically initialised FragNetPreTrain models and a batch with random targets."""
+    import copy
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    torch.manual_seed(seed)
+    hb = collate_fn_pt(synth.make_dataset("unimol", 40, seed=seed) + [synth.handmade("ion_pair")])
+    gen = torch.Generator().manual_seed(seed + 1)
+    for k in ("bnd_lngth", "bnd_angl", "dh_angl"):
+        hb[k] = torch.randn(hb[k].shape, generator=gen)
+    hb["y"] = torch.randn(hb["y"].shape, generator=gen)
+    m1 = FragNetPreTrain(num_layer=num_layer, drop_ratio=drop, edge_features=17).cuda().train()
+    m2 = copy.deepcopy(m1)
+    return m1, m2, {k: v.cuda() for k, v in hb.items()}
+
+
+def test_fused_step_equals_autograd_path_and_torch_adam():
+    """fnb_pretrain_step + fnb_adam_step against model(batch) / loss.backward() / torch.optim.Adam on a twin model."""
+    from fragnet_b200.train.fused import FusedPretrainStep
+    from fragnet_b200.train.pretrain_utils import pretrain_loss
+    m1, m2, b = _pretrain_pair(3)
+    fused = FusedPretrainStep(m1, lr=1e-3)
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    for it in range(3):
+        loss1 = fused.step(b)
+        opt.zero_grad()
+        loss2 = pretrain_loss(torch.nn.MSELoss(), m2(b), b)
+        loss2.backward()
+        if it == 0:
+            g1 = {k: p.grad.clone() for k, p in m1.named_parameters() if p.grad is not None}
+            g2 = {k: p.grad for k, p in m2.named_parameters() if p.grad is not None}
+            assert set(g1) == set(g2)
+            bad = {k: v for k, v in grad_errs([(k, g1[k], g2[k]) for k in g2]).items() if v > 1e-6}
+            assert not bad, bad
+        opt.step()
+        assert rel_err(loss1, loss2) <= 1e-6, it
+    p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    worst = max(rel_err(p1[k], p2[k]) for k in p2)
+    assert worst <= 1e-5, worst
+    # the model is still an ordinary nn.Module: state_dict round trip, eval-mode forward, evaluate() with predictions
+    sd = {k: v.clone() for k, v in m1.state_dict().items()}
+    m1.load_state_dict(sd, strict=True)
+    m1.eval()
+    loss_e, preds = fused.evaluate(b, return_predictions=True)
+    with torch.no_grad():
+        ref = m1(b)
+    for a, r in zip(preds, ref):
+        assert rel_err(a, r) <= 1e-6
+    assert rel_err(loss_e, pretrain_loss(torch.nn.MSELoss(), ref, b)) <= 1e-6
+
+
+def test_fused_step_dropout_training_is_seeded_and_finite():
+    from fragnet_b200 import ops
+    from fragnet_b200.train.fused import FusedPretrainStep
+    losses = []
+    for _ in range(2):
+        torch.manual_seed(11)
+        ops._rng_offset = 0
+        m1, _, b = _pretrain_pair(5, num_layer=4, drop=0.2)
+        fused = FusedPretrainStep(m1, lr=1e-4)
+        losses.append([float(fused.step(b)) for _ in range(3)])
+    assert losses[0] == losses[1] and all(x == x and x < 1e6 for x in losses[0])
