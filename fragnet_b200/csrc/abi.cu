@@ -1,4 +1,6 @@
 // Version and error strings of the C ABI (include/fragnet_b200.h).
+#include <cstdlib>
+
 #include "common.cuh"
 
 unsigned long long g_fnb_launches = 0;
@@ -17,4 +19,26 @@ extern "C" const char *fnb_error_string(int code) {
     case FNB_ERR_ALIGN: return "pointer or stride not 16-byte aligned";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
   }
+}
+
+// Library-owned auxiliary stream + fork/join events per device (created on first use, never destroyed): the
+// whole-encoder programs run the fragment-connection chain, which is independent of the bond/atom chain until the
+// fragment block of the last layer, on it.  FNB_STREAMS=1 in the environment keeps everything on the caller's stream.
+int fnb_aux_streams(FnbAux *out) {
+  static FnbAux aux[64];
+  static bool ready[64] = {};
+  static const bool single = [] { const char *e = getenv("FNB_STREAMS"); return e && e[0] == '1'; }();
+  if (single) return 1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+  if (!ready[dev]) {
+    FnbAux a{};
+    if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return 1;
+    if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return 1;
+    aux[dev] = a;
+    ready[dev] = true;
+  }
+  *out = aux[dev];
+  return 0;
 }

@@ -241,6 +241,14 @@ struct RangeJobs {
 };
 int fnb_launch_tile_ranges(const RangeJobs &jobs, cudaStream_t stream);
 
+// Auxiliary stream of the calling thread's current device (abi.cu); returns non-zero when only the caller's stream
+// should be used.
+struct FnbAux {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+int fnb_aux_streams(FnbAux *out);
+
 // Tensor-core (tcgen05, TF32) projection path, tc_gemm.cu.  Returns FNB_ERR_MODE when the shape cannot use TMA.
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
                        int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream);

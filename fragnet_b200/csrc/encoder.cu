@@ -129,6 +129,7 @@ struct BwdBufs {
   float *g_fbond, *dz_fb, *dSt_fb, *dh_fb, *dx_fbond;
   float *g_frag, *dz_f, *dSt_f, *d_hf;
   float *Wt;   // [n_layers][3][128*128] transposed K=128 projection weights
+  float *scratch2;   // scratch of the fragment-connection chain when it runs on the auxiliary stream
 };
 
 size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *base, BwdBufs *out) {
@@ -144,6 +145,7 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   b.g_frag = a.take<float>(z.Nf * kD); b.dz_f = a.take<float>(z.Ef * 4); b.dSt_f = a.take<float>(z.Nf * 4);
   b.d_hf = a.take<float>(z.Nf * kD);
   b.Wt = a.take<float>((size_t)o->n_layers * 3 * kD * kD);
+  b.scratch2 = a.take<float>(kScratchFloats);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -341,6 +343,25 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       FNB_CHECK_LAUNCH();
     }
   }
+  // The fragment-connection chain (projection_fb + its attention block, every layer) depends on nothing the bond /
+  // atom chain produces until the fragment block: it runs on the auxiliary stream, concurrently with the big graphs.
+  FnbAux aux{};
+  const bool two = fnb_aux_streams(&aux) == 0;
+  cudaStream_t sB = two ? aux.stream : stream;
+  void *sB_ = (void *)sB;
+  bool pending = false;   // work queued on sB that the caller's stream has not waited for yet
+  if (two) {
+    RC((int)cudaEventRecord(aux.fork, stream));
+    RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
+  }
+  auto join = [&]() -> int {
+    if (two && pending) {
+      RC((int)cudaEventRecord(aux.join, sB));
+      RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
+      pending = false;
+    }
+    return 0;
+  };
   for (int l = 0; l < o->n_layers; ++l) {
     const fnb_layer_params &P = L[l];
     LayerBufs &b = B[l];
@@ -390,7 +411,8 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     }
     // ---- fragment-connection graph (gat2.py:239-278); epilogue emits the fragment graph's edge term
     RC(fnb_proj_fwd(xfb_in, Wfb_in, P.bfb, z.Nfb, Kfb_in, P.f_a_b, AB_STRIDE, AB_T, AB_S, b.hfb, b.Sfb, o->precision,
-                    stream_));
+                    sB_));
+    pending = true;
     {
       fnb_gat_fwd_args f{};
       f.h = b.hfb; f.S = b.Sfb; f.edge_mode = FNB_EDGE_AFFINE6; f.We = P.We_fb; f.be = P.be_fb;
@@ -399,8 +421,9 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       f.mask_lo = P.frag_bond_mask >= 0 ? 2 * P.frag_bond_mask : -1;
       f.mask_hi = P.frag_bond_mask >= 0 ? 2 * P.frag_bond_mask + 2 : -1;
       if (frag) { f.next_alpha_e = P.f + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_frag; }
-      RC(fnb_gat_fwd_tiled(&plan->fbond, &f, stream_));
+      RC(fnb_gat_fwd_tiled(&plan->fbond, &f, sB_));
     }
+    if (frag || P.want_attention) RC(join());
     // ---- atom -> fragment pooling (gat2.py:234) and the fragment graph (gat2.py:283-316): only where its output lives
     if (frag) {
       RC(fnb_segment_sum(plan->pool_rowptr, plan->pool_col, z.Nf, pre_atom, b.hf, kD, P.f, A_STRIDE, A_T, A_S, b.Sf,
@@ -420,6 +443,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     }
     xa = y_atom; xb = y_bond; xfb = y_fbond;   // inputs of the next layer (post_act mode only has further layers)
   }
+  RC(join());
   return 0;
 }
 
@@ -466,6 +490,24 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     return wt_slot[layer][j] >= 0 ? W.Wt + (size_t)wt_slot[layer][j] * kD * kD : nullptr;
   };
 
+  // The fragment-connection blocks of all layers form one chain that only needs the fragment block of the last
+  // layer: it runs on the auxiliary stream with its own scratch, concurrently with the atom / bond blocks.
+  FnbAux aux{};
+  const bool two = fnb_aux_streams(&aux) == 0;
+  cudaStream_t sB = two ? aux.stream : stream;
+  void *sB_ = (void *)sB;
+  void *scratchB = two ? (void *)W.scratch2 : scratch;
+  bool forked = false;
+  auto fork = [&]() -> int {   // everything queued on the caller's stream so far is visible to sB
+    if (two && !forked) {
+      RC((int)cudaEventRecord(aux.fork, stream));
+      RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
+      RC((int)cudaMemsetAsync(W.scratch2, 0, kScratchCounters * sizeof(float), sB));
+      forked = true;
+    }
+    return 0;
+  };
+
   // gradients arriving at the four outputs of the current layer (post-activation copies in post_act mode)
   const float *dy_atom = io->g_atoms, *dy_bond = io->g_bond, *dy_fbond = io->g_fbond, *dy_frag = io->g_frags;
   for (int l = o->n_layers - 1; l >= 0; --l) {
@@ -500,13 +542,14 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     }
     // ---- fragment-connection graph block
     {
+      RC(fork());
       bool have = true;
       if (frag_bwd) {  // g = ReLU(Dropout) backward of dy + sum_h dz_f alpha_e; also d f[:, edge slice]
         RC(fnb_edge_table_bwd_fused(&plan->frag, W.dz_f, pre_fbond, P.f, A_STRIDE, A_E, y_fbond ? nullptr : dy_fbond,
                                     y_fbond ? dy_fbond : nullptr, y_fbond && dy_fbond ? y_fbond : nullptr, scale,
-                                    W.g_fbond, D.f, scratch, stream_));
+                                    W.g_fbond, D.f, scratchB, sB_));
       } else if (dy_fbond) {
-        RC(grad_combine(dy_fbond, y_fbond, scale, nullptr, nullptr, z.Nfb, W.g_fbond, stream));
+        RC(grad_combine(dy_fbond, y_fbond, scale, nullptr, nullptr, z.Nfb, W.g_fbond, sB));
       } else {
         have = false;
       }
@@ -515,24 +558,24 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         a.h = b.hfb; a.dout = W.g_fbond; a.p_saved = b.p_fb; a.edge_mode = FNB_EDGE_AFFINE6; a.We = P.We_fb;
         a.be = P.be_fb; a.alpha = P.f_a_b; a.alpha_stride = AB_STRIDE; a.off_t = AB_T; a.off_e = AB_E; a.off_s = AB_S;
         a.dz = W.dz_fb; a.dSt = W.dSt_fb; a.dh = W.dh_fb; a.d_alpha = D.f_a_b; a.d_bias = D.bfb; a.dWe = D.We_fb;
-        a.dbe = D.be_fb; a.scratch = scratch;
-        RC(fnb_gat_bwd_tiled(&plan->fbond, &a, stream_));
+        a.dbe = D.be_fb; a.scratch = scratchB;
+        RC(fnb_gat_bwd_tiled(&plan->fbond, &a, sB_));
         float *dx = need_dx ? W.dx_fbond : (o->need_dx_fbond ? io->dx_fbond : nullptr);
         if (l == 0 && b.k_pad[2] && !dx)
-          RC(fnb_tc_dw_launch(W.dh_fb, b.x_pad[2], z.Nfb, b.k_pad[2], P.K_fbond, D.Wfb, scratch_body(scratch), stream));
+          RC(fnb_tc_dw_launch(W.dh_fb, b.x_pad[2], z.Nfb, b.k_pad[2], P.K_fbond, D.Wfb, scratch_body(scratchB), sB));
         else
           RC(fnb_proj_bwd_impl(xfb, P.Wfb, wt_of(l, 2), W.dh_fb, z.Nfb, P.K_fbond, dx, D.Wfb, nullptr, o->precision,
-                               scratch, stream_));
+                               scratchB, sB_));
         dy_fbond = need_dx ? W.dx_fbond : nullptr;
       } else {
         dy_fbond = nullptr;
       }
       if (!have) {  // no gradient reaches this block: its parameters get zeros
-        RC((int)cudaMemsetAsync(D.f_a_b, 0, 4 * AB_STRIDE * 4, stream));
-        RC((int)cudaMemsetAsync(D.bfb, 0, kD * 4, stream));
-        RC((int)cudaMemsetAsync(D.We_fb, 0, 32 * 6 * 4, stream));
-        RC((int)cudaMemsetAsync(D.be_fb, 0, 32 * 4, stream));
-        RC((int)cudaMemsetAsync(D.Wfb, 0, (size_t)kD * P.K_fbond * 4, stream));
+        RC((int)cudaMemsetAsync(D.f_a_b, 0, 4 * AB_STRIDE * 4, sB));
+        RC((int)cudaMemsetAsync(D.bfb, 0, kD * 4, sB));
+        RC((int)cudaMemsetAsync(D.We_fb, 0, 32 * 6 * 4, sB));
+        RC((int)cudaMemsetAsync(D.be_fb, 0, 32 * 4, sB));
+        RC((int)cudaMemsetAsync(D.Wfb, 0, (size_t)kD * P.K_fbond * 4, sB));
       }
     }
     // ---- atom graph block: incoming gradient = activation backward + pooling backward
@@ -589,6 +632,10 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     }
     if (!frag_bwd && D.f) RC((int)cudaMemsetAsync(D.f, 0, 4 * A_STRIDE * 4, stream));
     dy_frag = nullptr;   // the fragment output of a lower layer is dead (overwritten unread, gat2.py:234)
+  }
+  if (two && forked) {
+    RC((int)cudaEventRecord(aux.join, sB));
+    RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
   }
   // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same RNG stream as the forward
   if (o->need_dx_atoms && io->dx_atoms && input_dropout(o)) {

@@ -41,6 +41,18 @@ def main():
         t1 = e.time_range.end
         t_first = t0 if t_first is None else min(t_first, t0)
         t_last = t1 if t_last is None else max(t_last, t1)
+    if os.environ.get("FNB_SEQ"):      # launch sequence of the last profiled step, in start order
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                     key=lambda e: e.time_range.start)
+        per = len(evs) // steps
+        last = evs[-per:]
+        t0 = last[0].time_range.start
+        print("# start_us  dur_us  gap_us  kernel   (last step)")
+        prev_end = t0
+        for e in last:
+            print(f"{e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:7.1f} "
+                  f"{e.time_range.start - prev_end:6.1f}  {e.name[:100]}")
+            prev_end = e.time_range.end
     rows = sorted(by.items(), key=lambda kv: -kv[1][1])
     print(f"batch {batch}: device busy {busy / steps:.1f} us/step over {sum(v[0] for v in by.values()) / steps:.1f} "
           f"launches/step; span {(t_last - t_first) / steps:.1f} us/step")
