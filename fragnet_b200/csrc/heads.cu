@@ -69,7 +69,7 @@ size_t fwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, FwdBufs *out) {
 }
 
 // ---- backward workspace -----------------------------------------------------------------------------------------------
-constexpr int kTailCtasMax = kNumSMs * 2;
+constexpr int kTailCtasMax = kNumSMs;
 __host__ __device__ constexpr int rec_floats(int IN, int MID) { return (MID * IN + MID + MID + 1 + IN + 3) & ~3; }
 constexpr int kRecSmall = rec_floats(64, 32);    // 2180
 constexpr int kRecWide = rec_floats(128, 64);    // 8452
@@ -80,6 +80,7 @@ struct BwdBufs {
   float *d_readout;                  // [G,256]
   float *dWpad_ba, *dWpad_da;        // [128,128] (rows 64.. are zero)
   float *rec_ba, *rec_da, *rec_fc;   // per-CTA records of the tail gradients
+  float *scratch2;                   // scratch of the energy-head chain (auxiliary stream)
 };
 
 size_t bwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, BwdBufs *out) {
@@ -92,6 +93,7 @@ size_t bwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, BwdBufs *out) {
   b.rec_ba = a.take<float>((size_t)kTailCtasMax * kRecSmall);
   b.rec_da = a.take<float>((size_t)kTailCtasMax * kRecSmall);
   b.rec_fc = a.take<float>((size_t)kTailCtasMax * kRecWide);
+  b.scratch2 = a.take<float>(kScratchFloats);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -333,14 +335,20 @@ struct SumJobs {
   int n;
 };
 __global__ void __launch_bounds__(256) k_head_sum_records(SumJobs s) {
+  // one CTA = 64 consecutive outputs of one segment; the records are split over 4 thread groups (fixed assignment and
+  // fixed combination order => deterministic), each load instruction reads 256 contiguous bytes of one record
+  __shared__ float part[4][64];
   const int seg = blockIdx.y;
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
+  if (blockIdx.x * 64 >= s.width[seg]) return;
   const int nb = s.n_blocks[seg], stride = s.stride[seg];
   const float *src = s.src[seg] + s.off[seg];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.width[seg]; i += gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    for (int b = 0; b < nb; ++b) acc += __ldg(src + (size_t)b * stride + i);
-    s.out[seg][i] = acc;
-  }
+  float acc = 0.f;
+  if (i < s.width[seg])
+    for (int b = grp; b < nb; b += 4) acc += __ldg(src + (size_t)b * stride + i);
+  part[grp][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (grp == 0 && i < s.width[seg]) s.out[seg][i] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
 }
 
 struct SumBuilder {
@@ -363,9 +371,7 @@ struct SumBuilder {
   }
   int launch(cudaStream_t stream) {
     if (s.n == 0) return 0;
-    int bx = (max_width + 255) / 256;
-    if (bx > 32) bx = 32;
-    k_head_sum_records<<<dim3(bx, s.n), 256, 0, stream>>>(s);
+    k_head_sum_records<<<dim3((max_width + 63) / 64, s.n), 256, 0, stream>>>(s);
     FNB_CHECK_LAUNCH();
     return 0;
   }
@@ -434,6 +440,28 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     k_head_pack<<<dim3(16, want_bl ? 6 : 2), 256, 0, stream>>>(p);
     FNB_CHECK_LAUNCH();
   }
+  // ---- energy head (graph readout pretrain_heads.py:93-96, first layer, tail): ~1e3 rows, latency-bound kernels that
+  // run on the auxiliary stream underneath the per-atom / per-bond heads
+  FnbAux aux{};
+  const bool two = fnb_aux_streams(&aux) == 0;
+  cudaStream_t sB = two ? aux.stream : stream;
+  void *sB_ = (void *)sB;
+  if (G > 0) {
+    if (two) {
+      RC((int)cudaEventRecord(aux.fork, stream));
+      RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
+    }
+    RC(fnb_segment_sum(io->mol_atom_ptr, nullptr, G, io->x_atoms, B.readout, 2 * kD, nullptr, 0, 0, 0, nullptr, sB_));
+    RC(fnb_segment_sum(io->mol_frag_ptr, nullptr, G, io->x_frags, B.readout + kD, 2 * kD, nullptr, 0, 0, 0, nullptr, sB_));
+    RC(fnb_proj_fwd(B.readout, P->fc.W0, P->fc.b0, G, 2 * kD, nullptr, 0, 0, 0, B.h0_fc, nullptr, precision, sB_));
+    TailJobs F{};
+    F.n = 1;
+    TailJob &t = F.j[0];
+    t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.out = io->energy;
+    k_mlp_tail_fwd<128, 64><<<dim3((unsigned)((G + 127) / 128), 1), 128, 0, sB>>>(F);
+    FNB_CHECK_LAUNCH();
+  }
+  (void)Nf;
   // ---- first layers on the projection kernels
   RC(fnb_proj_fwd(io->x_atoms, B.W0pad_ba, B.b0pad_ba, Na, kD, nullptr, 0, 0, 0, B.h0_ba, nullptr, precision, stream_));
   RC(fnb_proj_fwd(io->edge_feat, B.W0pad_da, B.b0pad_da, Ea, kD, nullptr, 0, 0, 0, B.h0_da, nullptr, precision, stream_));
@@ -447,15 +475,7 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     FNB_CHECK_LAUNCH();
     RC(fnb_proj_fwd(B.T, B.W0pad_bl, B.b0pad_bl, Ea, kD, nullptr, 0, 0, 0, B.h0_bl, nullptr, precision, stream_));
   }
-  // ---- graph readout (pretrain_heads.py:93-96) and the energy head's first layer
-  if (G > 0) {
-    RC(fnb_segment_sum(io->mol_atom_ptr, nullptr, G, io->x_atoms, B.readout, 2 * kD, nullptr, 0, 0, 0, nullptr, stream_));
-    RC(fnb_segment_sum(io->mol_frag_ptr, nullptr, G, io->x_frags, B.readout + kD, 2 * kD, nullptr, 0, 0, 0, nullptr,
-                       stream_));
-    RC(fnb_proj_fwd(B.readout, P->fc.W0, P->fc.b0, G, 2 * kD, nullptr, 0, 0, 0, B.h0_fc, nullptr, precision, stream_));
-  }
-  (void)Nf;
-  // ---- tails
+  // ---- tails of the per-atom / per-bond heads
   {
     TailJobs J{};
     int64_t most = 0;
@@ -474,14 +494,10 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
       k_mlp_tail_fwd<64, 32><<<dim3((unsigned)gx, J.n), 128, 0, stream>>>(J);
       FNB_CHECK_LAUNCH();
     }
-    if (G > 0) {
-      TailJobs F{};
-      F.n = 1;
-      TailJob &t = F.j[0];
-      t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.out = io->energy;
-      k_mlp_tail_fwd<128, 64><<<dim3((unsigned)((G + 127) / 128), 1), 128, 0, stream>>>(F);
-      FNB_CHECK_LAUNCH();
-    }
+  }
+  if (two && G > 0) {
+    RC((int)cudaEventRecord(aux.join, sB));
+    RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
   }
   return 0;
 }
@@ -505,22 +521,52 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
   if (bwd_layout(Na, Ea, G, (char *)bwd_workspace, &W) > bwd_workspace_bytes) return FNB_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
 
-  // ---- tails: dh0 of the three trained heads + per-CTA records of their tail gradients
+  FnbAux aux{};
+  const bool two = fnb_aux_streams(&aux) == 0;
+  cudaStream_t sB = two ? aux.stream : stream;
+  void *sB_ = (void *)sB;
+  void *scratchB = two ? (void *)W.scratch2 : scratch;
   int ctas_ba = 0, ctas_da = 0, ctas_fc = 0;
   {
     static bool done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
-    constexpr size_t smem_s = tail_bwd_smem<64, 32, 128>(), smem_w = tail_bwd_smem<128, 64, 64>();
     if (!done[dev]) {
       cudaError_t e = cudaFuncSetAttribute(k_mlp_tail_bwd<64, 32, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem_s);
+                                           (int)tail_bwd_smem<64, 32, 128>());
       if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(k_mlp_tail_bwd<128, 64, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+      e = cudaFuncSetAttribute(k_mlp_tail_bwd<128, 64, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tail_bwd_smem<128, 64, 64>());
       if (e != cudaSuccess) return (int)e;
       done[dev] = true;
     }
+  }
+  // ---- energy head on the auxiliary stream (its ~1e3-row kernels are latency-bound and hide under the other heads):
+  // tail, dX / dW of its first layer, readout backward of the fragments
+  if (G > 0) {
+    if (two) {
+      RC((int)cudaEventRecord(aux.fork, stream));
+      RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
+      RC((int)cudaMemsetAsync(W.scratch2, 0, kScratchCounters * sizeof(float), sB));
+    }
+    TailJobs F{};
+    F.n = 1;
+    ctas_fc = tail_grid(G, 64);
+    TailJob &t = F.j[0];
+    t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.gout = io->g_energy;
+    t.dh0 = W.dh0_fc; t.rec = W.rec_fc;
+    k_mlp_tail_bwd<128, 64, 256, 64><<<dim3(ctas_fc, 1), 256, tail_bwd_smem<128, 64, 64>(), sB>>>(F);
+    FNB_CHECK_LAUNCH();
+    RC(fnb_proj_bwd_impl(B.readout, P->fc.W0, nullptr, W.dh0_fc, G, 2 * kD, W.d_readout, D->fc.W0, nullptr, precision,
+                         scratchB, sB_));
+    RC(fnb_segment_gather(W.d_readout + kD, 2 * kD, io->frag_batch32, Nf, nullptr, io->g_frags, sB_));
+    if (two) RC((int)cudaEventRecord(aux.join, sB));
+  } else {
+    RC((int)cudaMemsetAsync(D->fc.W0, 0, sizeof(float) * kD * 2 * kD, stream));
+  }
+  // ---- tails of the per-atom / per-bond heads: dh0 + per-CTA records of their tail gradients
+  {
     TailJobs J{};
     auto add = [&](const float *h0, int64_t n, const fnb_mlp3_params &m, const float *gout, float *dh0, float *rec) {
       TailJob &t = J.j[J.n++];
@@ -533,15 +579,7 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
     const int gx = ctas_ba > ctas_da ? ctas_ba : ctas_da;
     // a job with fewer tiles than gx: its surplus CTAs return at once and write no record, so the record count of a
     // job is min(gx, tiles of the job) = its own tail_grid
-    k_mlp_tail_bwd<64, 32, 128, 128><<<dim3(gx, 2), 128, smem_s, stream>>>(J);
-    FNB_CHECK_LAUNCH();
-    TailJobs F{};
-    F.n = 1;
-    ctas_fc = tail_grid(G, 64);
-    TailJob &t = F.j[0];
-    t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.gout = io->g_energy;
-    t.dh0 = W.dh0_fc; t.rec = W.rec_fc;
-    k_mlp_tail_bwd<128, 64, 256, 64><<<dim3(ctas_fc, 1), 256, smem_w, stream>>>(F);
+    k_mlp_tail_bwd<64, 32, 128, 128><<<dim3(gx, 2), 128, tail_bwd_smem<64, 32, 128>(), stream>>>(J);
     FNB_CHECK_LAUNCH();
   }
   // ---- first layers: dX and dW on the projection kernels
@@ -556,13 +594,10 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
   else
     RC((int)cudaMemsetAsync(W.dWpad_da, 0, sizeof(float) * kPadMat, stream));
   if (G > 0) {
-    RC(fnb_proj_bwd_impl(B.readout, P->fc.W0, nullptr, W.dh0_fc, G, 2 * kD, W.d_readout, D->fc.W0, nullptr, precision,
-                         scratch, stream_));
-    // readout backward (pretrain_heads.py:93-96): every atom / fragment receives its molecule's gradient row
+    if (two) RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
+    // readout backward (pretrain_heads.py:93-96): every atom receives its molecule's gradient row on top of the
+    // bond-angle head's gradient
     RC(fnb_segment_gather(W.d_readout, 2 * kD, io->batch32, Na, W.dx_ba, io->g_atoms, stream_));
-    RC(fnb_segment_gather(W.d_readout + kD, 2 * kD, io->frag_batch32, Nf, nullptr, io->g_frags, stream_));
-  } else {
-    RC((int)cudaMemsetAsync(D->fc.W0, 0, sizeof(float) * kD * 2 * kD, stream));
   }
   // ---- parameter gradients of the tails and the 64-row slices of the padded first-layer gradients
   SumBuilder sb;
