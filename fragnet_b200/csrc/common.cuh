@@ -244,8 +244,10 @@ int fnb_launch_tile_ranges(const RangeJobs &jobs, cudaStream_t stream);
 // Auxiliary stream of the calling thread's current device (abi.cu); returns non-zero when only the caller's stream
 // should be used.
 struct FnbAux {
-  cudaStream_t stream;
+  cudaStream_t stream;       // independent chains (fragment-connection graph, energy head)
   cudaEvent_t fork, join;
+  cudaStream_t wstream;      // weight-gradient GEMMs: nothing downstream waits for them until the end of the pass
+  cudaEvent_t ready[2], done[2], wjoin;
 };
 int fnb_aux_streams(FnbAux *out);
 
@@ -258,5 +260,9 @@ struct TransposeBatch { const float *W[16]; int count; };
 int fnb_tc_transpose128_batched(const TransposeBatch &b, float *Wt_base, cudaStream_t stream);
 int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K,
                       float *dx, float *dW, float *db, int precision, void *scratch, void *stream);
+int fnb_proj_bwd_dx(const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K, float *dx, int precision,
+                    void *scratch, void *stream);
+int fnb_proj_bwd_dw(const float *x, const float *dh, int64_t n_rows, int K, float *dW, float *db, int precision,
+                    void *scratch, void *stream);
 int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols, int k_out, float *dW, float *scratch,
                      cudaStream_t stream);

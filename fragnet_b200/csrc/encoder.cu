@@ -130,6 +130,7 @@ struct BwdBufs {
   float *g_frag, *dz_f, *dSt_f, *d_hf;
   float *Wt;   // [n_layers][3][128*128] transposed K=128 projection weights
   float *scratch2;   // scratch of the fragment-connection chain when it runs on the auxiliary stream
+  float *scratch3;   // scratch of the weight-gradient stream
 };
 
 size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *base, BwdBufs *out) {
@@ -146,6 +147,7 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   b.d_hf = a.take<float>(z.Nf * kD);
   b.Wt = a.take<float>((size_t)o->n_layers * 3 * kD * kD);
   b.scratch2 = a.take<float>(kScratchFloats);
+  b.scratch3 = a.take<float>(kScratchFloats);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -384,6 +386,15 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     float *y_fbond = o->post_act ? (last ? io->out_fbond : b.y_fbond) : nullptr;
     float *y_frag = o->post_act ? (last ? io->out_frags : b.y_frag) : nullptr;
 
+    // ---- atom projection (gat2.py:189): needs only the previous layer's atoms, so it runs on the third stream
+    // underneath the bond block
+    if (two) {
+      RC((int)cudaEventRecord(aux.ready[0], stream));
+      RC((int)cudaStreamWaitEvent(aux.wstream, aux.ready[0], 0));
+    }
+    RC(fnb_proj_fwd(xa_in, Wa_in, P.ba, z.Na, Ka_in, P.a, A_STRIDE, A_T, A_S, b.ha, b.Sa, o->precision,
+                    two ? (void *)aux.wstream : stream_));
+    if (two) RC((int)cudaEventRecord(aux.done[0], aux.wstream));
     // ---- bond graph (gat2.py:138-176); epilogue emits the atom graph's edge term <new_bond[e], a_e[h]>
     RC(fnb_proj_fwd(xb_in, Wb_in, P.bb, z.Nb, Kb_in, P.a_b, AB_STRIDE, AB_T, AB_S, b.hb, b.Sb, o->precision, stream_));
     {
@@ -396,7 +407,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       RC(fnb_gat_fwd_tiled(&plan->bond, &f, stream_));
     }
     // ---- atom graph with self loops (gat2.py:179-231)
-    RC(fnb_proj_fwd(xa_in, Wa_in, P.ba, z.Na, Ka_in, P.a, A_STRIDE, A_T, A_S, b.ha, b.Sa, o->precision, stream_));
+    if (two) RC((int)cudaStreamWaitEvent(stream, aux.done[0], 0));
     {
       fnb_gat_fwd_args f{};
       f.h = b.ha; f.S = b.Sa; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = b.se_atom; f.out = pre_atom; f.y = y_atom;
@@ -508,6 +519,36 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     return 0;
   };
 
+  // Weight gradients of the atom / bond projections: nothing waits for them before the end of the pass, so they run
+  // on a third stream; the caller's stream only waits before it overwrites the dh buffer such a GEMM is reading.
+  cudaStream_t sW = two ? aux.wstream : stream;
+  void *sW_ = (void *)sW;
+  void *scratchW = two ? (void *)W.scratch3 : scratch;
+  bool w_used = false, w_pending[2] = {false, false};
+  auto w_begin = [&](int i) -> int {   // dh of graph i (0 atom, 1 bond) is complete on the caller's stream
+    if (!two) return 0;
+    RC((int)cudaEventRecord(aux.ready[i], stream));
+    RC((int)cudaStreamWaitEvent(sW, aux.ready[i], 0));
+    if (!w_used) {
+      RC((int)cudaMemsetAsync(W.scratch3, 0, kScratchCounters * sizeof(float), sW));
+      w_used = true;
+    }
+    return 0;
+  };
+  auto w_end = [&](int i) -> int {
+    if (!two) return 0;
+    RC((int)cudaEventRecord(aux.done[i], sW));
+    w_pending[i] = true;
+    return 0;
+  };
+  auto w_wait = [&](int i) -> int {    // before dh of graph i is overwritten (or at the end of the pass)
+    if (two && w_pending[i]) {
+      RC((int)cudaStreamWaitEvent(stream, aux.done[i], 0));
+      w_pending[i] = false;
+    }
+    return 0;
+  };
+
   // gradients arriving at the four outputs of the current layer (post-activation copies in post_act mode)
   const float *dy_atom = io->g_atoms, *dy_bond = io->g_bond, *dy_fbond = io->g_fbond, *dy_frag = io->g_frags;
   for (int l = o->n_layers - 1; l >= 0; --l) {
@@ -587,17 +628,21 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         a.h = b.ha; a.dout = W.g_atom; a.p_saved = b.p_a; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.a;
         a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_a; a.dSt = W.dSt_a;
         a.dh = W.dh_a; a.d_alpha = D.a; a.d_bias = D.ba; a.scratch = scratch;
+        RC(w_wait(0));
         RC(fnb_gat_bwd_tiled(&plan->atom, &a, stream_));
+        RC(w_begin(0));
         // bond features were this graph's edge vectors: their gradient, plus the activation backward of dy_bond
         RC(fnb_edge_table_bwd_fused(&plan->atom, W.dz_a, pre_bond, P.a, A_STRIDE, A_E, y_bond ? nullptr : dy_bond,
                                     y_bond ? dy_bond : nullptr, y_bond && dy_bond ? y_bond : nullptr, scale, W.g_bond,
                                     D.a, scratch, stream_));
         float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);
-        if (l == 0 && b.k_pad[1] && !dx)
-          RC(fnb_tc_dw_launch(W.dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratch), stream));
-        else
-          RC(fnb_proj_bwd_impl(xa, P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, D.Wa, nullptr, o->precision, scratch,
-                               stream_));
+        if (l == 0 && b.k_pad[1] && !dx) {
+          RC(fnb_tc_dw_launch(W.dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchW), sW));
+        } else {
+          RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, o->precision, scratch, stream_));
+          RC(fnb_proj_bwd_dw(xa, W.dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchW, sW_));
+        }
+        RC(w_end(0));
         dy_atom = need_dx ? W.dx_atom : nullptr;
       } else {
         RC((int)cudaMemsetAsync(D.a, 0, 4 * A_STRIDE * 4, stream));
@@ -613,13 +658,17 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         a.alpha = P.a_b; a.alpha_stride = AB_STRIDE; a.off_t = AB_T; a.off_e = AB_E; a.off_s = AB_S; a.dz = W.dz_b;
         a.dSt = W.dSt_b; a.dh = W.dh_b; a.d_alpha = D.a_b; a.d_bias = D.bb; a.dWe = D.We_b; a.dbe = D.be_b;
         a.scratch = scratch;
+        RC(w_wait(1));
         RC(fnb_gat_bwd_tiled(&plan->bond, &a, stream_));
+        RC(w_begin(1));
         float *dx = need_dx ? W.dx_bond : (o->need_dx_bond ? io->dx_bond : nullptr);
-        if (l == 0 && b.k_pad[0] && !dx)
-          RC(fnb_tc_dw_launch(W.dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratch), stream));
-        else
-          RC(fnb_proj_bwd_impl(xb, P.Wb, wt_of(l, 0), W.dh_b, z.Nb, P.K_bond, dx, D.Wb, nullptr, o->precision, scratch,
-                               stream_));
+        if (l == 0 && b.k_pad[0] && !dx) {
+          RC(fnb_tc_dw_launch(W.dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchW), sW));
+        } else {
+          RC(fnb_proj_bwd_dx(P.Wb, wt_of(l, 0), W.dh_b, z.Nb, P.K_bond, dx, o->precision, scratch, stream_));
+          RC(fnb_proj_bwd_dw(xb, W.dh_b, z.Nb, P.K_bond, D.Wb, nullptr, o->precision, scratchW, sW_));
+        }
+        RC(w_end(1));
         dy_bond = need_dx ? W.dx_bond : nullptr;
       } else {
         RC((int)cudaMemsetAsync(D.a_b, 0, 4 * AB_STRIDE * 4, stream));
@@ -637,6 +686,8 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     RC((int)cudaEventRecord(aux.join, sB));
     RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
   }
+  RC(w_wait(0));
+  RC(w_wait(1));
   // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same RNG stream as the forward
   if (o->need_dx_atoms && io->dx_atoms && input_dropout(o)) {
     const RngPlan ph = rng_plan(plan, o, L);

@@ -370,35 +370,41 @@ extern "C" int fnb_proj_bwd(const float *x, const float *W, const float *dh, int
 
 // Wt_pre: optional W^T [K=128,128] already transposed by the caller (the encoder program transposes every layer's
 // weights in one launch at the start of its backward pass).
-int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K,
-                      float *dx, float *dW, float *db, int precision, void *scratch, void *stream_) {
+// The two halves of the backward are separate so that a caller can run the weight gradient -- which nothing
+// downstream waits for -- on another stream than the input gradient (which feeds the next block).
+int fnb_proj_bwd_dx(const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K, float *dx, int precision,
+                    void *scratch, void *stream_) {
   if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
-  if (!x || !W || !dh || !dW || !scratch) return FNB_ERR_NULL;
-  if (precision != FNB_PRECISION_FP32 && precision != FNB_PRECISION_TF32) return FNB_ERR_MODE;
+  if (!dx || n_rows == 0) return 0;
+  if (!W || !dh) return FNB_ERR_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
-  bool dx_done = false;
-  if (dx && n_rows > 0 && precision == FNB_PRECISION_TF32 && K == kD) {
-    // dx = dh @ W as the same tensor-core kernel with B = W^T (staged in the head of the scratch buffer; the
-    // weight-gradient partials below are written after this kernel on the same stream)
+  if (precision == FNB_PRECISION_TF32 && K == kD) {
+    // dx = dh @ W as the forward tensor-core kernel with B = W^T
     const float *Wt = Wt_pre;
     int rc = 0;
     if (!Wt) {
+      if (!scratch) return FNB_ERR_NULL;
       rc = fnb_tc_transpose128_launch(W, scratch_body(scratch), stream);
       if (rc) return rc;
       Wt = scratch_body(scratch);
     }
     rc = fnb_tc_proj_launch(dh, Wt, nullptr, n_rows, kD, nullptr, 0, 0, 0, dx, nullptr, stream);
-    if (rc == 0) dx_done = true;
-    else if (rc != FNB_ERR_MODE) return rc;
+    if (rc != FNB_ERR_MODE) return rc;
   }
-  if (dx && n_rows > 0 && !dx_done) {
-    GemmArgs g;
-    g.A = dh; g.lda = kD; g.B = W; g.ldb = K; g.C = dx; g.ldc = K; g.M = n_rows; g.Kd = kD; g.Nc = K; g.bias = nullptr;
-    g.alpha = nullptr; g.alpha_stride = 0; g.off_t = 0; g.off_s = 0; g.S = nullptr;
-    dim3 grid((unsigned)((n_rows + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
-    k_gemm<false, false><<<grid, kGemmThreads, 0, stream>>>(g);
-    FNB_CHECK_LAUNCH();
-  }
+  GemmArgs g;
+  g.A = dh; g.lda = kD; g.B = W; g.ldb = K; g.C = dx; g.ldc = K; g.M = n_rows; g.Kd = kD; g.Nc = K; g.bias = nullptr;
+  g.alpha = nullptr; g.alpha_stride = 0; g.off_t = 0; g.off_s = 0; g.S = nullptr;
+  dim3 grid((unsigned)((n_rows + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
+  k_gemm<false, false><<<grid, kGemmThreads, 0, stream>>>(g);
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
+
+int fnb_proj_bwd_dw(const float *x, const float *dh, int64_t n_rows, int K, float *dW, float *db, int precision,
+                    void *scratch, void *stream_) {
+  if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
+  if (!x || !dh || !dW || !scratch) return FNB_ERR_NULL;
+  cudaStream_t stream = (cudaStream_t)stream_;
   if (precision == FNB_PRECISION_TF32 && K == kD && n_rows > 0 && !db) {
     const int rc = fnb_tc_dw_launch(dh, x, n_rows, kD, kD, dW, scratch_body(scratch), stream);
     if (rc != FNB_ERR_MODE) return rc;
@@ -418,6 +424,16 @@ int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const
   segs.rec_off[0] = 0;       segs.width[0] = 128 * K; segs.out[0] = dW; segs.row_len[0] = 128 * K; segs.out_stride[0] = 128 * K;
   segs.rec_off[1] = 128 * K; segs.width[1] = 128;     segs.out[1] = db; segs.row_len[1] = 128;     segs.out_stride[1] = 128;
   return fnb_launch_reduce_segments(scratch_body(scratch), (int)nb, (int)rec_stride, segs, stream);
+}
+
+int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K,
+                      float *dx, float *dW, float *db, int precision, void *scratch, void *stream_) {
+  if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
+  if (!x || !W || !dh || !dW || !scratch) return FNB_ERR_NULL;
+  if (precision != FNB_PRECISION_FP32 && precision != FNB_PRECISION_TF32) return FNB_ERR_MODE;
+  const int rc = fnb_proj_bwd_dx(W, Wt_pre, dh, n_rows, K, dx, precision, scratch, stream_);
+  if (rc) return rc;
+  return fnb_proj_bwd_dw(x, dh, n_rows, K, dW, db, precision, scratch, stream_);
 }
 
 extern "C" int fnb_node_scalars(const float *h, int64_t n_rows, const float *alpha, int alpha_stride, int off_t,

@@ -232,3 +232,14 @@ def test_flat_adam_equals_torch_adam():
     assert list(m2.state_dict().keys()) == keys
     for (k, a), (_, c) in zip(m1.state_dict().items(), m2.state_dict().items()):
         assert rel_err(c, a) <= 2e-5, k
+
+
+def test_device_prefetcher_yields_identical_batches():
+    from fragnet_b200.dataset.prefetch import DevicePrefetcher
+    host = [_batch("esol", 6, s) for s in range(5)]
+    got = list(DevicePrefetcher(iter(host), "cuda", depth=2))
+    assert len(got) == len(host)
+    for h, d in zip(host, got):
+        assert set(h) == set(d)
+        for k in h:
+            assert d[k].is_cuda and d[k].dtype == h[k].dtype and torch.equal(d[k].cpu(), h[k])
