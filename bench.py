@@ -338,12 +338,26 @@ def run_ours(args):
 
         def e2e_run(n):
             feed = iter(DevicePrefetcher((host_batches[i % args.rotate] for i in range(n)), dev, depth=2))
-            return lambda i: step(next(feed)).item()
+            state = {"b": next(feed)}
+
+            def one(i):
+                loss = step(state["b"])
+                state["b"] = next(feed, None)     # stage batch i+2 while step i runs on the GPU
+                loss.item()                       # per-step device -> host read of the loss
+            return one
 
         warm = e2e_run(min(3, args.warmup))
         for i in range(min(3, args.warmup)):
             warm(i)
-        ms_e2e, _ = timed(e2e_run(args.steps), args.steps)
+        barrier()
+        run = None
+
+        def e2e_step(i):                          # the prefetcher is created INSIDE the timed region (first step)
+            nonlocal run
+            if run is None:
+                run = e2e_run(args.steps)
+            run(i)
+        ms_e2e, _ = timed(e2e_step, args.steps)
         e2e = {"value": round(mols / (ms_e2e * 1e-3), 1), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)}
 

@@ -5,57 +5,102 @@ right before the forward (fragnet/train/pretrain/pretrain_utils.py:13-14, train/
 1024-molecule batch (19 tensors, int64 indices, one-hot fp32 features), i.e. ~1.2 ms of PCIe time that the GPU spends
 idle.  ``DevicePrefetcher`` wraps any iterable of batch dicts (a ``DataLoader`` with ``collate_fn_pt``) and issues
 the copies of the NEXT batches on a side stream from pinned memory while the current one is being consumed.
+
+Device memory comes from ``depth`` persistent slots of grow-only flat buffers (one per dtype), so the steady state
+performs no allocation and never touches the caching allocator from the copy stream.
 """
 from __future__ import annotations
 
 import collections
-from typing import Dict, Iterable, Iterator
+from typing import Dict, Iterable, Iterator, List
 
 import torch
+
+
+class _Slot:
+    """Grow-only device staging area: one flat buffer per dtype, handed out as aligned views."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buffers: Dict[torch.dtype, torch.Tensor] = {}
+        self.free_event = None          # recorded on the compute stream once the consumer has moved on
+
+    def views(self, host: Dict[str, torch.Tensor]):
+        """(views, grew): device views shaped like the tensors of ``host``; ``grew`` if a buffer was (re)allocated."""
+        grew = False
+        need: Dict[torch.dtype, int] = collections.defaultdict(int)
+        for v in host.values():
+            if isinstance(v, torch.Tensor):
+                need[v.dtype] += (v.numel() + 63) // 64 * 64
+        for dt, n in need.items():
+            buf = self.buffers.get(dt)
+            if buf is None or buf.numel() < n:
+                self.buffers[dt] = torch.empty(int(n * 1.25) + 64, dtype=dt, device=self.device)
+                grew = True
+        used: Dict[torch.dtype, int] = collections.defaultdict(int)
+        out = {}
+        for k, v in host.items():
+            if isinstance(v, torch.Tensor):
+                o = used[v.dtype]
+                out[k] = self.buffers[v.dtype][o:o + v.numel()].view(v.shape)
+                used[v.dtype] = o + (v.numel() + 63) // 64 * 64
+            else:
+                out[k] = v
+        return out, grew
 
 
 class DevicePrefetcher:
     """``for batch in DevicePrefetcher(loader, device): ...`` yields device-resident batch dicts.
 
-    ``depth`` batches are in flight (2 = double buffering).  Tensors that are not pinned are pinned first (use
-    ``DataLoader(pin_memory=True)`` to do that in the loader's workers)."""
+    ``depth`` batches are in flight (2 = double buffering).  A yielded batch stays valid until ``depth`` further
+    batches have been requested.  Host tensors that are not pinned are pinned first (``DataLoader(pin_memory=True)``
+    does that in the loader's workers)."""
 
     def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device, depth: int = 2):
         self.batches, self.device, self.depth = batches, torch.device(device), max(1, int(depth))
         if self.device.type != "cuda":
             raise ValueError("DevicePrefetcher stages batches onto a CUDA device")
         self._copy_stream = torch.cuda.Stream(self.device)
+        self._slots: List[_Slot] = [_Slot(self.device) for _ in range(self.depth + 1)]
 
-    def _stage(self, host: Dict[str, torch.Tensor]):
-        with torch.cuda.stream(self._copy_stream):
-            dev = {}
-            for k, v in host.items():
+    def _stage(self, host: Dict[str, torch.Tensor], slot: _Slot):
+        pinned = {k: (v if (not isinstance(v, torch.Tensor) or v.is_cuda or v.is_pinned()) else v.pin_memory())
+                  for k, v in host.items()}
+        dev, grew = slot.views(pinned)                   # (re)allocation, if any, happens on the current stream
+        cs = self._copy_stream
+        if slot.free_event is not None:
+            cs.wait_event(slot.free_event)               # the previous tenant of this slot has been consumed
+        if grew:
+            cs.wait_stream(torch.cuda.current_stream(self.device))   # stream-ordered reuse of freed memory
+        with torch.cuda.stream(cs):
+            for k, v in pinned.items():
                 if isinstance(v, torch.Tensor):
-                    if not v.is_cuda and not v.is_pinned():
-                        v = v.pin_memory()
-                    dev[k] = v.to(self.device, non_blocking=True)
-                else:
-                    dev[k] = v
+                    dev[k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(self._copy_stream)
-        return dev, ev, host          # the (pinned) host tensors stay alive until the copy has been waited for
+            ev.record(cs)
+        return dev, ev, pinned, slot                     # pinned host tensors stay alive until the copy was waited for
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         it = iter(self.batches)
         queue = collections.deque()
-        done = False
+        done, n_staged, last = False, 0, None
         while True:
+            cur = torch.cuda.current_stream(self.device)
+            if last is not None:                         # everything the consumer queued on the last batch precedes this
+                last.free_event = torch.cuda.Event()
+                last.free_event.record(cur)
+                last = None
             while not done and len(queue) < self.depth:
                 try:
-                    queue.append(self._stage(next(it)))
+                    host = next(it)
                 except StopIteration:
                     done = True
+                    break
+                queue.append(self._stage(host, self._slots[n_staged % len(self._slots)]))
+                n_staged += 1
             if not queue:
                 return
-            dev, ev, _host = queue.popleft()
-            cur = torch.cuda.current_stream(self.device)
+            dev, ev, _pinned, slot = queue.popleft()
             cur.wait_event(ev)
-            for v in dev.values():
-                if isinstance(v, torch.Tensor) and v.is_cuda:
-                    v.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
+            last = slot
             yield dev

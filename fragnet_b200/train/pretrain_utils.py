@@ -1,8 +1,15 @@
 """Pretraining step loop with the reference's semantics (fragnet/train/pretrain/pretrain_utils.py:4-57).
 
-Kept behaviour: every batch tensor is moved with ``.to(device)``; the loss is
-``2*MSE(dihedral) + MSE(angle) + MSE(energy)`` because the reference overwrites ``loss_lngth`` with the
-dihedral term before summing (pretrain_utils.py:22-26); the epoch loss is divided by the dataset size.
+Kept behaviour: the loss is ``2*MSE(dihedral) + MSE(angle) + MSE(energy)`` because the reference overwrites
+``loss_lngth`` with the dihedral term before summing (pretrain_utils.py:22-26); the epoch loss is the sum of the
+per-batch losses divided by the dataset size; ``train`` / ``validate`` keep their signatures, so
+``pretrain_gat2.py`` drives this class unchanged.
+
+What is different underneath: when the model is the drop-in ``FragNetPreTrain`` on a CUDA device, the criterion is
+``nn.MSELoss()`` and the optimizer a plain ``torch.optim.Adam`` -- the configuration of pretrain_gat2.py:98-165 --
+every batch runs as ONE library call (``FusedPretrainStep``: collate, forward, loss, backward, Adam) fed by a
+``DevicePrefetcher`` (pinned, double-buffered host-to-device copies on a side stream).  Anything else takes the
+generic ``model(batch)`` / ``loss.backward()`` / ``optimizer.step()`` path below, which is the reference's loop.
 """
 from __future__ import annotations
 
@@ -25,12 +32,64 @@ def pretrain_loss(loss_fn, preds, batch):
     return l_dh + loss_fn(angle, t_ba) + l_dh + loss_fn(energy.view(-1), y)
 
 
-class Trainer:
-    def __init__(self, loss_fn=None):
-        self.loss_fn = loss_fn
+def _plain_adam(optimizer) -> bool:
+    if type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+        return False
+    g = optimizer.param_groups[0]
+    return not (g.get("amsgrad") or g.get("maximize") or g.get("capturable") or g.get("differentiable")
+                or g.get("decoupled_weight_decay")) and len(optimizer.state) == 0
 
+
+class Trainer:
+    def __init__(self, loss_fn=None, fused: bool = True):
+        self.loss_fn = loss_fn
+        self.fused = fused
+        self._fused_steps = {}       # (id(model), id(optimizer)) -> FusedPretrainStep
+
+    # ---- fused path -----------------------------------------------------------------------------
+    def _fused_for(self, model, optimizer, device):
+        """The ``FusedPretrainStep`` bound to (model, optimizer), or None when the fused path does not apply."""
+        if not self.fused or torch.device(device).type != "cuda":
+            return None
+        if not (isinstance(self.loss_fn, torch.nn.MSELoss) and self.loss_fn.reduction == "mean"):
+            return None
+        key = (id(model), id(optimizer))
+        if key in self._fused_steps:
+            return self._fused_steps[key]
+        from ..model.gat.pretrain_heads import FragNetPreTrain
+        from .fused import FusedPretrainStep
+        ok = isinstance(model, FragNetPreTrain) and model.head._library_shapes() and \
+            next(model.parameters()).is_cuda and (optimizer is None or _plain_adam(optimizer))
+        fs = None
+        if ok:
+            g = optimizer.param_groups[0] if optimizer is not None else {}
+            fs = FusedPretrainStep(model, lr=g.get("lr", 1e-3), betas=g.get("betas", (0.9, 0.999)),
+                                   eps=g.get("eps", 1e-8), weight_decay=g.get("weight_decay", 0.0))
+        self._fused_steps[key] = fs
+        return fs
+
+    @staticmethod
+    def _run_pipelined(loader, device, launch):
+        """``launch(batch) -> loss tensor`` per batch; the next batches are staged while the GPU works and every
+        loss is read back (the reference's ``loss.item()`` per step)."""
+        from ..dataset.prefetch import DevicePrefetcher
+        feed = iter(DevicePrefetcher(loader, device, depth=2))
+        total, batch = 0.0, next(feed, None)
+        while batch is not None:
+            loss = launch(batch)
+            batch = next(feed, None)
+            total += loss.item()
+        return total
+
+    # ---- the reference's interface --------------------------------------------------------------
     def train(self, model, loader, optimizer, device):
         model.train()
+        fs = self._fused_for(model, optimizer, device)
+        if fs is not None:
+            def launch(batch):
+                fs.lr = float(optimizer.param_groups[0]["lr"])       # LR schedulers keep working
+                return fs.step(batch)
+            return self._run_pipelined(loader, device, launch) / len(loader.dataset)
         total = 0.0
         for batch in loader:
             for k in batch:
@@ -44,6 +103,11 @@ class Trainer:
 
     def validate(self, loader, model, device):
         model.eval()
+        fs = next((v for (mid, _), v in self._fused_steps.items() if mid == id(model) and v is not None), None)
+        if fs is None:
+            fs = self._fused_for(model, None, device)
+        if fs is not None:
+            return self._run_pipelined(loader, device, fs.evaluate) / len(loader.dataset)
         total = 0.0
         with torch.no_grad():
             for batch in loader:

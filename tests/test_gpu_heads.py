@@ -226,3 +226,37 @@ def test_fused_step_dropout_training_is_seeded_and_finite():
         fused = FusedPretrainStep(m1, lr=1e-4)
         losses.append([float(fused.step(b)) for _ in range(3)])
     assert losses[0] == losses[1] and all(x == x and x < 1e6 for x in losses[0])
+
+
+def test_trainer_fused_path_equals_generic_loop():
+    """The reference's Trainer interface (pretrain_utils.py:4-57) through a DataLoader: the fused path (one library
+    call per batch + prefetcher) and the generic nn.Module / autograd / torch.optim.Adam loop train twin models alike."""
+    import copy
+    from torch.utils.data import DataLoader
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet.train.pretrain.pretrain_utils import Trainer
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    mols = synth.make_dataset("unimol", 48, seed=9)
+    gen = torch.Generator().manual_seed(2)
+    for m in mols:
+        m.bnd_angl = torch.randn(m.bnd_angl.shape, generator=gen)
+        m.dh_angl = torch.randn(m.dh_angl.shape, generator=gen)
+        m.y = torch.randn(m.y.shape, generator=gen)
+    loader = DataLoader(mols, collate_fn=collate_fn_pt, batch_size=16, shuffle=False, drop_last=True)
+    torch.manual_seed(4)
+    m1 = FragNetPreTrain(num_layer=2, drop_ratio=0.0, edge_features=17).cuda()
+    m2 = copy.deepcopy(m1)
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    t1, t2 = Trainer(torch.nn.MSELoss()), Trainer(torch.nn.MSELoss(), fused=False)
+    for _ in range(2):
+        l1 = t1.train(m1, loader, o1, "cuda")
+        l2 = t2.train(m2, loader, o2, "cuda")
+        assert abs(l1 - l2) <= 1e-5 * abs(l2)
+    assert t1._fused_for(m1, o1, "cuda") is not None and not t2._fused_steps
+    p2 = dict(m2.named_parameters())
+    # six Adam steps: the update is ~lr * sign(g) for small g, so rounding-level gradient differences show up at 1e-5
+    assert max(rel_err(p, p2[k]) for k, p in m1.named_parameters()) <= 1e-4
+    v1, v2 = t1.validate(loader, m1, "cuda"), t2.validate(loader, m2, "cuda")
+    assert abs(v1 - v2) <= 1e-5 * abs(v2)

@@ -236,10 +236,12 @@ def test_flat_adam_equals_torch_adam():
 
 def test_device_prefetcher_yields_identical_batches():
     from fragnet_b200.dataset.prefetch import DevicePrefetcher
-    host = [_batch("esol", 6, s) for s in range(5)]
-    got = list(DevicePrefetcher(iter(host), "cuda", depth=2))
-    assert len(got) == len(host)
-    for h, d in zip(host, got):
+    host = [_batch("esol", 6 + s, s) for s in range(7)]
+    n = 0
+    for h, d in zip(host, DevicePrefetcher(iter(host), "cuda", depth=2)):   # a batch is valid until 2 more are requested
         assert set(h) == set(d)
         for k in h:
-            assert d[k].is_cuda and d[k].dtype == h[k].dtype and torch.equal(d[k].cpu(), h[k])
+            assert d[k].is_cuda and d[k].dtype == h[k].dtype and d[k].shape == h[k].shape
+            assert torch.equal(d[k].cpu(), h[k]), k
+        n += 1
+    assert n == len(host)
