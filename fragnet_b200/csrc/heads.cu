@@ -321,6 +321,208 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
   if (tid < IN) rec[MID * IN + 2 * MID + 1 + tid] = b0acc;
 }
 
+// Backward tail of the two big heads (IN = 64, MID = 32) as three register-tiled FP32 GEMMs per 128-row tile, all
+// operands in shared memory (the first version was thread-per-row with broadcast weight loads and ran at the
+// shared-memory return bandwidth, 4 FMA per LDS.128: 118 us for 80 k rows; here 11-16 FMA per LDS.128):
+//   P1  H1pre[r,j] = b1[j] + sum_k A[r,k] W1[j,k]      thread = 8 rows x 4 j     A = ReLU(h0) tile, row-major
+//       D1[r,j]    = H1pre > 0 ? g[r] W2[j] : 0        (+ per-thread partials of db1, dW2, db2)
+//   P2  dh0[r,k]   = A[r,k] > 0 ? sum_j D1[r,j] W1[j,k] : 0    thread = 8 rows x 8 k   (+ db0 partials) -> global
+//   P3  dW1[j,k]  += sum_r D1[r,j] A[r,k]              thread = 4 j x 4 k, accumulated over all tiles of the CTA
+// Rows of a thread are interleaved (r = rg + 16 i) so that the 4 row groups of a warp hit distinct banks.
+constexpr int TB_ROWS = 128, TB_SA = 68, TB_SD = 36;
+constexpr size_t kTailBwd2Smem = sizeof(float) * (2 * 64 * 32 + TB_ROWS * TB_SA + TB_ROWS * TB_SD + TB_ROWS + 64);
+
+__global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
+  constexpr int IN = 64, MID = 32, REC = rec_floats(64, 32);
+  const TailJob &job = J.j[blockIdx.y];
+  extern __shared__ __align__(16) float smem[];
+  float *sW1t = smem;                       // [IN][MID]   W1t[k][j] = W1[j][k]
+  float *sW1 = sW1t + IN * MID;             // [MID][IN]
+  float *sA = sW1 + IN * MID;               // [TB_ROWS][TB_SA]
+  float *sD1 = sA + TB_ROWS * TB_SA;        // [TB_ROWS][TB_SD]
+  float *sg = sD1 + TB_ROWS * TB_SD;        // [TB_ROWS]
+  float *sb1 = sg + TB_ROWS;                // [32] b1, [32] W2
+  float *sred = sA;                         // [16][80] end-of-kernel partials (the tile is dead by then)
+  const int tid = threadIdx.x;
+  const int64_t n_tiles = (job.n + TB_ROWS - 1) / TB_ROWS;
+  if (blockIdx.x >= n_tiles && blockIdx.x > 0) return;   // CTA 0 always runs: it writes a (possibly zero) record
+  for (int i = tid; i < IN * MID; i += 128) {
+    const float w = __ldg(job.W1 + i);      // i = j * IN + k
+    sW1[i] = w;
+    sW1t[(i & (IN - 1)) * MID + (i >> 6)] = w;
+  }
+  if (tid < MID) {
+    sb1[tid] = __ldg(job.b1 + tid);
+    sb1[32 + tid] = __ldg(job.W2 + tid);
+  }
+  const int rg = tid >> 3, g8 = tid & 7;    // P1: j = 4 g8 .. +3;  P2: k = 4 g8 .. +3 and 32 + 4 g8 .. +3
+  const int jb = tid >> 4, kb = tid & 15;   // P3: j = 4 jb .. +3, k = 4 kb .. +3
+  float wacc[4][4];
+#pragma unroll
+  for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wacc[p_][q] = 0.f;
+  float db1p[4] = {0.f, 0.f, 0.f, 0.f}, dw2p[4] = {0.f, 0.f, 0.f, 0.f}, db0p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float db2p = 0.f;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * TB_ROWS;
+    __syncthreads();   // previous tile fully consumed (also publishes the weights on the first pass)
+    // ---- stage A = ReLU(h0[:, 0:64]) and g
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int idx = it * 128 + tid, r = idx >> 4, c4 = idx & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < job.n) v = ldg4(job.h0 + (r0 + r) * kD + c4 * 4);
+      st4(sA + r * TB_SA + c4 * 4, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
+    }
+    sg[tid] = r0 + tid < job.n ? __ldg(job.gout + r0 + tid) : 0.f;
+    __syncthreads();
+    // ---- P1
+    {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+#pragma unroll 2
+      for (int k4 = 0; k4 < IN / 4; ++k4) {
+        float4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = ld4(sW1t + (k4 * 4 + u) * MID + g8 * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = ld4(sA + (rg + 16 * i) * TB_SA + k4 * 4);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[i][0] = fmaf(av[u], w[u].x, acc[i][0]);
+            acc[i][1] = fmaf(av[u], w[u].y, acc[i][1]);
+            acc[i][2] = fmaf(av[u], w[u].z, acc[i][2]);
+            acc[i][3] = fmaf(av[u], w[u].w, acc[i][3]);
+          }
+        }
+      }
+      const float4 b1v = ld4(sb1 + g8 * 4), w2v = ld4(sb1 + 32 + g8 * 4);
+      const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w}, w2a[4] = {w2v.x, w2v.y, w2v.z, w2v.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rg + 16 * i;
+        const float g = sg[r];
+        float d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float pre = acc[i][q] + b1a[q];
+          d[q] = pre > 0.f ? g * w2a[q] : 0.f;
+          db1p[q] += d[q];
+          dw2p[q] = fmaf(g, fmaxf(pre, 0.f), dw2p[q]);
+        }
+        if (g8 == 0) db2p += g;
+        st4(sD1 + r * TB_SD + g8 * 4, make_float4(d[0], d[1], d[2], d[3]));
+      }
+    }
+    __syncthreads();
+    // ---- P2
+    {
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[i][q] = 0.f;
+#pragma unroll 1
+      for (int j4 = 0; j4 < MID / 4; ++j4) {
+        float4 wl[4], wh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          wl[u] = ld4(sW1 + (j4 * 4 + u) * IN + g8 * 4);
+          wh[u] = ld4(sW1 + (j4 * 4 + u) * IN + 32 + g8 * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 dv = ld4(sD1 + (rg + 16 * i) * TB_SD + j4 * 4);
+          const float da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[i][0] = fmaf(da[u], wl[u].x, acc[i][0]);
+            acc[i][1] = fmaf(da[u], wl[u].y, acc[i][1]);
+            acc[i][2] = fmaf(da[u], wl[u].z, acc[i][2]);
+            acc[i][3] = fmaf(da[u], wl[u].w, acc[i][3]);
+            acc[i][4] = fmaf(da[u], wh[u].x, acc[i][4]);
+            acc[i][5] = fmaf(da[u], wh[u].y, acc[i][5]);
+            acc[i][6] = fmaf(da[u], wh[u].z, acc[i][6]);
+            acc[i][7] = fmaf(da[u], wh[u].w, acc[i][7]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rg + 16 * i;
+        const float4 al = ld4(sA + r * TB_SA + g8 * 4), ah = ld4(sA + r * TB_SA + 32 + g8 * 4);
+        float4 lo, hi;
+        lo.x = al.x > 0.f ? acc[i][0] : 0.f; lo.y = al.y > 0.f ? acc[i][1] : 0.f;
+        lo.z = al.z > 0.f ? acc[i][2] : 0.f; lo.w = al.w > 0.f ? acc[i][3] : 0.f;
+        hi.x = ah.x > 0.f ? acc[i][4] : 0.f; hi.y = ah.y > 0.f ? acc[i][5] : 0.f;
+        hi.z = ah.z > 0.f ? acc[i][6] : 0.f; hi.w = ah.w > 0.f ? acc[i][7] : 0.f;
+        db0p[0] += lo.x; db0p[1] += lo.y; db0p[2] += lo.z; db0p[3] += lo.w;
+        db0p[4] += hi.x; db0p[5] += hi.y; db0p[6] += hi.z; db0p[7] += hi.w;
+        if (r0 + r < job.n) {
+          float *dp = job.dh0 + (r0 + r) * kD;
+          st4(dp + g8 * 4, lo);
+          st4(dp + 32 + g8 * 4, hi);
+          st4(dp + 64 + g8 * 4, make_float4(0.f, 0.f, 0.f, 0.f));   // columns 64.. of the padded first layer
+          st4(dp + 96 + g8 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+    }
+    // ---- P3 (reads sD1 and sA only: no barrier needed after P2)
+#pragma unroll 4
+    for (int r = 0; r < TB_ROWS; ++r) {
+      const float4 dv = ld4(sD1 + r * TB_SD + jb * 4), av = ld4(sA + r * TB_SA + kb * 4);
+      const float da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int p_ = 0; p_ < 4; ++p_) {
+        wacc[p_][0] = fmaf(da[p_], av.x, wacc[p_][0]);
+        wacc[p_][1] = fmaf(da[p_], av.y, wacc[p_][1]);
+        wacc[p_][2] = fmaf(da[p_], av.z, wacc[p_][2]);
+        wacc[p_][3] = fmaf(da[p_], av.w, wacc[p_][3]);
+      }
+    }
+  }
+  // ---- CTA record: [dW1 MID*IN][db1 MID][dW2 MID][db2 1][db0 IN]
+  float *rec = job.rec + (size_t)blockIdx.x * REC;
+#pragma unroll
+  for (int p_ = 0; p_ < 4; ++p_)
+    st4(rec + (jb * 4 + p_) * IN + kb * 4, make_float4(wacc[p_][0], wacc[p_][1], wacc[p_][2], wacc[p_][3]));
+  // vector sums: 16 row groups share every (g8) column set; combine them in fixed order through shared memory
+  __syncthreads();
+  float *mine = sred + rg * 80;            // [db1 32][dW2 32][db2 8 (one per g8, only g8 == 0 is non-zero)] ... db0 separately
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    mine[g8 * 4 + q] = db1p[q];
+    mine[32 + g8 * 4 + q] = dw2p[q];
+  }
+  mine[64 + g8] = db2p;
+  __syncthreads();
+  if (tid < 65) {
+    float s_ = 0.f;
+    const int col = tid < 64 ? tid : 64;   // 64: db2 (g8 == 0 slot)
+    for (int g = 0; g < 16; ++g) s_ += sred[g * 80 + col];
+    rec[MID * IN + col] = s_;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    mine[g8 * 4 + q] = db0p[q];
+    mine[32 + g8 * 4 + q] = db0p[4 + q];
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float s_ = 0.f;
+    for (int g = 0; g < 16; ++g) s_ += sred[g * 80 + tid];
+    rec[MID * IN + 2 * MID + 1 + tid] = s_;
+  }
+}
+
 template <int IN, int MID, int ROWS>
 constexpr size_t tail_bwd_smem() {
   return sizeof(float) * ((size_t)IN * MID + 2 * (size_t)ROWS * (IN + 4) + 2 * (size_t)ROWS * (MID + 1) + ROWS);
@@ -533,8 +735,8 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
     if (!done[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(k_mlp_tail_bwd<64, 32, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)tail_bwd_smem<64, 32, 128>());
+      cudaError_t e = cudaFuncSetAttribute(k_mlp_tail_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kTailBwd2Smem);
       if (e != cudaSuccess) return (int)e;
       e = cudaFuncSetAttribute(k_mlp_tail_bwd<128, 64, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)tail_bwd_smem<128, 64, 64>());
@@ -579,7 +781,7 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
     const int gx = ctas_ba > ctas_da ? ctas_ba : ctas_da;
     // a job with fewer tiles than gx: its surplus CTAs return at once and write no record, so the record count of a
     // job is min(gx, tiles of the job) = its own tail_grid
-    k_mlp_tail_bwd<64, 32, 128, 128><<<dim3(gx, 2), 128, tail_bwd_smem<64, 32, 128>(), stream>>>(J);
+    k_mlp_tail_bwd2<<<dim3(gx, 2), 128, kTailBwd2Smem, stream>>>(J);
     FNB_CHECK_LAUNCH();
   }
   // ---- first layers: dX and dW on the projection kernels
