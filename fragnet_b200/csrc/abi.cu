@@ -46,3 +46,8 @@ int fnb_aux_streams(FnbAux *out) {
   *out = aux[dev];
   return 0;
 }
+
+bool fnb_pdl_enabled() {
+  static const bool on = [] { const char *e = getenv("FNB_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}

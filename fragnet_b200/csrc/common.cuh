@@ -69,6 +69,28 @@ __device__ __forceinline__ float pick(const float4 &v, int i) {
 }
 __device__ __forceinline__ float leaky(float z) { return z > 0.f ? z : kNegSlope * z; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A step is ~140 short kernels (10-40 us) in stream order; with the programmatic-stream-serialization attribute the
+// next kernel's CTAs are scheduled while the last CTAs of the previous one drain, and block in pdl_wait() until the
+// previous grid has completed and flushed.  Every kernel launched through fnb_launch() calls pdl_wait() before its
+// first access to global memory and pdl_launch_dependents() once its main loop is done.  Both are no-ops for a
+// kernel launched without the attribute (FNB_PDL=0 in the environment turns the attribute off).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool fnb_pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t fnb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = fnb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- mbarrier + bulk asynchronous copy (TMA engine, 1-D): global -> shared memory ---------------------------------
 namespace bulk {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256) k_grad_combine(const float *__restrict__ 
                                                       const int *__restrict__ seg_of, int64_t n_rows,
                                                       float *__restrict__ g) {
   const int64_t total = n_rows * 32;
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i >> 5;
     const int c = (int)(i & 31) * 4;
@@ -253,7 +254,8 @@ int grad_combine(const float *dy, const float *y, float scale, const float *pool
   if (n_rows == 0) return 0;
   int64_t blocks = (n_rows * 32 + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  k_grad_combine<<<(int)blocks, 256, 0, stream>>>(dy, y, scale, pooled, seg_of, n_rows, g);
+  if (cudaError_t le = fnb_launch(k_grad_combine, dim3((int)blocks), dim3(256), 0, stream, dy, y, scale, pooled, seg_of, n_rows, g))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict
     }
   const bool valid = col < segs.width[seg] && (col % segs.row_len[seg]) < segs.valid_len[seg];
   float acc = 0.f;
+  pdl_wait();
   if (valid) {
     const float *src = partials + segs.rec_off[seg] + col;
     for (int b = ty; b < n_blocks; b += 32) acc += src[(int64_t)b * pstride];
@@ -384,7 +385,8 @@ int fnb_launch_reduce_segments(const float *partials, int n_blocks, int pstride,
     cols += segs.padded_width[i];
   }
   if (cols == 0) return 0;
-  k_reduce_partials<<<cols / 8, 256, 0, stream>>>(partials, n_blocks, pstride, segs);
+  if (cudaError_t le = fnb_launch(k_reduce_partials, dim3(cols / 8), dim3(256), 0, stream, partials, n_blocks, pstride, segs))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(Fwd
   __shared__ float s_coef[28];
   __shared__ __align__(16) float s_na[4 * kD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, head = lane >> 3;
+  pdl_wait();
   if (MODE == FNB_EDGE_AFFINE1) edge_coef_prologue<1>(a.We, a.be, a.alpha_e, a.alpha_e_stride, s_coef);
   if (MODE == FNB_EDGE_AFFINE6) edge_coef_prologue<6>(a.We, a.be, a.alpha_e, a.alpha_e_stride, s_coef);
   if (a.next_alpha)  // consumer graph's edge slice, 4 heads x 128 columns
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(Fwd
       phase ^= 1;
     }
   }
+  pdl_launch_dependents();
 }
 
 // ================================================================================================
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
   const int c_head = (NC == 8) ? (c & 3) : (c < 24 ? c / 6 : c - 24);
   const int c_k = (NC == 8) ? (c < 4 ? 0 : -1) : (c < 24 ? c % 6 : -1);  // -1: bias term (attribute = 1)
   float cacc = 0.f;
+  pdl_wait();
 
   const int n_tiles = (a.n_nodes + a.npc - 1) / a.npc;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -463,6 +466,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
     }
   }
 
+  pdl_launch_dependents();
   if (NC > 1) {
     // CTA record of the coefficient gradients, then the cross-CTA tree; the finishing CTA turns d_coef into the
     // gradients of the embedding and of the edge slice of the head vector (App. A.5).
@@ -521,6 +525,7 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
   __shared__ __align__(16) float s_dSs[T_NPC * 4];
   static_assert(BWD_CAP * 4 >= T_WARPS * 384, "per-warp records must fit the staging array");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, head = lane >> 3;
+  pdl_wait();
   const float4 at = ldg4(a.alpha + (int64_t)head * a.alpha_stride + a.off_t + (lane & 7) * 4);
   const float4 as = ldg4(a.alpha + (int64_t)head * a.alpha_stride + a.off_s + (lane & 7) * 4);
   float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -621,6 +626,7 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
   }
 
   // CTA record: [0,128) d alpha_t[4,32] (index head*32 + col = lane*4 + i), [128,256) d alpha_s, [256,384) colsum(dh)
+  pdl_launch_dependents();
   __syncthreads();
   float *s_w = s_p;
 #pragma unroll
@@ -670,6 +676,7 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_edge_table_bwd_tiled(TableT a)
   __shared__ __align__(16) float s_fin[512];
   __shared__ __align__(16) float s_ae[4 * kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
   for (int i = threadIdx.x; i < 4 * kD; i += T_THREADS)
     s_ae[i] = __ldg(a.alpha + (int64_t)(i >> 7) * a.alpha_stride + a.off_e + (i & 127));
   __syncthreads();
@@ -707,6 +714,7 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_edge_table_bwd_tiled(TableT a)
       acc[hh].w = fmaf(d4[hh], f.w, acc[hh].w);
     }
   }
+  pdl_launch_dependents();
 #pragma unroll
   for (int hh = 0; hh < 4; ++hh) st4(s_w + warp * 512 + hh * 128 + lane * 4, acc[hh]);
   __syncthreads();
@@ -770,7 +778,8 @@ int launch_fwd(const FwdT &a, bool staged, cudaStream_t stream) {
     if (rc) return rc;
     k_gat_fwd_tiled<MODE, true><<<tile_grid(a.n_nodes, kRangeTile, 2), T_THREADS, smem, stream>>>(a);
   } else {
-    k_gat_fwd_tiled<MODE, false><<<tile_grid(a.n_nodes, a.npc, 6), T_THREADS, 0, stream>>>(a);
+    const cudaError_t le = fnb_launch(k_gat_fwd_tiled<MODE, false>, dim3(tile_grid(a.n_nodes, a.npc, 6)), dim3(T_THREADS), 0, stream, a);
+    if (le != cudaSuccess) return (int)le;
   }
   FNB_CHECK_LAUNCH();
   return 0;
@@ -849,12 +858,12 @@ extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, 
   const bool affine = b->edge_mode == FNB_EDGE_AFFINE1 || b->edge_mode == FNB_EDGE_AFFINE6;
   if (affine && (!g->edge_attr || !b->We || !b->be || !b->dWe || !b->dbe)) return FNB_ERR_NULL;
   if (b->edge_mode == FNB_EDGE_AFFINE1) {
-    k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE1><<<grid, T_THREADS, 0, stream>>>(d);
+    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE1>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
   } else if (b->edge_mode == FNB_EDGE_AFFINE6) {
     if (reinterpret_cast<uintptr_t>(g->edge_attr) & 7u) return FNB_ERR_ALIGN;
-    k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE6><<<grid, T_THREADS, 0, stream>>>(d);
+    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE6>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
   } else if (b->edge_mode == FNB_EDGE_NONE || b->edge_mode == FNB_EDGE_TABLE) {
-    k_gat_bwd_dst_tiled<FNB_EDGE_NONE><<<grid, T_THREADS, 0, stream>>>(d);
+    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_NONE>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
   } else {
     return FNB_ERR_MODE;
   }
@@ -865,7 +874,7 @@ extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, 
   s.off_s = b->off_s; s.dh = b->dh; s.d_alpha = b->d_alpha; s.d_bias = b->d_bias; s.scratch = (float *)b->scratch;
   s.n_nodes = (int)g->n_nodes;
   s.npc = d.npc;
-  k_gat_bwd_src_tiled<<<grid, T_THREADS, 0, stream>>>(s);
+  if (cudaError_t le = fnb_launch(k_gat_bwd_src_tiled, dim3(grid), dim3(T_THREADS), 0, stream, s)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }
@@ -889,7 +898,7 @@ extern "C" int fnb_edge_table_bwd_fused(const fnb_graph *g, const float *dz, con
   int64_t blocks = (g->n_real_edges + T_WARPS - 1) / T_WARPS;
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
   if (blocks < 1) blocks = 1;
-  k_edge_table_bwd_tiled<<<(int)blocks, T_THREADS, 0, (cudaStream_t)stream_>>>(a);
+  if (cudaError_t le = fnb_launch(k_edge_table_bwd_tiled, dim3((int)blocks), dim3(T_THREADS), 0, (cudaStream_t)stream_, a)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }

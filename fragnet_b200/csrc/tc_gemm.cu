@@ -138,12 +138,6 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
   const uint32_t bar_acc_full = smem_u32(&bars[2 * TC_STAGES + 1]);   // [2]
   const uint32_t bar_acc_empty = smem_u32(&bars[2 * TC_STAGES + 3]);  // [2]
 
-  for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
-    s_bias[i] = g.bias ? g.bias[i] : 0.f;
-    const int hh = i >> 5, j = i & 31;
-    s_at[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_t + j] : 0.f;
-    s_as[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_s + j] : 0.f;
-  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -161,6 +155,13 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                  "r"(TC_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();   // barriers and TMEM are set up while the previous kernel drains; global memory only from here on
+  for (int i = threadIdx.x; i < 128; i += TC_THREADS) {
+    s_bias[i] = g.bias ? g.bias[i] : 0.f;
+    const int hh = i >> 5, j = i & 31;
+    s_at[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_t + j] : 0.f;
+    s_as[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_s + j] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -253,6 +254,7 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     }
   }
 
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -313,6 +315,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -365,6 +368,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -456,7 +460,7 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
   }
   const int64_t n_tiles = (M + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-  k_tc_proj<<<grid, TC_THREADS, smem, stream>>>(tm_a, tm_b, g);
+  if (cudaError_t le = fnb_launch(k_tc_proj, dim3(grid), dim3(TC_THREADS), smem, stream, tm_a, tm_b, g)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }
@@ -507,7 +511,9 @@ int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols
       done[dev] = true;
     }
   }
-  k_tc_dw<<<grid, TC_THREADS, smem, stream>>>(tm_dh, tm_x, scratch, n_rb, per, n_chunks, n_stages, tmem_cols);
+  if (cudaError_t le = fnb_launch(k_tc_dw, dim3(grid), dim3(TC_THREADS), smem, stream, tm_dh, tm_x, scratch, n_rb, per, n_chunks,
+                                  n_stages, tmem_cols))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   // second stage: record [128][x_cols] -> dW [128][k_out]
   ReduceSegments segs{};
