@@ -15,6 +15,7 @@ namespace {
 __global__ void __launch_bounds__(256) k_dropout_relu_fwd(const float *__restrict__ x, float *__restrict__ y, int64_t n,
                                                           float p, float scale, int relu, uint64_t seed,
                                                           uint64_t offset, int vec_ok) {
+  pdl_wait();
   const int64_t n4 = (n + 3) >> 2;
   PostAct pa;
   pa.p = p; pa.scale = scale; pa.training = 1; pa.relu = relu; pa.seed = seed; pa.offset = offset;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) k_dropout_relu_fwd(const float *__restric
 
 __global__ void __launch_bounds__(256) k_relu_fwd(const float *__restrict__ x, float *__restrict__ y, int64_t n,
                                                   int vec_ok) {
+  pdl_wait();
   const int64_t n4 = (n + 3) >> 2;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = q << 2;
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(256) k_relu_fwd(const float *__restrict__ x, f
 
 __global__ void __launch_bounds__(256) k_dropout_relu_bwd(const float *__restrict__ dy, const float *__restrict__ y,
                                                           float *__restrict__ dx, int64_t n, float scale, int vec_ok) {
+  pdl_wait();
   const int64_t n4 = (n + 3) >> 2;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = q << 2;
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(256) k_dropout_relu_bwd(const float *__restric
 __global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                               float *__restrict__ v, int64_t n, float b1, float b2, float eps,
                                               float weight_decay, float step_size, float inv_sqrt_bc2) {
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i];
     const float pi = p[i];
@@ -103,8 +107,9 @@ extern "C" int fnb_dropout_relu_fwd(const float *x, float *y, int64_t n, float p
   const int vec_ok = fnb_aligned16(x) && fnb_aligned16(y);
   const int64_t n4 = (n + 3) >> 2;
   if (training && p > 0.f) {
-    k_dropout_relu_fwd<<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, 1.f / (1.f - p), relu, seed, offset,
-                                                                     vec_ok);
+    if (cudaError_t le = fnb_launch(k_dropout_relu_fwd, dim3(ew_grid(n4)), dim3(256), 0, (cudaStream_t)stream, x, y, n, p,
+                                    1.f / (1.f - p), relu, seed, offset, vec_ok))
+      return (int)le;
   } else if (relu) {
     k_relu_fwd<<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(x, y, n, vec_ok);
   } else {
@@ -125,7 +130,9 @@ extern "C" int fnb_dropout_relu_bwd(const float *dy, const float *y, float *dx, 
   if (!dy || !y || !dx) return FNB_ERR_NULL;
   const int vec_ok = fnb_aligned16(dy) && fnb_aligned16(y) && fnb_aligned16(dx);
   const float scale = (training && p > 0.f) ? 1.f / (1.f - p) : 1.f;
-  k_dropout_relu_bwd<<<ew_grid((n + 3) >> 2), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n, scale, vec_ok);
+  if (cudaError_t le = fnb_launch(k_dropout_relu_bwd, dim3(ew_grid((n + 3) >> 2)), dim3(256), 0, (cudaStream_t)stream, dy, y, dx,
+                                  n, scale, vec_ok))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }
@@ -136,8 +143,9 @@ extern "C" int fnb_adam_step(float *param, const float *grad, float *exp_avg, fl
   if (n == 0) return 0;
   if (!param || !grad || !exp_avg || !exp_avg_sq) return FNB_ERR_NULL;
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  k_adam<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
-                                                      weight_decay, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)));
+  if (cudaError_t le = fnb_launch(k_adam, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq,
+                                  n, beta1, beta2, eps, weight_decay, (float)(lr / bc1), (float)(1.0 / sqrt(bc2))))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }

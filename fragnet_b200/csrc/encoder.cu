@@ -224,6 +224,7 @@ struct PadJobs {
   int n;
 };
 __global__ void __launch_bounds__(256) k_pad_cols(PadJobs j) {
+  pdl_wait();
   const int job = blockIdx.y;
   const int K = j.K[job], kp = j.k_pad[job];
   const int64_t total = j.rows[job] * (kp >> 2);
@@ -343,7 +344,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     if (pj.n && most > 0) {
       int64_t blocks = (most + 255) / 256;
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-      k_pad_cols<<<dim3((unsigned)blocks, pj.n), 256, 0, stream>>>(pj);
+      if (cudaError_t le = fnb_launch(k_pad_cols, dim3((unsigned)blocks, pj.n), dim3(256), 0, stream, pj)) return (int)le;
       FNB_CHECK_LAUNCH();
     }
   }

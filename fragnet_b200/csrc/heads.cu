@@ -108,6 +108,7 @@ struct PackJobs {
   float *Wr_blk[3];
 };
 __global__ void __launch_bounds__(256) k_head_pack(PackJobs p) {
+  pdl_wait();
   const int job = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kPadMat; i += gridDim.x * blockDim.x) {
     const int r = i >> 7, c = i & 127;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(256) k_head_pack(PackJobs p) {
 // T[i,:] = ReLU(U[ei0[i],:] + V[ei1[i],:] + T[i,:])   (the activation in front of bl_layers[0], pretrain_heads.py:72-73)
 __global__ void __launch_bounds__(256) k_bl_combine(const float *__restrict__ U, const float *__restrict__ V,
                                                     float *__restrict__ T, const int64_t *__restrict__ ei, int64_t n_edges) {
+  pdl_wait();
   const int64_t total = n_edges * 32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = i >> 5;
@@ -193,6 +195,7 @@ __device__ __forceinline__ void tail_hidden(const float *rp, const float *sW1t, 
 
 template <int IN, int MID>
 __global__ void __launch_bounds__(128) k_mlp_tail_fwd(TailJobs J) {
+  pdl_wait();
   const TailJob &job = J.j[blockIdx.y];
   __shared__ __align__(16) float sW1t[IN * MID];
   __shared__ float sb1[MID], sW2[MID], sb2[1];
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(128) k_mlp_tail_fwd(TailJobs J) {
 // threads of a row read one contiguous 64-byte chunk of shared memory per step), plus one of the vector sums.
 template <int IN, int MID, int THREADS, int ROWS>
 __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
+  pdl_wait();
   constexpr int KPT = MID * IN / THREADS;      // k per thread in the dW1 phase
   static_assert(MID * 4 == THREADS && KPT * 4 == IN, "dW1 ownership needs THREADS = 4 * MID");
   constexpr int SA = IN + 4, SD = MID + 1;     // shared-memory row strides
@@ -333,6 +337,7 @@ constexpr int TB_ROWS = 128, TB_SA = 68, TB_SD = 36;
 constexpr size_t kTailBwd2Smem = sizeof(float) * (2 * 64 * 32 + TB_ROWS * TB_SA + TB_ROWS * TB_SD + TB_ROWS + 64);
 
 __global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
+  pdl_wait();
   constexpr int IN = 64, MID = 32, REC = rec_floats(64, 32);
   const TailJob &job = J.j[blockIdx.y];
   extern __shared__ __align__(16) float smem[];
@@ -537,6 +542,7 @@ struct SumJobs {
   int n;
 };
 __global__ void __launch_bounds__(256) k_head_sum_records(SumJobs s) {
+  pdl_wait();
   // one CTA = 64 consecutive outputs of one segment; the records are split over 4 thread groups (fixed assignment and
   // fixed combination order => deterministic), each load instruction reads 256 contiguous bytes of one record
   __shared__ float part[4][64];
@@ -573,7 +579,7 @@ struct SumBuilder {
   }
   int launch(cudaStream_t stream) {
     if (s.n == 0) return 0;
-    k_head_sum_records<<<dim3((max_width + 63) / 64, s.n), 256, 0, stream>>>(s);
+    if (cudaError_t le = fnb_launch(k_head_sum_records, dim3((max_width + 63) / 64, s.n), dim3(256), 0, stream, s)) return (int)le;
     FNB_CHECK_LAUNCH();
     return 0;
   }
@@ -639,7 +645,7 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
       p.W0[2] = P->bl.W0; p.b0[2] = P->bl.b0; p.Wpad[2] = B.W0pad_bl; p.WpadT[2] = nullptr; p.bpad[2] = B.b0pad_bl;
       p.Wr = P->Wr; p.Wr_blk[0] = B.Wr_a; p.Wr_blk[1] = B.Wr_b; p.Wr_blk[2] = B.Wr_e;
     }
-    k_head_pack<<<dim3(16, want_bl ? 6 : 2), 256, 0, stream>>>(p);
+    if (cudaError_t le = fnb_launch(k_head_pack, dim3(16, want_bl ? 6 : 2), dim3(256), 0, stream, p)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
   // ---- energy head (graph readout pretrain_heads.py:93-96, first layer, tail): ~1e3 rows, latency-bound kernels that
@@ -660,7 +666,7 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     F.n = 1;
     TailJob &t = F.j[0];
     t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.out = io->energy;
-    k_mlp_tail_fwd<128, 64><<<dim3((unsigned)((G + 127) / 128), 1), 128, 0, sB>>>(F);
+    if (cudaError_t le = fnb_launch(k_mlp_tail_fwd<128, 64>, dim3((unsigned)((G + 127) / 128), 1), dim3(128), 0, sB, F)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
   (void)Nf;
@@ -673,7 +679,7 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     RC(fnb_proj_fwd(io->edge_feat, B.Wr_e, P->br, Ea, kD, nullptr, 0, 0, 0, B.T, nullptr, precision, stream_));
     int64_t blocks = (Ea * 32 + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    k_bl_combine<<<(int)blocks, 256, 0, stream>>>(B.U, B.V, B.T, io->edge_index, Ea);
+    if (cudaError_t le = fnb_launch(k_bl_combine, dim3((int)blocks), dim3(256), 0, stream, B.U, B.V, B.T, io->edge_index, Ea)) return (int)le;
     FNB_CHECK_LAUNCH();
     RC(fnb_proj_fwd(B.T, B.W0pad_bl, B.b0pad_bl, Ea, kD, nullptr, 0, 0, 0, B.h0_bl, nullptr, precision, stream_));
   }
@@ -693,7 +699,7 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     if (J.n) {
       int64_t gx = (most + 127) / 128;
       if (gx > kNumSMs * 8) gx = kNumSMs * 8;
-      k_mlp_tail_fwd<64, 32><<<dim3((unsigned)gx, J.n), 128, 0, stream>>>(J);
+      if (cudaError_t le = fnb_launch(k_mlp_tail_fwd<64, 32>, dim3((unsigned)gx, J.n), dim3(128), 0, stream, J)) return (int)le;
       FNB_CHECK_LAUNCH();
     }
   }
@@ -758,7 +764,8 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
     TailJob &t = F.j[0];
     t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.gout = io->g_energy;
     t.dh0 = W.dh0_fc; t.rec = W.rec_fc;
-    k_mlp_tail_bwd<128, 64, 256, 64><<<dim3(ctas_fc, 1), 256, tail_bwd_smem<128, 64, 64>(), sB>>>(F);
+    if (cudaError_t le = fnb_launch(k_mlp_tail_bwd<128, 64, 256, 64>, dim3(ctas_fc, 1), dim3(256), tail_bwd_smem<128, 64, 64>(), sB, F))
+      return (int)le;
     FNB_CHECK_LAUNCH();
     RC(fnb_proj_bwd_impl(B.readout, P->fc.W0, nullptr, W.dh0_fc, G, 2 * kD, W.d_readout, D->fc.W0, nullptr, precision,
                          scratchB, sB_));
@@ -781,7 +788,7 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
     const int gx = ctas_ba > ctas_da ? ctas_ba : ctas_da;
     // a job with fewer tiles than gx: its surplus CTAs return at once and write no record, so the record count of a
     // job is min(gx, tiles of the job) = its own tail_grid
-    k_mlp_tail_bwd2<<<dim3(gx, 2), 128, kTailBwd2Smem, stream>>>(J);
+    if (cudaError_t le = fnb_launch(k_mlp_tail_bwd2, dim3(gx, 2), dim3(128), kTailBwd2Smem, stream, J)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
   // ---- first layers: dX and dW on the projection kernels
@@ -826,6 +833,7 @@ struct MseArgs {
   float *scratch;
 };
 __global__ void __launch_bounds__(256) k_mse_sum(MseArgs a) {
+  pdl_wait();
   __shared__ float s_part[8];
   __shared__ float s_rec[4], s_fin[4];
   const int64_t total = a.begin[a.n_terms];
@@ -873,7 +881,7 @@ extern "C" int fnb_mse_sum_loss(const fnb_mse_term *terms, int n_terms, float *l
   a.begin[n_terms] = total;
   int64_t blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
-  k_mse_sum<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  if (cudaError_t le = fnb_launch(k_mse_sum, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, a)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }

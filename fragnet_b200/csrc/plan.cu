@@ -62,6 +62,7 @@ __device__ __forceinline__ bool edge_nodes_of(const GDesc &G, int e, int &d, int
 }
 
 __global__ void k_plan_histogram(PlanArgs a) {
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.e_total; i += gridDim.x * blockDim.x) {
     const int gi = graph_of_edge(a, i);
     const GDesc &G = a.g[gi];
@@ -111,6 +112,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *total) {
   return res;
 }
 __global__ void __launch_bounds__(kScanBlock) k_plan_scan_tiles(ScanArrays2 a) {
+  pdl_wait();
   const int which = blockIdx.y;
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   int v[kScanItems], sum = 0;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(kScanBlock) k_plan_scan_tiles(ScanArrays2 a) {
   if (threadIdx.x == 0) a.tile_sums[which][blockIdx.x] = total;
 }
 __global__ void __launch_bounds__(kScanBlock) k_plan_scan_sums(ScanArrays2 a, int n_tiles) {
+  pdl_wait();
   const int which = blockIdx.x;
   int *ts = a.tile_sums[which];
   __shared__ int total;
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(kScanBlock) k_plan_scan_sums(ScanArrays2 a, in
   if (threadIdx.x == 0) a.out[which][a.n] = carry;
 }
 __global__ void __launch_bounds__(kScanBlock) k_plan_scan_apply(ScanArrays2 a) {
+  pdl_wait();
   const int which = blockIdx.y;
   const int add = a.tile_sums[which][blockIdx.x];
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
@@ -154,6 +158,7 @@ __global__ void __launch_bounds__(kScanBlock) k_plan_scan_apply(ScanArrays2 a) {
 
 // Claim a position inside the destination / source segment (arbitrary order; fixed by the rank kernels).
 __global__ void k_plan_claim(PlanArgs a) {
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.e_total; i += gridDim.x * blockDim.x) {
     const int gi = graph_of_edge(a, i);
     const GDesc &G = a.g[gi];
@@ -171,6 +176,7 @@ __global__ void k_plan_claim(PlanArgs a) {
 
 // One thread per claimed position: rank of its edge id inside its segment -> final slot; also the row pointers.
 __global__ void k_plan_rank_forward(PlanArgs a) {
+  pdl_wait();
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int i = t0; i < a.e_total; i += stride) {
     int gi = 0;
@@ -212,6 +218,7 @@ __global__ void k_plan_rank_forward(PlanArgs a) {
 }
 
 __global__ void k_plan_rank_reverse(PlanArgs a) {
+  pdl_wait();
   const int n_rev = a.x_src[a.n_total];  // edges of the graphs that have a reverse CSR
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rev; i += gridDim.x * blockDim.x) {
     int gi = 0;
@@ -248,6 +255,7 @@ __device__ __forceinline__ int lower_bound64(const int64_t *ids, int n, int64_t 
 // int64 -> int32 narrowing of atom_to_frag_ids / batch / frag_batch, and the molecule boundaries of the sorted
 // batch vectors (data.py:896-901) for the readout (gat2.py:820-821).
 __global__ void k_plan_aux(AuxArgs a) {
+  pdl_wait();
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int i = t0; i < a.n_atoms; i += stride) {
     a.a2f32[i] = (int)a.a2f[i];
@@ -420,7 +428,7 @@ extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, siz
     if (err != cudaSuccess) return (int)err;
   }
   if (z.e_total > 0) {
-    k_plan_histogram<<<grid_for(z.e_total), 256, 0, stream>>>(a);
+    if (cudaError_t le = fnb_launch(k_plan_histogram, dim3(grid_for(z.e_total)), dim3(256), 0, stream, a)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
   ScanArrays2 sc;
@@ -428,23 +436,25 @@ extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, siz
   sc.in[1] = L.cnt_src; sc.out[1] = L.x_src; sc.tile_sums[1] = L.tiles1;
   sc.n = z.n_total_nodes;
   if (z.n_tiles > 0) {
-    k_plan_scan_tiles<<<dim3(z.n_tiles, 2), kScanBlock, 0, stream>>>(sc);
+    if (cudaError_t le = fnb_launch(k_plan_scan_tiles, dim3(z.n_tiles, 2), dim3(kScanBlock), 0, stream, sc)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
-  k_plan_scan_sums<<<2, kScanBlock, 0, stream>>>(sc, z.n_tiles);
+  if (cudaError_t le = fnb_launch(k_plan_scan_sums, dim3(2), dim3(kScanBlock), 0, stream, sc, z.n_tiles)) return (int)le;
   FNB_CHECK_LAUNCH();
   if (z.n_tiles > 0) {
-    k_plan_scan_apply<<<dim3(z.n_tiles, 2), kScanBlock, 0, stream>>>(sc);
+    if (cudaError_t le = fnb_launch(k_plan_scan_apply, dim3(z.n_tiles, 2), dim3(kScanBlock), 0, stream, sc)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
   if (z.e_total > 0) {
-    k_plan_claim<<<grid_for(z.e_total), 256, 0, stream>>>(a);
+    if (cudaError_t le = fnb_launch(k_plan_claim, dim3(grid_for(z.e_total)), dim3(256), 0, stream, a)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
-  k_plan_rank_forward<<<grid_for(z.e_total > z.n_total_nodes ? z.e_total : z.n_total_nodes), 256, 0, stream>>>(a);
+  if (cudaError_t le = fnb_launch(k_plan_rank_forward, dim3(grid_for(z.e_total > z.n_total_nodes ? z.e_total : z.n_total_nodes)), dim3(256), 0,
+                                  stream, a))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   if (z.e_total > 0) {
-    k_plan_rank_reverse<<<grid_for(z.e_total), 256, 0, stream>>>(a);
+    if (cudaError_t le = fnb_launch(k_plan_rank_reverse, dim3(grid_for(z.e_total)), dim3(256), 0, stream, a)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
   {  // source ranges of every 64-node tile (forward and reverse CSR of the four graphs): one launch
@@ -472,7 +482,8 @@ extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, siz
   x.a2f = in->atom_to_frag_ids; x.batch = in->batch; x.frag_batch = in->frag_batch; x.a2f32 = L.a2f32;
   x.batch32 = L.batch32; x.frag_batch32 = L.frag_batch32; x.atom_ptr = L.atom_ptr; x.frag_ptr = L.frag_ptr;
   x.n_atoms = (int)in->n_atoms; x.n_frags = (int)in->n_frags; x.n_graphs = (int)in->n_graphs;
-  k_plan_aux<<<grid_for(in->n_atoms > in->n_graphs ? in->n_atoms : in->n_graphs + 1), 256, 0, stream>>>(x);
+  if (cudaError_t le = fnb_launch(k_plan_aux, dim3(grid_for(in->n_atoms > in->n_graphs ? in->n_atoms : in->n_graphs + 1)), dim3(256), 0, stream, x))
+    return (int)le;
   FNB_CHECK_LAUNCH();
 
   fnb_graph *gs[4] = {&out->bond, &out->atom, &out->fbond, &out->frag};

@@ -28,6 +28,7 @@ struct GemmArgs {
 
 template <bool TRANS_B, bool EPI>
 __global__ void __launch_bounds__(kGemmThreads) k_gemm(GemmArgs g) {
+  pdl_wait();
   __shared__ float As[BM][BK + 1];
   __shared__ __align__(16) float Bs[BK][BN];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -130,6 +131,7 @@ constexpr int kDwRows = 32;
 __global__ void __launch_bounds__(256) k_proj_dw(const float *__restrict__ dh, const float *__restrict__ x, int64_t n_rows,
                                                  int K, int64_t rows_per_block, float *__restrict__ partials,
                                                  int64_t rec_stride) {
+  pdl_wait();
   __shared__ __align__(16) float dhs[kDwRows][128];
   __shared__ __align__(16) float xs[kDwRows][128];
   const int tid = threadIdx.x, tk = tid & 15, to = tid >> 4;
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(256) k_proj_rowsparse_fwd(const float *__restr
                                                              const float *__restrict__ alpha, int alpha_stride,
                                                              int off_t, int off_s, float *__restrict__ h,
                                                              float *__restrict__ S) {
+  pdl_wait();
   extern __shared__ float s_W[];  // [128][K+1]
   const int ld = K + 1;
   for (int idx = threadIdx.x; idx < 128 * K; idx += blockDim.x) s_W[(idx / K) * ld + idx % K] = __ldg(W + idx);
@@ -358,7 +361,7 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
   g.A = x; g.lda = K; g.B = W; g.ldb = K; g.C = h; g.ldc = kD; g.M = n_rows; g.Kd = K; g.Nc = kD; g.bias = b;
   g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s; g.S = S;
   dim3 grid((unsigned)((n_rows + BM - 1) / BM), 1);
-  k_gemm<true, true><<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(g);
+  if (cudaError_t le = fnb_launch(k_gemm<true, true>, grid, dim3(kGemmThreads), 0, (cudaStream_t)stream, g)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }
@@ -395,7 +398,7 @@ int fnb_proj_bwd_dx(const float *W, const float *Wt_pre, const float *dh, int64_
   g.A = dh; g.lda = kD; g.B = W; g.ldb = K; g.C = dx; g.ldc = K; g.M = n_rows; g.Kd = kD; g.Nc = K; g.bias = nullptr;
   g.alpha = nullptr; g.alpha_stride = 0; g.off_t = 0; g.off_s = 0; g.S = nullptr;
   dim3 grid((unsigned)((n_rows + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
-  k_gemm<false, false><<<grid, kGemmThreads, 0, stream>>>(g);
+  if (cudaError_t le = fnb_launch(k_gemm<false, false>, grid, dim3(kGemmThreads), 0, stream, g)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }
@@ -417,7 +420,9 @@ int fnb_proj_bwd_dw(const float *x, const float *dh, int64_t n_rows, int K, floa
   if (rows_per_block < kDwRows) rows_per_block = kDwRows;
   const int64_t rec_stride = (int64_t)128 * K + 128;
   dim3 grid((unsigned)nb, (unsigned)((K + 127) / 128));
-  k_proj_dw<<<grid, 256, 0, stream>>>(dh, x, n_rows, K, rows_per_block, scratch_body(scratch), rec_stride);
+  if (cudaError_t le = fnb_launch(k_proj_dw, grid, dim3(256), 0, stream, dh, x, n_rows, K, rows_per_block, scratch_body(scratch),
+                                  rec_stride))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   ReduceSegments segs{};
   segs.n = db ? 2 : 1;

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) k_segment_sum(const int *__restrict__ row
                                                      float *__restrict__ out, int64_t out_stride,
                                                      const float *__restrict__ alpha, int alpha_stride, int off_t,
                                                      int off_s, float *__restrict__ S) {
+  pdl_wait();
   const int lane = threadIdx.x & 31, head = lane >> 3;
   float4 at = make_float4(0.f, 0.f, 0.f, 0.f), as = at;
   if (S) {
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(256) k_segment_sum(const int *__restrict__ row
 __global__ void __launch_bounds__(256) k_segment_gather(const float *__restrict__ g, int64_t g_stride,
                                                         const int *__restrict__ seg_of, int64_t n_rows,
                                                         const float *base, float *dx) {
+  pdl_wait();
   const int64_t total = n_rows * 32;  // float4 elements
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i >> 5;
@@ -86,8 +88,9 @@ extern "C" int fnb_segment_sum(const int32_t *rowptr, const int32_t *col, int64_
   if (S && ((alpha_stride & 3) || (off_t & 3) || (off_s & 3) || !fnb_aligned16(alpha))) return FNB_ERR_ALIGN;
   int64_t blocks = (n_segments + 7) / 8;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  k_segment_sum<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(rowptr, col, n_segments, x, out, out_stride, alpha,
-                                                               alpha_stride, off_t, off_s, S);
+  if (cudaError_t le = fnb_launch(k_segment_sum, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, rowptr, col, n_segments, x, out, out_stride,
+                                  alpha, alpha_stride, off_t, off_s, S))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }
@@ -100,7 +103,8 @@ extern "C" int fnb_segment_gather(const float *g, int64_t g_stride, const int32_
   if ((g_stride & 3) || !fnb_aligned16(g) || !fnb_aligned16(dx) || !fnb_aligned16(base)) return FNB_ERR_ALIGN;
   int64_t blocks = (n_rows * 32 + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  k_segment_gather<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, g_stride, seg_of, n_rows, base, dx);
+  if (cudaError_t le = fnb_launch(k_segment_gather, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, g, g_stride, seg_of, n_rows, base, dx))
+    return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }

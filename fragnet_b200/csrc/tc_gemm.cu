@@ -387,6 +387,7 @@ __global__ void k_transpose_128(const float *__restrict__ W, float *__restrict__
 }
 
 __global__ void k_transpose_128_batched(TransposeBatch b, float *__restrict__ Wt_base) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const float *W = b.W[blockIdx.z];
   float *Wt = Wt_base + (size_t)blockIdx.z * 128 * 128;
@@ -473,7 +474,7 @@ int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream) {
 
 int fnb_tc_transpose128_batched(const TransposeBatch &b, float *Wt_base, cudaStream_t stream) {
   if (b.count <= 0) return 0;
-  k_transpose_128_batched<<<dim3(4, 4, b.count), dim3(32, 8), 0, stream>>>(b, Wt_base);
+  if (cudaError_t le = fnb_launch(k_transpose_128_batched, dim3(4, 4, b.count), dim3(32, 8), 0, stream, b, Wt_base)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;
 }
