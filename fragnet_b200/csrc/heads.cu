@@ -81,6 +81,7 @@ struct BwdBufs {
   float *dWpad_ba, *dWpad_da;        // [128,128] (rows 64.. are zero)
   float *rec_ba, *rec_da, *rec_fc;   // per-CTA records of the tail gradients
   float *scratch2;                   // scratch of the energy-head chain (auxiliary stream)
+  float *scratch3;                   // scratch of the weight-gradient stream
 };
 
 size_t bwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, BwdBufs *out) {
@@ -94,6 +95,7 @@ size_t bwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, BwdBufs *out) {
   b.rec_da = a.take<float>((size_t)kTailCtasMax * kRecSmall);
   b.rec_fc = a.take<float>((size_t)kTailCtasMax * kRecWide);
   b.scratch2 = a.take<float>(kScratchFloats);
+  b.scratch3 = a.take<float>(kScratchFloats);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -247,48 +249,78 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = tile * ROWS;
     const int rows = (int)min((int64_t)ROWS, job.n - r0);
-    // ---- phase 1: thread per row
-    if (tid < ROWS) {
-      float *a_row = s_a + tid * SA, *d_row = s_dh0 + tid * SA;
-      if (tid < rows) {
-        const int64_t row = r0 + tid;
-        const float *rp = job.h0 + row * kD;
-        float acc[MID];
-        tail_hidden<IN, MID>(rp, sW1t, sb1, acc);
-        const float g = __ldg(job.gout + row);
-        s_g[tid] = g;
+    // ---- phase 1: FOUR threads per row (row = tid % ROWS, quarter q = tid / ROWS): a thread computes MID/4 hidden
+    // units, then IN/4 columns of dh0 -- a quarter of the serial chain of the thread-per-row form, which at ~1e3 rows
+    // (the energy head) is pure latency
+    {
+      static_assert(THREADS == 4 * ROWS && (MID % 16) == 0 && (IN % 16) == 0, "phase 1 splits a row over 4 threads");
+      constexpr int JQ = MID / 4, KQ = IN / 4;
+      const int r = tid % ROWS, q = tid / ROWS;
+      const bool live = r < rows;
+      const int64_t row = r0 + r;
+      const float *rp = job.h0 + (live ? row : 0) * kD;
+      float g = 0.f;
+      if (live) {
+        g = __ldg(job.gout + row);
+        float acc[JQ];
 #pragma unroll
-        for (int j = 0; j < MID; ++j) {
-          const float h1 = fmaxf(acc[j], 0.f);
-          s_h1g[tid * SD + j] = g * h1;
-          acc[j] = acc[j] > 0.f ? g * sW2[j] : 0.f;   // d1[j]
-          s_d1[tid * SD + j] = acc[j];
-        }
-        float *dp = job.dh0 + row * kD;
+        for (int j = 0; j < JQ; ++j) acc[j] = sb1[q * JQ + j];
 #pragma unroll 2
         for (int k4 = 0; k4 < IN / 4; ++k4) {
+          const float4 a = ldg4(rp + k4 * 4);
+          const float av[4] = {fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float *w = sW1t + (k4 * 4 + u) * MID + q * JQ;
+#pragma unroll
+            for (int j4 = 0; j4 < JQ / 4; ++j4) {
+              const float4 wv = ld4(w + j4 * 4);
+              acc[j4 * 4 + 0] = fmaf(av[u], wv.x, acc[j4 * 4 + 0]);
+              acc[j4 * 4 + 1] = fmaf(av[u], wv.y, acc[j4 * 4 + 1]);
+              acc[j4 * 4 + 2] = fmaf(av[u], wv.z, acc[j4 * 4 + 2]);
+              acc[j4 * 4 + 3] = fmaf(av[u], wv.w, acc[j4 * 4 + 3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < JQ; ++j) {
+          const int jj = q * JQ + j;
+          s_h1g[r * SD + jj] = g * fmaxf(acc[j], 0.f);
+          s_d1[r * SD + jj] = acc[j] > 0.f ? g * sW2[jj] : 0.f;
+        }
+      }
+      if (q == 0) s_g[r] = g;
+      __syncthreads();   // the row's four quarters of d1 are in shared memory
+      if (live) {
+        float d1[MID];
+#pragma unroll
+        for (int j = 0; j < MID; ++j) d1[j] = s_d1[r * SD + j];
+        float *dp = job.dh0 + row * kD;
+        float *a_row = s_a + r * SA, *d_row = s_dh0 + r * SA;
+#pragma unroll 1
+        for (int k4 = q * (KQ / 4); k4 < (q + 1) * (KQ / 4); ++k4) {
           const float4 a = ldg4(rp + k4 * 4);
           const float av[4] = {a.x, a.y, a.z, a.w};
           float dv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float *w = sW1t + (k4 * 4 + u) * MID;
-            float s = 0.f;
+            float s_ = 0.f;
 #pragma unroll
             for (int j4 = 0; j4 < MID / 4; ++j4) {
               const float4 wv = ld4(w + j4 * 4);
-              s = fmaf(acc[j4 * 4 + 0], wv.x, s);
-              s = fmaf(acc[j4 * 4 + 1], wv.y, s);
-              s = fmaf(acc[j4 * 4 + 2], wv.z, s);
-              s = fmaf(acc[j4 * 4 + 3], wv.w, s);
+              s_ = fmaf(d1[j4 * 4 + 0], wv.x, s_);
+              s_ = fmaf(d1[j4 * 4 + 1], wv.y, s_);
+              s_ = fmaf(d1[j4 * 4 + 2], wv.z, s_);
+              s_ = fmaf(d1[j4 * 4 + 3], wv.w, s_);
             }
-            dv[u] = av[u] > 0.f ? s : 0.f;
+            dv[u] = av[u] > 0.f ? s_ : 0.f;
           }
           st4(dp + k4 * 4, make_float4(dv[0], dv[1], dv[2], dv[3]));
           st4(d_row + k4 * 4, make_float4(dv[0], dv[1], dv[2], dv[3]));
           st4(a_row + k4 * 4, make_float4(fmaxf(av[0], 0.f), fmaxf(av[1], 0.f), fmaxf(av[2], 0.f), fmaxf(av[3], 0.f)));
         }
-        if (IN < kD) {
+        if (IN < kD && q == 0) {
 #pragma unroll
           for (int k4 = IN / 4; k4 < kD / 4; ++k4) st4(dp + k4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
         }
@@ -323,6 +355,70 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
   if ((tid & 3) == 1) rec[MID * IN + MID + oj] = vacc;
   if (tid == 0) rec[MID * IN + 2 * MID] = b2acc;
   if (tid < IN) rec[MID * IN + 2 * MID + 1 + tid] = b0acc;
+}
+
+// Forward tail of the big heads (IN = 64, MID = 32), register-tiled like k_mlp_tail_bwd2's first GEMM: the ReLU(h0) tile
+// in shared memory, a thread computes 8 rows x 4 hidden units (10.7 FMA per LDS.128 instead of 4), the 32-wide dot
+// with W2 is finished by three shuffles over the 8 threads that share a row group.
+__global__ void __launch_bounds__(128, 4) k_mlp_tail_fwd2(TailJobs J) {
+  pdl_wait();
+  constexpr int IN = 64, MID = 32, ROWS = 128, SA = 68;
+  const TailJob &job = J.j[blockIdx.y];
+  __shared__ __align__(16) float sW1t[IN * MID];
+  __shared__ __align__(16) float sA[ROWS * SA];
+  __shared__ __align__(16) float sb1[MID], sW2[MID];
+  __shared__ float sb2[1];
+  const int tid = threadIdx.x;
+  const int64_t n_tiles = (job.n + ROWS - 1) / ROWS;
+  if (blockIdx.x >= n_tiles) return;
+  load_tail_weights<IN, MID>(job, sW1t, sb1, sW2, sb2);
+  const int rg = tid >> 3, g8 = tid & 7;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * ROWS;
+    __syncthreads();
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int idx = it * 128 + tid, r = idx >> 4, c4 = idx & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < job.n) v = ldg4(job.h0 + (r0 + r) * kD + c4 * 4);
+      st4(sA + r * SA + c4 * 4, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+#pragma unroll 2
+    for (int k4 = 0; k4 < IN / 4; ++k4) {
+      float4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = ld4(sW1t + (k4 * 4 + u) * MID + g8 * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = ld4(sA + (rg + 16 * i) * SA + k4 * 4);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[i][0] = fmaf(av[u], w[u].x, acc[i][0]);
+          acc[i][1] = fmaf(av[u], w[u].y, acc[i][1]);
+          acc[i][2] = fmaf(av[u], w[u].z, acc[i][2]);
+          acc[i][3] = fmaf(av[u], w[u].w, acc[i][3]);
+        }
+      }
+    }
+    const float4 b1v = ld4(sb1 + g8 * 4), w2v = ld4(sW2 + g8 * 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float o = fmaxf(acc[i][0] + b1v.x, 0.f) * w2v.x + fmaxf(acc[i][1] + b1v.y, 0.f) * w2v.y +
+                fmaxf(acc[i][2] + b1v.z, 0.f) * w2v.z + fmaxf(acc[i][3] + b1v.w, 0.f) * w2v.w;
+      o += __shfl_xor_sync(kFull, o, 1);
+      o += __shfl_xor_sync(kFull, o, 2);
+      o += __shfl_xor_sync(kFull, o, 4);
+      const int64_t row = r0 + rg + 16 * i;
+      if (g8 == 0 && row < job.n) job.out[row] = o + sb2[0];
+    }
+  }
 }
 
 // Backward tail of the two big heads (IN = 64, MID = 32) as three register-tiled FP32 GEMMs per 128-row tile, all
@@ -699,7 +795,7 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     if (J.n) {
       int64_t gx = (most + 127) / 128;
       if (gx > kNumSMs * 8) gx = kNumSMs * 8;
-      if (cudaError_t le = fnb_launch(k_mlp_tail_fwd<64, 32>, dim3((unsigned)gx, J.n), dim3(128), 0, stream, J)) return (int)le;
+      if (cudaError_t le = fnb_launch(k_mlp_tail_fwd2, dim3((unsigned)gx, J.n), dim3(128), 0, stream, J)) return (int)le;
       FNB_CHECK_LAUNCH();
     }
   }
@@ -767,10 +863,12 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
     if (cudaError_t le = fnb_launch(k_mlp_tail_bwd<128, 64, 256, 64>, dim3(ctas_fc, 1), dim3(256), tail_bwd_smem<128, 64, 64>(), sB, F))
       return (int)le;
     FNB_CHECK_LAUNCH();
-    RC(fnb_proj_bwd_impl(B.readout, P->fc.W0, nullptr, W.dh0_fc, G, 2 * kD, W.d_readout, D->fc.W0, nullptr, precision,
-                         scratchB, sB_));
+    // input gradient first: the atoms' gradient on the caller's stream waits for d_readout, nothing waits for dW
+    RC(fnb_proj_bwd_dx(P->fc.W0, nullptr, W.dh0_fc, G, 2 * kD, W.d_readout, precision, scratchB, sB_));
     RC(fnb_segment_gather(W.d_readout + kD, 2 * kD, io->frag_batch32, Nf, nullptr, io->g_frags, sB_));
     if (two) RC((int)cudaEventRecord(aux.join, sB));
+    RC(fnb_proj_bwd_dw(B.readout, W.dh0_fc, G, 2 * kD, D->fc.W0, nullptr, precision, scratchB, sB_));
+    if (two) RC((int)cudaEventRecord(aux.wjoin, sB));
   } else {
     RC((int)cudaMemsetAsync(D->fc.W0, 0, sizeof(float) * kD * 2 * kD, stream));
   }
@@ -791,17 +889,28 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
     if (cudaError_t le = fnb_launch(k_mlp_tail_bwd2, dim3(gx, 2), dim3(128), kTailBwd2Smem, stream, J)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
-  // ---- first layers: dX and dW on the projection kernels
-  if (Na > 0)
-    RC(fnb_proj_bwd_impl(io->x_atoms, B.W0pad_ba, B.W0padT_ba, W.dh0_ba, Na, kD, W.dx_ba, W.dWpad_ba, nullptr, precision,
-                         scratch, stream_));
-  else
-    RC((int)cudaMemsetAsync(W.dWpad_ba, 0, sizeof(float) * kPadMat, stream));
-  if (Ea > 0)
-    RC(fnb_proj_bwd_impl(io->edge_feat, B.W0pad_da, B.W0padT_da, W.dh0_da, Ea, kD, io->g_edge, W.dWpad_da, nullptr, precision,
-                         scratch, stream_));
-  else
-    RC((int)cudaMemsetAsync(W.dWpad_da, 0, sizeof(float) * kPadMat, stream));
+  // ---- first layers: dX on the caller's stream (it feeds the encoder backward), dW on the weight-gradient stream
+  cudaStream_t sW = two ? aux.wstream : stream;
+  void *sW_ = (void *)sW;
+  void *scratchW = two ? (void *)W.scratch3 : scratch;
+  if (two) {
+    RC((int)cudaEventRecord(aux.ready[0], stream));     // dh0 of both heads is complete
+    RC((int)cudaStreamWaitEvent(sW, aux.ready[0], 0));
+    RC((int)cudaMemsetAsync(W.scratch3, 0, kScratchCounters * sizeof(float), sW));
+  }
+  if (Na > 0) {
+    RC(fnb_proj_bwd_dx(B.W0pad_ba, B.W0padT_ba, W.dh0_ba, Na, kD, W.dx_ba, precision, scratch, stream_));
+    RC(fnb_proj_bwd_dw(io->x_atoms, W.dh0_ba, Na, kD, W.dWpad_ba, nullptr, precision, scratchW, sW_));
+  } else {
+    RC((int)cudaMemsetAsync(W.dWpad_ba, 0, sizeof(float) * kPadMat, sW));
+  }
+  if (Ea > 0) {
+    RC(fnb_proj_bwd_dx(B.W0pad_da, B.W0padT_da, W.dh0_da, Ea, kD, io->g_edge, precision, scratch, stream_));
+    RC(fnb_proj_bwd_dw(io->edge_feat, W.dh0_da, Ea, kD, W.dWpad_da, nullptr, precision, scratchW, sW_));
+  } else {
+    RC((int)cudaMemsetAsync(W.dWpad_da, 0, sizeof(float) * kPadMat, sW));
+  }
+  if (two) RC((int)cudaEventRecord(aux.done[0], sW));
   if (G > 0) {
     if (two) RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
     // readout backward (pretrain_heads.py:93-96): every atom receives its molecule's gradient row on top of the
@@ -815,6 +924,8 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
   sb.add_tail(W.rec_fc, ctas_fc, 128, 64, D->fc.W1, D->fc.b1, D->fc.W2, D->fc.b2, D->fc.b0);
   sb.add(W.dWpad_ba, 1, 0, 0, 64 * kD, D->ba.W0);
   sb.add(W.dWpad_da, 1, 0, 0, 64 * kD, D->da.W0);
+  if (two && G > 0) RC((int)cudaStreamWaitEvent(stream, aux.wjoin, 0));   // energy head's records and dW are complete
+  if (two) RC((int)cudaStreamWaitEvent(stream, aux.done[0], 0));           // padded first-layer weight gradients
   return sb.launch(stream);
 }
 

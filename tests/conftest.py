@@ -16,6 +16,9 @@ FP32_REL_TOL = 1e-5
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The CPU oracle's fp32 reductions are partitioned over the intra-op threads: pin their number so that the
+    # reference values do not depend on how many cores the box running the tests happens to have.
+    torch.set_num_threads(min(8, torch.get_num_threads()))
 
 
 def pytest_collection_modifyitems(config, items):
