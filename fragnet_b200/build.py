@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libfragnet_b200.so")
     os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB_PATH + ".tmp"
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"      # several ranks may build at once: private output, atomic rename
     cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-o", tmp, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
