@@ -37,7 +37,9 @@ int fnb_aux_streams(FnbAux *out) {
     if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return 1;
     if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return 1;
     if (cudaStreamCreateWithFlags(&a.wstream, cudaStreamNonBlocking) != cudaSuccess) return 1;
-    cudaEvent_t *evs[5] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.wjoin};
+    if (cudaStreamCreateWithFlags(&a.astream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    cudaEvent_t *evs[9] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.wjoin,
+                           &a.a_fork, &a.a_dz, &a.a_table, &a.a_join};
     for (cudaEvent_t *e : evs)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return 1;
     aux[dev] = a;

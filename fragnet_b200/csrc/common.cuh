@@ -270,6 +270,8 @@ struct FnbAux {
   cudaEvent_t fork, join;
   cudaStream_t wstream;      // weight-gradient GEMMs: nothing downstream waits for them until the end of the pass
   cudaEvent_t ready[2], done[2], wjoin;
+  cudaStream_t astream;      // atom-graph chain (it only meets the bond chain at the edge-term kernels)
+  cudaEvent_t a_fork, a_dz, a_table, a_join;
 };
 int fnb_aux_streams(FnbAux *out);
 

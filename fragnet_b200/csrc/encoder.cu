@@ -131,6 +131,7 @@ struct BwdBufs {
   float *Wt;   // [n_layers][3][128*128] transposed K=128 projection weights
   float *scratch2;   // scratch of the fragment-connection chain when it runs on the auxiliary stream
   float *scratch3;   // scratch of the weight-gradient stream
+  float *scratch4;   // scratch of the atom-graph stream
 };
 
 size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *base, BwdBufs *out) {
@@ -148,6 +149,7 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   b.Wt = a.take<float>((size_t)o->n_layers * 3 * kD * kD);
   b.scratch2 = a.take<float>(kScratchFloats);
   b.scratch3 = a.take<float>(kScratchFloats);
+  b.scratch4 = a.take<float>(kScratchFloats);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -359,11 +361,19 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     RC((int)cudaEventRecord(aux.fork, stream));
     RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
   }
+  cudaStream_t sA = two ? aux.astream : stream;
+  void *sA_ = (void *)sA;
+  bool a_pending = false;
   auto join = [&]() -> int {
     if (two && pending) {
       RC((int)cudaEventRecord(aux.join, sB));
       RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
       pending = false;
+    }
+    if (two && a_pending) {
+      RC((int)cudaEventRecord(aux.a_join, sA));
+      RC((int)cudaStreamWaitEvent(stream, aux.a_join, 0));
+      a_pending = false;
     }
     return 0;
   };
@@ -389,15 +399,13 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
     float *y_fbond = o->post_act ? (last ? io->out_fbond : b.y_fbond) : nullptr;
     float *y_frag = o->post_act ? (last ? io->out_frags : b.y_frag) : nullptr;
 
-    // ---- atom projection (gat2.py:189): needs only the previous layer's atoms, so it runs on the third stream
-    // underneath the bond block
-    if (two) {
-      RC((int)cudaEventRecord(aux.ready[0], stream));
-      RC((int)cudaStreamWaitEvent(aux.wstream, aux.ready[0], 0));
+    // ---- atom chain (gat2.py:179-231) on its own stream: the projection needs only the previous layer's atoms (produced
+    // on this same stream), the attention block additionally the bond block's edge term of this layer
+    if (two && l == 0) {
+      RC((int)cudaEventRecord(aux.a_fork, stream));
+      RC((int)cudaStreamWaitEvent(sA, aux.a_fork, 0));
     }
-    RC(fnb_proj_fwd(xa_in, Wa_in, P.ba, z.Na, Ka_in, P.a, A_STRIDE, A_T, A_S, b.ha, b.Sa, o->precision,
-                    two ? (void *)aux.wstream : stream_));
-    if (two) RC((int)cudaEventRecord(aux.done[0], aux.wstream));
+    RC(fnb_proj_fwd(xa_in, Wa_in, P.ba, z.Na, Ka_in, P.a, A_STRIDE, A_T, A_S, b.ha, b.Sa, o->precision, sA_));
     // ---- bond graph (gat2.py:138-176); epilogue emits the atom graph's edge term <new_bond[e], a_e[h]>
     RC(fnb_proj_fwd(xb_in, Wb_in, P.bb, z.Nb, Kb_in, P.a_b, AB_STRIDE, AB_T, AB_S, b.hb, b.Sb, o->precision, stream_));
     {
@@ -410,18 +418,22 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       RC(fnb_gat_fwd_tiled(&plan->bond, &f, stream_));
     }
     // ---- atom graph with self loops (gat2.py:179-231)
-    if (two) RC((int)cudaStreamWaitEvent(stream, aux.done[0], 0));
+    if (two) {
+      RC((int)cudaEventRecord(aux.a_dz, stream));          // the bond block of this layer is queued
+      RC((int)cudaStreamWaitEvent(sA, aux.a_dz, 0));
+    }
     {
       fnb_gat_fwd_args f{};
       f.h = b.ha; f.S = b.Sa; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = b.se_atom; f.out = pre_atom; f.y = y_atom;
       f.post = post_of(o, ph.atom[l]); f.p_saved = want_p ? b.p_a : nullptr;
       f.mask_lo = P.atom_mask >= 0 ? P.atom_mask : -1; f.mask_hi = P.atom_mask >= 0 ? P.atom_mask + 1 : -1;
-      RC(fnb_gat_fwd_tiled(&plan->atom, &f, stream_));
+      RC(fnb_gat_fwd_tiled(&plan->atom, &f, sA_));
       if (P.atom_mask_list && P.n_atom_mask > 0) {
-        k_zero_rows<<<(int)((P.n_atom_mask * 32 + 255) / 256), 256, 0, stream>>>(pre_atom, y_atom, P.atom_mask_list,
-                                                                               P.n_atom_mask);
+        k_zero_rows<<<(int)((P.n_atom_mask * 32 + 255) / 256), 256, 0, sA>>>(pre_atom, y_atom, P.atom_mask_list,
+                                                                           P.n_atom_mask);
         FNB_CHECK_LAUNCH();
       }
+      a_pending = true;
     }
     // ---- fragment-connection graph (gat2.py:239-278); epilogue emits the fragment graph's edge term
     RC(fnb_proj_fwd(xfb_in, Wfb_in, P.bfb, z.Nfb, Kfb_in, P.f_a_b, AB_STRIDE, AB_T, AB_S, b.hfb, b.Sfb, o->precision,
@@ -528,9 +540,9 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
   void *sW_ = (void *)sW;
   void *scratchW = two ? (void *)W.scratch3 : scratch;
   bool w_used = false, w_pending[2] = {false, false};
-  auto w_begin = [&](int i) -> int {   // dh of graph i (0 atom, 1 bond) is complete on the caller's stream
+  auto w_begin = [&](int i, cudaStream_t producer) -> int {   // dh of graph i (0 atom, 1 bond) is complete on `producer`
     if (!two) return 0;
-    RC((int)cudaEventRecord(aux.ready[i], stream));
+    RC((int)cudaEventRecord(aux.ready[i], producer));
     RC((int)cudaStreamWaitEvent(sW, aux.ready[i], 0));
     if (!w_used) {
       RC((int)cudaMemsetAsync(W.scratch3, 0, kScratchCounters * sizeof(float), sW));
@@ -544,13 +556,20 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     w_pending[i] = true;
     return 0;
   };
-  auto w_wait = [&](int i) -> int {    // before dh of graph i is overwritten (or at the end of the pass)
+  auto w_wait = [&](int i, cudaStream_t waiter) -> int {   // before dh of graph i is overwritten (or at the end of the pass)
     if (two && w_pending[i]) {
-      RC((int)cudaStreamWaitEvent(stream, aux.done[i], 0));
+      RC((int)cudaStreamWaitEvent(waiter, aux.done[i], 0));
       w_pending[i] = false;
     }
     return 0;
   };
+  // The atom blocks of all layers form a chain of their own (dy_atom of layer l-1 is the dX of layer l's atom
+  // projection); it meets the bond chain only where the edge-term kernel needs dz of the atom graph.  It runs on a
+  // fourth stream; the bond chain on the caller's stream is the critical path.
+  cudaStream_t sA = two ? aux.astream : stream;
+  void *sA_ = (void *)sA;
+  void *scratchA = two ? (void *)W.scratch4 : scratch;
+  bool a_forked = false, a_table_pending = false;
 
   // gradients arriving at the four outputs of the current layer (post-activation copies in post_act mode)
   const float *dy_atom = io->g_atoms, *dy_bond = io->g_bond, *dy_fbond = io->g_fbond, *dy_frag = io->g_frags;
@@ -626,23 +645,41 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     {
       const bool have = dy_atom != nullptr || d_hf != nullptr;
       if (have) {
-        RC(grad_combine(dy_atom, y_atom, scale, d_hf, plan->a2f, z.Na, W.g_atom, stream));
+        if (two && !a_forked) {   // the caller's gradients and the fragment block's pooled gradient are visible to sA
+          RC((int)cudaEventRecord(aux.a_fork, stream));
+          RC((int)cudaStreamWaitEvent(sA, aux.a_fork, 0));
+          RC((int)cudaMemsetAsync(W.scratch4, 0, kScratchCounters * sizeof(float), sA));
+          a_forked = true;
+        }
+        if (two && a_table_pending) {   // the edge-term kernel of the layer above has consumed dz of the atom graph
+          RC((int)cudaStreamWaitEvent(sA, aux.a_table, 0));
+          a_table_pending = false;
+        }
+        RC(grad_combine(dy_atom, y_atom, scale, d_hf, plan->a2f, z.Na, W.g_atom, sA));
         fnb_gat_bwd_args a{};
         a.h = b.ha; a.dout = W.g_atom; a.p_saved = b.p_a; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.a;
         a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_a; a.dSt = W.dSt_a;
-        a.dh = W.dh_a; a.d_alpha = D.a; a.d_bias = D.ba; a.scratch = scratch;
-        RC(w_wait(0));
-        RC(fnb_gat_bwd_tiled(&plan->atom, &a, stream_));
-        RC(w_begin(0));
+        a.dh = W.dh_a; a.d_alpha = D.a; a.d_bias = D.ba; a.scratch = scratchA;
+        RC(w_wait(0, sA));
+        RC(fnb_gat_bwd_tiled(&plan->atom, &a, sA_));
+        RC(w_begin(0, sA));
+        if (two) {
+          RC((int)cudaEventRecord(aux.a_dz, sA));
+          RC((int)cudaStreamWaitEvent(stream, aux.a_dz, 0));
+        }
         // bond features were this graph's edge vectors: their gradient, plus the activation backward of dy_bond
         RC(fnb_edge_table_bwd_fused(&plan->atom, W.dz_a, pre_bond, P.a, A_STRIDE, A_E, y_bond ? nullptr : dy_bond,
                                     y_bond ? dy_bond : nullptr, y_bond && dy_bond ? y_bond : nullptr, scale, W.g_bond,
                                     D.a, scratch, stream_));
+        if (two) {
+          RC((int)cudaEventRecord(aux.a_table, stream));
+          a_table_pending = true;
+        }
         float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);
         if (l == 0 && b.k_pad[1] && !dx) {
           RC(fnb_tc_dw_launch(W.dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchW), sW));
         } else {
-          RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, o->precision, scratch, stream_));
+          RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, o->precision, scratchA, sA_));
           RC(fnb_proj_bwd_dw(xa, W.dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchW, sW_));
         }
         RC(w_end(0));
@@ -661,9 +698,9 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         a.alpha = P.a_b; a.alpha_stride = AB_STRIDE; a.off_t = AB_T; a.off_e = AB_E; a.off_s = AB_S; a.dz = W.dz_b;
         a.dSt = W.dSt_b; a.dh = W.dh_b; a.d_alpha = D.a_b; a.d_bias = D.bb; a.dWe = D.We_b; a.dbe = D.be_b;
         a.scratch = scratch;
-        RC(w_wait(1));
+        RC(w_wait(1, stream));
         RC(fnb_gat_bwd_tiled(&plan->bond, &a, stream_));
-        RC(w_begin(1));
+        RC(w_begin(1, stream));
         float *dx = need_dx ? W.dx_bond : (o->need_dx_bond ? io->dx_bond : nullptr);
         if (l == 0 && b.k_pad[0] && !dx) {
           RC(fnb_tc_dw_launch(W.dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchW), sW));
@@ -689,8 +726,12 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     RC((int)cudaEventRecord(aux.join, sB));
     RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
   }
-  RC(w_wait(0));
-  RC(w_wait(1));
+  if (two && a_forked) {
+    RC((int)cudaEventRecord(aux.a_join, sA));
+    RC((int)cudaStreamWaitEvent(stream, aux.a_join, 0));
+  }
+  RC(w_wait(0, stream));
+  RC(w_wait(1, stream));
   // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same RNG stream as the forward
   if (o->need_dx_atoms && io->dx_atoms && input_dropout(o)) {
     const RngPlan ph = rng_plan(plan, o, L);
