@@ -275,6 +275,14 @@ struct FnbAux {
 };
 int fnb_aux_streams(FnbAux *out);
 
+int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts *opts, const fnb_layer_params *layers,
+                             const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
+                             void *stream, cudaEvent_t plan_ready);
+int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
+                                     const fnb_pretrain_head_io *io, int precision, void *workspace,
+                                     size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
+                                     void *scratch, void *stream, int defer_join);
+
 // Tensor-core (tcgen05, TF32) projection path, tc_gemm.cu.  Returns FNB_ERR_MODE when the shape cannot use TMA.
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
                        int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream);

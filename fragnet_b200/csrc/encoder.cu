@@ -312,6 +312,16 @@ extern "C" uint64_t fnb_encoder_rng_span(const fnb_batch_plan *plan, const fnb_e
 extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
                                    const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
                                    void *stream_) {
+  return fnb_encoder_forward_impl(plan, o, L, io, workspace, workspace_bytes, scratch, stream_, nullptr);
+}
+
+// plan_ready: optional event after which the ARRAYS of `plan` are complete (its sizes and pointers are valid at call
+// time).  fnb_pretrain_step builds the plan on an auxiliary stream while the plan-independent head of the forward
+// (input dropout, operand padding, the three layer-0 projections) runs; the first attention kernel of every stream
+// waits for the event.
+int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
+                             const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
+                             void *stream_, cudaEvent_t plan_ready) {
   RC(check_common(plan, o, L, io));
   if (!workspace || !scratch) return FNB_ERR_NULL;
   LayerBufs B[16];
@@ -415,6 +425,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       f.post = post_of(o, ph.bond[l]); f.p_saved = want_p ? b.p_b : nullptr;
       f.mask_lo = P.bond_mask >= 0 ? P.bond_mask : -1; f.mask_hi = P.bond_mask >= 0 ? P.bond_mask + 2 : -1;
       f.next_alpha_e = P.a + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_atom;
+      if (plan_ready && l == 0) RC((int)cudaStreamWaitEvent(stream, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->bond, &f, stream_));
     }
     // ---- atom graph with self loops (gat2.py:179-231)
@@ -427,6 +438,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       f.h = b.ha; f.S = b.Sa; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = b.se_atom; f.out = pre_atom; f.y = y_atom;
       f.post = post_of(o, ph.atom[l]); f.p_saved = want_p ? b.p_a : nullptr;
       f.mask_lo = P.atom_mask >= 0 ? P.atom_mask : -1; f.mask_hi = P.atom_mask >= 0 ? P.atom_mask + 1 : -1;
+      if (plan_ready && l == 0 && two) RC((int)cudaStreamWaitEvent(sA, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->atom, &f, sA_));
       if (P.atom_mask_list && P.n_atom_mask > 0) {
         k_zero_rows<<<(int)((P.n_atom_mask * 32 + 255) / 256), 256, 0, sA>>>(pre_atom, y_atom, P.atom_mask_list,
@@ -447,6 +459,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
       f.mask_lo = P.frag_bond_mask >= 0 ? 2 * P.frag_bond_mask : -1;
       f.mask_hi = P.frag_bond_mask >= 0 ? 2 * P.frag_bond_mask + 2 : -1;
       if (frag) { f.next_alpha_e = P.f + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_frag; }
+      if (plan_ready && l == 0 && two) RC((int)cudaStreamWaitEvent(sB, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->fbond, &f, sB_));
     }
     if (frag || P.want_attention) RC(join());

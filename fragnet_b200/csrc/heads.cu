@@ -806,10 +806,13 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
   return 0;
 }
 
-extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
-                                           const fnb_pretrain_head_io *io, int precision, void *workspace,
-                                           size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
-                                           void *scratch, void *stream_) {
+// defer_join != 0: the weight gradients still running on the auxiliary streams are NOT joined into the caller's
+// stream at return (fnb_pretrain_step joins them through the encoder backward that follows, which ends by waiting for
+// those in-order streams).
+int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
+                                     const fnb_pretrain_head_io *io, int precision, void *workspace,
+                                     size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
+                                     void *scratch, void *stream_, int defer_join) {
   RC(check_io(P, io));
   if (!D || !workspace || !bwd_workspace || !scratch) return FNB_ERR_NULL;
   if (!io->g_bond_angle || !io->g_dihedral || !io->g_energy) return FNB_ERR_NULL;
@@ -910,6 +913,12 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
   } else {
     RC((int)cudaMemsetAsync(W.dWpad_da, 0, sizeof(float) * kPadMat, sW));
   }
+  {  // the 64-row slices of the padded first-layer gradients, on the stream that produced them
+    SumBuilder cp;
+    cp.add(W.dWpad_ba, 1, 0, 0, 64 * kD, D->ba.W0);
+    cp.add(W.dWpad_da, 1, 0, 0, 64 * kD, D->da.W0);
+    RC(cp.launch(sW));
+  }
   if (two) RC((int)cudaEventRecord(aux.done[0], sW));
   if (G > 0) {
     if (two) RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
@@ -922,11 +931,20 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
   sb.add_tail(W.rec_ba, ctas_ba, 64, 32, D->ba.W1, D->ba.b1, D->ba.W2, D->ba.b2, D->ba.b0);
   sb.add_tail(W.rec_da, ctas_da, 64, 32, D->da.W1, D->da.b1, D->da.W2, D->da.b2, D->da.b0);
   sb.add_tail(W.rec_fc, ctas_fc, 128, 64, D->fc.W1, D->fc.b1, D->fc.W2, D->fc.b2, D->fc.b0);
-  sb.add(W.dWpad_ba, 1, 0, 0, 64 * kD, D->ba.W0);
-  sb.add(W.dWpad_da, 1, 0, 0, 64 * kD, D->da.W0);
-  if (two && G > 0) RC((int)cudaStreamWaitEvent(stream, aux.wjoin, 0));   // energy head's records and dW are complete
-  if (two) RC((int)cudaStreamWaitEvent(stream, aux.done[0], 0));           // padded first-layer weight gradients
-  return sb.launch(stream);
+  RC(sb.launch(stream));
+  if (two && !defer_join) {
+    if (G > 0) RC((int)cudaStreamWaitEvent(stream, aux.wjoin, 0));   // energy head's first-layer weight gradient
+    RC((int)cudaStreamWaitEvent(stream, aux.done[0], 0));            // first-layer weight gradients of the other heads
+  }
+  return 0;
+}
+
+extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
+                                           const fnb_pretrain_head_io *io, int precision, void *workspace,
+                                           size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
+                                           void *scratch, void *stream_) {
+  return fnb_pretrain_heads_backward_impl(P, D, io, precision, workspace, workspace_bytes, bwd_workspace,
+                                          bwd_workspace_bytes, scratch, stream_, 0);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------

@@ -121,15 +121,28 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   StepBufs B;
   if (step_layout(a, (char *)workspace, &B) > workspace_bytes) return FNB_ERR_WORKSPACE;
 
-  // ---- on-device collate (north-star kernel a)
+  // ---- on-device collate (north-star kernel a): on an auxiliary stream, underneath the plan-independent head of the
+  // forward pass (input dropout, operand padding, layer-0 projections)
   fnb_batch_plan plan{};
-  RC(fnb_batch_plan_build(in, B.plan_arena, B.plan_bytes, &plan, stream));
+  FnbAux aux{};
+  const bool two = fnb_aux_streams(&aux) == 0;
+  cudaEvent_t plan_ready = nullptr;
+  if (two) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RC((int)cudaEventRecord(aux.ready[1], s));               // the batch tensors are complete on the caller's stream
+    RC((int)cudaStreamWaitEvent(aux.wstream, aux.ready[1], 0));
+    RC(fnb_batch_plan_build(in, B.plan_arena, B.plan_bytes, &plan, (void *)aux.wstream));
+    RC((int)cudaEventRecord(aux.wjoin, aux.wstream));
+    plan_ready = aux.wjoin;
+  } else {
+    RC(fnb_batch_plan_build(in, B.plan_arena, B.plan_bytes, &plan, stream));
+  }
   // ---- encoder forward (FragNet.forward, gat2.py:381-442)
   fnb_encoder_opts o = opts_of(a);
   fnb_encoder_io eio{};
   eio.x_atoms = a->x_atoms; eio.x_bond = a->x_bond; eio.x_fbond = a->x_fbond;
   eio.out_atoms = B.out_atoms; eio.out_frags = B.out_frags; eio.out_bond = B.out_bond; eio.out_fbond = B.out_fbond;
-  RC(fnb_encoder_forward(&plan, &o, a->layers, &eio, B.enc_ws, B.enc_bytes, scratch, stream));
+  RC(fnb_encoder_forward_impl(&plan, &o, a->layers, &eio, B.enc_ws, B.enc_bytes, scratch, stream, plan_ready));
   // ---- heads (PretrainTask.forward, pretrain_heads.py:64-102)
   fnb_pretrain_head_io hio{};
   hio.x_atoms = B.out_atoms; hio.x_frags = B.out_frags; hio.edge_feat = B.out_bond; hio.edge_index = in->edge_index;
@@ -152,8 +165,9 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   // ---- backward: heads, then the encoder
   hio.g_dihedral = B.d_dihedral; hio.g_bond_angle = B.d_bond_angle; hio.g_energy = B.d_energy;
   hio.g_atoms = B.g_atoms; hio.g_frags = B.g_frags; hio.g_edge = B.g_edge;
-  RC(fnb_pretrain_heads_backward(a->heads, a->head_grads, &hio, a->precision, B.head_ws, B.head_bytes, B.head_bws,
-                                 B.head_bws_bytes, scratch, stream));
+  // (the heads' weight gradients keep running on the auxiliary streams; the encoder backward ends by joining them)
+  RC(fnb_pretrain_heads_backward_impl(a->heads, a->head_grads, &hio, a->precision, B.head_ws, B.head_bytes, B.head_bws,
+                                      B.head_bws_bytes, scratch, stream, 1));
   eio.g_atoms = B.g_atoms; eio.g_frags = B.g_frags; eio.g_bond = B.g_edge; eio.g_fbond = nullptr;
   RC(fnb_encoder_backward(&plan, &o, a->layers, a->layer_grads, &eio, B.enc_ws, B.enc_bytes, B.enc_bws, B.enc_bws_bytes,
                           scratch, stream));
