@@ -281,7 +281,11 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
 int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
                                      const fnb_pretrain_head_io *io, int precision, void *workspace,
                                      size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
-                                     void *scratch, void *stream, int defer_join);
+                                     void *scratch, void *stream, int defer_join, const fnb_mse_term *fused,
+                                     float *loss_out);
+int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_io *io, int precision,
+                                    void *workspace, size_t workspace_bytes, void *scratch, void *stream,
+                                    int skip_tails);
 
 // Tensor-core (tcgen05, TF32) projection path, tc_gemm.cu.  Returns FNB_ERR_MODE when the shape cannot use TMA.
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,

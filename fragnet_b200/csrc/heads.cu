@@ -82,6 +82,7 @@ struct BwdBufs {
   float *rec_ba, *rec_da, *rec_fc;   // per-CTA records of the tail gradients
   float *scratch2;                   // scratch of the energy-head chain (auxiliary stream)
   float *scratch3;                   // scratch of the weight-gradient stream
+  float *loss_parts;                 // [4] per-head shares of the fused loss
 };
 
 size_t bwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, BwdBufs *out) {
@@ -96,6 +97,7 @@ size_t bwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, BwdBufs *out) {
   b.rec_fc = a.take<float>((size_t)kTailCtasMax * kRecWide);
   b.scratch2 = a.take<float>(kScratchFloats);
   b.scratch3 = a.take<float>(kScratchFloats);
+  b.loss_parts = a.take<float>(4);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -152,6 +154,11 @@ struct TailJob {
   const float *gout;      // backward: [n] gradient of out
   float *dh0;             // backward: [n,128] gradient of h0 (columns IN.. written as zero)
   float *rec;             // backward: per-CTA records
+  // fused loss (training step): with target != NULL the kernel forms the prediction itself and uses
+  // gout[r] = 2 * loss_coef * (pred[r] - target[r]); the CTA's share of loss_coef * sum (pred - target)^2 goes into the
+  // spare slot at the end of its record
+  const float *target;
+  float loss_coef;
 };
 struct TailJobs {
   TailJob j[3];
@@ -233,10 +240,12 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
   float *s_h1g = s_d1 + ROWS * SD;             // [ROWS][SD]   gout * ReLU(hidden)
   float *s_g = s_h1g + ROWS * SD;              // [ROWS]
   __shared__ float sb1[MID], sW2[MID], sb2[1];
+  __shared__ float s_part[ROWS * 8], s_loss[ROWS];
   const int tid = threadIdx.x;
   const int64_t n_tiles = (job.n + ROWS - 1) / ROWS;
   if (blockIdx.x >= n_tiles && blockIdx.x > 0) return;   // CTA 0 always runs: it writes a (possibly zero) record
   load_tail_weights<IN, MID>(job, sW1t, sb1, sW2, sb2);
+  float lossacc = 0.f;   // tid == 0
   const int oj = tid >> 2, ok0 = (tid & 3) * 4;
   float wacc[KPT];
 #pragma unroll
@@ -249,20 +258,23 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = tile * ROWS;
     const int rows = (int)min((int64_t)ROWS, job.n - r0);
-    // ---- phase 1: FOUR threads per row (row = tid % ROWS, quarter q = tid / ROWS): a thread computes MID/4 hidden
-    // units, then IN/4 columns of dh0 -- a quarter of the serial chain of the thread-per-row form, which at ~1e3 rows
-    // (the energy head) is pure latency
+    // ---- phase 1: SPLIT = THREADS / ROWS threads per row (row = tid % ROWS, part q = tid / ROWS): a thread computes
+    // MID / SPLIT hidden units, then IN / SPLIT columns of dh0 -- 1/SPLIT of the serial chain of the thread-per-row
+    // form, which at ~1e3 rows (the energy head) is pure latency
     {
-      static_assert(THREADS == 4 * ROWS && (MID % 16) == 0 && (IN % 16) == 0, "phase 1 splits a row over 4 threads");
-      constexpr int JQ = MID / 4, KQ = IN / 4;
+      constexpr int SPLIT = THREADS / ROWS, JQ = MID / SPLIT, KQ = IN / SPLIT;
+      static_assert(THREADS == SPLIT * ROWS && (JQ % 4) == 0 && (KQ % 4) == 0 && SPLIT <= 8, "phase 1 row split");
       const int r = tid % ROWS, q = tid / ROWS;
       const bool live = r < rows;
       const int64_t row = r0 + r;
       const float *rp = job.h0 + (live ? row : 0) * kD;
+      const bool fused = job.target != nullptr;
       float g = 0.f;
+      float acc[JQ];
+#pragma unroll
+      for (int j = 0; j < JQ; ++j) acc[j] = 0.f;
       if (live) {
-        g = __ldg(job.gout + row);
-        float acc[JQ];
+        g = __ldg((fused ? job.target : job.gout) + row);
 #pragma unroll
         for (int j = 0; j < JQ; ++j) acc[j] = sb1[q * JQ + j];
 #pragma unroll 2
@@ -282,6 +294,23 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
             }
           }
         }
+      }
+      if (fused) {   // the row's prediction = sum of the SPLIT partial dots with W2 (+ b2); g held the target
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < JQ; ++j) o = fmaf(fmaxf(acc[j], 0.f), sW2[q * JQ + j], o);
+        s_part[r * 8 + q] = o;
+        __syncthreads();
+        float pred = sb2[0];
+#pragma unroll
+        for (int qq = 0; qq < SPLIT; ++qq) pred += s_part[r * 8 + qq];
+        const float diff = live ? pred - g : 0.f;
+        g = 2.f * job.loss_coef * diff;
+        if (q == 0) s_loss[r] = job.loss_coef * diff * diff;
+      } else if (q == 0) {
+        s_loss[r] = 0.f;
+      }
+      if (live) {
 #pragma unroll
         for (int j = 0; j < JQ; ++j) {
           const int jj = q * JQ + j;
@@ -342,7 +371,10 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
       if ((tid & 3) == 0) vacc += d;
       else if ((tid & 3) == 1) vacc += s_h1g[r * SD + oj];
       if (tid < IN) b0acc += s_dh0[r * SA + tid];
-      if (tid == 0) b2acc += s_g[r];
+      if (tid == 0) {
+        b2acc += s_g[r];
+        lossacc += s_loss[r];
+      }
     }
     __syncthreads();
   }
@@ -353,7 +385,10 @@ __global__ void __launch_bounds__(THREADS) k_mlp_tail_bwd(TailJobs J) {
     st4(rec + oj * IN + ok0 + q4 * 16, make_float4(wacc[q4 * 4], wacc[q4 * 4 + 1], wacc[q4 * 4 + 2], wacc[q4 * 4 + 3]));
   if ((tid & 3) == 0) rec[MID * IN + oj] = vacc;
   if ((tid & 3) == 1) rec[MID * IN + MID + oj] = vacc;
-  if (tid == 0) rec[MID * IN + 2 * MID] = b2acc;
+  if (tid == 0) {
+    rec[MID * IN + 2 * MID] = b2acc;
+    rec[MID * IN + 2 * MID + 1 + IN] = lossacc;   // spare slot of the record (rec_floats rounds up to 4)
+  }
   if (tid < IN) rec[MID * IN + 2 * MID + 1 + tid] = b0acc;
 }
 
@@ -430,7 +465,7 @@ __global__ void __launch_bounds__(128, 4) k_mlp_tail_fwd2(TailJobs J) {
 //   P3  dW1[j,k]  += sum_r D1[r,j] A[r,k]              thread = 4 j x 4 k, accumulated over all tiles of the CTA
 // Rows of a thread are interleaved (r = rg + 16 i) so that the 4 row groups of a warp hit distinct banks.
 constexpr int TB_ROWS = 128, TB_SA = 68, TB_SD = 36;
-constexpr size_t kTailBwd2Smem = sizeof(float) * (2 * 64 * 32 + TB_ROWS * TB_SA + TB_ROWS * TB_SD + TB_ROWS + 64);
+constexpr size_t kTailBwd2Smem = sizeof(float) * (2 * 64 * 32 + TB_ROWS * TB_SA + TB_ROWS * TB_SD + TB_ROWS + 68);
 
 __global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
   pdl_wait();
@@ -456,6 +491,9 @@ __global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
     sb1[tid] = __ldg(job.b1 + tid);
     sb1[32 + tid] = __ldg(job.W2 + tid);
   }
+  if (tid == 0) sb1[64] = __ldg(job.b2);
+  const bool fused = job.target != nullptr;
+  float lossp = 0.f;
   const int rg = tid >> 3, g8 = tid & 7;    // P1: j = 4 g8 .. +3;  P2: k = 4 g8 .. +3 and 32 + 4 g8 .. +3
   const int jb = tid >> 4, kb = tid & 15;   // P3: j = 4 jb .. +3, k = 4 kb .. +3
   float wacc[4][4];
@@ -477,7 +515,7 @@ __global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
       if (r0 + r < job.n) v = ldg4(job.h0 + (r0 + r) * kD + c4 * 4);
       st4(sA + r * TB_SA + c4 * 4, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
     }
-    sg[tid] = r0 + tid < job.n ? __ldg(job.gout + r0 + tid) : 0.f;
+    sg[tid] = r0 + tid < job.n ? __ldg((fused ? job.target : job.gout) + r0 + tid) : 0.f;
     __syncthreads();
     // ---- P1
     {
@@ -509,7 +547,17 @@ __global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rg + 16 * i;
-        const float g = sg[r];
+        float g = sg[r];
+        if (fused) {   // prediction of the row: the 8 lanes of a row group hold 4 hidden units each
+          float o = fmaxf(acc[i][0] + b1a[0], 0.f) * w2a[0] + fmaxf(acc[i][1] + b1a[1], 0.f) * w2a[1] +
+                    fmaxf(acc[i][2] + b1a[2], 0.f) * w2a[2] + fmaxf(acc[i][3] + b1a[3], 0.f) * w2a[3];
+          o += __shfl_xor_sync(kFull, o, 1);
+          o += __shfl_xor_sync(kFull, o, 2);
+          o += __shfl_xor_sync(kFull, o, 4);
+          const float diff = r0 + r < job.n ? (o + sb1[64]) - g : 0.f;   // g held the target
+          g = 2.f * job.loss_coef * diff;
+          if (g8 == 0) lossp = fmaf(job.loss_coef * diff, diff, lossp);
+        }
         float d[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -603,12 +651,13 @@ __global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
     mine[32 + g8 * 4 + q] = dw2p[q];
   }
   mine[64 + g8] = db2p;
+  mine[72 + g8] = lossp;
   __syncthreads();
-  if (tid < 65) {
+  if (tid < 66) {
     float s_ = 0.f;
-    const int col = tid < 64 ? tid : 64;   // 64: db2 (g8 == 0 slot)
+    const int col = tid < 64 ? tid : (tid == 64 ? 64 : 72);   // 64: db2, 72: loss share (g8 == 0 slots)
     for (int g = 0; g < 16; ++g) s_ += sred[g * 80 + col];
-    rec[MID * IN + col] = s_;
+    rec[tid < 65 ? MID * IN + col : MID * IN + 2 * MID + 1 + IN] = s_;
   }
   __syncthreads();
 #pragma unroll
@@ -653,6 +702,15 @@ __global__ void __launch_bounds__(256) k_head_sum_records(SumJobs s) {
   part[grp][threadIdx.x & 63] = acc;
   __syncthreads();
   if (grp == 0 && i < s.width[seg]) s.out[seg][i] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
+}
+
+__global__ void k_loss_total(const float *__restrict__ parts, int n, float *__restrict__ loss) {
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    float s_ = 0.f;
+    for (int i = 0; i < n; ++i) s_ += parts[i];
+    loss[0] = s_;
+  }
 }
 
 struct SumBuilder {
@@ -724,14 +782,22 @@ extern "C" size_t fnb_pretrain_heads_bwd_workspace_bytes(int64_t n_atoms, int64_
 extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, const fnb_pretrain_head_io *io,
                                           int precision, void *workspace, size_t workspace_bytes, void *scratch,
                                           void *stream_) {
+  return fnb_pretrain_heads_forward_impl(P, io, precision, workspace, workspace_bytes, scratch, stream_, 0);
+}
+
+// skip_tails != 0: only the first layers and the readout (what the backward needs); the training step forms the
+// predictions inside the backward tails (fused loss) and never materialises them.
+int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_io *io, int precision,
+                                    void *workspace, size_t workspace_bytes, void *scratch, void *stream_,
+                                    int skip_tails) {
   RC(check_io(P, io));
   if (!workspace || !scratch) return FNB_ERR_NULL;
-  if (!io->bond_angle || !io->dihedral || !io->energy) return FNB_ERR_NULL;
+  if (!skip_tails && (!io->bond_angle || !io->dihedral || !io->energy)) return FNB_ERR_NULL;
   const int64_t Na = io->n_atoms, Ea = io->n_edges, G = io->n_graphs, Nf = io->n_frags;
   FwdBufs B;
   if (fwd_layout(Na, Ea, G, (char *)workspace, &B) > workspace_bytes) return FNB_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
-  const bool want_bl = io->bond_length != nullptr && Ea > 0;
+  const bool want_bl = io->bond_length != nullptr && Ea > 0 && !skip_tails;
 
   {  // padded / split operands (one launch)
     PackJobs p{};
@@ -758,12 +824,14 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     RC(fnb_segment_sum(io->mol_atom_ptr, nullptr, G, io->x_atoms, B.readout, 2 * kD, nullptr, 0, 0, 0, nullptr, sB_));
     RC(fnb_segment_sum(io->mol_frag_ptr, nullptr, G, io->x_frags, B.readout + kD, 2 * kD, nullptr, 0, 0, 0, nullptr, sB_));
     RC(fnb_proj_fwd(B.readout, P->fc.W0, P->fc.b0, G, 2 * kD, nullptr, 0, 0, 0, B.h0_fc, nullptr, precision, sB_));
-    TailJobs F{};
-    F.n = 1;
-    TailJob &t = F.j[0];
-    t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.out = io->energy;
-    if (cudaError_t le = fnb_launch(k_mlp_tail_fwd<128, 64>, dim3((unsigned)((G + 127) / 128), 1), dim3(128), 0, sB, F)) return (int)le;
-    FNB_CHECK_LAUNCH();
+    if (!skip_tails) {
+      TailJobs F{};
+      F.n = 1;
+      TailJob &t = F.j[0];
+      t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.out = io->energy;
+      if (cudaError_t le = fnb_launch(k_mlp_tail_fwd<128, 64>, dim3((unsigned)((G + 127) / 128), 1), dim3(128), 0, sB, F)) return (int)le;
+      FNB_CHECK_LAUNCH();
+    }
   }
   (void)Nf;
   // ---- first layers on the projection kernels
@@ -780,7 +848,7 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
     RC(fnb_proj_fwd(B.T, B.W0pad_bl, B.b0pad_bl, Ea, kD, nullptr, 0, 0, 0, B.h0_bl, nullptr, precision, stream_));
   }
   // ---- tails of the per-atom / per-bond heads
-  {
+  if (!skip_tails) {
     TailJobs J{};
     int64_t most = 0;
     auto add = [&](const float *h0, int64_t n, const fnb_mlp3_params &m, float *out) {
@@ -812,10 +880,14 @@ extern "C" int fnb_pretrain_heads_forward(const fnb_pretrain_head_params *P, con
 int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
                                      const fnb_pretrain_head_io *io, int precision, void *workspace,
                                      size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
-                                     void *scratch, void *stream_, int defer_join) {
+                                     void *scratch, void *stream_, int defer_join, const fnb_mse_term *fused,
+                                     float *loss_out) {
   RC(check_io(P, io));
   if (!D || !workspace || !bwd_workspace || !scratch) return FNB_ERR_NULL;
-  if (!io->g_bond_angle || !io->g_dihedral || !io->g_energy) return FNB_ERR_NULL;
+  // fused != NULL: [0] bond angle, [1] dihedral, [2] energy targets and weights; the tails then compute
+  // g = 2 w / n (pred - target) themselves and loss_out receives sum_t w_t mean((pred_t - target_t)^2)
+  if (!fused && (!io->g_bond_angle || !io->g_dihedral || !io->g_energy)) return FNB_ERR_NULL;
+  if (fused && (!loss_out || !fused[0].target || !fused[1].target || !fused[2].target)) return FNB_ERR_NULL;
   if (!io->g_atoms || !io->g_frags || !io->g_edge) return FNB_ERR_NULL;
   if (!io->batch32 || !io->frag_batch32) return FNB_ERR_NULL;
   const fnb_mlp3_grads *gm[3] = {&D->ba, &D->da, &D->fc};
@@ -843,8 +915,8 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
       cudaError_t e = cudaFuncSetAttribute(k_mlp_tail_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kTailBwd2Smem);
       if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(k_mlp_tail_bwd<128, 64, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)tail_bwd_smem<128, 64, 64>());
+      e = cudaFuncSetAttribute(k_mlp_tail_bwd<128, 64, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tail_bwd_smem<128, 64, 32>());
       if (e != cudaSuccess) return (int)e;
       done[dev] = true;
     }
@@ -859,11 +931,12 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
     }
     TailJobs F{};
     F.n = 1;
-    ctas_fc = tail_grid(G, 64);
+    ctas_fc = tail_grid(G, 32);
     TailJob &t = F.j[0];
     t.h0 = B.h0_fc; t.n = G; t.W1 = P->fc.W1; t.b1 = P->fc.b1; t.W2 = P->fc.W2; t.b2 = P->fc.b2; t.gout = io->g_energy;
     t.dh0 = W.dh0_fc; t.rec = W.rec_fc;
-    if (cudaError_t le = fnb_launch(k_mlp_tail_bwd<128, 64, 256, 64>, dim3(ctas_fc, 1), dim3(256), tail_bwd_smem<128, 64, 64>(), sB, F))
+    if (fused) { t.target = fused[2].target; t.loss_coef = fused[2].weight / (float)G; }
+    if (cudaError_t le = fnb_launch(k_mlp_tail_bwd<128, 64, 256, 32>, dim3(ctas_fc, 1), dim3(256), tail_bwd_smem<128, 64, 32>(), sB, F))
       return (int)le;
     FNB_CHECK_LAUNCH();
     // input gradient first: the atoms' gradient on the caller's stream waits for d_readout, nothing waits for dW
@@ -886,6 +959,10 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
     ctas_da = tail_grid(Ea, 128);
     add(B.h0_ba, Na, P->ba, io->g_bond_angle, W.dh0_ba, W.rec_ba);
     add(B.h0_da, Ea, P->da, io->g_dihedral, W.dh0_da, W.rec_da);
+    if (fused) {
+      J.j[0].target = fused[0].target; J.j[0].loss_coef = Na > 0 ? fused[0].weight / (float)Na : 0.f;
+      J.j[1].target = fused[1].target; J.j[1].loss_coef = Ea > 0 ? fused[1].weight / (float)Ea : 0.f;
+    }
     const int gx = ctas_ba > ctas_da ? ctas_ba : ctas_da;
     // a job with fewer tiles than gx: its surplus CTAs return at once and write no record, so the record count of a
     // job is min(gx, tiles of the job) = its own tail_grid
@@ -931,7 +1008,17 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
   sb.add_tail(W.rec_ba, ctas_ba, 64, 32, D->ba.W1, D->ba.b1, D->ba.W2, D->ba.b2, D->ba.b0);
   sb.add_tail(W.rec_da, ctas_da, 64, 32, D->da.W1, D->da.b1, D->da.W2, D->da.b2, D->da.b0);
   sb.add_tail(W.rec_fc, ctas_fc, 128, 64, D->fc.W1, D->fc.b1, D->fc.W2, D->fc.b2, D->fc.b0);
+  if (fused) {
+    sb.add(W.rec_ba, ctas_ba, kRecSmall, 64 * 32 + 2 * 32 + 1 + 64, 1, W.loss_parts + 0);
+    sb.add(W.rec_da, ctas_da, kRecSmall, 64 * 32 + 2 * 32 + 1 + 64, 1, W.loss_parts + 1);
+    sb.add(W.rec_fc, ctas_fc, kRecWide, 128 * 64 + 2 * 64 + 1 + 128, 1, W.loss_parts + 2);
+  }
   RC(sb.launch(stream));
+  if (fused) {
+    if (cudaError_t le = fnb_launch(k_loss_total, dim3(1), dim3(32), 0, stream, (const float *)W.loss_parts, 3, loss_out))
+      return (int)le;
+    FNB_CHECK_LAUNCH();
+  }
   if (two && !defer_join) {
     if (G > 0) RC((int)cudaStreamWaitEvent(stream, aux.wjoin, 0));   // energy head's first-layer weight gradient
     RC((int)cudaStreamWaitEvent(stream, aux.done[0], 0));            // first-layer weight gradients of the other heads
@@ -944,7 +1031,7 @@ extern "C" int fnb_pretrain_heads_backward(const fnb_pretrain_head_params *P, co
                                            size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
                                            void *scratch, void *stream_) {
   return fnb_pretrain_heads_backward_impl(P, D, io, precision, workspace, workspace_bytes, bwd_workspace,
-                                          bwd_workspace_bytes, scratch, stream_, 0);
+                                          bwd_workspace_bytes, scratch, stream_, 0, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------

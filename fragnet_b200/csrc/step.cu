@@ -153,21 +153,25 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   hio.bond_angle = a->bond_angle ? a->bond_angle : B.bond_angle;
   hio.dihedral = a->dihedral ? a->dihedral : B.dihedral;
   hio.energy = a->energy ? a->energy : B.energy;
-  RC(fnb_pretrain_heads_forward(a->heads, &hio, a->precision, B.head_ws, B.head_bytes, scratch, stream));
+  // Training without prediction outputs: the tails' forward, the loss and the gradients of the predictions are formed
+  // inside the backward tails (fused loss) -- three launches and one synchronisation point between the heads fewer.
+  const bool fuse_loss = a->backward && !a->bond_length && !a->bond_angle && !a->dihedral && !a->energy;
+  RC(fnb_pretrain_heads_forward_impl(a->heads, &hio, a->precision, B.head_ws, B.head_bytes, scratch, stream, fuse_loss));
   // ---- loss (pretrain_utils.py:22-26): 2 x dihedral + bond angle + energy, and the gradients of the predictions
   fnb_mse_term terms[3];
   terms[0].pred = hio.dihedral;   terms[0].target = a->t_dihedral;   terms[0].n = in->n_bonds;  terms[0].weight = 2.f;
   terms[1].pred = hio.bond_angle; terms[1].target = a->t_bond_angle; terms[1].n = in->n_atoms;  terms[1].weight = 1.f;
   terms[2].pred = hio.energy;     terms[2].target = a->t_energy;     terms[2].n = in->n_graphs; terms[2].weight = 1.f;
   terms[0].grad = B.d_dihedral; terms[1].grad = B.d_bond_angle; terms[2].grad = B.d_energy;
-  RC(fnb_mse_sum_loss(terms, 3, a->loss, scratch, stream));
+  if (!fuse_loss) RC(fnb_mse_sum_loss(terms, 3, a->loss, scratch, stream));
   if (!a->backward) return 0;
   // ---- backward: heads, then the encoder
   hio.g_dihedral = B.d_dihedral; hio.g_bond_angle = B.d_bond_angle; hio.g_energy = B.d_energy;
   hio.g_atoms = B.g_atoms; hio.g_frags = B.g_frags; hio.g_edge = B.g_edge;
+  const fnb_mse_term fused[3] = {terms[1], terms[0], terms[2]};   // bond angle, dihedral, energy
   // (the heads' weight gradients keep running on the auxiliary streams; the encoder backward ends by joining them)
   RC(fnb_pretrain_heads_backward_impl(a->heads, a->head_grads, &hio, a->precision, B.head_ws, B.head_bytes, B.head_bws,
-                                      B.head_bws_bytes, scratch, stream, 1));
+                                      B.head_bws_bytes, scratch, stream, 1, fuse_loss ? fused : nullptr, a->loss));
   eio.g_atoms = B.g_atoms; eio.g_frags = B.g_frags; eio.g_bond = B.g_edge; eio.g_fbond = nullptr;
   RC(fnb_encoder_backward(&plan, &o, a->layers, a->layer_grads, &eio, B.enc_ws, B.enc_bytes, B.enc_bws, B.enc_bws_bytes,
                           scratch, stream));

