@@ -56,14 +56,32 @@ class DevicePrefetcher:
     batches have been requested.  Host tensors that are not pinned are pinned first (``DataLoader(pin_memory=True)``
     does that in the loader's workers)."""
 
-    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device, depth: int = 2):
+    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device, depth: int = 2, hot_path_only: bool = False):
+        """``hot_path_only=True`` moves only what the GAT2 path reads: ``edge_attr`` and ``cnx_attr`` are dropped
+        (``FragNet.forward`` never reads them: gat2.py:381-442 takes ``node_features_bonds`` / ``edge_attr_fbonds``),
+        and ``x_frags`` -- whose VALUES are overwritten unread by the atom->fragment pooling (gat2.py:234), only its
+        row count matters -- arrives as a ``meta`` tensor of the same shape.  ~20 % fewer PCIe bytes per batch."""
         self.batches, self.device, self.depth = batches, torch.device(device), max(1, int(depth))
+        self.hot_path_only = bool(hot_path_only)
         if self.device.type != "cuda":
             raise ValueError("DevicePrefetcher stages batches onto a CUDA device")
         self._copy_stream = torch.cuda.Stream(self.device)
         self._slots: List[_Slot] = [_Slot(self.device) for _ in range(self.depth + 1)]
 
+    _UNREAD = ("edge_attr", "cnx_attr")
+
     def _stage(self, host: Dict[str, torch.Tensor], slot: _Slot):
+        shape_only = None
+        if self.hot_path_only:
+            host = {k: v for k, v in host.items() if k not in self._UNREAD}
+            if isinstance(host.get("x_frags"), torch.Tensor):
+                shape_only = host.pop("x_frags")
+        dev, ev, pinned, slot = self._stage_tensors(host, slot)
+        if shape_only is not None:
+            dev["x_frags"] = torch.empty(shape_only.shape, dtype=shape_only.dtype, device="meta")
+        return dev, ev, pinned, slot
+
+    def _stage_tensors(self, host: Dict[str, torch.Tensor], slot: _Slot):
         pinned = {k: (v if (not isinstance(v, torch.Tensor) or v.is_cuda or v.is_pinned()) else v.pin_memory())
                   for k, v in host.items()}
         dev, grew = slot.views(pinned)                   # (re)allocation, if any, happens on the current stream

@@ -245,3 +245,12 @@ def test_device_prefetcher_yields_identical_batches():
             assert torch.equal(d[k].cpu(), h[k]), k
         n += 1
     assert n == len(host)
+    # hot_path_only: the tensors the GAT2 path never reads stay on the host; the model output is unchanged
+    from fragnet.model.gat.gat2 import FragNetFineTune
+    torch.manual_seed(0)
+    m = FragNetFineTune(num_layer=2, drop_ratio=0.0, h1=32, h2=32, h3=32, h4=32).cuda().eval()
+    lean = next(iter(DevicePrefetcher(iter(host[:1]), "cuda", hot_path_only=True)))
+    assert "edge_attr" not in lean and "cnx_attr" not in lean and lean["x_frags"].device.type == "meta"
+    assert lean["x_frags"].shape == host[0]["x_frags"].shape
+    with torch.no_grad():
+        assert torch.equal(m(lean), m({k: v.cuda() for k, v in host[0].items()}))
