@@ -408,8 +408,9 @@ int fnb_proj_bwd_dw(const float *x, const float *dh, int64_t n_rows, int K, floa
   if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
   if (!x || !dh || !dW || !scratch) return FNB_ERR_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (precision == FNB_PRECISION_TF32 && K == kD && n_rows > 0 && !db) {
-    const int rc = fnb_tc_dw_launch(dh, x, n_rows, kD, kD, dW, scratch_body(scratch), stream);
+  if (precision == FNB_PRECISION_TF32 && (K & 31) == 0 && K <= 256 && n_rows > 0 && !db) {
+    // tensor-core path for every TMA-addressable width (K = 128: the attention projections; K = 256: the energy head)
+    const int rc = fnb_tc_dw_launch(dh, x, n_rows, K, K, dW, scratch_body(scratch), stream);
     if (rc != FNB_ERR_MODE) return rc;
   }
   int64_t nb = (n_rows + 255) / 256;
