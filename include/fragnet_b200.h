@@ -13,10 +13,12 @@
  *   - the last argument is the cudaStream_t to launch on (passed as void*);
  *   - return value: 0 = ok, negative = argument validation error (see fnb_error_string),
  *     positive = cudaError_t of a failed launch;
- *   - re-entrant; process-wide state is limited to a diagnostic launch counter and, per device, three lazily created
- *     auxiliary streams (+ events) that the encoder / heads / step programs fork onto and join back from before they
- *     return (FNB_STREAMS=1 in the environment keeps every launch on the caller's stream, FNB_PDL=0 turns programmatic
- *     dependent launch off);  all feature matrices are row-major fp32 with D = 128
+ *   - the kernel-level entry points are re-entrant; the program-level ones (fnb_encoder_*, fnb_pretrain_heads_*,
+ *     fnb_pretrain_step) fork onto three lazily created, library-owned auxiliary streams (+ events) per device and join
+ *     back before they return, so one host thread per device should drive them (the reference's loops are single
+ *     threaded).  FNB_STREAMS=1 in the environment keeps every launch on the caller's stream, FNB_PDL=0 turns
+ *     programmatic dependent launch off.  Process-wide state otherwise: a diagnostic launch counter;
+ *   - all feature matrices are row-major fp32 with D = 128
  *     columns, H = 4 heads of d = 32 (the only geometry FragNet's gat2 uses with emb_dim 128);
  *   - graph indices handed in are int64 (as produced by the reference's collate_fn,
  *     fragnet/dataset/data.py:931-948); the CSR arrays produced and consumed are int32.
