@@ -409,10 +409,10 @@ def run_ours(args):
                 del big
         if not args.no_cpu_baseline and world == 1:
             with contextlib.redirect_stdout(io.StringIO()):
-                rate, _ = cpu_oracle_rate(args.shape, 128, 3, 1)
+                rate, _ = cpu_oracle_rate(args.shape, 512, 10, 1)        # ~10-15 s of host work
             cpu = {"value": round(rate, 2), "unit": "molecules/s", "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"128 {args.shape}-shaped molecules per step, 1 warm-up + 3 timed steps "
-                             "(fwd+bwd+Adam, train mode)"}
+                   "sample": f"512 {args.shape}-shaped molecules per step, 1 warm-up + 10 timed steps "
+                             "(fwd+bwd+Adam, train mode, all host threads)"}
         counts = batch_counts(host_batches[0])
         line = {"metric": METRIC, "value": round(value, 1), "unit": "molecules/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),

@@ -75,7 +75,15 @@ __device__ __forceinline__ float leaky(float z) { return z > 0.f ? z : kNegSlope
 // previous grid has completed and flushed.  Every kernel launched through fnb_launch() calls pdl_wait() before its
 // first access to global memory and pdl_launch_dependents() once its main loop is done.  Both are no-ops for a
 // kernel launched without the attribute (FNB_PDL=0 in the environment turns the attribute off).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef FNB_PDL_EARLY
+#define FNB_PDL_EARLY 0   // 1: signal the dependents right after pdl_wait() instead of after the main loop (experiment)
+#endif
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if FNB_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool fnb_pdl_enabled();
 template <class... KArgs, class... Args>
