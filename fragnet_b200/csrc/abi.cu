@@ -37,9 +37,17 @@ int fnb_aux_streams(FnbAux *out) {
     if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return 1;
     if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return 1;
     if (cudaStreamCreateWithFlags(&a.wstream, cudaStreamNonBlocking) != cudaSuccess) return 1;
-    if (cudaStreamCreateWithFlags(&a.astream, cudaStreamNonBlocking) != cudaSuccess) return 1;
-    cudaEvent_t *evs[9] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.wjoin,
-                           &a.a_fork, &a.a_dz, &a.a_table, &a.a_join};
+    {
+      // Experiment switch FNB_PRIO=1: highest priority for the atom chain, whose short kernels otherwise wait for an
+      // SM slot behind the ~850 CTAs of a bond-graph launch.  Measured SLOWER (profiles/r3d_*: 1.370 vs 1.334 ms per
+      // step: the bond kernels it displaces are the critical path and the step is throughput-bound), hence off.
+      int least = 0, greatest = 0;
+      const char *e = getenv("FNB_PRIO");
+      const bool prio = e && e[0] == '1' && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess;
+      if (cudaStreamCreateWithPriority(&a.astream, cudaStreamNonBlocking, prio ? greatest : 0) != cudaSuccess) return 1;
+    }
+    cudaEvent_t *evs[11] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.done2[0], &a.done2[1], &a.wjoin,
+                            &a.a_fork, &a.a_dz, &a.a_table, &a.a_join};
     for (cudaEvent_t *e : evs)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return 1;
     aux[dev] = a;

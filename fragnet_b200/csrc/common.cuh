@@ -277,11 +277,25 @@ struct FnbAux {
   cudaStream_t stream;       // independent chains (fragment-connection graph, energy head)
   cudaEvent_t fork, join;
   cudaStream_t wstream;      // weight-gradient GEMMs: nothing downstream waits for them until the end of the pass
-  cudaEvent_t ready[2], done[2], wjoin;
+  cudaEvent_t ready[2], done[2], done2[2], wjoin;   // done / done2: even / odd layers (dh is double-buffered)
   cudaStream_t astream;      // atom-graph chain (it only meets the bond chain at the edge-term kernels)
   cudaEvent_t a_fork, a_dz, a_table, a_join;
 };
 int fnb_aux_streams(FnbAux *out);
+
+// Destination pass of the attention backward with the incoming gradient assembled in the same launch (gat_tiled.cu:
+// dst_grad_row): args->dout is WRITTEN by the destination pass and read by the source pass.  Between the two launches `after_dst`
+// (optional) is recorded and `before_src` (optional) is waited for.  Bond graph (FNB_EDGE_AFFINE1) only.
+struct FnbDstFuse {
+  const float *dz_up;        // [E_up,4] dz of the consumer graph (its real edge e = this graph's node e), or NULL
+  const int *slot_of_eid;    // consumer graph's edge id -> slot
+  const float *alpha_up;     // consumer head vector at its edge slice, [4, alpha_up_stride]
+  int alpha_up_stride;
+  const float *g_base, *dy, *y;
+  float scale;
+};
+int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *args, const FnbDstFuse *fuse,
+                            cudaEvent_t after_dst, cudaEvent_t before_src, void *stream);
 
 int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts *opts, const fnb_layer_params *layers,
                              const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,

@@ -124,8 +124,8 @@ size_t layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_l
 }
 
 struct BwdBufs {
-  float *g_bond, *dz_b, *dSt_b, *dh_b, *dx_bond;
-  float *g_atom, *dz_a, *dSt_a, *dh_a, *dx_atom;
+  float *g_bond, *dz_b, *dSt_b, *dh_b, *dh_b2, *dx_bond;   // dh: one buffer per layer parity, so that a layer's
+  float *g_atom, *dz_a, *dSt_a, *dh_a, *dh_a2, *dx_atom;   // source pass never waits for the weight-gradient GEMM above it
   float *g_fbond, *dz_fb, *dSt_fb, *dh_fb, *dx_fbond;
   float *g_frag, *dz_f, *dSt_f, *d_hf;
   float *Wt;   // [n_layers][3][128*128] transposed K=128 projection weights
@@ -139,9 +139,9 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   Arena a{base, 0};
   BwdBufs b{};
   b.g_bond = a.take<float>(z.Nb * kD); b.dz_b = a.take<float>(z.Eb * 4); b.dSt_b = a.take<float>(z.Nb * 4);
-  b.dh_b = a.take<float>(z.Nb * kD); b.dx_bond = a.take<float>(z.Nb * kD);
+  b.dh_b = a.take<float>(z.Nb * kD); b.dh_b2 = a.take<float>(z.Nb * kD); b.dx_bond = a.take<float>(z.Nb * kD);
   b.g_atom = a.take<float>(z.Na * kD); b.dz_a = a.take<float>(z.Ea * 4); b.dSt_a = a.take<float>(z.Na * 4);
-  b.dh_a = a.take<float>(z.Na * kD); b.dx_atom = a.take<float>(z.Na * kD);
+  b.dh_a = a.take<float>(z.Na * kD); b.dh_a2 = a.take<float>(z.Na * kD); b.dx_atom = a.take<float>(z.Na * kD);
   b.g_fbond = a.take<float>(z.Nfb * kD); b.dz_fb = a.take<float>(z.Efb * 4); b.dSt_fb = a.take<float>(z.Nfb * 4);
   b.dh_fb = a.take<float>(z.Nfb * kD); b.dx_fbond = a.take<float>(z.Nfb * kD);
   b.g_frag = a.take<float>(z.Nf * kD); b.dz_f = a.take<float>(z.Ef * 4); b.dSt_f = a.take<float>(z.Nf * 4);
@@ -552,7 +552,8 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
   cudaStream_t sW = two ? aux.wstream : stream;
   void *sW_ = (void *)sW;
   void *scratchW = two ? (void *)W.scratch3 : scratch;
-  bool w_used = false, w_pending[2] = {false, false};
+  bool w_used = false, w_pending[2][2] = {{false, false}, {false, false}};   // [graph][layer parity]
+  auto done_ev = [&](int i, int par) { return par ? aux.done2[i] : aux.done[i]; };
   auto w_begin = [&](int i, cudaStream_t producer) -> int {   // dh of graph i (0 atom, 1 bond) is complete on `producer`
     if (!two) return 0;
     RC((int)cudaEventRecord(aux.ready[i], producer));
@@ -563,16 +564,17 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     }
     return 0;
   };
-  auto w_end = [&](int i) -> int {
+  auto w_end = [&](int i, int par) -> int {
     if (!two) return 0;
-    RC((int)cudaEventRecord(aux.done[i], sW));
-    w_pending[i] = true;
+    RC((int)cudaEventRecord(done_ev(i, par), sW));
+    w_pending[i][par] = true;
     return 0;
   };
-  auto w_wait = [&](int i, cudaStream_t waiter) -> int {   // before dh of graph i is overwritten (or at the end of the pass)
-    if (two && w_pending[i]) {
-      RC((int)cudaStreamWaitEvent(waiter, aux.done[i], 0));
-      w_pending[i] = false;
+  // before the dh buffer `par` of graph i is overwritten, i.e. two layers later (or at the end of the pass)
+  auto w_wait = [&](int i, int par, cudaStream_t waiter) -> int {
+    if (two && w_pending[i][par]) {
+      RC((int)cudaStreamWaitEvent(waiter, done_ev(i, par), 0));
+      w_pending[i][par] = false;
     }
     return 0;
   };
@@ -602,6 +604,8 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     const float *pre_bond = o->post_act ? b.pre_bond : io->out_bond;
     const float *pre_fbond = o->post_act ? b.pre_fbond : io->out_fbond;
     const bool need_dx = l > 0;
+    const int par = l & 1;
+    float *dh_a = par ? W.dh_a2 : W.dh_a, *dh_b = par ? W.dh_b2 : W.dh_b;
 
     // ---- fragment graph block (only where it ran and a gradient arrives)
     const float *d_hf = nullptr;
@@ -672,36 +676,31 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         fnb_gat_bwd_args a{};
         a.h = b.ha; a.dout = W.g_atom; a.p_saved = b.p_a; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.a;
         a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_a; a.dSt = W.dSt_a;
-        a.dh = W.dh_a; a.d_alpha = D.a; a.d_bias = D.ba; a.scratch = scratchA;
-        RC(w_wait(0, sA));
-        RC(fnb_gat_bwd_tiled(&plan->atom, &a, sA_));
+        a.dh = dh_a; a.d_alpha = D.a; a.d_bias = D.ba; a.scratch = scratchA;
+        RC(w_wait(0, par, sA));
+        // the bond graph's destination pass (caller's stream) only needs dz of this graph: the event sits between the
+        // two launches
+        RC(fnb_gat_bwd_tiled_fused(&plan->atom, &a, nullptr, two ? aux.a_dz : nullptr, nullptr, sA_));
+        if (two) RC((int)cudaStreamWaitEvent(stream, aux.a_dz, 0));
         RC(w_begin(0, sA));
-        if (two) {
-          RC((int)cudaEventRecord(aux.a_dz, sA));
-          RC((int)cudaStreamWaitEvent(stream, aux.a_dz, 0));
-        }
-        // bond features were this graph's edge vectors: their gradient, plus the activation backward of dy_bond
-        RC(fnb_edge_table_bwd_fused(&plan->atom, W.dz_a, pre_bond, P.a, A_STRIDE, A_E, y_bond ? nullptr : dy_bond,
-                                    y_bond ? dy_bond : nullptr, y_bond && dy_bond ? y_bond : nullptr, scale, W.g_bond,
-                                    D.a, scratch, stream_));
-        if (two) {
-          RC((int)cudaEventRecord(aux.a_table, stream));
-          a_table_pending = true;
-        }
         float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);
         if (l == 0 && b.k_pad[1] && !dx) {
-          RC(fnb_tc_dw_launch(W.dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchW), sW));
+          RC(fnb_tc_dw_launch(dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchW), sW));
         } else {
-          RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), W.dh_a, z.Na, P.K_atom, dx, o->precision, scratchA, sA_));
-          RC(fnb_proj_bwd_dw(xa, W.dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchW, sW_));
+          RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), dh_a, z.Na, P.K_atom, dx, o->precision, scratchA, sA_));
+          RC(fnb_proj_bwd_dw(xa, dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchW, sW_));
         }
-        RC(w_end(0));
+        // bond features were this graph's edge vectors (gat2.py:203-208): the head-vector gradient of that term stays
+        // on the atom chain, behind the dX GEMM the next layer waits for; the row gradient is assembled inside the
+        // bond graph's destination pass
+        RC(fnb_edge_table_bwd_fused(&plan->atom, W.dz_a, pre_bond, P.a, A_STRIDE, A_E, nullptr, nullptr, nullptr, scale,
+                                    nullptr, D.a, scratchA, sA_));
+        RC(w_end(0, par));
         dy_atom = need_dx ? W.dx_atom : nullptr;
       } else {
         RC((int)cudaMemsetAsync(D.a, 0, 4 * A_STRIDE * 4, stream));
         RC((int)cudaMemsetAsync(D.ba, 0, kD * 4, stream));
         RC((int)cudaMemsetAsync(D.Wa, 0, (size_t)kD * P.K_atom * 4, stream));
-        if (dy_bond) RC(grad_combine(dy_bond, y_bond, scale, nullptr, nullptr, z.Nb, W.g_bond, stream));
         dy_atom = nullptr;
       }
       // ---- bond graph block
@@ -709,19 +708,29 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         fnb_gat_bwd_args a{};
         a.h = b.hb; a.dout = W.g_bond; a.p_saved = b.p_b; a.edge_mode = FNB_EDGE_AFFINE1; a.We = P.We_b; a.be = P.be_b;
         a.alpha = P.a_b; a.alpha_stride = AB_STRIDE; a.off_t = AB_T; a.off_e = AB_E; a.off_s = AB_S; a.dz = W.dz_b;
-        a.dSt = W.dSt_b; a.dh = W.dh_b; a.d_alpha = D.a_b; a.d_bias = D.bb; a.dWe = D.We_b; a.dbe = D.be_b;
+        a.dSt = W.dSt_b; a.dh = dh_b; a.d_alpha = D.a_b; a.d_bias = D.bb; a.dWe = D.We_b; a.dbe = D.be_b;
         a.scratch = scratch;
-        RC(w_wait(1, stream));
-        RC(fnb_gat_bwd_tiled(&plan->bond, &a, stream_));
+        // incoming gradient = edge term of the atom graph (dz_a) + ReLU(Dropout) backward of dy_bond, assembled by
+        // the destination pass; the atom chain may overwrite dz_a once that launch is done
+        FnbDstFuse fz{};
+        fz.dz_up = have ? W.dz_a : nullptr; fz.slot_of_eid = plan->atom.slot_of_eid; fz.alpha_up = P.a + A_E;
+        fz.alpha_up_stride = A_STRIDE; fz.g_base = y_bond ? nullptr : dy_bond; fz.dy = y_bond ? dy_bond : nullptr;
+        fz.y = y_bond && dy_bond ? y_bond : nullptr; fz.scale = scale;
+        // (the weight-gradient GEMM two layers above read this dh buffer: only the source pass has to wait for it)
+        const bool wait_w = two && w_pending[1][par];
+        w_pending[1][par] = false;
+        RC(fnb_gat_bwd_tiled_fused(&plan->bond, &a, &fz, two && have ? aux.a_table : nullptr,
+                                   wait_w ? done_ev(1, par) : nullptr, stream_));
+        if (two && have) a_table_pending = true;
         RC(w_begin(1, stream));
         float *dx = need_dx ? W.dx_bond : (o->need_dx_bond ? io->dx_bond : nullptr);
         if (l == 0 && b.k_pad[0] && !dx) {
-          RC(fnb_tc_dw_launch(W.dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchW), sW));
+          RC(fnb_tc_dw_launch(dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchW), sW));
         } else {
-          RC(fnb_proj_bwd_dx(P.Wb, wt_of(l, 0), W.dh_b, z.Nb, P.K_bond, dx, o->precision, scratch, stream_));
-          RC(fnb_proj_bwd_dw(xb, W.dh_b, z.Nb, P.K_bond, D.Wb, nullptr, o->precision, scratchW, sW_));
+          RC(fnb_proj_bwd_dx(P.Wb, wt_of(l, 0), dh_b, z.Nb, P.K_bond, dx, o->precision, scratch, stream_));
+          RC(fnb_proj_bwd_dw(xb, dh_b, z.Nb, P.K_bond, D.Wb, nullptr, o->precision, scratchW, sW_));
         }
-        RC(w_end(1));
+        RC(w_end(1, par));
         dy_bond = need_dx ? W.dx_bond : nullptr;
       } else {
         RC((int)cudaMemsetAsync(D.a_b, 0, 4 * AB_STRIDE * 4, stream));
@@ -743,8 +752,8 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     RC((int)cudaEventRecord(aux.a_join, sA));
     RC((int)cudaStreamWaitEvent(stream, aux.a_join, 0));
   }
-  RC(w_wait(0, stream));
-  RC(w_wait(1, stream));
+  for (int i = 0; i < 2; ++i)
+    for (int p2 = 0; p2 < 2; ++p2) RC(w_wait(i, p2, stream));
   // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same RNG stream as the forward
   if (o->need_dx_atoms && io->dx_atoms && input_dropout(o)) {
     const RngPlan ph = rng_plan(plan, o, L);

@@ -334,6 +334,14 @@ struct DstT {
   int alpha_e_stride;
   float *dWe, *dbe, *d_alpha_e;
   int npc;
+  // FUSE: the incoming gradient is assembled here instead of by a separate pass over the rows (see dst_grad_row)
+  const float *f_dz;       // [E_up,4] dz of the consumer graph whose edge e is this graph's node e, or NULL
+  const int *f_slot;       // consumer graph's slot_of_eid
+  const float *f_alpha;    // consumer head vector, edge slice: [4, f_stride] (128 columns used)
+  int f_stride;
+  const float *f_base, *f_dy, *f_y;
+  float f_scale;
+  float *g_out;            // [N,128] assembled gradient, read by the source pass
 };
 
 template <int MODE> struct CoefT { static constexpr int NC = 1, PARTS = 1, IN = 1; };
@@ -344,10 +352,44 @@ __device__ __forceinline__ float dz_of(float p, float dp, float delta) {
   return fabsf(p) * (dp - delta) * (signbit(p) ? kNegSlope : 1.f);
 }
 
+// Gradient arriving at row t of this graph's output.  FUSE: the row is assembled on the fly,
+//   g[t,:] = sum_h dz_up[slot_up[t],h] alpha_up[h,:]  (+ g_base[t,:])  (+ dy[t,:] (y[t,:] > 0) scale)
+// i.e. the edge-term backward of the consumer graph (gat2.py:203-208: this graph's output rows are the consumer's edge
+// vectors) plus the ReLU(Dropout) backward of gat2.py:414-418, in the summation order of k_edge_table_bwd_tiled, and
+// written once for the source pass -- a whole pass over [N,128] leaves the critical path of the backward.
+template <bool FUSE>
+__device__ __forceinline__ float4 dst_grad_row(const DstT &a, int t, const float *s_ae) {
+  const int lane = threadIdx.x & 31;
+  const int64_t o = (int64_t)t * kD + lane * 4;
+  if (!FUSE) return ldg4(a.dout + o);
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.f_dz) {
+    const float4 dz = ldg4(a.f_dz + (int64_t)__ldg(a.f_slot + t) * 4);
+    const float4 ae0 = ld4(s_ae + lane * 4), ae1 = ld4(s_ae + 128 + lane * 4), ae2 = ld4(s_ae + 256 + lane * 4),
+                 ae3 = ld4(s_ae + 384 + lane * 4);
+    g.x = dz.x * ae0.x + dz.y * ae1.x + dz.z * ae2.x + dz.w * ae3.x;
+    g.y = dz.x * ae0.y + dz.y * ae1.y + dz.z * ae2.y + dz.w * ae3.y;
+    g.z = dz.x * ae0.z + dz.y * ae1.z + dz.z * ae2.z + dz.w * ae3.z;
+    g.w = dz.x * ae0.w + dz.y * ae1.w + dz.z * ae2.w + dz.w * ae3.w;
+  }
+  if (a.f_base) {
+    const float4 b = ldg4(a.f_base + o);
+    g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w;
+  }
+  if (a.f_dy) {
+    const float4 d = ldg4(a.f_dy + o), y = ldg4(a.f_y + o);
+    g.x += y.x > 0.f ? d.x * a.f_scale : 0.f;
+    g.y += y.y > 0.f ? d.y * a.f_scale : 0.f;
+    g.z += y.z > 0.f ? d.z * a.f_scale : 0.f;
+    g.w += y.w > 0.f ? d.w * a.f_scale : 0.f;
+  }
+  st4(a.g_out + o, g);
+  return g;
+}
+
 // Hub node on the destination side: warp 0, edges one at a time (dp parked in dz between the two passes).
-__device__ void dst_hub(const DstT &a, int t, int beg, int end) {
+__device__ void dst_hub(const DstT &a, int t, int beg, int end, const float4 g) {
   const int lane = threadIdx.x & 31, head = lane >> 3;
-  const float4 g = ldg4(a.dout + (int64_t)t * kD + lane * 4);
   float delta = 0.f;  // this lane's head
   for (int slot = beg; slot < end; ++slot) {
     const float4 v = ldg4(a.h + (int64_t)__ldg(a.col + slot) * kD + lane * 4);
@@ -369,7 +411,7 @@ __device__ void dst_hub(const DstT &a, int t, int beg, int end) {
   }
 }
 
-template <int MODE>
+template <int MODE, bool FUSE>
 __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
   constexpr int NC = CoefT<MODE>::NC, PARTS = CoefT<MODE>::PARTS, IN = CoefT<MODE>::IN;
   __shared__ int s_rowptr[T_NPC + 1];
@@ -378,6 +420,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
   __shared__ __align__(16) float s_dp[BWD_CAP * 4];
   __shared__ float s_red[PARTS * NC];
   __shared__ float s_rec[32], s_fin[32];
+  __shared__ __align__(16) float s_ae[FUSE ? 4 * kD : 4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, head = lane >> 3;
   // coefficient-gradient lane: coefficient c, slots part, part + PARTS, ...
   const bool coef_thread = NC > 1 && tid < NC * PARTS;
@@ -385,6 +428,8 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
   const int c_head = (NC == 8) ? (c & 3) : (c < 24 ? c / 6 : c - 24);
   const int c_k = (NC == 8) ? (c < 4 ? 0 : -1) : (c < 24 ? c % 6 : -1);  // -1: bias term (attribute = 1)
   float cacc = 0.f;
+  if (FUSE && a.f_dz)   // parameters, not produced by the preceding launch: staged before the dependency wait
+    for (int i = tid; i < 4 * kD; i += T_THREADS) s_ae[i] = __ldg(a.f_alpha + (int64_t)(i >> 7) * a.f_stride + (i & 127));
   pdl_wait();
 
   const int n_tiles = (a.n_nodes + a.npc - 1) / a.npc;
@@ -398,7 +443,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
       const int le = subtile_end(s_rowptr, lb, nn, BWD_CAP);
       if (le == lb) {
         const int beg = s_rowptr[lb], end = s_rowptr[lb + 1];
-        if (warp == 0) dst_hub(a, n0 + lb, beg, end);
+        if (warp == 0) dst_hub(a, n0 + lb, beg, end, dst_grad_row<FUSE>(a, n0 + lb, s_ae));
         if (NC > 1) {
           __syncthreads();  // warp 0's dz is visible to the block
           if (coef_thread)
@@ -420,7 +465,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
       // ---- phase A: dp per edge, one warp per node
       for (int n = lb + warp; n < le; n += T_WARPS) {
         const int b = s_rowptr[n] - e0, e = s_rowptr[n + 1] - e0;
-        const float4 g = ldg4(a.dout + (int64_t)(n0 + n) * kD + lane * 4);
+        const float4 g = dst_grad_row<FUSE>(a, n0 + n, s_ae);
         int j = b;
         for (; j + 4 <= e; j += 4) {
           float4 v[4];
@@ -688,23 +733,25 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_edge_table_bwd_tiled(TableT a)
     const float4 f = ldg4(a.feat + (int64_t)e * kD + lane * 4);
     const float4 ae0 = ld4(s_ae + lane * 4), ae1 = ld4(s_ae + 128 + lane * 4), ae2 = ld4(s_ae + 256 + lane * 4),
                  ae3 = ld4(s_ae + 384 + lane * 4);
-    float4 g;
-    g.x = dz.x * ae0.x + dz.y * ae1.x + dz.z * ae2.x + dz.w * ae3.x;
-    g.y = dz.x * ae0.y + dz.y * ae1.y + dz.z * ae2.y + dz.w * ae3.y;
-    g.z = dz.x * ae0.z + dz.y * ae1.z + dz.z * ae2.z + dz.w * ae3.z;
-    g.w = dz.x * ae0.w + dz.y * ae1.w + dz.z * ae2.w + dz.w * ae3.w;
-    if (a.g_base) {
-      const float4 o = ld4(a.g_base + (int64_t)e * kD + lane * 4);
-      g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+    if (a.g_feat) {   // NULL: only the head-vector gradient (the row gradient is assembled by the consumer's destination pass)
+      float4 g;
+      g.x = dz.x * ae0.x + dz.y * ae1.x + dz.z * ae2.x + dz.w * ae3.x;
+      g.y = dz.x * ae0.y + dz.y * ae1.y + dz.z * ae2.y + dz.w * ae3.y;
+      g.z = dz.x * ae0.z + dz.y * ae1.z + dz.z * ae2.z + dz.w * ae3.z;
+      g.w = dz.x * ae0.w + dz.y * ae1.w + dz.z * ae2.w + dz.w * ae3.w;
+      if (a.g_base) {
+        const float4 o = ld4(a.g_base + (int64_t)e * kD + lane * 4);
+        g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+      }
+      if (a.dy) {
+        const float4 d = ldg4(a.dy + (int64_t)e * kD + lane * 4), o = ldg4(a.y + (int64_t)e * kD + lane * 4);
+        g.x += o.x > 0.f ? d.x * a.scale : 0.f;
+        g.y += o.y > 0.f ? d.y * a.scale : 0.f;
+        g.z += o.z > 0.f ? d.z * a.scale : 0.f;
+        g.w += o.w > 0.f ? d.w * a.scale : 0.f;
+      }
+      st4(a.g_feat + (int64_t)e * kD + lane * 4, g);
     }
-    if (a.dy) {
-      const float4 d = ldg4(a.dy + (int64_t)e * kD + lane * 4), o = ldg4(a.y + (int64_t)e * kD + lane * 4);
-      g.x += o.x > 0.f ? d.x * a.scale : 0.f;
-      g.y += o.y > 0.f ? d.y * a.scale : 0.f;
-      g.z += o.z > 0.f ? d.z * a.scale : 0.f;
-      g.w += o.w > 0.f ? d.w * a.scale : 0.f;
-    }
-    st4(a.g_feat + (int64_t)e * kD + lane * 4, g);
     const float d4[4] = {dz.x, dz.y, dz.z, dz.w};
 #pragma unroll
     for (int hh = 0; hh < 4; ++hh) {
@@ -838,11 +885,22 @@ extern "C" int fnb_gat_fwd_tiled(const fnb_graph *g, const fnb_gat_fwd_args *f, 
 }
 
 extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, void *stream_) {
+  return fnb_gat_bwd_tiled_fused(g, b, nullptr, nullptr, nullptr, stream_);
+}
+
+int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *b, const FnbDstFuse *fz, cudaEvent_t after_dst,
+                            cudaEvent_t before_src, void *stream_) {
   if (!graph_ok(g) || !b) return g && b ? FNB_ERR_SIZE : FNB_ERR_NULL;
   if (g->n_nodes == 0) return 0;
   if (!g->rowptr || !g->rrowptr || !g->rslot || !g->rdst || !b->h || !b->dout || !b->dSt || !b->dh || !b->alpha ||
       !b->d_alpha || !b->scratch || (g->n_edges > 0 && (!g->col || !b->p_saved || !b->dz)))
     return FNB_ERR_NULL;
+  if (fz) {
+    if ((fz->dz_up && (!fz->slot_of_eid || !fz->alpha_up)) || (fz->dy == nullptr) != (fz->y == nullptr)) return FNB_ERR_NULL;
+    if ((fz->alpha_up_stride & 3) || !fnb_aligned16(fz->alpha_up) || !fnb_aligned16(fz->dz_up) ||
+        !fnb_aligned16(fz->g_base) || !fnb_aligned16(fz->dy) || !fnb_aligned16(fz->y))
+      return FNB_ERR_ALIGN;
+  }
   if ((b->alpha_stride & 3) || (b->off_t & 3) || (b->off_s & 3) || (b->off_e & 3) || !fnb_aligned16(b->alpha) ||
       !fnb_aligned16(b->h) || !fnb_aligned16(b->dout) || !fnb_aligned16(b->dh) || !fnb_aligned16(b->dz) ||
       !fnb_aligned16(b->p_saved) || !fnb_aligned16(b->dSt) || !fnb_aligned16(b->scratch))
@@ -854,20 +912,37 @@ extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, 
   d.We = b->We; d.be = b->be; d.alpha_e = b->alpha + b->off_e; d.alpha_e_stride = b->alpha_stride;
   d.dWe = b->dWe; d.dbe = b->dbe; d.d_alpha_e = b->d_alpha + b->off_e;
   d.npc = pick_npc(g->n_nodes);
+  d.f_dz = nullptr; d.f_slot = nullptr; d.f_alpha = nullptr; d.f_stride = 0; d.f_base = d.f_dy = d.f_y = nullptr;
+  d.f_scale = 1.f; d.g_out = nullptr;
+  if (fz) {   // the incoming gradient is assembled into b->dout by the destination pass
+    d.f_dz = fz->dz_up; d.f_slot = fz->slot_of_eid; d.f_alpha = fz->alpha_up; d.f_stride = fz->alpha_up_stride;
+    d.f_base = fz->g_base; d.f_dy = fz->dy; d.f_y = fz->y; d.f_scale = fz->scale;
+    d.g_out = const_cast<float *>(b->dout);
+  }
   const int grid = tile_grid(g->n_nodes, d.npc, 6);
   const bool affine = b->edge_mode == FNB_EDGE_AFFINE1 || b->edge_mode == FNB_EDGE_AFFINE6;
   if (affine && (!g->edge_attr || !b->We || !b->be || !b->dWe || !b->dbe)) return FNB_ERR_NULL;
   if (b->edge_mode == FNB_EDGE_AFFINE1) {
-    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE1>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
+    if (fz) {
+      if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE1, true>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
+    } else {
+      if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE1, false>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
+    }
+  } else if (fz) {
+    return FNB_ERR_MODE;   // only the bond graph (AFFINE1) has a fused variant
   } else if (b->edge_mode == FNB_EDGE_AFFINE6) {
     if (reinterpret_cast<uintptr_t>(g->edge_attr) & 7u) return FNB_ERR_ALIGN;
-    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE6>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
+    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE6, false>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
   } else if (b->edge_mode == FNB_EDGE_NONE || b->edge_mode == FNB_EDGE_TABLE) {
-    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_NONE>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
+    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_NONE, false>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
   } else {
     return FNB_ERR_MODE;
   }
   FNB_CHECK_LAUNCH();
+  if (after_dst)   // consumers of the destination pass's inputs (the consumer graph's dz) may be overwritten from here on
+    if (cudaError_t ee = cudaEventRecord(after_dst, stream)) return (int)ee;
+  if (before_src)  // readers of the buffer the source pass overwrites (args->dh), on another stream
+    if (cudaError_t ee = cudaStreamWaitEvent(stream, before_src, 0)) return (int)ee;
   SrcT s;
   s.rrowptr = g->rrowptr; s.rslot = g->rslot; s.rdst = g->rdst; s.h = b->h; s.dout = b->dout; s.p_saved = b->p_saved;
   s.dz = b->dz; s.dSt = b->dSt; s.alpha = b->alpha; s.alpha_stride = b->alpha_stride; s.off_t = b->off_t;
@@ -885,7 +960,7 @@ extern "C" int fnb_edge_table_bwd_fused(const fnb_graph *g, const float *dz, con
                                         void *scratch, void *stream_) {
   if (!graph_ok(g)) return g ? FNB_ERR_SIZE : FNB_ERR_NULL;
   if (!alpha || !d_alpha || !scratch) return FNB_ERR_NULL;
-  if (g->n_real_edges > 0 && (!dz || !g->slot_of_eid || !feat || !g_feat)) return FNB_ERR_NULL;
+  if (g->n_real_edges > 0 && (!dz || !g->slot_of_eid || !feat)) return FNB_ERR_NULL;
   if ((dy == nullptr) != (y == nullptr)) return FNB_ERR_NULL;
   if ((alpha_stride & 3) || (off_e & 3) || !fnb_aligned16(alpha) || !fnb_aligned16(feat) || !fnb_aligned16(g_feat) ||
       !fnb_aligned16(dz) || !fnb_aligned16(g_base) || !fnb_aligned16(dy) || !fnb_aligned16(y) ||

@@ -17,7 +17,8 @@
  *     fnb_pretrain_step) fork onto three lazily created, library-owned auxiliary streams (+ events) per device and join
  *     back before they return, so one host thread per device should drive them (the reference's loops are single
  *     threaded).  FNB_STREAMS=1 in the environment keeps every launch on the caller's stream, FNB_PDL=0 turns
- *     programmatic dependent launch off.  Process-wide state otherwise: a diagnostic launch counter;
+ *     programmatic dependent launch off, FNB_PRIO=1 gives the atom-chain stream the highest priority (measured slower).
+ *     Process-wide state otherwise: a diagnostic launch counter;
  *   - all feature matrices are row-major fp32 with D = 128
  *     columns, H = 4 heads of d = 32 (the only geometry FragNet's gat2 uses with emb_dim 128);
  *   - graph indices handed in are int64 (as produced by the reference's collate_fn,

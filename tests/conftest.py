@@ -38,13 +38,15 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def grad_errs(pairs, floor=1e-4):
+def grad_errs(pairs, floor=1e-3):
     """Gradient parity metric: per tensor, max|a-b| / max(max|b|, floor * largest gradient entry of the model).
 
     Some GAT2 gradients are sums that cancel to rounding noise (softmax is shift invariant, so e.g. the bias of the
     edge-attribute embedding only gets the LeakyReLU slope residual: entries ~1e-9 next to ~1e-2 elsewhere); for
     those tensors a pure per-tensor relative error compares noise with noise, hence the floor tied to the model's
-    overall gradient scale.  ``pairs``: iterable of (name, got, want).  Returns {name: err}."""
+    overall gradient scale (1e-3 of it: at 1e-4 the layer-0 edge-embedding weight of the 21-molecule pretraining
+    test, max entry 6e-5 in a model whose gradients reach 0.5, sat at 3-7e-5 = 2-4e-9 absolute and crossed the
+    tolerance from run to run).  ``pairs``: iterable of (name, got, want).  Returns {name: err}."""
     pairs = [(k, a.detach().double().cpu(), b.detach().double().cpu()) for k, a, b in pairs]
     scale = max((float(b.abs().max()) for _, _, b in pairs if b.numel()), default=0.0)
     out = {}
