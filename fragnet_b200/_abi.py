@@ -59,6 +59,8 @@ SIGNATURES = {
     "fnb_pretrain_step_workspace_bytes": (_sz, [_vp]),
     "fnb_pretrain_step_rng_span": (_u64, [_vp]),
     "fnb_pretrain_step": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "fnb_arena_workspace_bytes": (_sz, [_i64, _i32]),
+    "fnb_arena_assemble": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _sz, _vp, _vp]),
 }
 
 
@@ -87,7 +89,18 @@ class CGatBwdArgs(C.Structure):
                 ("dz", _vp), ("dSt", _vp), ("dh", _vp), ("d_alpha", _vp), ("d_bias", _vp), ("dWe", _vp), ("dbe", _vp),
                 ("scratch", _vp)]
 
-ABI_VERSION = 4
+class CArenaKind(C.Structure):
+    _fields_ = [("counts", _vp), ("prefix", _vp)]
+
+
+class CArenaJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("kind", C.c_int32), ("offset_kind", C.c_int32), ("width", C.c_int32),
+                ("mode", C.c_int32)]
+
+
+ARENA_COPY32, ARENA_INDEX, ARENA_FILL = 0, 1, 2
+ARENA_MAX_KINDS, ARENA_MAX_JOBS = 24, 32
+ABI_VERSION = 5
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_TF32 = 0, 1
 

@@ -1,0 +1,219 @@
+"""Packed per-dataset arena + on-device batch assembly.
+
+The reference assembles every batch on the host: ``collate_fn`` / ``collate_fn_pt`` (fragnet/dataset/data.py:877-948,
+:951-1032) ``torch.cat`` the per-molecule tensors and add node-count offsets built by Python loops over the molecule
+list (``get_incr_*``, data.py:11-113), then the training loop moves all 16 / 19 tensors with ``batch[k].to(device)``
+(train/pretrain/pretrain_utils.py:13-14).  At B200 step rates that host work and the ~40 MB of PCIe traffic per
+1 024-molecule batch are the end-to-end bound.
+
+``MoleculeArena`` uploads the dataset ONCE (all molecules' tensors concatenated per key, index tensors kept
+molecule-local as int32) and ``arena.batch(ids)`` produces, with two kernel launches (``fnb_arena_assemble``), exactly the
+dict ``collate_fn_pt([data_list[i] for i in ids])`` would give after ``.to(device)``: same keys, shapes, dtypes and
+values.  Per step the host only ships the molecule ids and sums a few per-molecule counts (to size the outputs).
+``ArenaLoader`` is the ``DataLoader(dataset, collate_fn=collate_fn_pt, ...)`` replacement for the training loops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterator, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _abi
+
+# batch key -> (record attribute, concatenation dim).  Order = key order of the reference's dict (data.py:931-948).
+_FEATURES = [
+    ("x_atoms", "x_atoms"), ("x_frags", "x_frags"), ("edge_attr", "edge_attr"), ("cnx_attr", "cnx_attr"),
+    ("node_features_bonds", "node_features_bonds"), ("edge_attr_bonds", "edge_attr_bonds"),
+    ("node_features_fbonds", "node_feautures_fbondg"), ("edge_attr_fbonds", "edge_attr_fbondg"),
+]
+_PRETRAIN = [("bnd_lngth", "bnd_lngth"), ("bnd_angl", "bnd_angl"), ("dh_angl", "dh_angl")]
+# index key -> (record attribute, node-count kind whose batch prefix is added)   (get_incr_*, data.py:11-113)
+_INDEX2 = [
+    ("edge_index", "edge_index", "n_atoms"), ("frag_index", "frag_index", "n_frags"),
+    ("edge_index_bonds_graph", "edge_index_bonds", "n_bnodes"), ("edge_index_fbonds", "edge_index_fbondg", "n_fbnodes"),
+]
+_KEY_ORDER = ["x_atoms", "edge_index", "frag_index", "x_frags", "edge_attr", "cnx_attr", "batch", "frag_batch",
+              "atom_to_frag_ids", "node_features_bonds", "edge_index_bonds_graph", "edge_attr_bonds",
+              "node_features_fbonds", "edge_index_fbonds", "edge_attr_fbonds", "bnd_lngth", "bnd_angl", "dh_angl", "y"]
+
+
+class _Kind:
+    def __init__(self, counts: np.ndarray, device):
+        self.counts_host = counts.astype(np.int64)
+        prefix = np.zeros(len(counts), dtype=np.int64)
+        if len(counts) > 1:
+            np.cumsum(self.counts_host[:-1], out=prefix[1:])
+        if len(counts) and int(self.counts_host.max()) >= 2 ** 31:
+            raise ValueError("a molecule with >= 2^31 rows does not fit the arena")
+        self.counts = torch.from_numpy(self.counts_host.astype(np.int32)).to(device)
+        self.prefix = torch.from_numpy(prefix).to(device)
+
+
+class MoleculeArena:
+    """Device-resident packed dataset.  ``data_list``: the per-molecule records the reference's collate takes
+    (attributes of ``CreateData.create_data_point``, data.py:437-482)."""
+
+    def __init__(self, data_list: Sequence, device, pretrain: Optional[bool] = None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("MoleculeArena lives in CUDA device memory (there is no CPU path)")
+        self.n_mols = len(data_list)
+        if pretrain is None:
+            pretrain = self.n_mols > 0 and hasattr(data_list[0], "bnd_lngth")
+        self.pretrain = bool(pretrain)
+        self._lib = _abi.load()
+        dev = self.device
+        self._kinds: Dict[str, _Kind] = {}
+        self._kind_ids: Dict[str, int] = {}
+        self._store: Dict[str, torch.Tensor] = {}
+        self._jobs: List[tuple] = []     # (key, row, src tensor, kind id, offset kind id, width, mode)
+        self._shape: Dict[str, tuple] = {}   # key -> (layout, dtype, trailing shape, kind name)
+
+        def kind(name: str, counts) -> int:
+            if name not in self._kinds:
+                if len(self._kinds) >= _abi.ARENA_MAX_KINDS:
+                    raise ValueError("too many row-count kinds")
+                self._kinds[name] = _Kind(np.asarray(counts, dtype=np.int64), dev)
+                self._kind_ids[name] = len(self._kind_ids)
+            return self._kind_ids[name]
+
+        def cat(parts, dim=0):
+            return torch.cat(list(parts), dim=dim) if self.n_mols else torch.zeros(0)
+
+        # node-count kinds (the offsets of the index tensors)
+        kind("n_atoms", [d.x_atoms.shape[0] for d in data_list])
+        kind("n_frags", [int(d.n_frags.item()) for d in data_list])
+        kind("n_bnodes", [d.node_features_bonds.shape[0] for d in data_list])
+        kind("n_fbnodes", [d.node_feautures_fbondg.shape[0] for d in data_list])
+
+        feats = list(_FEATURES) + (list(_PRETRAIN) if self.pretrain else [])
+        for key, attr in feats:
+            parts = [getattr(d, attr) for d in data_list]
+            if any(p.dtype != torch.float32 for p in parts):
+                raise TypeError(f"{key}: the arena stores float32 feature tensors")
+            k = kind("rows:" + key, [p.shape[0] for p in parts])
+            trailing = tuple(parts[0].shape[1:]) if parts else ()
+            width = int(np.prod(trailing)) if trailing else 1
+            self._store[key] = cat(parts).contiguous().to(dev)
+            self._shape[key] = ("rows", torch.float32, trailing, "rows:" + key)
+            self._jobs.append((key, 0, self._store[key], k, 0, width, _abi.ARENA_COPY32))
+        # y: torch.cat(...).type(torch.float)  (data.py:946)
+        ys = [d.y.to(torch.float32) for d in data_list]
+        k = kind("rows:y", [p.shape[0] for p in ys])
+        trailing = tuple(ys[0].shape[1:]) if ys else ()
+        self._store["y"] = cat(ys).contiguous().to(dev)
+        self._shape["y"] = ("rows", torch.float32, trailing, "rows:y")
+        self._jobs.append(("y", 0, self._store["y"], k, 0, int(np.prod(trailing)) if trailing else 1, _abi.ARENA_COPY32))
+        # [2, E] index tensors: one flat molecule-local int32 array per row
+        for key, attr, node_kind in _INDEX2:
+            parts = [getattr(d, attr) for d in data_list]
+            k = kind("cols:" + key, [p.shape[1] for p in parts])
+            for r in (0, 1):
+                flat = cat([p[r].to(torch.int64) for p in parts])
+                if flat.numel() and (int(flat.max()) >= 2 ** 31 or int(flat.min()) < 0):
+                    raise ValueError(f"{key}: molecule-local indices must fit int32")
+                self._store[f"{key}/{r}"] = flat.to(torch.int32).contiguous().to(dev)
+                self._jobs.append((key, r, self._store[f"{key}/{r}"], k, self._kind_ids[node_kind], 1, _abi.ARENA_INDEX))
+            self._shape[key] = ("index2", torch.int64, (), "cols:" + key)
+        # atom -> fragment membership: 1-D, offset by the fragments before the molecule (data.py:59-75)
+        parts = [d.atom_id_frag_id.to(torch.int64) for d in data_list]
+        k = kind("rows:atom_to_frag_ids", [p.shape[0] for p in parts])
+        self._store["atom_to_frag_ids"] = cat(parts).to(torch.int32).contiguous().to(dev)
+        self._shape["atom_to_frag_ids"] = ("rows", torch.int64, (), "rows:atom_to_frag_ids")
+        self._jobs.append(("atom_to_frag_ids", 0, self._store["atom_to_frag_ids"], k, self._kind_ids["n_frags"], 1,
+                           _abi.ARENA_INDEX))
+        # molecule position per atom / fragment (data.py:905-913)
+        self._shape["batch"] = ("rows", torch.int64, (), "n_atoms")
+        self._jobs.append(("batch", 0, None, self._kind_ids["n_atoms"], 0, 1, _abi.ARENA_FILL))
+        self._shape["frag_batch"] = ("rows", torch.int64, (), "n_frags")
+        self._jobs.append(("frag_batch", 0, None, self._kind_ids["n_frags"], 0, 1, _abi.ARENA_FILL))
+        if len(self._jobs) > _abi.ARENA_MAX_JOBS:
+            raise ValueError("too many arena jobs")
+
+        self._ckinds = (_abi.CArenaKind * len(self._kinds))()
+        for name, i in self._kind_ids.items():
+            self._ckinds[i].counts = self._kinds[name].counts.data_ptr()
+            self._ckinds[i].prefix = self._kinds[name].prefix.data_ptr()
+        self._keys = [k for k in _KEY_ORDER if k in self._shape]
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ws: Optional[torch.Tensor] = None
+        self.nbytes = sum(t.numel() * t.element_size() for t in self._store.values())
+
+    def __len__(self) -> int:
+        return self.n_mols
+
+    def batch_nbytes(self, ids) -> int:
+        """Bytes of the batch dict the reference would move host -> device for these molecules."""
+        ids = np.asarray(ids, dtype=np.int64)
+        total = 0
+        for key in self._keys:
+            layout, dtype, trailing, kname = self._shape[key]
+            rows = int(self._kinds[kname].counts_host[ids].sum())
+            width = int(np.prod(trailing)) if trailing else 1
+            total += rows * width * (2 if layout == "index2" else 1) * (8 if dtype == torch.int64 else 4)
+        return total
+
+    def batch(self, mol_ids, ids_device: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """The batch dict of ``collate_fn_pt([data_list[i] for i in mol_ids])`` on the device, assembled on the device.
+
+        ``mol_ids``: host sequence / numpy array / CPU tensor of molecule indices (they size the outputs);
+        ``ids_device``: the same ids already on the device (otherwise they are copied from pinned memory on the
+        current stream).  No host synchronisation."""
+        if isinstance(mol_ids, torch.Tensor):
+            ids = mol_ids.detach().cpu().numpy().astype(np.int64, copy=False)
+        else:
+            ids = np.asarray(mol_ids, dtype=np.int64)
+        g = int(ids.shape[0])
+        if g and (int(ids.min()) < 0 or int(ids.max()) >= self.n_mols):
+            raise IndexError("molecule id out of range")
+        dev = self.device
+        if ids_device is None:
+            pinned = torch.from_numpy(np.ascontiguousarray(ids)).pin_memory()
+            ids_device = torch.empty(g, dtype=torch.int64, device=dev)
+            ids_device.copy_(pinned, non_blocking=True)
+        out: Dict[str, torch.Tensor] = {}
+        totals = {name: int(k.counts_host[ids].sum()) for name, k in self._kinds.items()}
+        for key in self._keys:
+            layout, dtype, trailing, kname = self._shape[key]
+            n = totals[kname]
+            shape = (2, n) if layout == "index2" else (n,) + tuple(trailing)
+            out[key] = torch.empty(shape, dtype=dtype, device=dev)
+        if g == 0:
+            return out
+        cjobs = (_abi.CArenaJob * len(self._jobs))()
+        for i, (key, row, src, kind, okind, width, mode) in enumerate(self._jobs):
+            dst = out[key]
+            cjobs[i].src = src.data_ptr() if src is not None else None
+            cjobs[i].dst = dst.data_ptr() + (row * dst.shape[1] * 8 if row else 0)
+            cjobs[i].kind, cjobs[i].offset_kind, cjobs[i].width, cjobs[i].mode = kind, okind, width, mode
+        need = self._lib.fnb_arena_workspace_bytes(g, len(self._kinds))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(int(need * 1.5) + 256, dtype=torch.uint8, device=dev)
+        rc = self._lib.fnb_arena_assemble(ids_device.data_ptr(), g, self.n_mols, self._ckinds, len(self._kinds), cjobs,
+                                          len(self._jobs), self._ws.data_ptr(), self._ws.numel(),
+                                          self._status.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"fnb_arena_assemble: {self._lib.fnb_error_string(rc).decode()}")
+        return out
+
+
+class ArenaLoader:
+    """``DataLoader(dataset, batch_size, shuffle, drop_last, collate_fn=collate_fn_pt)`` over a ``MoleculeArena``:
+    iterates device-resident batch dicts (reference loops: pretrain_gat2.py:140-147, pretrain_utils.py:12-14)."""
+
+    def __init__(self, arena: MoleculeArena, batch_size: int, shuffle: bool = False, drop_last: bool = False,
+                 generator: Optional[torch.Generator] = None):
+        self.arena, self.batch_size, self.shuffle, self.drop_last = arena, int(batch_size), shuffle, drop_last
+        self.generator = generator
+
+    def __len__(self) -> int:
+        n = len(self.arena)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
+        n = len(self.arena)
+        order = torch.randperm(n, generator=self.generator).numpy() if self.shuffle else np.arange(n, dtype=np.int64)
+        for b in range(len(self)):
+            yield self.arena.batch(order[b * self.batch_size:(b + 1) * self.batch_size])

@@ -36,7 +36,7 @@ extern "C" {
 
 #define FNB_D 128 /* embedding width  */
 #define FNB_H 4   /* attention heads  */
-#define FNB_ABI_VERSION 4
+#define FNB_ABI_VERSION 5
 
 /* edge-term modes of the fused attention kernels */
 /* arithmetic of the dense projections */
@@ -438,6 +438,45 @@ uint64_t fnb_pretrain_step_rng_span(const fnb_pretrain_step_args *args);
 /* workspace: 256-byte aligned, fnb_pretrain_step_workspace_bytes() bytes. */
 int fnb_pretrain_step(const fnb_pretrain_step_args *args, void *workspace, size_t workspace_bytes, void *scratch,
                       void *stream);
+
+/* ---- device-side batch assembly from a packed dataset arena (arena.cu) ---------------------------
+ * Replaces, for a dataset resident in device memory, collate_fn / collate_fn_pt (fragnet/dataset/data.py:877-948,
+ * :951-1032), the node-count offsets of get_incr_* (data.py:11-113) and the per-tensor batch[k].to(device) of the
+ * training loops (train/pretrain/pretrain_utils.py:13-14, train/utils.py:335-336): the only per-step host -> device
+ * traffic is the list of molecule ids.
+ *
+ * The arena stores every batch tensor as the concatenation over ALL molecules of the dataset (4-byte elements; index
+ * tensors molecule-local int32, one flat array per index row).  A kind is a row-count space: counts[mol] rows per
+ * molecule and prefix[mol] = exclusive prefix sum of counts over the dataset (both device arrays of n_mols entries).
+ * A job emits one output tensor (or one row of a [2,E] index tensor) for the molecules mol_ids[0..n_batch):
+ *   FNB_ARENA_COPY32  dst[rows, width] 4-byte elements copied from src
+ *   FNB_ARENA_INDEX   dst[rows] int64 = src[rows] int32 (molecule-local) + number of `offset_kind` rows of the
+ *                     molecules before it in this batch (integer arithmetic: no 2^24 ceiling, cf. data.py:883)
+ *   FNB_ARENA_FILL    dst[rows] int64 = position of the molecule in the batch (`batch`, `frag_batch`)
+ * The caller sizes dst from host copies of the counts; a molecule id outside [0, n_mols) contributes no rows and sets
+ * *status (optional device int32) to 1. */
+#define FNB_ARENA_MAX_KINDS 24
+#define FNB_ARENA_MAX_JOBS 32
+#define FNB_ARENA_COPY32 0
+#define FNB_ARENA_INDEX 1
+#define FNB_ARENA_FILL 2
+typedef struct fnb_arena_kind {
+  const int32_t *counts;
+  const int64_t *prefix;
+} fnb_arena_kind;
+typedef struct fnb_arena_job {
+  const void *src;
+  void *dst;
+  int32_t kind;
+  int32_t offset_kind;   /* FNB_ARENA_INDEX only */
+  int32_t width;         /* FNB_ARENA_COPY32: elements per row */
+  int32_t mode;
+} fnb_arena_job;
+size_t fnb_arena_workspace_bytes(int64_t n_batch, int n_kinds);
+/* kinds / jobs are HOST arrays (copied into the launch parameters); workspace is 16-byte aligned device memory. */
+int fnb_arena_assemble(const int64_t *mol_ids, int64_t n_batch, int64_t n_mols, const fnb_arena_kind *kinds,
+                       int n_kinds, const fnb_arena_job *jobs, int n_jobs, void *workspace, size_t workspace_bytes,
+                       int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

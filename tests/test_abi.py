@@ -40,6 +40,9 @@ def test_argument_validation_needs_no_gpu():
     assert lib.fnb_dropout_relu_fwd(None, None, 4, 1.5, 1, 1, 0, 0, None) == -2
     assert lib.fnb_gat_fwd_tiled(None, None, None) == -1
     assert lib.fnb_gat_bwd_tiled(None, None, None) == -1
+    assert lib.fnb_arena_assemble(None, 4, 10, None, 1, None, 0, None, 0, None, None) == -1
+    assert lib.fnb_arena_assemble(None, 4, 10, None, 99, None, 0, None, 0, None, None) == -2
+    assert lib.fnb_arena_workspace_bytes(1024, 20) >= 20 * (2 * 1024 + 1) * 8
 
 
 def test_no_cpu_fallback_in_product_path():
@@ -64,7 +67,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
              ("fnb_encoder_opts", A.CEncoderOpts), ("fnb_encoder_io", A.CEncoderIO), ("fnb_mlp3_params", A.CMlp3),
              ("fnb_mlp3_grads", A.CMlp3), ("fnb_pretrain_head_params", A.CPretrainHeadParams),
              ("fnb_pretrain_head_grads", A.CPretrainHeadParams), ("fnb_pretrain_head_io", A.CPretrainHeadIO),
-             ("fnb_mse_term", A.CMseTerm), ("fnb_pretrain_step_args", A.CPretrainStepArgs)]
+             ("fnb_mse_term", A.CMseTerm), ("fnb_pretrain_step_args", A.CPretrainStepArgs),
+             ("fnb_arena_kind", A.CArenaKind), ("fnb_arena_job", A.CArenaJob)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fragnet_b200.h"', 'int main(void){']
     for cname, cls in pairs:
         lines.append(f'printf("{cname} %zu", sizeof({cname}));')
