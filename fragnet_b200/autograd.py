@@ -192,6 +192,22 @@ class DropoutReluFn(torch.autograd.Function):
         return ops.dropout_relu_fwd(dy, p, training, False, seed, offset), None, None, None
 
 
+class PoolFn(torch.autograd.Function):
+    """x_frags = scatter_add(x_atoms, atom_to_frag_ids) (reference gat2.py:234, gat2_lite.py:140) as a standalone op
+    over the membership CSR of the batch plan; backward gathers the fragment gradient back to the member atoms."""
+
+    @staticmethod
+    def forward(ctx, plan: LayerPlan, x_atoms):
+        x_atoms = ops._f32c(x_atoms)
+        ctx.plan, ctx.n = plan, x_atoms.shape[0]
+        pool = plan.pool
+        return ops.segment_sum(pool.rowptr, pool.col, plan.n_frags, x_atoms)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, ops.segment_gather(ops._f32c(g), ops.D, ctx.plan.a2f32, ctx.n)
+
+
 class ReadoutFn(torch.autograd.Function):
     """cat(scatter_add(x_atoms, batch), scatter_add(x_frags, frag_batch)) written in place into one
     [G,256] tensor (reference gat2.py:820-823, pretrain_heads.py:93-96)."""

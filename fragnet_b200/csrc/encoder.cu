@@ -275,9 +275,11 @@ int check_common(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fn
   if (o->n_layers < 1 || o->n_layers > 16) return FNB_ERR_SIZE;
   if (!o->post_act && o->n_layers != 1) return FNB_ERR_MODE;
   if (!(o->drop_p >= 0.f && o->drop_p < 1.f)) return FNB_ERR_SIZE;
-  if (!io->x_atoms || !io->x_bond || !io->x_fbond || !io->out_atoms || !io->out_bond || !io->out_fbond)
-    return FNB_ERR_NULL;
   const Sizes z = sizes_of(plan);
+  // a graph without nodes (gat2_lite runs with empty fragment-side graphs) has no feature rows to point at
+  if ((z.Na > 0 && (!io->x_atoms || !io->out_atoms)) || (z.Nb > 0 && (!io->x_bond || !io->out_bond)) ||
+      (z.Nfb > 0 && (!io->x_fbond || !io->out_fbond)))
+    return FNB_ERR_NULL;
   if (z.Na != plan->n_atoms || z.Nf != plan->n_frags) return FNB_ERR_SIZE;
   // the atom graph's edges are the bond graph's nodes, the fragment graph's edges the fragment-connection nodes
   if (plan->atom.n_real_edges != z.Nb || plan->frag.n_real_edges != z.Nfb) return FNB_ERR_SIZE;

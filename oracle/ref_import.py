@@ -59,6 +59,18 @@ def load():
     return types.SimpleNamespace(gat2=gat2, pretrain_heads=heads)
 
 
+def load_lite():
+    """The reference's ``gat2_lite`` module (its ``from .pretrain_heads import PretrainTask``, gat2_lite.py:283, is
+    satisfied by the ``pretrain_heads`` loaded above under the same private package)."""
+    load()
+    pkg = sys.modules.get(_PKG)
+    if pkg is None:
+        pkg = types.ModuleType(_PKG)
+        pkg.__path__ = []
+        sys.modules[_PKG] = pkg
+    return _load("gat2_lite", "fragnet/model/gat/gat2_lite.py")
+
+
 @contextlib.contextmanager
 def quiet():
     """The reference layer prints on every forward (gat2.py:172); silence it."""
