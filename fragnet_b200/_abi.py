@@ -100,7 +100,7 @@ class CArenaJob(C.Structure):
 
 ARENA_COPY32, ARENA_INDEX, ARENA_FILL = 0, 1, 2
 ARENA_MAX_KINDS, ARENA_MAX_JOBS = 24, 32
-ABI_VERSION = 5
+ABI_VERSION = 6
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_TF32 = 0, 1
 
@@ -146,7 +146,8 @@ class CLayerParams(C.Structure):
     _fields_ = [(n, _vp) for n in PARAM_FIELDS] + [
         ("K_atom", _i32), ("K_bond", _i32), ("K_fbond", _i32), ("run_frag_block", _i32), ("want_attention", _i32),
         ("bond_mask", _i64), ("frag_bond_mask", _i64), ("atom_mask", _i64), ("atom_mask_list", _vp),
-        ("n_atom_mask", _i64)]
+        ("n_atom_mask", _i64), ("bond_mask_rows", _vp), ("n_bond_mask_rows", _i64), ("fbond_mask_rows", _vp),
+        ("n_fbond_mask_rows", _i64)]
 
 
 class CLayerGrads(C.Structure):

@@ -26,8 +26,8 @@ class LayerSwitches:
     """Per-layer switches that are not tensors (mirrors the non-pointer tail of ``fnb_layer_params``)."""
     run_frag_block: bool = True
     want_attention: bool = False
-    bond_mask: Optional[int] = None
-    frag_bond_mask: Optional[int] = None
+    bond_mask: object = None            # int m (rows m, m+1: gat2.py:173-176), or a sequence / tensor of such m
+    frag_bond_mask: object = None       # int k (rows 2k, 2k+1: gat2.py:275-278), or a sequence / tensor of such k
     atom_mask: object = None            # int, or a sequence / tensor of atom rows (gat2.py:227-231)
 
 
@@ -55,8 +55,21 @@ def _layer_structs(cfg: EncoderConfig, params, dev):
             setattr(arr[l], name, t.data_ptr())
         arr[l].K_bond, arr[l].K_fbond, arr[l].K_atom = ps[0].shape[1], ps[2].shape[1], ps[8].shape[1]
         arr[l].run_frag_block, arr[l].want_attention = int(sw.run_frag_block), int(sw.want_attention)
-        arr[l].bond_mask = -1 if sw.bond_mask is None else int(sw.bond_mask)
-        arr[l].frag_bond_mask = -1 if sw.frag_bond_mask is None else int(sw.frag_bond_mask)
+        arr[l].bond_mask, arr[l].frag_bond_mask = -1, -1
+        arr[l].bond_mask_rows, arr[l].n_bond_mask_rows, arr[l].fbond_mask_rows, arr[l].n_fbond_mask_rows = None, 0, None, 0
+        for value, scale, single, rows_f, n_f in ((sw.bond_mask, 1, "bond_mask", "bond_mask_rows", "n_bond_mask_rows"),
+                                                  (sw.frag_bond_mask, 2, "frag_bond_mask", "fbond_mask_rows",
+                                                   "n_fbond_mask_rows")):
+            if value is None:
+                continue
+            if isinstance(value, int):
+                setattr(arr[l], single, value)
+                continue
+            first = torch.as_tensor(value, device=dev).reshape(-1).to(torch.int64) * scale     # first row of each pair
+            rows = torch.stack((first, first + 1), dim=1).reshape(-1).to(torch.int32).contiguous()
+            cfg._keep.append(rows)
+            setattr(arr[l], rows_f, rows.data_ptr())
+            setattr(arr[l], n_f, rows.numel())
         arr[l].atom_mask, arr[l].atom_mask_list, arr[l].n_atom_mask = -1, None, 0
         am = sw.atom_mask
         if am is not None:

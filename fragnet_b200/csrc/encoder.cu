@@ -243,12 +243,16 @@ __global__ void __launch_bounds__(256) k_pad_cols(PadJobs j) {
   }
 }
 
-__global__ void k_zero_rows(float *__restrict__ a, float *__restrict__ b, const int *__restrict__ rows, int64_t n) {
+// Rows listed in `rows` of up to two [N,128] tensors -- and of the [N,4] edge term the consumer graph reads in their
+// place (<0, alpha_e> = 0) -- are zeroed: the list form of the masks of gat2.py:173-176, :227-231, :275-278.
+__global__ void k_zero_rows(float *__restrict__ a, float *__restrict__ b, float *__restrict__ se,
+                            const int *__restrict__ rows, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * 32; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = __ldg(rows + (i >> 5));
     const int c = (int)(i & 31) * 4;
     if (a) st4(a + r * kD + c, make_float4(0.f, 0.f, 0.f, 0.f));
     if (b) st4(b + r * kD + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (se && c == 0) st4(se + r * 4, make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 
@@ -429,6 +433,11 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
       f.next_alpha_e = P.a + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_atom;
       if (plan_ready && l == 0) RC((int)cudaStreamWaitEvent(stream, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->bond, &f, stream_));
+      if (P.bond_mask_rows && P.n_bond_mask_rows > 0) {
+        k_zero_rows<<<(int)((P.n_bond_mask_rows * 32 + 255) / 256), 256, 0, stream>>>(pre_bond, y_bond, b.se_atom,
+                                                                                    P.bond_mask_rows, P.n_bond_mask_rows);
+        FNB_CHECK_LAUNCH();
+      }
     }
     // ---- atom graph with self loops (gat2.py:179-231)
     if (two) {
@@ -443,7 +452,7 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
       if (plan_ready && l == 0 && two) RC((int)cudaStreamWaitEvent(sA, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->atom, &f, sA_));
       if (P.atom_mask_list && P.n_atom_mask > 0) {
-        k_zero_rows<<<(int)((P.n_atom_mask * 32 + 255) / 256), 256, 0, sA>>>(pre_atom, y_atom, P.atom_mask_list,
+        k_zero_rows<<<(int)((P.n_atom_mask * 32 + 255) / 256), 256, 0, sA>>>(pre_atom, y_atom, nullptr, P.atom_mask_list,
                                                                            P.n_atom_mask);
         FNB_CHECK_LAUNCH();
       }
@@ -463,6 +472,11 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
       if (frag) { f.next_alpha_e = P.f + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_frag; }
       if (plan_ready && l == 0 && two) RC((int)cudaStreamWaitEvent(sB, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->fbond, &f, sB_));
+      if (P.fbond_mask_rows && P.n_fbond_mask_rows > 0) {
+        k_zero_rows<<<(int)((P.n_fbond_mask_rows * 32 + 255) / 256), 256, 0, sB>>>(
+            pre_fbond, y_fbond, frag ? b.se_frag : nullptr, P.fbond_mask_rows, P.n_fbond_mask_rows);
+        FNB_CHECK_LAUNCH();
+      }
     }
     if (frag || P.want_attention) RC(join());
     // ---- atom -> fragment pooling (gat2.py:234) and the fragment graph (gat2.py:283-316): only where its output lives

@@ -36,7 +36,7 @@ extern "C" {
 
 #define FNB_D 128 /* embedding width  */
 #define FNB_H 4   /* attention heads  */
-#define FNB_ABI_VERSION 5
+#define FNB_ABI_VERSION 6
 
 /* edge-term modes of the fused attention kernels */
 /* arithmetic of the dense projections */
@@ -254,6 +254,14 @@ typedef struct fnb_layer_params {
   int64_t atom_mask;                  /* -1 = none; row zeroed (gat2.py:227-231) */
   const int32_t *atom_mask_list;      /* optional device list of rows to zero, n_atom_mask entries */
   int64_t n_atom_mask;
+  /* list forms of bond_mask / frag_bond_mask: device lists of ROWS of new_bond_features / new_fbond_features to
+   * zero (a masked bond m contributes rows m and m+1, a masked fragment link k rows 2k and 2k+1); used by the
+   * batched mask attribution, where every replica of a molecule carries its own mask (viz.py:960-984, 1026-1050,
+   * 1145-1169 run one batch-1 forward per mask instead) */
+  const int32_t *bond_mask_rows;
+  int64_t n_bond_mask_rows;
+  const int32_t *fbond_mask_rows;
+  int64_t n_fbond_mask_rows;
 } fnb_layer_params;
 
 typedef struct fnb_layer_grads { /* same shapes as the parameters; every tensor is written (not accumulated) */
