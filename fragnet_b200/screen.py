@@ -1,0 +1,65 @@
+"""Batched inference screening (BASELINE.json configs[2]): a dataset resident in HBM, predictions and attention
+weights streamed back to the host.
+
+The reference screens with ``test_fn`` (fragnet/train/utils.py:59-76): per batch a host collate, 16 blocking
+``.to(device)`` copies, the forward, and a blocking ``.cpu()`` per result.  ``screen`` keeps three things in flight:
+the on-device assembly of batch ``i+1`` (``MoleculeArena``), the forward of batch ``i`` and the device-to-host copy of
+the results of batch ``i-1`` (pinned double buffers, side stream), and yields host tensors one batch behind.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .dataset.arena import MoleculeArena
+
+
+def screen(model, arena: MoleculeArena, batch_size: int = 4096, ids: Optional[Sequence[int]] = None,
+           depth: int = 2) -> Iterator[Tuple[np.ndarray, Tuple[torch.Tensor, ...]]]:
+    """Yields ``(molecule ids, outputs on the host)`` per batch, in order.  ``model(batch)`` may return a tensor
+    (``FragNetFineTune``) or a tuple (``FragNetFineTuneViz``: prediction + four attention tensors).  The yielded
+    tensors live in pinned buffers that are reused ``depth`` batches later: copy what must outlive that."""
+    dev = arena.device
+    order = np.arange(len(arena), dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+    chunks = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
+    if not chunks:
+        return
+    copy_stream = torch.cuda.Stream(dev)
+    slots = [None] * (depth + 1)           # pinned host buffers per slot
+    pending = []                           # (ids, host tensors, event)
+    was_training = model.training
+    model.eval()
+    try:
+        nxt = arena.batch(chunks[0])
+        for i, ch in enumerate(chunks):
+            batch = nxt
+            with torch.no_grad():
+                out = model(batch)
+            outs = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+            if i + 1 < len(chunks):
+                nxt = arena.batch(chunks[i + 1])        # queued behind forward i; its host work overlaps the GPU
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+            s = i % len(slots)
+            if slots[s] is None or any(h.shape != o.shape or h.dtype != o.dtype for h, o in zip(slots[s], outs)) \
+                    or len(slots[s]) != len(outs):
+                slots[s] = tuple(torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs)
+            copy_stream.wait_event(done)
+            with torch.cuda.stream(copy_stream):
+                for h, o in zip(slots[s], outs):
+                    h.copy_(o, non_blocking=True)
+                    o.record_stream(copy_stream)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            pending.append((ch, slots[s], ev))
+            if len(pending) >= depth:
+                c, hs, e = pending.pop(0)
+                e.synchronize()
+                yield c, hs
+        for c, hs, e in pending:
+            e.synchronize()
+            yield c, hs
+    finally:
+        model.train(was_training)
