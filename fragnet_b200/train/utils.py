@@ -1,0 +1,169 @@
+"""Finetuning loops with the reference's semantics: drop-ins for ``EarlyStopping`` (fragnet/train/utils.py:13-56),
+``test_fn`` (:59-76) and ``TrainerFineTune`` (:307-520; ``target_type`` ``regr`` and ``clsf``), the callers of the GAT2
+path in train/finetune/finetune_gat2.py:119-288.
+
+Same signatures, same returned quantities (epoch loss = sum of the per-batch losses / dataset size; ``test`` returns
+``(mse, targets, predictions)`` resp. ``(roc_auc, targets, predictions)``).  What differs underneath: host batches are
+staged by ``DevicePrefetcher`` (pinned, double-buffered copies on a side stream, only the tensors the model reads)
+instead of 16 blocking ``batch[k].to(device)`` calls per step (utils.py:335-336), and the per-batch losses are summed
+on the device and read back once per epoch instead of one ``loss.item()`` synchronisation per step (utils.py:344).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+class EarlyStopping:
+    """Stops when the validation loss has not improved by ``delta`` for ``patience`` epochs; checkpoints the best
+    ``state_dict`` to ``chkpoint_name`` (utils.py:13-56)."""
+
+    def __init__(self, patience=7, verbose=False, delta=0, chkpoint_name="gnn_best.pt"):
+        self.patience, self.verbose, self.delta, self.chkpoint_name = patience, verbose, delta, chkpoint_name
+        self.counter, self.best_score, self.early_stop, self.val_loss_min = 0, None, False, np.inf
+
+    def __call__(self, val_loss, model):
+        score = -val_loss
+        if self.best_score is None:
+            self.best_score = score
+            self.save_checkpoint(val_loss, model)
+        elif score < self.best_score + self.delta:
+            self.counter += 1
+            print(f"EarlyStopping counter: {self.counter} out of {self.patience}")
+            if self.counter >= self.patience:
+                self.early_stop = True
+        else:
+            self.best_score = score
+            self.save_checkpoint(val_loss, model)
+            self.counter = 0
+
+    def save_checkpoint(self, val_loss, model):
+        if self.verbose:
+            print(f"Validation loss decreased ({self.val_loss_min:.6f} --> {val_loss:.6f}).  Saving model ...")
+        torch.save(model.state_dict(), self.chkpoint_name)
+        self.val_loss_min = val_loss
+
+
+def _batches(loader, device, model=None):
+    """Device-resident batch dicts of ``loader``: prefetched for CUDA devices, moved key by key otherwise.  For this
+    package's own models only the tensors the GAT2 path reads are moved."""
+    device = torch.device(device)
+    if device.type == "cuda":
+        from ..dataset.prefetch import DevicePrefetcher
+        ours = model is not None and type(model).__module__.startswith("fragnet_b200.")
+        yield from DevicePrefetcher(loader, device, depth=2, hot_path_only=ours)
+    else:
+        for batch in loader:
+            yield {k: v.to(device) for k, v in batch.items()}
+
+
+def compute_bce_loss(prediction, target):
+    """Masked BCE-with-logits: labels < -0.5 are missing (utils.py:296-303)."""
+    is_valid = target > -0.5
+    loss_mat = nn.BCEWithLogitsLoss(reduction="none")(prediction, target)
+    loss_mat = torch.where(is_valid, loss_mat, torch.zeros_like(loss_mat))
+    return torch.sum(loss_mat) / torch.sum(is_valid)
+
+
+def test_fn(loader, model, device):
+    """utils.py:59-76: ``(mse, targets, predictions)`` over a loader."""
+    model.eval()
+    target, predicted = [], []
+    with torch.no_grad():
+        for batch in _batches(loader, device, model):
+            predicted.append(model(batch).reshape(-1))
+            target.append(batch["y"].reshape(-1))
+    t = torch.cat(target).cpu().numpy() if target else np.zeros(0, dtype=np.float32)
+    p = torch.cat(predicted).cpu().numpy() if predicted else np.zeros(0, dtype=np.float32)
+    return float(np.mean((t - p) ** 2)) if t.size else float("nan"), t, p
+
+
+test_fn.__test__ = False      # not a pytest test
+
+
+class TrainerFineTune:
+    """utils.py:307-520 for ``target_type`` ``regr`` (MSE) and ``clsf`` (masked BCE, ROC-AUC validation)."""
+
+    def __init__(self, target_pos=None, target_type="regr", n_multi_task_heads=0):
+        self.target_pos = target_pos
+        self.n_multi_task_heads = n_multi_task_heads
+        if target_type == "regr":
+            self.train, self.validate, self.test = self.train_regr, self.validate_regr, self.test_regr
+            self.loss_fn = nn.MSELoss()
+        elif target_type == "clsf":
+            self.train, self.validate, self.test = self.train_clsf_bce, self.validate_clsf_bce, self.test_clsf_bce
+            self.loss_fn = nn.BCEWithLogitsLoss(reduction="none")
+        else:
+            raise NotImplementedError(f"target_type {target_type!r}: only 'regr' and 'clsf' drive the gat2 path here")
+
+    # ---- regression (utils.py:330-385)
+    def train_regr(self, model, loader, optimizer, scheduler, device, val_loader):
+        model.train()
+        total = None
+        for batch in _batches(loader, device, model):
+            optimizer.zero_grad()
+            loss = self.loss_fn(model(batch).view(-1), batch["y"])
+            loss.backward()
+            total = loss.detach().double() if total is None else total + loss.detach().double()
+            optimizer.step()
+        if scheduler:
+            self.validate(model, val_loader, device)
+            scheduler.step()
+        return (float(total) if total is not None else 0.0) / len(loader.dataset)
+
+    def validate_regr(self, model, loader, device):
+        model.eval()
+        total = None
+        with torch.no_grad():
+            for batch in _batches(loader, device, model):
+                loss = self.loss_fn(model(batch).view(-1), batch["y"]).double()
+                total = loss if total is None else total + loss
+        return (float(total) if total is not None else 0.0) / len(loader.dataset)
+
+    def test_regr(self, model, loader, device):
+        return test_fn(loader, model, device)
+
+    # ---- binary / multi-label classification with missing labels (utils.py:406-470)
+    def _bce(self, out, y):
+        labels = y.view(out.shape)
+        is_valid = labels > -0.5
+        loss_mat = torch.where(is_valid, self.loss_fn(out, labels), torch.zeros_like(out))
+        return torch.sum(loss_mat) / torch.sum(is_valid)
+
+    def train_clsf_bce(self, model, loader, optimizer, scheduler, device, val_loader):
+        model.train()
+        total = None
+        for batch in _batches(loader, device, model):
+            loss = self._bce(model(batch), batch["y"])
+            optimizer.zero_grad()
+            loss.backward()
+            total = loss.detach().double() if total is None else total + loss.detach().double()
+            optimizer.step()
+        if scheduler:
+            scheduler.step(self.validate(model, val_loader, device))
+        return (float(total) if total is not None else 0.0) / len(loader.dataset)
+
+    def _scores(self, model, loader, device):
+        model.eval()
+        target, predicted = [], []
+        with torch.no_grad():
+            for batch in _batches(loader, device, model):
+                out = model(batch)
+                predicted.append(torch.sigmoid(out))
+                target.append(batch["y"].view(out.shape))
+        return torch.cat(target).cpu().numpy(), torch.cat(predicted).cpu().numpy()
+
+    def validate_clsf_bce(self, model, loader, device):
+        """Negative mean ROC-AUC over the label columns that have both classes (lower is better)."""
+        return -self.test_clsf_bce(model, loader, device)[0]
+
+    def test_clsf_bce(self, model, loader, device):
+        from sklearn.metrics import roc_auc_score
+        target, predicted = self._scores(model, loader, device)
+        aucs = []
+        for c in range(target.shape[1]):
+            valid = target[:, c] > -0.5
+            if valid.any() and len(np.unique(target[valid, c])) == 2:
+                aucs.append(roc_auc_score(target[valid, c], predicted[valid, c]))
+        return (float(np.mean(aucs)) if aucs else float("nan")), target, predicted

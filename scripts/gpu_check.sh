@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 tag=${1:-run}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
-for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_tiled.py tests/test_gpu_model.py tests/test_gpu_heads.py tests/test_gpu_tc.py; do
+for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_tiled.py tests/test_gpu_model.py tests/test_gpu_heads.py tests/test_gpu_tc.py tests/test_gpu_arena.py tests/test_gpu_attribution.py tests/test_lite.py tests/test_viz.py tests/test_finetune_loop.py; do
   timeout 600 python -m pytest $f -q --no-header -p no:cacheprovider -m gpu 2>&1 | tail -120 > gpurun_out/${tag}_$(basename $f .py).log
 done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1
@@ -16,7 +16,7 @@ if [ "${2:-}" = "ncu" ]; then
     --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-roofline \
     > gpurun_out/${tag}_ncu_bench.log 2>&1
 fi
-for f in gpurun_out/${tag}_test_gpu_*.log gpurun_out/${tag}_smoke.log; do echo "== $f"; tail -n 4 $f; done
+for f in gpurun_out/${tag}_test_*.log gpurun_out/${tag}_smoke.log; do echo "== $f"; tail -n 4 $f; done
 tail -n 2 gpurun_out/${tag}_bench.log gpurun_out/${tag}_bench_fp32.log
 if [ "${3:-}" = "full" ]; then
   # one `ncu --set full` capture of the message-passing kernels (bond-graph launches of layer >= 1)
