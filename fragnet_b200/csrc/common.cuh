@@ -285,14 +285,16 @@ int fnb_aux_streams(FnbAux *out);
 
 // Destination pass of the attention backward with the incoming gradient assembled in the same launch (gat_tiled.cu:
 // dst_grad_row): args->dout is WRITTEN by the destination pass and read by the source pass.  Between the two launches `after_dst`
-// (optional) is recorded and `before_src` (optional) is waited for.  Bond graph (FNB_EDGE_AFFINE1) only.
+// (optional) is recorded and `before_src` (optional) is waited for.
 struct FnbDstFuse {
   const float *dz_up;        // [E_up,4] dz of the consumer graph (its real edge e = this graph's node e), or NULL
   const int *slot_of_eid;    // consumer graph's edge id -> slot
   const float *alpha_up;     // consumer head vector at its edge slice, [4, alpha_up_stride]
   int alpha_up_stride;
-  const float *g_base, *dy, *y;
+  const float *g_base, *dy, *y;   // y == NULL: dy is taken as is (bare-layer mode)
   float scale;
+  const float *pool;         // [n_seg,128] gradient of sum-pooled rows to hand back to their members, or NULL
+  const int *seg_of;         // [N]
 };
 int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *args, const FnbDstFuse *fuse,
                             cudaEvent_t after_dst, cudaEvent_t before_src, void *stream);

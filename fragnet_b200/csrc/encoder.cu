@@ -186,37 +186,6 @@ fnb_post_act post_of(const fnb_encoder_opts *o, uint64_t counter) {
   return pa;
 }
 
-// g[i,:] = (dy ? dy[i,:] * (y[i,:] > 0) * scale : 0) + (base ? base[i,:] : 0) + (pooled ? pooled[seg_of[i],:] : 0)
-// -- the ReLU(Dropout) backward (gat2.py:414-418), an additive gradient and the atom->fragment pooling backward
-// (gat2.py:234) in one pass.  With y == NULL, dy is taken as is (bare-layer mode).
-__global__ void __launch_bounds__(256) k_grad_combine(const float *__restrict__ dy, const float *__restrict__ y,
-                                                      float scale, const float *__restrict__ pooled,
-                                                      const int *__restrict__ seg_of, int64_t n_rows,
-                                                      float *__restrict__ g) {
-  const int64_t total = n_rows * 32;
-  pdl_wait();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i >> 5;
-    const int c = (int)(i & 31) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dy) {
-      v = ldg4(dy + r * kD + c);
-      if (y) {
-        const float4 o = ldg4(y + r * kD + c);
-        v.x = o.x > 0.f ? v.x * scale : 0.f;
-        v.y = o.y > 0.f ? v.y * scale : 0.f;
-        v.z = o.z > 0.f ? v.z * scale : 0.f;
-        v.w = o.w > 0.f ? v.w * scale : 0.f;
-      }
-    }
-    if (pooled) {
-      const float4 q = ldg4(pooled + (int64_t)__ldg(seg_of + r) * kD + c);
-      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-    }
-    st4(g + r * kD + c, v);
-  }
-}
-
 // dst[r, 0:k_pad] = [src[r, 0:K] | 0]: up to 6 matrices per launch (blockIdx.y).
 struct PadJobs {
   const float *src[6];
@@ -254,17 +223,6 @@ __global__ void k_zero_rows(float *__restrict__ a, float *__restrict__ b, float 
     if (b) st4(b + r * kD + c, make_float4(0.f, 0.f, 0.f, 0.f));
     if (se && c == 0) st4(se + r * 4, make_float4(0.f, 0.f, 0.f, 0.f));
   }
-}
-
-int grad_combine(const float *dy, const float *y, float scale, const float *pooled, const int *seg_of, int64_t n_rows,
-                 float *g, cudaStream_t stream) {
-  if (n_rows == 0) return 0;
-  int64_t blocks = (n_rows * 32 + 255) / 256;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  if (cudaError_t le = fnb_launch(k_grad_combine, dim3((int)blocks), dim3(256), 0, stream, dy, y, scale, pooled, seg_of, n_rows, g))
-    return (int)le;
-  FNB_CHECK_LAUNCH();
-  return 0;
 }
 
 #define RC(expr)            \
@@ -628,34 +586,34 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     bool frag_bwd = frag && dy_frag != nullptr;
     if (frag_bwd) {
       if (!D.f) return FNB_ERR_NULL;
-      RC(grad_combine(dy_frag, y_frag, scale, nullptr, nullptr, z.Nf, W.g_frag, stream));
       fnb_gat_bwd_args a{};
       a.h = b.hf; a.dout = W.g_frag; a.p_saved = b.p_f; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.f;
       a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_f; a.dSt = W.dSt_f;
       a.dh = W.d_hf; a.d_alpha = D.f; a.d_bias = nullptr; a.scratch = scratch;
-      RC(fnb_gat_bwd_tiled(&plan->frag, &a, stream_));
+      FnbDstFuse fz{};      // ReLU(Dropout) backward of dy_frag inside the destination pass
+      fz.dy = dy_frag; fz.y = y_frag; fz.scale = scale;
+      RC(fnb_gat_bwd_tiled_fused(&plan->frag, &a, &fz, nullptr, nullptr, stream_));
       d_hf = W.d_hf;
     }
     // ---- fragment-connection graph block
     {
       RC(fork());
-      bool have = true;
-      if (frag_bwd) {  // g = ReLU(Dropout) backward of dy + sum_h dz_f alpha_e; also d f[:, edge slice]
-        RC(fnb_edge_table_bwd_fused(&plan->frag, W.dz_f, pre_fbond, P.f, A_STRIDE, A_E, y_fbond ? nullptr : dy_fbond,
-                                    y_fbond ? dy_fbond : nullptr, y_fbond && dy_fbond ? y_fbond : nullptr, scale,
-                                    W.g_fbond, D.f, scratchB, sB_));
-      } else if (dy_fbond) {
-        RC(grad_combine(dy_fbond, y_fbond, scale, nullptr, nullptr, z.Nfb, W.g_fbond, sB));
-      } else {
-        have = false;
-      }
+      // incoming gradient = ReLU(Dropout) backward of dy_fbond + (last layer) the fragment graph's edge term
+      // sum_h dz_f alpha_e, assembled inside the destination pass; d f[:, edge slice] by the edge-table kernel
+      const bool have = frag_bwd || dy_fbond != nullptr;
+      if (frag_bwd)
+        RC(fnb_edge_table_bwd_fused(&plan->frag, W.dz_f, pre_fbond, P.f, A_STRIDE, A_E, nullptr, nullptr, nullptr, scale,
+                                    nullptr, D.f, scratchB, sB_));
       if (have) {
         fnb_gat_bwd_args a{};
         a.h = b.hfb; a.dout = W.g_fbond; a.p_saved = b.p_fb; a.edge_mode = FNB_EDGE_AFFINE6; a.We = P.We_fb;
         a.be = P.be_fb; a.alpha = P.f_a_b; a.alpha_stride = AB_STRIDE; a.off_t = AB_T; a.off_e = AB_E; a.off_s = AB_S;
         a.dz = W.dz_fb; a.dSt = W.dSt_fb; a.dh = W.dh_fb; a.d_alpha = D.f_a_b; a.d_bias = D.bfb; a.dWe = D.We_fb;
         a.dbe = D.be_fb; a.scratch = scratchB;
-        RC(fnb_gat_bwd_tiled(&plan->fbond, &a, sB_));
+        FnbDstFuse fz{};
+        fz.dz_up = frag_bwd ? W.dz_f : nullptr; fz.slot_of_eid = plan->frag.slot_of_eid; fz.alpha_up = P.f + A_E;
+        fz.alpha_up_stride = A_STRIDE; fz.dy = dy_fbond; fz.y = dy_fbond ? y_fbond : nullptr; fz.scale = scale;
+        RC(fnb_gat_bwd_tiled_fused(&plan->fbond, &a, &fz, nullptr, nullptr, sB_));
         float *dx = need_dx ? W.dx_fbond : (o->need_dx_fbond ? io->dx_fbond : nullptr);
         if (l == 0 && b.k_pad[2] && !dx)
           RC(fnb_tc_dw_launch(W.dh_fb, b.x_pad[2], z.Nfb, b.k_pad[2], P.K_fbond, D.Wfb, scratch_body(scratchB), sB));
@@ -688,7 +646,6 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
           RC((int)cudaStreamWaitEvent(sA, aux.a_table, 0));
           a_table_pending = false;
         }
-        RC(grad_combine(dy_atom, y_atom, scale, d_hf, plan->a2f, z.Na, W.g_atom, sA));
         fnb_gat_bwd_args a{};
         a.h = b.ha; a.dout = W.g_atom; a.p_saved = b.p_a; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.a;
         a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_a; a.dSt = W.dSt_a;
@@ -696,7 +653,9 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         RC(w_wait(0, par, sA));
         // the bond graph's destination pass (caller's stream) only needs dz of this graph: the event sits between the
         // two launches
-        RC(fnb_gat_bwd_tiled_fused(&plan->atom, &a, nullptr, two ? aux.a_dz : nullptr, nullptr, sA_));
+        FnbDstFuse fza{};     // ReLU(Dropout) backward of dy_atom + pooling backward of the fragment gradient
+        fza.dy = dy_atom; fza.y = dy_atom ? y_atom : nullptr; fza.scale = scale; fza.pool = d_hf; fza.seg_of = plan->a2f;
+        RC(fnb_gat_bwd_tiled_fused(&plan->atom, &a, &fza, two ? aux.a_dz : nullptr, nullptr, sA_));
         if (two) RC((int)cudaStreamWaitEvent(stream, aux.a_dz, 0));
         RC(w_begin(0, sA));
         float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);

@@ -341,6 +341,8 @@ struct DstT {
   int f_stride;
   const float *f_base, *f_dy, *f_y;
   float f_scale;
+  const float *f_pool;     // [n_seg,128] gradient of the pooled rows (atom -> fragment sum pooling), or NULL
+  const int *f_seg;        // [N] segment of every row
   float *g_out;            // [N,128] assembled gradient, read by the source pass
 };
 
@@ -353,7 +355,7 @@ __device__ __forceinline__ float dz_of(float p, float dp, float delta) {
 }
 
 // Gradient arriving at row t of this graph's output.  FUSE: the row is assembled on the fly,
-//   g[t,:] = sum_h dz_up[slot_up[t],h] alpha_up[h,:]  (+ g_base[t,:])  (+ dy[t,:] (y[t,:] > 0) scale)
+//   g[t,:] = sum_h dz_up[slot_up[t],h] alpha_up[h,:]  (+ g_base[t,:])  (+ dy[t,:] (y[t,:] > 0) scale)  (+ pool[seg[t],:])
 // i.e. the edge-term backward of the consumer graph (gat2.py:203-208: this graph's output rows are the consumer's edge
 // vectors) plus the ReLU(Dropout) backward of gat2.py:414-418, in the summation order of k_edge_table_bwd_tiled, and
 // written once for the source pass -- a whole pass over [N,128] leaves the critical path of the backward.
@@ -377,11 +379,20 @@ __device__ __forceinline__ float4 dst_grad_row(const DstT &a, int t, const float
     g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w;
   }
   if (a.f_dy) {
-    const float4 d = ldg4(a.f_dy + o), y = ldg4(a.f_y + o);
-    g.x += y.x > 0.f ? d.x * a.f_scale : 0.f;
-    g.y += y.y > 0.f ? d.y * a.f_scale : 0.f;
-    g.z += y.z > 0.f ? d.z * a.f_scale : 0.f;
-    g.w += y.w > 0.f ? d.w * a.f_scale : 0.f;
+    const float4 d = ldg4(a.f_dy + o);
+    if (a.f_y) {
+      const float4 y = ldg4(a.f_y + o);
+      g.x += y.x > 0.f ? d.x * a.f_scale : 0.f;
+      g.y += y.y > 0.f ? d.y * a.f_scale : 0.f;
+      g.z += y.z > 0.f ? d.z * a.f_scale : 0.f;
+      g.w += y.w > 0.f ? d.w * a.f_scale : 0.f;
+    } else {
+      g.x += d.x; g.y += d.y; g.z += d.z; g.w += d.w;
+    }
+  }
+  if (a.f_pool) {   // pooling backward (gat2.py:234): every member row receives its fragment's gradient
+    const float4 q = ldg4(a.f_pool + (int64_t)__ldg(a.f_seg + t) * kD + lane * 4);
+    g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
   }
   st4(a.g_out + o, g);
   return g;
@@ -896,9 +907,10 @@ int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *b, const
       !b->d_alpha || !b->scratch || (g->n_edges > 0 && (!g->col || !b->p_saved || !b->dz)))
     return FNB_ERR_NULL;
   if (fz) {
-    if ((fz->dz_up && (!fz->slot_of_eid || !fz->alpha_up)) || (fz->dy == nullptr) != (fz->y == nullptr)) return FNB_ERR_NULL;
+    if ((fz->dz_up && (!fz->slot_of_eid || !fz->alpha_up)) || (fz->y && !fz->dy) || (fz->pool && !fz->seg_of))
+      return FNB_ERR_NULL;
     if ((fz->alpha_up_stride & 3) || !fnb_aligned16(fz->alpha_up) || !fnb_aligned16(fz->dz_up) ||
-        !fnb_aligned16(fz->g_base) || !fnb_aligned16(fz->dy) || !fnb_aligned16(fz->y))
+        !fnb_aligned16(fz->g_base) || !fnb_aligned16(fz->dy) || !fnb_aligned16(fz->y) || !fnb_aligned16(fz->pool))
       return FNB_ERR_ALIGN;
   }
   if ((b->alpha_stride & 3) || (b->off_t & 3) || (b->off_s & 3) || (b->off_e & 3) || !fnb_aligned16(b->alpha) ||
@@ -913,31 +925,34 @@ int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *b, const
   d.dWe = b->dWe; d.dbe = b->dbe; d.d_alpha_e = b->d_alpha + b->off_e;
   d.npc = pick_npc(g->n_nodes);
   d.f_dz = nullptr; d.f_slot = nullptr; d.f_alpha = nullptr; d.f_stride = 0; d.f_base = d.f_dy = d.f_y = nullptr;
-  d.f_scale = 1.f; d.g_out = nullptr;
+  d.f_scale = 1.f; d.g_out = nullptr; d.f_pool = nullptr; d.f_seg = nullptr;
   if (fz) {   // the incoming gradient is assembled into b->dout by the destination pass
     d.f_dz = fz->dz_up; d.f_slot = fz->slot_of_eid; d.f_alpha = fz->alpha_up; d.f_stride = fz->alpha_up_stride;
     d.f_base = fz->g_base; d.f_dy = fz->dy; d.f_y = fz->y; d.f_scale = fz->scale;
+    d.f_pool = fz->pool; d.f_seg = fz->seg_of;
     d.g_out = const_cast<float *>(b->dout);
   }
   const int grid = tile_grid(g->n_nodes, d.npc, 6);
   const bool affine = b->edge_mode == FNB_EDGE_AFFINE1 || b->edge_mode == FNB_EDGE_AFFINE6;
   if (affine && (!g->edge_attr || !b->We || !b->be || !b->dWe || !b->dbe)) return FNB_ERR_NULL;
+  const bool fuse = fz != nullptr;
+#define FNB_LAUNCH_DST(MODE)                                                                                         \
+  do {                                                                                                               \
+    const cudaError_t le = fuse ? fnb_launch(k_gat_bwd_dst_tiled<MODE, true>, dim3(grid), dim3(T_THREADS), 0, stream, d) \
+                                : fnb_launch(k_gat_bwd_dst_tiled<MODE, false>, dim3(grid), dim3(T_THREADS), 0, stream, d); \
+    if (le != cudaSuccess) return (int)le;                                                                           \
+  } while (0)
   if (b->edge_mode == FNB_EDGE_AFFINE1) {
-    if (fz) {
-      if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE1, true>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
-    } else {
-      if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE1, false>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
-    }
-  } else if (fz) {
-    return FNB_ERR_MODE;   // only the bond graph (AFFINE1) has a fused variant
+    FNB_LAUNCH_DST(FNB_EDGE_AFFINE1);
   } else if (b->edge_mode == FNB_EDGE_AFFINE6) {
     if (reinterpret_cast<uintptr_t>(g->edge_attr) & 7u) return FNB_ERR_ALIGN;
-    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_AFFINE6, false>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
+    FNB_LAUNCH_DST(FNB_EDGE_AFFINE6);
   } else if (b->edge_mode == FNB_EDGE_NONE || b->edge_mode == FNB_EDGE_TABLE) {
-    if (cudaError_t le = fnb_launch(k_gat_bwd_dst_tiled<FNB_EDGE_NONE, false>, dim3(grid), dim3(T_THREADS), 0, stream, d)) return (int)le;
+    FNB_LAUNCH_DST(FNB_EDGE_NONE);
   } else {
     return FNB_ERR_MODE;
   }
+#undef FNB_LAUNCH_DST
   FNB_CHECK_LAUNCH();
   if (after_dst)   // consumers of the destination pass's inputs (the consumer graph's dz) may be overwritten from here on
     if (cudaError_t ee = cudaEventRecord(after_dst, stream)) return (int)ee;

@@ -1,3 +1,4 @@
+set -e; python -c "from fragnet_b200 import _abi; _abi.load()"; set +e
 set -u
 tag=$1
 mkdir -p gpurun_out
