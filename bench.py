@@ -361,20 +361,35 @@ def run_ours(args):
     # ---- end to end through the public API with HOST (pinned) batches: H2D + step + loss read back
     e2e = None
     if not args.no_e2e:
-        h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+        # what Trainer's fused path stages (DevicePrefetcher(hot_path_only=True)): every tensor of the batch dict except
+        # edge_attr / cnx_attr (never read by FragNet.forward, gat2.py:381-442) and the VALUES of x_frags (overwritten
+        # unread by the pooling, gat2.py:234)
+        h2d = sum(v.numel() * v.element_size() for k, v in host_batches[0].items()
+                  if k not in ("edge_attr", "cnx_attr", "x_frags"))
 
         # public path: DevicePrefetcher (pinned host batches -> device on a copy stream, double buffered) feeding
         # the step; every batch is copied inside the timed region and every step's loss is read back
         from fragnet_b200.dataset.prefetch import DevicePrefetcher
 
+        from fragnet_b200.train.fused import LaggedScalars
+
+        reader = LaggedScalars(lag=1)     # three pinned floats, allocated once (cudaHostAlloc synchronises the device)
+
         def e2e_run(n):
-            feed = iter(DevicePrefetcher((host_batches[i % args.rotate] for i in range(n)), dev, depth=2))
-            state = {"b": next(feed)}
+            feed = iter(DevicePrefetcher((host_batches[i % args.rotate] for i in range(n)), dev, depth=2,
+                                         hot_path_only=True))
+            state = {"b": next(feed), "sum": 0.0, "read": 0}
 
             def one(i):
                 loss = step(state["b"])
                 state["b"] = next(feed, None)     # stage batch i+2 while step i runs on the GPU
-                loss.item()                       # per-step device -> host read of the loss
+                # every step's loss is copied device -> host (pinned) behind its step and collected once the next
+                # step has been enqueued; the last one is collected inside the timed region too
+                vals = reader.push(loss) + (reader.drain() if i == n - 1 else [])
+                state["sum"] += sum(vals)
+                state["read"] += len(vals)
+                if i == n - 1:
+                    assert state["read"] == n and state["sum"] == state["sum"]
             return one
 
         warm = e2e_run(min(3, args.warmup))
@@ -390,7 +405,10 @@ def run_ours(args):
             run(i)
         ms_e2e, _ = timed(e2e_step, args.steps)
         e2e = {"value": round(mols / (ms_e2e * 1e-3), 1), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)}
+               "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
+               "batch_dict_bytes": sum(v.numel() * v.element_size() for v in host_batches[0].values()),
+               "loss_read": "every step's loss is copied to pinned host memory behind its step and collected one step "
+                            "later (after the next step has been enqueued); all reads inside the timed region"}
 
     # ---- the same loop fed by the device-resident packed arena: the per-step host -> device traffic
     # is the list of molecule ids; the batch dict is assembled on the device inside the timed region
@@ -400,21 +418,27 @@ def run_ours(args):
 
         from fragnet_b200 import synth
         from fragnet_b200.dataset.arena import MoleculeArena
+        from fragnet_b200.train.fused import LaggedScalars
         pool = synth.make_dataset(args.shape, min(args.pool, args.batch * args.rotate), seed=100 + rank)
         arena = MoleculeArena(pool, dev)
         rng = np.random.default_rng(100 + rank)
         id_lists = [rng.integers(0, len(pool), size=args.batch) for _ in range(args.rotate)]
 
-        def arena_run():
-            state = {"b": arena.batch(id_lists[0])}
+        reader = LaggedScalars(lag=1)
+
+        def arena_run(n):
+            state = {"b": arena.batch(id_lists[0]), "read": 0}
 
             def one(i):
                 loss = step(state["b"])
                 state["b"] = arena.batch(id_lists[(i + 1) % args.rotate])   # assembled behind step i on the same stream
-                loss.item()
+                vals = reader.push(loss) + (reader.drain() if i == n - 1 else [])
+                state["read"] += len(vals)
+                if i == n - 1:
+                    assert state["read"] == n
             return one
 
-        warm = arena_run()
+        warm = arena_run(min(3, args.warmup))
         for i in range(min(3, args.warmup)):
             warm(i)
         barrier()
@@ -423,7 +447,7 @@ def run_ours(args):
         def arena_step(i):
             nonlocal run_a
             if run_a is None:
-                run_a = arena_run()
+                run_a = arena_run(args.steps)
             run_a(i)
         ms_a, _ = timed(arena_step, args.steps)
         e2e_arena = {"value": round(mols / (ms_a * 1e-3), 1), "unit": "molecules/s",

@@ -144,6 +144,29 @@ class MoleculeArena:
     def __len__(self) -> int:
         return self.n_mols
 
+    _ID_SLOTS = 8
+
+    def _stage_ids(self, ids: np.ndarray) -> torch.Tensor:
+        """Molecule ids -> device through a ring of persistent pinned buffers (a fresh ``pin_memory()`` per batch
+        ends in ``cudaHostAlloc`` -- a device-synchronising call -- as soon as the host runs ahead of the GPU)."""
+        g = int(ids.shape[0])
+        ring = getattr(self, "_id_ring", None)
+        if ring is None or ring[0][0].numel() < g:
+            cap = max(g, 1024)
+            ring = [(torch.empty(cap, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(self._ID_SLOTS)]
+            self._id_ring, self._id_next, self._id_used = ring, 0, [False] * self._ID_SLOTS
+        k = self._id_next
+        self._id_next = (k + 1) % self._ID_SLOTS
+        host, ev = ring[k]
+        if self._id_used[k]:
+            ev.synchronize()                     # the copy that last read this slot (8 batches ago) has completed
+        host[:g].numpy()[:] = ids
+        out = torch.empty(g, dtype=torch.int64, device=self.device)
+        out.copy_(host[:g], non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self._id_used[k] = True
+        return out
+
     def batch_nbytes(self, ids) -> int:
         """Bytes of the batch dict the reference would move host -> device for these molecules."""
         ids = np.asarray(ids, dtype=np.int64)
@@ -170,11 +193,14 @@ class MoleculeArena:
             raise IndexError("molecule id out of range")
         dev = self.device
         if ids_device is None:
-            pinned = torch.from_numpy(np.ascontiguousarray(ids)).pin_memory()
-            ids_device = torch.empty(g, dtype=torch.int64, device=dev)
-            ids_device.copy_(pinned, non_blocking=True)
+            ids_device = self._stage_ids(ids)
         out: Dict[str, torch.Tensor] = {}
-        totals = {name: int(k.counts_host[ids].sum()) for name, k in self._kinds.items()}
+        if getattr(self, "_count_matrix", None) is None:      # [n_kinds, n_mols]: one fancy-index + one sum per batch
+            self._count_names = list(self._kinds)
+            self._count_matrix = np.stack([self._kinds[n].counts_host for n in self._count_names]) \
+                if self.n_mols else np.zeros((len(self._count_names), 0), dtype=np.int64)
+        sums = self._count_matrix[:, ids].sum(axis=1)
+        totals = {name: int(v) for name, v in zip(self._count_names, sums)}
         for key in self._keys:
             layout, dtype, trailing, kname = self._shape[key]
             n = totals[kname]

@@ -186,3 +186,40 @@ class FusedPretrainStep:
         """Forward + loss without gradients (Trainer.validate, pretrain_utils.py:33-57)."""
         loss, preds = self._run(batch, backward=False, want_preds=return_predictions)
         return (loss, preds) if return_predictions else loss
+
+
+class LaggedScalars:
+    """Every step's scalar result (the loss) read back to the host WITHOUT stalling the launch of the next step.
+
+    The reference reads ``loss.item()`` right after ``optimizer.step()`` (pretrain_utils.py:28): the host then waits
+    for the whole step and the GPU idles while the next step is being enqueued.  Here the 4-byte device-to-host copy
+    of step ``i`` is queued behind step ``i`` into a pinned slot, and collected once step ``i + lag`` has been enqueued
+    (``push`` returns the values that have become due, in step order; ``drain`` returns the rest)."""
+
+    def __init__(self, lag: int = 1):
+        import collections
+        self.lag = max(0, int(lag))
+        n = self.lag + 2
+        self._host = torch.empty(n, dtype=torch.float32).pin_memory()
+        self._events = [torch.cuda.Event() for _ in range(n)]
+        self._pending = collections.deque()
+        self._count = 0
+
+    def _collect(self, keep: int) -> List[float]:
+        out = []
+        while len(self._pending) > keep:
+            s = self._pending.popleft()
+            self._events[s].synchronize()
+            out.append(float(self._host[s]))
+        return out
+
+    def push(self, value: torch.Tensor) -> List[float]:
+        s = self._count % len(self._events)
+        self._count += 1
+        self._host[s:s + 1].copy_(value.detach().reshape(1), non_blocking=True)
+        self._events[s].record(torch.cuda.current_stream(value.device))
+        self._pending.append(s)
+        return self._collect(self.lag)
+
+    def drain(self) -> List[float]:
+        return self._collect(0)

@@ -71,14 +71,22 @@ class Trainer:
     @staticmethod
     def _run_pipelined(loader, device, launch):
         """``launch(batch) -> loss tensor`` per batch; the next batches are staged while the GPU works and every
-        loss is read back (the reference's ``loss.item()`` per step)."""
+        loss is read back (the reference's ``loss.item()`` per step), one step behind the launches so that the GPU
+        never waits for the host.  The sum runs in step order over the same fp32 values: identical to the reference's
+        ``total_loss += loss.item()``."""
         from ..dataset.prefetch import DevicePrefetcher
-        feed = iter(DevicePrefetcher(loader, device, depth=2))
+        from .fused import LaggedScalars
+        # this path only runs the drop-in FragNetPreTrain: tensors the GAT2 path never reads stay on the host
+        feed = iter(DevicePrefetcher(loader, device, depth=2, hot_path_only=True))
+        reader = LaggedScalars(lag=1)
         total, batch = 0.0, next(feed, None)
         while batch is not None:
             loss = launch(batch)
             batch = next(feed, None)
-            total += loss.item()
+            for v in reader.push(loss):
+                total += v
+        for v in reader.drain():
+            total += v
         return total
 
     # ---- the reference's interface --------------------------------------------------------------

@@ -17,7 +17,8 @@ import bench  # noqa: E402
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-    step, batches = bench.make_step(batch=batch, autograd_path=len(sys.argv) > 3 and sys.argv[3] == "autograd")
+    shape = sys.argv[4] if len(sys.argv) > 4 else "unimol"
+    step, batches = bench.make_step(batch=batch, shape=shape, autograd_path=len(sys.argv) > 3 and sys.argv[3] == "autograd")
     for i in range(5):
         step(batches[i % len(batches)])
     torch.cuda.synchronize()
