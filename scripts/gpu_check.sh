@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 tag=${1:-run}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
-for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_tiled.py tests/test_gpu_model.py tests/test_gpu_heads.py tests/test_gpu_tc.py tests/test_gpu_arena.py tests/test_gpu_attribution.py tests/test_lite.py tests/test_viz.py tests/test_finetune_loop.py; do
+for f in tests/test_gpu_csr.py tests/test_gpu_kernels.py tests/test_gpu_tiled.py tests/test_gpu_model.py tests/test_gpu_heads.py tests/test_gpu_tc.py tests/test_gpu_arena.py tests/test_gpu_fullsize.py tests/test_gpu_attribution.py tests/test_lite.py tests/test_viz.py tests/test_finetune_loop.py; do
   timeout 600 python -m pytest $f -q --no-header -p no:cacheprovider -m gpu 2>&1 | tail -120 > gpurun_out/${tag}_$(basename $f .py).log
 done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1
