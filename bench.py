@@ -238,6 +238,11 @@ def cpu_oracle_rate(shape, n_mols, steps, warmup, seed=0):
     return n_mols / statistics.mean(times), statistics.mean(times)
 
 
+def workload_name(shape):
+    """``config.workload`` of both arms (BASELINE.json configs[1])."""
+    return f"FragNetPreTrain exps/pt/unimol_exp1s4 step (4 layers, 4 heads, emb 128, drop 0.2, Adam), {shape}-shaped molecules"
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -252,8 +257,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"FragNetPreTrain unimol_exp1s4 step, {args.shape}-shaped molecules",
-                       "per_gpu_batch": args.batch, "sample_batch": n_mols},
+            "config": {"workload": workload_name(args.shape), "per_gpu_batch": args.batch,
+                       "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}",
+                       "sample_batch": n_mols},
             "cpu_baseline": {"value": round(rate, 2), "unit": "molecules/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": round(rate, 2), "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -485,8 +491,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.precision == "fp32" else "f32 (tf32-in/f32-acc tensor-core projections)",
                 "data": "synthetic",
-                "config": {"workload": f"FragNetPreTrain exps/pt/unimol_exp1s4 step (4 layers, 4 heads, emb 128, "
-                                       f"drop 0.2, Adam), {args.shape}-shaped molecules",
+                "config": {"workload": workload_name(args.shape),
                            "per_gpu_batch": args.batch, "global_batch": args.batch * world,
                            "parallelism": f"dp{world}", "batch0_counts": counts,
                            "cache": f"{args.rotate} distinct batches rotated; fwd+bwd working set > 126 MB L2; CSR plans rebuilt every step",
