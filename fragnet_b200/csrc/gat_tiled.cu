@@ -63,7 +63,16 @@ struct FwdT {
   float *next_Se;
   int npc;
   const int *tile_range;
+  int prefetch;   // FNB_PREFETCH=1: phase 1 asks L2 for the source rows phase 3 will gather
 };
+
+__device__ __forceinline__ void prefetch_row_l2(const float *row) {
+  const char *p = reinterpret_cast<const char *>(row);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 256));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 384));
+}
 
 template <int MODE>
 __device__ __forceinline__ float4 edge_term_t(const FwdT &a, int slot, const float *coef) {
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(Fwd
       for (int i = tid; i < cnt; i += T_THREADS) {
         const int slot = e0 + i;
         const int s = __ldg(a.col + slot), t = __ldg(a.row + slot);
+        if (a.prefetch) prefetch_row_l2(a.h + (int64_t)s * kD);
         st4(s_l + i * 4, edge_logit<MODE>(a, slot, t, s, s_coef, staged ? s_S : nullptr, lo));
         s_src[i] = s;
       }
@@ -871,6 +881,10 @@ extern "C" int fnb_gat_fwd_tiled(const fnb_graph *g, const fnb_gat_fwd_args *f, 
   a.next_alpha = f->next_alpha_e; a.next_stride = f->next_alpha_stride; a.next_Se = f->next_Se;
   a.npc = pick_npc(g->n_nodes);
   a.tile_range = g->tile_range;
+  {
+    static const int pf = [] { const char *e = getenv("FNB_PREFETCH"); return e && e[0] == '1' ? 1 : 0; }();
+    a.prefetch = pf;
+  }
   const bool staged = use_staging() && g->tile_range != nullptr && a.npc == kRangeTile;
   cudaStream_t stream = (cudaStream_t)stream_;
   switch (f->edge_mode) {
