@@ -63,6 +63,7 @@ struct FwdT {
   float *next_Se;
   int npc;
   const int *tile_range;
+  int deep;       // mean in-degree >= kDeepDegree: the DEEP instantiation
   int prefetch;   // FNB_PREFETCH=1: phase 1 asks L2 for the source rows phase 3 will gather
 };
 
@@ -194,14 +195,19 @@ __device__ void fwd_hub(const FwdT &a, int t, int beg, int end, const float *coe
   fwd_store_row(a, t, acc, s_na);
 }
 
-template <int MODE, bool STAGED>
-__global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(FwdT a) {
+// DEEP: the instantiation for graphs with a high mean in-degree (fragment-connection graphs of multi-component salts,
+// ~60 edges per node: profiles/r3o_ncu_full_stress.md): 8 row gathers in flight per warp instead of 4 (fewer
+// latency round trips per node; 64 registers, 4 CTAs per SM) and a warp-parallel softmax phase (8 lanes per
+// (node, head) with shuffle reductions instead of one thread walking the whole segment while 3/4 of the CTA waits).
+template <int MODE, bool STAGED, bool DEEP = false>
+__global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : (DEEP ? 4 : 6)) k_gat_fwd_tiled(FwdT a) {
   extern __shared__ __align__(128) float s_dyn[];   // STAGED: [ROWS_CAP][128] rows of h, then [ROWS_CAP][8] rows of S
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int s_stage[2];
   __shared__ int s_rowptr[T_NPC + 1];
-  __shared__ int s_src[FWD_CAP];
-  __shared__ __align__(16) float s_l[FWD_CAP * 4];
+  constexpr int CAP = DEEP ? 2 * FWD_CAP : FWD_CAP;   // DEEP: longer sub-tiles, fewer phase barriers per node
+  __shared__ int s_src[CAP];
+  __shared__ __align__(16) float s_l[CAP * 4];
   __shared__ float s_coef[28];
   __shared__ __align__(16) float s_na[4 * kD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, head = lane >> 3;
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(Fwd
     if (staged) bulk::mbar_wait(bar_S, phase);
     int lb = 0;
     while (lb < nn) {
-      const int le = subtile_end(s_rowptr, lb, nn, FWD_CAP);
+      const int le = subtile_end(s_rowptr, lb, nn, CAP);
       if (le == lb) {  // hub node (CTA-uniform branch)
         if (warp == 0) fwd_hub<MODE>(a, n0 + lb, s_rowptr[lb], s_rowptr[lb + 1], s_coef, s_na);
         ++lb;
@@ -260,6 +266,27 @@ __global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(Fwd
       }
       __syncthreads();
       // ---- phase 2: softmax per (node, head)
+      if (DEEP) {   // one warp per node, 8 lanes per head, edges strided over the 8 lanes
+        const int sub = lane & 7;
+        for (int n = lb + warp; n < le; n += T_WARPS) {
+          const int b = s_rowptr[n] - e0, e = s_rowptr[n + 1] - e0;
+          float m = -INFINITY;
+          for (int j = b + sub; j < e; j += 8) m = fmaxf(m, s_l[j * 4 + head]);
+          m = fmaxf(m, __shfl_xor_sync(kFull, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(kFull, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(kFull, m, 4));
+          float den = 0.f;
+          for (int j = b + sub; j < e; j += 8) {
+            const float l = s_l[j * 4 + head];
+            const float ex = expf(l - m);
+            den += ex;
+            s_l[j * 4 + head] = l > 0.f ? ex : -ex;
+          }
+          den = head_sum(den);
+          const float inv = 1.f / den;
+          for (int j = b + sub; j < e; j += 8) s_l[j * 4 + head] *= inv;
+        }
+      } else {
       for (int q = tid; q < (le - lb) * 4; q += T_THREADS) {
         const int n = lb + (q >> 2), hh = q & 3;
         const int b = s_rowptr[n] - e0, e = s_rowptr[n + 1] - e0;
@@ -274,6 +301,7 @@ __global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(Fwd
         }
         const float inv = 1.f / den;
         for (int j = b; j < e; ++j) s_l[j * 4 + hh] *= inv;
+      }
       }
       __syncthreads();
       // ---- phase 3: save p (coalesced), then one warp per node aggregates source rows
@@ -292,6 +320,24 @@ __global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : 6) k_gat_fwd_tiled(Fwd
             acc.y = fmaf(pj, v.y, acc.y);
             acc.z = fmaf(pj, v.z, acc.z);
             acc.w = fmaf(pj, v.w, acc.w);
+          }
+        }
+        if (DEEP) {
+          for (; j + 8 <= e; j += 8) {
+            float4 v[8];
+            float pj[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              v[u] = ldg4(a.h + (int64_t)s_src[j + u] * kD + lane * 4);
+              pj[u] = fabsf(s_l[(j + u) * 4 + head]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc.x = fmaf(pj[u], v[u].x, acc.x);
+              acc.y = fmaf(pj[u], v[u].y, acc.y);
+              acc.z = fmaf(pj[u], v[u].z, acc.z);
+              acc.w = fmaf(pj[u], v[u].w, acc.w);
+            }
           }
         }
         for (; j + 4 <= e; j += 4) {
@@ -583,11 +629,13 @@ struct SrcT {
   int npc;
 };
 
-__global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
+template <bool DEEP>
+__global__ void __launch_bounds__(T_THREADS, DEEP ? 3 : 5) k_gat_bwd_src_tiled(SrcT a) {
   __shared__ int s_rowptr[T_NPC + 1];
-  __shared__ int s_t[BWD_CAP];
-  __shared__ __align__(16) float s_p[BWD_CAP * 4];   // reused as the 8 x 384 per-warp records at the end
-  __shared__ __align__(16) float s_dz[BWD_CAP * 4];  // reused as CTA record [384] + final [384]
+  constexpr int CAP = DEEP ? 1024 : BWD_CAP;
+  __shared__ int s_t[CAP];
+  __shared__ __align__(16) float s_p[CAP * 4];   // reused as the 8 x 384 per-warp records at the end
+  __shared__ __align__(16) float s_dz[CAP * 4];  // reused as CTA record [384] + final [384]
   __shared__ __align__(16) float s_dSs[T_NPC * 4];
   static_assert(BWD_CAP * 4 >= T_WARPS * 384, "per-warp records must fit the staging array");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, head = lane >> 3;
@@ -618,7 +666,7 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
     __syncthreads();
     int lb = 0;
     while (lb < nn) {
-      const int le = subtile_end(s_rowptr, lb, nn, BWD_CAP);
+      const int le = subtile_end(s_rowptr, lb, nn, CAP);
       if (le == lb) {  // hub source node: warp 0, reverse slots one at a time
         if (warp == 0) {
           const int beg = s_rowptr[lb], end = s_rowptr[lb + 1];
@@ -647,6 +695,16 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
       }
       __syncthreads();
       // ---- phase 2: dSs per (node, head)
+      if (DEEP) {
+        const int sub = lane & 7;
+        for (int n = lb + warp; n < le; n += T_WARPS) {
+          const int b = s_rowptr[n] - r0, e = s_rowptr[n + 1] - r0;
+          float sdz = 0.f;
+          for (int j = b + sub; j < e; j += 8) sdz += s_dz[j * 4 + head];
+          sdz = head_sum(sdz);
+          if (sub == 0) s_dSs[(n - lb) * 4 + head] = sdz;
+        }
+      } else {
       for (int q = tid; q < (le - lb) * 4; q += T_THREADS) {
         const int n = lb + (q >> 2), hh = q & 3;
         const int b = s_rowptr[n] - r0, e = s_rowptr[n + 1] - r0;
@@ -654,12 +712,31 @@ __global__ void __launch_bounds__(T_THREADS, 5) k_gat_bwd_src_tiled(SrcT a) {
         for (int j = b; j < e; ++j) s += s_dz[j * 4 + hh];
         s_dSs[(n - lb) * 4 + hh] = s;
       }
+      }
       __syncthreads();
       // ---- phase 3: one warp per source node gathers the destination gradients
       for (int n = lb + warp; n < le; n += T_WARPS) {
         const int b = s_rowptr[n] - r0, e = s_rowptr[n + 1] - r0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int j = b;
+        if (DEEP) {
+          for (; j + 8 <= e; j += 8) {
+            float4 v[8];
+            float pj[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              v[u] = ldg4(a.dout + (int64_t)s_t[j + u] * kD + lane * 4);
+              pj[u] = s_p[(j + u) * 4 + head];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc.x = fmaf(pj[u], v[u].x, acc.x);
+              acc.y = fmaf(pj[u], v[u].y, acc.y);
+              acc.z = fmaf(pj[u], v[u].z, acc.z);
+              acc.w = fmaf(pj[u], v[u].w, acc.w);
+            }
+          }
+        }
         for (; j + 4 <= e; j += 4) {
           float4 v[4];
           float pj[4];
@@ -845,12 +922,21 @@ int launch_fwd(const FwdT &a, bool staged, cudaStream_t stream) {
     const int rc = allow_smem(k_gat_fwd_tiled<MODE, true>, smem, done);
     if (rc) return rc;
     k_gat_fwd_tiled<MODE, true><<<tile_grid(a.n_nodes, kRangeTile, 2), T_THREADS, smem, stream>>>(a);
+  } else if (a.deep) {
+    const cudaError_t le = fnb_launch(k_gat_fwd_tiled<MODE, false, true>, dim3(tile_grid(a.n_nodes, a.npc, 4)), dim3(T_THREADS), 0, stream, a);
+    if (le != cudaSuccess) return (int)le;
   } else {
     const cudaError_t le = fnb_launch(k_gat_fwd_tiled<MODE, false>, dim3(tile_grid(a.n_nodes, a.npc, 6)), dim3(T_THREADS), 0, stream, a);
     if (le != cudaSuccess) return (int)le;
   }
   FNB_CHECK_LAUNCH();
   return 0;
+}
+
+// Mean in-degree from which the DEEP instantiations pay (FNB_DEEP=0 disables, FNB_DEEP=<degree> overrides).
+inline bool deep_graph(const fnb_graph *g) {
+  static const int thr = [] { const char *e = getenv("FNB_DEEP"); return e ? atoi(e) : 24; }();
+  return thr > 0 && g->n_nodes > 0 && g->n_edges >= (int64_t)thr * g->n_nodes;
 }
 
 inline bool graph_ok(const fnb_graph *g) {
@@ -885,6 +971,7 @@ extern "C" int fnb_gat_fwd_tiled(const fnb_graph *g, const fnb_gat_fwd_args *f, 
     static const int pf = [] { const char *e = getenv("FNB_PREFETCH"); return e && e[0] == '1' ? 1 : 0; }();
     a.prefetch = pf;
   }
+  a.deep = deep_graph(g) ? 1 : 0;
   const bool staged = use_staging() && g->tile_range != nullptr && a.npc == kRangeTile;
   cudaStream_t stream = (cudaStream_t)stream_;
   switch (f->edge_mode) {
@@ -949,7 +1036,8 @@ int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *b, const
   const int grid = tile_grid(g->n_nodes, d.npc, 6);
   const bool affine = b->edge_mode == FNB_EDGE_AFFINE1 || b->edge_mode == FNB_EDGE_AFFINE6;
   if (affine && (!g->edge_attr || !b->We || !b->be || !b->dWe || !b->dbe)) return FNB_ERR_NULL;
-  const bool fuse = fz != nullptr;
+  // (a DEEP destination pass was measured slower on the stress shape: 672 vs 648 us, gpurun_out r3p)
+  const bool fuse = fz != nullptr, deep = deep_graph(g);
 #define FNB_LAUNCH_DST(MODE)                                                                                         \
   do {                                                                                                               \
     const cudaError_t le = fuse ? fnb_launch(k_gat_bwd_dst_tiled<MODE, true>, dim3(grid), dim3(T_THREADS), 0, stream, d) \
@@ -978,7 +1066,11 @@ int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *b, const
   s.off_s = b->off_s; s.dh = b->dh; s.d_alpha = b->d_alpha; s.d_bias = b->d_bias; s.scratch = (float *)b->scratch;
   s.n_nodes = (int)g->n_nodes;
   s.npc = d.npc;
-  if (cudaError_t le = fnb_launch(k_gat_bwd_src_tiled, dim3(grid), dim3(T_THREADS), 0, stream, s)) return (int)le;
+  if (deep) {
+    if (cudaError_t le = fnb_launch(k_gat_bwd_src_tiled<true>, dim3(tile_grid(g->n_nodes, d.npc, 3)), dim3(T_THREADS), 0, stream, s)) return (int)le;
+  } else {
+    if (cudaError_t le = fnb_launch(k_gat_bwd_src_tiled<false>, dim3(grid), dim3(T_THREADS), 0, stream, s)) return (int)le;
+  }
   FNB_CHECK_LAUNCH();
   return 0;
 }
