@@ -478,7 +478,10 @@ __device__ void dst_hub(const DstT &a, int t, int beg, int end, const float4 g) 
   }
 }
 
-template <int MODE, bool FUSE>
+// DEEP (mean in-degree >= 24): only the softmax-backward phase changes (one warp per node, 8 lanes per head) -- with
+// ~60 edges per node a thread per (node, head) leaves 3/4 of the CTA waiting at the barrier.  Deeper gathers at lower
+// occupancy were measured slower here (the per-edge dot + head reduction keeps the warps busy).
+template <int MODE, bool FUSE, bool DEEP = false>
 __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
   constexpr int NC = CoefT<MODE>::NC, PARTS = CoefT<MODE>::PARTS, IN = CoefT<MODE>::IN;
   __shared__ int s_rowptr[T_NPC + 1];
@@ -552,6 +555,23 @@ __global__ void __launch_bounds__(T_THREADS, 6) k_gat_bwd_dst_tiled(DstT a) {
       }
       __syncthreads();
       // ---- phase B: softmax backward per (node, head)
+      if (DEEP) {
+        const int sub = lane & 7;
+        for (int n = lb + warp; n < le; n += T_WARPS) {
+          const int b = s_rowptr[n] - e0, e = s_rowptr[n + 1] - e0;
+          float delta = 0.f;
+          for (int j = b + sub; j < e; j += 8) delta = fmaf(fabsf(s_p[j * 4 + head]), s_dp[j * 4 + head], delta);
+          delta = head_sum(delta);
+          float dst = 0.f;
+          for (int j = b + sub; j < e; j += 8) {
+            const float v = dz_of(s_p[j * 4 + head], s_dp[j * 4 + head], delta);
+            s_dp[j * 4 + head] = v;
+            dst += v;
+          }
+          dst = head_sum(dst);
+          if (sub == 0) a.dSt[(int64_t)(n0 + n) * 4 + head] = dst;
+        }
+      } else
       for (int q = tid; q < (le - lb) * 4; q += T_THREADS) {
         const int n = lb + (q >> 2), hh = q & 3;
         const int b = s_rowptr[n] - e0, e = s_rowptr[n + 1] - e0;
@@ -1036,12 +1056,16 @@ int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *b, const
   const int grid = tile_grid(g->n_nodes, d.npc, 6);
   const bool affine = b->edge_mode == FNB_EDGE_AFFINE1 || b->edge_mode == FNB_EDGE_AFFINE6;
   if (affine && (!g->edge_attr || !b->We || !b->be || !b->dWe || !b->dbe)) return FNB_ERR_NULL;
-  // (a DEEP destination pass was measured slower on the stress shape: 672 vs 648 us, gpurun_out r3p)
   const bool fuse = fz != nullptr, deep = deep_graph(g);
 #define FNB_LAUNCH_DST(MODE)                                                                                         \
   do {                                                                                                               \
-    const cudaError_t le = fuse ? fnb_launch(k_gat_bwd_dst_tiled<MODE, true>, dim3(grid), dim3(T_THREADS), 0, stream, d) \
-                                : fnb_launch(k_gat_bwd_dst_tiled<MODE, false>, dim3(grid), dim3(T_THREADS), 0, stream, d); \
+    cudaError_t le;                                                                                                  \
+    if (deep)                                                                                                        \
+      le = fuse ? fnb_launch(k_gat_bwd_dst_tiled<MODE, true, true>, dim3(grid), dim3(T_THREADS), 0, stream, d)       \
+                : fnb_launch(k_gat_bwd_dst_tiled<MODE, false, true>, dim3(grid), dim3(T_THREADS), 0, stream, d);     \
+    else                                                                                                             \
+      le = fuse ? fnb_launch(k_gat_bwd_dst_tiled<MODE, true>, dim3(grid), dim3(T_THREADS), 0, stream, d)             \
+                : fnb_launch(k_gat_bwd_dst_tiled<MODE, false>, dim3(grid), dim3(T_THREADS), 0, stream, d);           \
     if (le != cudaSuccess) return (int)le;                                                                           \
   } while (0)
   if (b->edge_mode == FNB_EDGE_AFFINE1) {
