@@ -17,7 +17,10 @@
  *     fnb_pretrain_step) fork onto three lazily created, library-owned auxiliary streams (+ events) per device and join
  *     back before they return, so one host thread per device should drive them (the reference's loops are single
  *     threaded).  FNB_STREAMS=1 in the environment keeps every launch on the caller's stream, FNB_PDL=0 turns
- *     programmatic dependent launch off, FNB_PRIO=1 gives the atom-chain stream the highest priority (measured slower).
+ *     programmatic dependent launch off, FNB_DEEP=<mean in-degree> sets the threshold from which the attention
+ *     kernels use their deep-gather instantiations (default 24, 0 = never); experiment switches that measured slower
+ *     and are off: FNB_PRIO=1 (highest priority for the atom-chain stream), FNB_PREFETCH=1 (L2 prefetch of the source
+ *     rows), FNB_STAGE=1 (bulk-copy staging of the source-row range).
  *     Process-wide state otherwise: a diagnostic launch counter;
  *   - all feature matrices are row-major fp32 with D = 128
  *     columns, H = 4 heads of d = 32 (the only geometry FragNet's gat2 uses with emb_dim 128);
