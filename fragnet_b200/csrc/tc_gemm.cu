@@ -28,6 +28,7 @@ constexpr int TC_BK = 32;                                  // fp32 elements = 12
 constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB per 128x32 K-block
 constexpr int TC_STAGES = 6;
 constexpr int TC_MAX_KB = 8;                               // K <= 256
+constexpr int TC_EPI_LD = 36;                              // padded row length of the epilogue staging block
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;                          // two 128-column FP32 accumulators
 constexpr int UMMA_K = 8;                                  // K per tcgen05.mma for kind::tf32 (32 bytes)
@@ -118,6 +119,7 @@ struct TcArgs {
   float *S;             // [M,8] or NULL
   int64_t M;
   int n_kb;             // K-blocks of 32
+  int n_stages;         // depth of the A ring (<= TC_STAGES; fewer for K = 256 so that W + ring + staging fit)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -126,6 +128,10 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
   __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 1 + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[128], s_at[128], s_as[128];
+  // Epilogue staging, one [32 rows][32 + 4 columns] block per epilogue warp: a thread owns one ROW of the accumulator
+  // (TMEM lane), so storing its 32 columns directly would make every warp-wide store touch 32 different 16-byte
+  // pieces; through this block a store instruction covers four full 128-byte lines instead.
+  __shared__ __align__(16) float s_stage[4][32 * TC_EPI_LD];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem: [W: n_kb x 16 KiB][A ring: TC_STAGES x 16 KiB], 1024-byte aligned for the 128B swizzle
@@ -181,7 +187,7 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
           tma_load_2d(smem_a + stage * TC_STAGE_BYTES, &tm_a, bar_full + 8 * stage, kb * TC_BK, (int)(tile * TC_BM));
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)g.n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -209,7 +215,7 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             tc_mma_tf32(tmem_d, da, db, kIdescTf32, (kb | k) != 0);
           }
           tc_commit(bar_empty + 8 * stage);                     // frees the A slot once these MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)g.n_stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(bar_acc_full + 8 * acc);                      // accumulator complete -> epilogue
       }
@@ -222,8 +228,10 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
-      const int64_t row = tile * TC_BM + warp * 32 + lane;
+      const int64_t row0 = tile * TC_BM + warp * 32;      // first row of this warp's quarter of the tile
+      const int64_t row = row0 + lane;
       const bool in = row < g.M;
+      float *stg = s_stage[warp];
       float st[4], ss[4];
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) {
@@ -239,10 +247,15 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         }
         st[hh] = a_t;
         ss[hh] = a_s;
-        if (in) {
-          float *cp = g.C + row * TC_BN + hh * 32;
+        __syncwarp();                                       // the previous chunk has been read out of the block
 #pragma unroll
-          for (int q = 0; q < 8; ++q) st4(cp + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        for (int q = 0; q < 8; ++q)
+          st4(stg + lane * TC_EPI_LD + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                       // 4 rows x 128 bytes per store instruction
+          const int rr = 4 * i + (lane >> 3), cc = (lane & 7) * 4;
+          if (row0 + rr < g.M) st4(g.C + (row0 + rr) * TC_BN + hh * 32 + cc, ld4(stg + rr * TC_EPI_LD + cc));
         }
       }
       tc_fence_before();
@@ -446,15 +459,19 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
   TcArgs g;
   g.C = C; g.bias = bias; g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s;
   g.S = alpha ? S : nullptr; g.M = M; g.n_kb = (K + TC_BK - 1) / TC_BK;
-  const size_t smem = (size_t)(g.n_kb + TC_STAGES) * TC_STAGE_BYTES + 1024;
+  // W (n_kb blocks) + the A ring + 1 KB alignment slack must fit next to ~21 KB of static shared memory
+  constexpr size_t kDynMax = (size_t)204 * 1024;
+  g.n_stages = TC_STAGES;
+  while (g.n_stages > 2 && (size_t)(g.n_kb + g.n_stages) * TC_STAGE_BYTES + 1024 > kDynMax) --g.n_stages;
+  const size_t smem = (size_t)(g.n_kb + g.n_stages) * TC_STAGE_BYTES + 1024;
+  if (smem > kDynMax) return FNB_ERR_MODE;
   {  // opt in to the largest dynamic shared memory this kernel can ask for, once per device
     static bool done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
     if (!done[dev]) {
-      const cudaError_t e = cudaFuncSetAttribute(k_tc_proj, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (TC_MAX_KB + TC_STAGES) * TC_STAGE_BYTES + 1024);
+      const cudaError_t e = cudaFuncSetAttribute(k_tc_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynMax);
       if (e != cudaSuccess) return (int)e;
       done[dev] = true;
     }
