@@ -371,14 +371,25 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
   } else {
     mbar_wait(bar_done, 0);
     tc_fence_after();
-    float *rec = partials + ((int64_t)blockIdx.x * 128 + warp * 32 + lane) * n_cols;
+    // Every MMA has retired: the operand ring is free and serves as the staging block of the stores (one
+    // [32][32 + 4] block per warp), so that a store instruction writes four full 128-byte lines of the partial
+    // instead of 32 separate 16-byte pieces (a thread owns one ROW of the accumulator).
+    float *stg = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw))) + warp * 32 * TC_EPI_LD;
+    float *rec0 = partials + ((int64_t)blockIdx.x * 128 + warp * 32) * n_cols;
     for (int c = 0; c < n_chunks; ++c) {
       uint32_t r[32];
       tc_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, r);
+      __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        st4(rec + c * 32 + 4 * q, make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                              __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+        st4(stg + lane * TC_EPI_LD + 4 * q, make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), cc = (lane & 7) * 4;
+        st4(rec0 + (int64_t)rr * n_cols + c * 32 + cc, ld4(stg + rr * TC_EPI_LD + cc));
+      }
     }
   }
   pdl_launch_dependents();
