@@ -665,9 +665,9 @@ __global__ void __launch_bounds__(T_THREADS, DEEP ? 3 : 5) k_gat_bwd_src_tiled(S
   float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  auto finish_row = [&](int s, float4 acc, float gs) {
-    const float gt = __ldg(a.dSt + (int64_t)s * 4 + head);
-    const float4 hr = ldg4(a.h + (int64_t)s * kD + lane * 4);
+  // (gt, hr: dSt and the node's own row, loaded by the caller BEFORE its gather loop so that their latency hides
+  // under the gathers instead of adding a second round trip per node)
+  auto finish_row = [&](int s, float4 acc, float gs, float gt, float4 hr) {
     acc.x += gt * at.x + gs * as.x;
     acc.y += gt * at.y + gs * as.y;
     acc.z += gt * at.z + gs * as.z;
@@ -699,7 +699,8 @@ __global__ void __launch_bounds__(T_THREADS, DEEP ? 3 : 5) k_gat_bwd_src_tiled(S
             const float4 v = ldg4(a.dout + (int64_t)__ldg(a.rdst + r) * kD + lane * 4);
             acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y); acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
           }
-          finish_row(n0 + lb, acc, gs);
+          finish_row(n0 + lb, acc, gs, __ldg(a.dSt + (int64_t)(n0 + lb) * 4 + head),
+                     ldg4(a.h + (int64_t)(n0 + lb) * kD + lane * 4));
         }
         ++lb;
         continue;
@@ -737,6 +738,8 @@ __global__ void __launch_bounds__(T_THREADS, DEEP ? 3 : 5) k_gat_bwd_src_tiled(S
       // ---- phase 3: one warp per source node gathers the destination gradients
       for (int n = lb + warp; n < le; n += T_WARPS) {
         const int b = s_rowptr[n] - r0, e = s_rowptr[n + 1] - r0;
+        const float gt = __ldg(a.dSt + (int64_t)(n0 + n) * 4 + head);
+        const float4 hr = ldg4(a.h + (int64_t)(n0 + n) * kD + lane * 4);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int j = b;
         if (DEEP) {
@@ -781,7 +784,7 @@ __global__ void __launch_bounds__(T_THREADS, DEEP ? 3 : 5) k_gat_bwd_src_tiled(S
           acc.z = fmaf(pj, v.z, acc.z);
           acc.w = fmaf(pj, v.w, acc.w);
         }
-        finish_row(n0 + n, acc, s_dSs[(n - lb) * 4 + head]);
+        finish_row(n0 + n, acc, s_dSs[(n - lb) * 4 + head], gt, hr);
       }
       lb = le;
       if (lb < nn) __syncthreads();
