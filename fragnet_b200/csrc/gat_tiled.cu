@@ -650,7 +650,7 @@ struct SrcT {
 };
 
 template <bool DEEP>
-__global__ void __launch_bounds__(T_THREADS, DEEP ? 3 : 5) k_gat_bwd_src_tiled(SrcT a) {
+__global__ void __launch_bounds__(T_THREADS, DEEP ? 3 : 4) k_gat_bwd_src_tiled(SrcT a) {
   __shared__ int s_rowptr[T_NPC + 1];
   constexpr int CAP = DEEP ? 1024 : BWD_CAP;
   __shared__ int s_t[CAP];
