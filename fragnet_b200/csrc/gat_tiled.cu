@@ -199,8 +199,11 @@ __device__ void fwd_hub(const FwdT &a, int t, int beg, int end, const float *coe
 // ~60 edges per node: profiles/r3o_ncu_full_stress.md): 8 row gathers in flight per warp instead of 4 (fewer
 // latency round trips per node; 64 registers, 4 CTAs per SM) and a warp-parallel softmax phase (8 lanes per
 // (node, head) with shuffle reductions instead of one thread walking the whole segment while 3/4 of the CTA waits).
-template <int MODE, bool STAGED, bool DEEP = false>
-__global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : (DEEP ? 4 : 6)) k_gat_fwd_tiled(FwdT a) {
+// WIDE: the same code compiled for 5 CTAs per SM (48 registers, no spills) instead of 6 (40 registers, 12 bytes
+// spilled).  Measured on the bond graph: batch 1 024 (843 tiles = one wave at 6 per SM) 38.6 us at 6 per SM vs 43.5 us
+// at 5; batch 4 096 (3 359 tiles) 127.6 us vs 119.7 us -- so graphs with more tiles than one 6-per-SM wave take WIDE.
+template <int MODE, bool STAGED, bool DEEP = false, bool WIDE = false>
+__global__ void __launch_bounds__(T_THREADS, STAGED ? 2 : (DEEP ? 4 : (WIDE ? 5 : 6))) k_gat_fwd_tiled(FwdT a) {
   extern __shared__ __align__(128) float s_dyn[];   // STAGED: [ROWS_CAP][128] rows of h, then [ROWS_CAP][8] rows of S
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int s_stage[2];
@@ -947,6 +950,9 @@ int launch_fwd(const FwdT &a, bool staged, cudaStream_t stream) {
     k_gat_fwd_tiled<MODE, true><<<tile_grid(a.n_nodes, kRangeTile, 2), T_THREADS, smem, stream>>>(a);
   } else if (a.deep) {
     const cudaError_t le = fnb_launch(k_gat_fwd_tiled<MODE, false, true>, dim3(tile_grid(a.n_nodes, a.npc, 4)), dim3(T_THREADS), 0, stream, a);
+    if (le != cudaSuccess) return (int)le;
+  } else if (((int64_t)a.n_nodes + a.npc - 1) / a.npc > (int64_t)kNumSMs * 6) {
+    const cudaError_t le = fnb_launch(k_gat_fwd_tiled<MODE, false, false, true>, dim3(tile_grid(a.n_nodes, a.npc, 5)), dim3(T_THREADS), 0, stream, a);
     if (le != cudaSuccess) return (int)le;
   } else {
     const cudaError_t le = fnb_launch(k_gat_fwd_tiled<MODE, false>, dim3(tile_grid(a.n_nodes, a.npc, 6)), dim3(T_THREADS), 0, stream, a);
