@@ -40,6 +40,13 @@ def test_arena_batches_equal_host_collate(pretrain):
         _same(got, host(picked))
         _same(got, collate_oracle.collate(picked, pretrain=pretrain))
     assert int(arena._status.item()) == 0
+    # validity contract: a batch lives in one of SLOTS persistent device slots and survives SLOTS - 1 further batches
+    first = arena.batch(cases[1])
+    for _ in range(MoleculeArena.SLOTS - 1):
+        arena.batch(cases[0])
+    _same(first, host([ds[int(i)] for i in cases[1]]))
+    again = arena.batch(cases[2])
+    assert again["x_atoms"].data_ptr() == first["x_atoms"].data_ptr()      # the slot is reused from here on
 
 
 def test_arena_ragged_and_empty():
