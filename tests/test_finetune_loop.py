@@ -60,3 +60,17 @@ def test_train_regr_epoch_equals_the_reference_loop():
     mse, t, p = tr.test(m1, val, "cuda")
     assert abs(v * len(val.dataset) - mse) <= 1e-5 * max(1.0, mse) and t.shape == p.shape == (8,)
     assert test_fn(val, m1, "cuda")[0] == mse
+
+
+def test_error_behaviour_without_a_gpu():
+    """The product path has no CPU fallback: host-side entry points fail loudly instead of computing on the CPU."""
+    from fragnet.train.utils import TrainerFineTune
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.arena import MoleculeArena
+    from fragnet_b200.dataset.prefetch import DevicePrefetcher
+    with pytest.raises(NotImplementedError):
+        TrainerFineTune(target_type="clsf_ms")
+    with pytest.raises(ValueError):
+        MoleculeArena(synth.make_dataset("esol", 2, seed=0), "cpu")
+    with pytest.raises(ValueError):
+        DevicePrefetcher([], "cpu")
