@@ -25,18 +25,14 @@ class EarlyStopping:
 
     def __call__(self, val_loss, model):
         score = -val_loss
-        if self.best_score is None:
-            self.best_score = score
+        improved = self.best_score is None or score >= self.best_score + self.delta
+        if improved:
+            self.best_score, self.counter = score, 0
             self.save_checkpoint(val_loss, model)
-        elif score < self.best_score + self.delta:
-            self.counter += 1
-            print(f"EarlyStopping counter: {self.counter} out of {self.patience}")
-            if self.counter >= self.patience:
-                self.early_stop = True
-        else:
-            self.best_score = score
-            self.save_checkpoint(val_loss, model)
-            self.counter = 0
+            return
+        self.counter += 1
+        print(f"EarlyStopping counter: {self.counter} out of {self.patience}")
+        self.early_stop = self.counter >= self.patience
 
     def save_checkpoint(self, val_loss, model):
         if self.verbose:
@@ -97,29 +93,32 @@ class TrainerFineTune:
         else:
             raise NotImplementedError(f"target_type {target_type!r}: only 'regr' and 'clsf' drive the gat2 path here")
 
+    # ---- one pass over a loader: per-batch losses summed on the device, read back once
+    def _epoch(self, model, loader, device, loss_of, optimizer=None):
+        total = torch.zeros((), dtype=torch.float64, device=device)
+        for batch in _batches(loader, device, model):
+            if optimizer is not None:
+                optimizer.zero_grad()
+            loss = loss_of(batch)
+            if optimizer is not None:
+                loss.backward()
+                optimizer.step()
+            total += loss.detach().double()
+        return float(total) / len(loader.dataset)
+
     # ---- regression (utils.py:330-385)
     def train_regr(self, model, loader, optimizer, scheduler, device, val_loader):
         model.train()
-        total = None
-        for batch in _batches(loader, device, model):
-            optimizer.zero_grad()
-            loss = self.loss_fn(model(batch).view(-1), batch["y"])
-            loss.backward()
-            total = loss.detach().double() if total is None else total + loss.detach().double()
-            optimizer.step()
+        mean = self._epoch(model, loader, device, lambda b: self.loss_fn(model(b).view(-1), b["y"]), optimizer)
         if scheduler:
             self.validate(model, val_loader, device)
             scheduler.step()
-        return (float(total) if total is not None else 0.0) / len(loader.dataset)
+        return mean
 
     def validate_regr(self, model, loader, device):
         model.eval()
-        total = None
         with torch.no_grad():
-            for batch in _batches(loader, device, model):
-                loss = self.loss_fn(model(batch).view(-1), batch["y"]).double()
-                total = loss if total is None else total + loss
-        return (float(total) if total is not None else 0.0) / len(loader.dataset)
+            return self._epoch(model, loader, device, lambda b: self.loss_fn(model(b).view(-1), b["y"]))
 
     def test_regr(self, model, loader, device):
         return test_fn(loader, model, device)
@@ -133,16 +132,10 @@ class TrainerFineTune:
 
     def train_clsf_bce(self, model, loader, optimizer, scheduler, device, val_loader):
         model.train()
-        total = None
-        for batch in _batches(loader, device, model):
-            loss = self._bce(model(batch), batch["y"])
-            optimizer.zero_grad()
-            loss.backward()
-            total = loss.detach().double() if total is None else total + loss.detach().double()
-            optimizer.step()
+        mean = self._epoch(model, loader, device, lambda b: self._bce(model(b), b["y"]), optimizer)
         if scheduler:
             scheduler.step(self.validate(model, val_loader, device))
-        return (float(total) if total is not None else 0.0) / len(loader.dataset)
+        return mean
 
     def _scores(self, model, loader, device):
         model.eval()
