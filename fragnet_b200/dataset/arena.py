@@ -255,21 +255,47 @@ class MoleculeArena:
         return out
 
 
+def epoch_batches(n: int, batch_size: int, shuffle: bool = False, drop_last: bool = False,
+                  generator: Optional[torch.Generator] = None, rank: int = 0, world: int = 1):
+    """Molecule ids of every batch of one epoch for this rank (host-side, no device work).
+
+    ``world == 1``: the batches of ``DataLoader(dataset, batch_size, shuffle, drop_last)``.  ``world > 1`` (SURVEY.md
+    section 8(e): molecules are independent, rank ``r`` takes a contiguous share of every step): the epoch is cut into
+    global batches of ``batch_size * world`` molecules (``batch_size`` = per-GPU batch, BASELINE configs[3]) and rank
+    ``r`` gets slice ``[r * batch_size, (r + 1) * batch_size)`` of each; every rank must pass a generator in the same
+    state so that the shuffles agree.  All ranks get the same NUMBER of batches (a ragged tail is split evenly; with
+    ``drop_last`` the incomplete global batch is dropped), so the gradient all-reduce never waits for a missing step."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("rank / world")
+    order = torch.randperm(n, generator=generator).numpy() if shuffle else np.arange(n, dtype=np.int64)
+    gb = batch_size * world
+    out = []
+    for start in range(0, n, gb):
+        chunk = order[start:start + gb]
+        if len(chunk) < gb:
+            if drop_last or len(chunk) < world:
+                break
+            per = len(chunk) // world             # ragged tail: equal shares, the remainder (< world) is dropped
+            out.append(chunk[rank * per:(rank + 1) * per])
+        else:
+            out.append(chunk[rank * batch_size:(rank + 1) * batch_size])
+    return out
+
+
 class ArenaLoader:
     """``DataLoader(dataset, batch_size, shuffle, drop_last, collate_fn=collate_fn_pt)`` over a ``MoleculeArena``:
-    iterates device-resident batch dicts (reference loops: pretrain_gat2.py:140-147, pretrain_utils.py:12-14)."""
+    iterates device-resident batch dicts (reference loops: pretrain_gat2.py:140-147, pretrain_utils.py:12-14).
+    ``rank`` / ``world`` shard every step over the data-parallel ranks (``epoch_batches``)."""
 
     def __init__(self, arena: MoleculeArena, batch_size: int, shuffle: bool = False, drop_last: bool = False,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, rank: int = 0, world: int = 1):
         self.arena, self.batch_size, self.shuffle, self.drop_last = arena, int(batch_size), shuffle, drop_last
-        self.generator = generator
+        self.generator, self.rank, self.world = generator, int(rank), int(world)
 
     def __len__(self) -> int:
-        n = len(self.arena)
-        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+        return len(epoch_batches(len(self.arena), self.batch_size, False, self.drop_last, None, self.rank, self.world))
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
-        n = len(self.arena)
-        order = torch.randperm(n, generator=self.generator).numpy() if self.shuffle else np.arange(n, dtype=np.int64)
-        for b in range(len(self)):
-            yield self.arena.batch(order[b * self.batch_size:(b + 1) * self.batch_size])
+        for ids in epoch_batches(len(self.arena), self.batch_size, self.shuffle, self.drop_last, self.generator,
+                                 self.rank, self.world):
+            yield self.arena.batch(ids)

@@ -2,6 +2,8 @@
 import os
 import socket
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -60,3 +62,27 @@ def test_flat_grad_sync_equals_mean_of_rank_grads(tmp_path):
     for k in want:
         assert torch.allclose(got[k], want[k] / 2, atol=1e-6), k
     assert got["dead.weight"] is None and got["dead.bias"] is None
+
+
+def test_epoch_batches_shard_every_step_over_the_ranks():
+    """Host-side batch schedule of ArenaLoader: world 1 = DataLoader semantics; world W = disjoint equal slices of
+    every global batch, the same number of steps on every rank, identical shuffles from identical generators."""
+    import numpy as np
+    from fragnet_b200.dataset.arena import epoch_batches
+    n, bs = 103, 8
+    one = epoch_batches(n, bs)
+    assert [len(b) for b in one] == [8] * 12 + [7] and np.array_equal(np.concatenate(one), np.arange(n))
+    assert len(epoch_batches(n, bs, drop_last=True)) == 12
+    for drop in (False, True):
+        per_rank = [epoch_batches(n, bs, shuffle=True, drop_last=drop, generator=torch.Generator().manual_seed(5),
+                                  rank=r, world=4) for r in range(4)]
+        steps = {len(b) for b in per_rank}
+        assert len(steps) == 1                                   # every rank runs the same number of steps
+        for step in range(steps.pop()):
+            sizes = {len(per_rank[r][step]) for r in range(4)}
+            assert len(sizes) == 1                               # ... with equal shares
+        seen = np.concatenate([np.concatenate(b) for b in per_rank])
+        assert len(np.unique(seen)) == len(seen)                 # disjoint
+        assert len(seen) == (96 if drop else 100)                # 3 global batches of 32 (+ 4 x 1 of the tail of 7)
+    with pytest.raises(ValueError):
+        epoch_batches(10, 2, rank=2, world=2)
