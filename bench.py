@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--shape", default="unimol", choices=["esol", "unimol", "stress"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct batches cycled through")
     ap.add_argument("--pool", type=int, default=512, help="distinct synthetic molecules generated")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp32_simt"],
                     help="arithmetic of the dense projections (everything else is fp32)")
     ap.add_argument("--autograd", action="store_true",
                     help="drive the step through nn.Module / autograd / FlatAdam instead of the one-call fused step")
@@ -268,7 +268,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="tf32", rank=0, world=1, dev=None,
+def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="fp32", rank=0, world=1, dev=None,
               return_host=False, autograd_path=False):
     """The timed unit: ``step(batch_dict)`` = on-device collate + forward + loss + backward + gradient all-reduce
     (world > 1) + Adam on one batch.  Returns (step, device batches[, pinned host batches])."""
@@ -489,7 +489,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": round(value, 1), "unit": "molecules/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.precision == "fp32" else "f32 (tf32-in/f32-acc tensor-core projections)",
+                "dtype": {"fp32": "f32 (3xTF32 split tensor-core projections, f32-grade)", "fp32_simt": "f32",
+                          "tf32": "f32 (tf32-in/f32-acc tensor-core projections)"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.shape),
                            "per_gpu_batch": args.batch, "global_batch": args.batch * world,

@@ -102,7 +102,7 @@ ARENA_COPY32, ARENA_INDEX, ARENA_FILL = 0, 1, 2
 ARENA_MAX_KINDS, ARENA_MAX_JOBS = 24, 32
 ABI_VERSION = 6
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
-PRECISION_FP32, PRECISION_TF32 = 0, 1
+PRECISION_FP32, PRECISION_TF32, PRECISION_TF32X3 = 0, 1, 2
 
 _lib = None
 

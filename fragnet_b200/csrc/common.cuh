@@ -312,8 +312,9 @@ int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb
                                     int skip_tails);
 
 // Tensor-core (tcgen05, TF32) projection path, tc_gemm.cu.  Returns FNB_ERR_MODE when the shape cannot use TMA.
+// x3 != 0: 3xTF32 (error-compensated, FP32-grade) instead of one TF32 product.
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
-                       int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream);
+                       int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream, int x3);
 int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream);
 // Up to 16 [128,128] matrices transposed by one launch: Wt_base + i * 128 * 128 = Ws[i]^T.
 struct TransposeBatch { const float *W[16]; int count; };
@@ -325,4 +326,7 @@ int fnb_proj_bwd_dx(const float *W, const float *Wt_pre, const float *dh, int64_
 int fnb_proj_bwd_dw(const float *x, const float *dh, int64_t n_rows, int K, float *dW, float *db, int precision,
                     void *scratch, void *stream);
 int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols, int k_out, float *dW, float *scratch,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int x3);
+static inline bool fnb_tc_precision(int precision) {
+  return precision == FNB_PRECISION_TF32 || precision == FNB_PRECISION_TF32X3;
+}

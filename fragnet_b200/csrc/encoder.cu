@@ -59,7 +59,7 @@ bool input_dropout(const fnb_encoder_opts *o) { return o->post_act && o->trainin
 // multiple of the 32-column K block of the tensor-core kernels: in TF32 mode the inputs and weights are zero-padded
 // once per pass to the next multiple of 32 columns and take the same tcgen05 kernels as every other layer.
 int pad_width(const fnb_encoder_opts *o, int K) {
-  if (o->precision != FNB_PRECISION_TF32 || (K & 31) == 0 || K > 224) return 0;
+  if (!fnb_tc_precision(o->precision) || (K & 31) == 0 || K > 224) return 0;
   return (K + 31) & ~31;
 }
 
@@ -474,7 +474,8 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
   const Sizes z = sizes_of(plan);
   cudaStream_t stream = (cudaStream_t)stream_;
   const float scale = (o->post_act && o->training && o->drop_p > 0.f) ? 1.f / (1.f - o->drop_p) : 1.f;
-  const bool tf32 = o->precision == FNB_PRECISION_TF32;
+  const bool tf32 = fnb_tc_precision(o->precision);
+  const int x3 = o->precision == FNB_PRECISION_TF32X3;
 
   // W^T of every K = 128 projection in one launch per 16 matrices (used by the tensor-core dX GEMMs)
   int wt_slot[16][3];
@@ -616,7 +617,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         RC(fnb_gat_bwd_tiled_fused(&plan->fbond, &a, &fz, nullptr, nullptr, sB_));
         float *dx = need_dx ? W.dx_fbond : (o->need_dx_fbond ? io->dx_fbond : nullptr);
         if (l == 0 && b.k_pad[2] && !dx)
-          RC(fnb_tc_dw_launch(W.dh_fb, b.x_pad[2], z.Nfb, b.k_pad[2], P.K_fbond, D.Wfb, scratch_body(scratchB), sB));
+          RC(fnb_tc_dw_launch(W.dh_fb, b.x_pad[2], z.Nfb, b.k_pad[2], P.K_fbond, D.Wfb, scratch_body(scratchB), sB, x3));
         else
           RC(fnb_proj_bwd_impl(xfb, P.Wfb, wt_of(l, 2), W.dh_fb, z.Nfb, P.K_fbond, dx, D.Wfb, nullptr, o->precision,
                                scratchB, sB_));
@@ -660,7 +661,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         RC(w_begin(0, sA));
         float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);
         if (l == 0 && b.k_pad[1] && !dx) {
-          RC(fnb_tc_dw_launch(dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchW), sW));
+          RC(fnb_tc_dw_launch(dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchW), sW, x3));
         } else {
           RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), dh_a, z.Na, P.K_atom, dx, o->precision, scratchA, sA_));
           RC(fnb_proj_bwd_dw(xa, dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchW, sW_));
@@ -700,7 +701,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         RC(w_begin(1, stream));
         float *dx = need_dx ? W.dx_bond : (o->need_dx_bond ? io->dx_bond : nullptr);
         if (l == 0 && b.k_pad[0] && !dx) {
-          RC(fnb_tc_dw_launch(dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchW), sW));
+          RC(fnb_tc_dw_launch(dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchW), sW, x3));
         } else {
           RC(fnb_proj_bwd_dx(P.Wb, wt_of(l, 0), dh_b, z.Nb, P.K_bond, dx, o->precision, scratch, stream_));
           RC(fnb_proj_bwd_dw(xb, dh_b, z.Nb, P.K_bond, D.Wb, nullptr, o->precision, scratchW, sW_));

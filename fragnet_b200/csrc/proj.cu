@@ -331,9 +331,9 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
   if (!x || !W || !h) return FNB_ERR_NULL;
   if (S && !alpha) return FNB_ERR_NULL;
   if (!fnb_aligned16(h)) return FNB_ERR_ALIGN;
-  if (precision == FNB_PRECISION_TF32) {
+  if (fnb_tc_precision(precision)) {
     const int rc = fnb_tc_proj_launch(x, W, b, n_rows, K, S ? alpha : nullptr, alpha_stride, off_t, off_s, h, S,
-                                      (cudaStream_t)stream);
+                                      (cudaStream_t)stream, precision == FNB_PRECISION_TF32X3);
     if (rc != FNB_ERR_MODE) return rc;   // shapes TMA cannot address (K*4 % 16 != 0) take the SIMT kernel below
   } else if (precision != FNB_PRECISION_FP32) {
     return FNB_ERR_MODE;
@@ -381,7 +381,7 @@ int fnb_proj_bwd_dx(const float *W, const float *Wt_pre, const float *dh, int64_
   if (!dx || n_rows == 0) return 0;
   if (!W || !dh) return FNB_ERR_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (precision == FNB_PRECISION_TF32 && K == kD) {
+  if (fnb_tc_precision(precision) && K == kD) {
     // dx = dh @ W as the forward tensor-core kernel with B = W^T
     const float *Wt = Wt_pre;
     int rc = 0;
@@ -391,7 +391,8 @@ int fnb_proj_bwd_dx(const float *W, const float *Wt_pre, const float *dh, int64_
       if (rc) return rc;
       Wt = scratch_body(scratch);
     }
-    rc = fnb_tc_proj_launch(dh, Wt, nullptr, n_rows, kD, nullptr, 0, 0, 0, dx, nullptr, stream);
+    rc = fnb_tc_proj_launch(dh, Wt, nullptr, n_rows, kD, nullptr, 0, 0, 0, dx, nullptr, stream,
+                            precision == FNB_PRECISION_TF32X3);
     if (rc != FNB_ERR_MODE) return rc;
   }
   GemmArgs g;
@@ -408,9 +409,10 @@ int fnb_proj_bwd_dw(const float *x, const float *dh, int64_t n_rows, int K, floa
   if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
   if (!x || !dh || !dW || !scratch) return FNB_ERR_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (precision == FNB_PRECISION_TF32 && (K & 31) == 0 && K <= 256 && n_rows > 0 && !db) {
+  if (fnb_tc_precision(precision) && (K & 31) == 0 && K <= 256 && n_rows > 0 && !db) {
     // tensor-core path for every TMA-addressable width (K = 128: the attention projections; K = 256: the energy head)
-    const int rc = fnb_tc_dw_launch(dh, x, n_rows, K, K, dW, scratch_body(scratch), stream);
+    const int rc = fnb_tc_dw_launch(dh, x, n_rows, K, K, dW, scratch_body(scratch), stream,
+                                    precision == FNB_PRECISION_TF32X3);
     if (rc != FNB_ERR_MODE) return rc;
   }
   int64_t nb = (n_rows + 255) / 256;
@@ -436,7 +438,7 @@ int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const
                       float *dx, float *dW, float *db, int precision, void *scratch, void *stream_) {
   if (n_rows < 0 || K <= 0 || K > kProjBwdMaxK) return FNB_ERR_SIZE;
   if (!x || !W || !dh || !dW || !scratch) return FNB_ERR_NULL;
-  if (precision != FNB_PRECISION_FP32 && precision != FNB_PRECISION_TF32) return FNB_ERR_MODE;
+  if (precision != FNB_PRECISION_FP32 && !fnb_tc_precision(precision)) return FNB_ERR_MODE;
   const int rc = fnb_proj_bwd_dx(W, Wt_pre, dh, n_rows, K, dx, precision, scratch, stream_);
   if (rc) return rc;
   return fnb_proj_bwd_dw(x, dh, n_rows, K, dW, db, precision, scratch, stream_);

@@ -18,6 +18,8 @@
 // north star allows for the projections; the strict-FP32 path (proj.cu) remains the parity reference.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -111,6 +113,57 @@ __device__ __forceinline__ uint64_t make_desc_sw128_kmajor(uint32_t saddr) {
 // Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128.
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
 
+// ---- 3xTF32 (error-compensated TF32) ---------------------------------------------------------------------------------
+// The 1e-5 parity mode cannot use one TF32 product (10-bit mantissas: ~1e-3), and the FP32 FFMA GEMMs (proj.cu) cost
+// 8x the tensor-core kernels (132 us vs 16 us per bond-graph projection).  Both operands are therefore split on chip,
+//   x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)      (x - hi is exact in FP32; |lo| <= 2^-11 |x|)
+// and the product is accumulated as  A_hi W_hi + A_hi W_lo + A_lo W_hi  in the same FP32 TMEM accumulator (the
+// dropped lo*lo term is <= 2^-22 relative).  The GEMMs are HBM-bound, so three MMAs per K-step are free; what has to
+// be paid for is shared memory (every operand block exists twice) and a converter stage between TMA and the MMA
+// issuer: four extra warps wait for a landed block, rewrite it in place as hi, write lo next to it, make the writes
+// visible to the async proxy (fence.proxy.async) and arrive on the barrier the MMA warp waits for.
+// Round-to-nearest (ties away) to TF32 as two integer instructions: add half an ulp of the 10-bit mantissa, clear the
+// 13 low bits (cvt.rna.tf32.f32 compiles to the same plus an isfinite test; Inf / NaN stay Inf / NaN here as well).
+__device__ __forceinline__ float rna_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+// lo = x - hi is exact in FP32 and has at most 13 significant bits; the MMA reads its 11 leading ones (a residual of
+// <= 2^-21 |x|, the same order as the dropped lo*lo term), so it is stored as is.
+__device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo) {
+  hi = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+  lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+}
+// Splits `bytes` (multiple of 16) at shared-memory pointer `src` in place; lo goes to `src + lo_off`.
+__device__ __forceinline__ void split_block(uint8_t *src, uint32_t bytes, uint32_t lo_off, int tid, int nthreads) {
+  const uint32_t step = (uint32_t)nthreads * 16u;
+  uint32_t o = (uint32_t)tid * 16u;
+  for (; o + step < bytes; o += 2 * step) {   // two independent 16-byte pieces per iteration
+    const float4 v0 = *reinterpret_cast<const float4 *>(src + o);
+    const float4 v1 = *reinterpret_cast<const float4 *>(src + o + step);
+    float4 h0, l0, h1, l1;
+    split4(v0, h0, l0);
+    split4(v1, h1, l1);
+    *reinterpret_cast<float4 *>(src + o) = h0;
+    *reinterpret_cast<float4 *>(src + o + lo_off) = l0;
+    *reinterpret_cast<float4 *>(src + o + step) = h1;
+    *reinterpret_cast<float4 *>(src + o + step + lo_off) = l1;
+  }
+  if (o < bytes) {
+    float4 hi, lo;
+    split4(*reinterpret_cast<const float4 *>(src + o), hi, lo);
+    *reinterpret_cast<float4 *>(src + o) = hi;
+    *reinterpret_cast<float4 *>(src + o + lo_off) = lo;
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int X3_CONV_THREADS = 256;                       // converter warps 6..13
+constexpr int X3_THREADS = 192 + X3_CONV_THREADS;
+constexpr int X3_BN = 64;                                  // output columns per CTA (two CTAs share a row tile)
+constexpr int X3_W_BYTES = X3_BN * TC_BK * 4;              // 8 KiB per 64x32 K-block of W
+constexpr int X3_MAX_STAGES = 4;
+constexpr uint32_t kIdescTf32N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((X3_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+
 struct TcArgs {
   float *C;             // [M,128]
   const float *bias;    // [128] or NULL
@@ -120,6 +173,7 @@ struct TcArgs {
   int64_t M;
   int n_kb;             // K-blocks of 32
   int n_stages;         // depth of the A ring (<= TC_STAGES; fewer for K = 256 so that W + ring + staging fit)
+  int dbg;              // FNB_X3_DBG experiments (k_tc_proj3): 1 = converters only signal, 2 = hi*hi only, 4 = no stores
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -277,6 +331,429 @@ k_tc_proj(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3xTF32 version of k_tc_proj (the 1e-5 parity mode).  hi and lo of W and of every A block double the shared memory
+// per byte in flight, so a CTA owns HALF of the output columns (64 = two heads): W_hi + W_lo of its half are 64 KiB
+// (K = 128) and leave room for a 4-deep ring of [A_hi | A_lo] blocks.  The two CTAs of a pair (blockIdx.x = 2 pair +
+// half) walk the same row tiles at the same time, so the second read of an A block is an L2 hit and HBM traffic is
+// unchanged.  Warp roles: 0-3 epilogue, 4 TMA producer, 5 MMA issuer, 6-9 converters.
+__global__ void __launch_bounds__(X3_THREADS, 1)
+k_tc_proj3(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * X3_MAX_STAGES + 2 + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[X3_BN], s_at[X3_BN], s_as[X3_BN];
+  __shared__ __align__(16) float s_stage[4][32 * TC_EPI_LD];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = blockIdx.x & 1;                  // which 64 output columns
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  uint8_t *smem_al = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  const uint32_t smem_base = smem_u32(smem_al);
+  const uint32_t w_bytes = (uint32_t)g.n_kb * X3_W_BYTES;
+  const uint32_t smem_w = smem_base;                         // [W_hi | W_lo]
+  const uint32_t smem_a = smem_base + 2 * w_bytes;           // ring of [A_hi 16 KiB | A_lo 16 KiB]
+  constexpr uint32_t kStage = 2 * TC_STAGE_BYTES;
+  const uint32_t bar_full = smem_u32(&bars[0]);                          // [S] TMA -> converters
+  const uint32_t bar_conv = smem_u32(&bars[X3_MAX_STAGES]);              // [S] converters -> MMA
+  const uint32_t bar_empty = smem_u32(&bars[2 * X3_MAX_STAGES]);         // [S] MMA -> TMA
+  const uint32_t bar_w = smem_u32(&bars[3 * X3_MAX_STAGES]);
+  const uint32_t bar_wconv = smem_u32(&bars[3 * X3_MAX_STAGES + 1]);
+  const uint32_t bar_acc_full = smem_u32(&bars[3 * X3_MAX_STAGES + 2]);  // [2]
+  const uint32_t bar_acc_empty = smem_u32(&bars[3 * X3_MAX_STAGES + 4]); // [2]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < X3_MAX_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, X3_CONV_THREADS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_w, 1);
+    mbar_init(bar_wconv, X3_CONV_THREADS);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(2 * X3_BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();
+  for (int i = threadIdx.x; i < X3_BN; i += X3_THREADS) {
+    const int col = half * X3_BN + i, hh = col >> 5, j = col & 31;
+    s_bias[i] = g.bias ? g.bias[col] : 0.f;
+    s_at[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_t + j] : 0.f;
+    s_as[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_s + j] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int64_t n_tiles = (g.M + TC_BM - 1) / TC_BM;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, w_bytes);
+      for (int kb = 0; kb < g.n_kb; ++kb) tma_load_2d(smem_w + kb * X3_W_BYTES, &tm_b, bar_w, kb * TC_BK, half * X3_BN);
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+          tma_load_2d(smem_a + stage * kStage, &tm_a, bar_full + 8 * stage, kb * TC_BK, (int)(tile * TC_BM));
+          if (++stage == (uint32_t)g.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(bar_wconv, 0);
+      tc_fence_after();
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int64_t tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * X3_BN;
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          mbar_wait(bar_conv + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_a + stage * kStage, a_lo = a_hi + TC_STAGE_BYTES;
+          const uint32_t b_hi = smem_w + kb * X3_W_BYTES, b_lo = b_hi + w_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+            const uint32_t ko = k * UMMA_K * 4;
+            const uint64_t dah = make_desc_sw128_kmajor(a_hi + ko), dal = make_desc_sw128_kmajor(a_lo + ko);
+            const uint64_t dbh = make_desc_sw128_kmajor(b_hi + ko), dbl = make_desc_sw128_kmajor(b_lo + ko);
+            if (g.dbg & 2) {   // experiment: hi*hi only
+              tc_mma_tf32(tmem_d, dah, dbh, kIdescTf32N64, (kb | k) != 0);
+              continue;
+            }
+            tc_mma_tf32(tmem_d, dal, dbh, kIdescTf32N64, (kb | k) != 0);   // small terms first
+            tc_mma_tf32(tmem_d, dah, dbl, kIdescTf32N64, 1);
+            tc_mma_tf32(tmem_d, dah, dbh, kIdescTf32N64, 1);
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == (uint32_t)g.n_stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_acc_full + 8 * acc);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 6) {
+    // ===== converters: hi in place, lo beside it =====
+    const int ct = threadIdx.x - 192;
+    mbar_wait(bar_w, 0);
+    split_block(smem_al, w_bytes, w_bytes, ct, X3_CONV_THREADS);
+    fence_proxy_async_smem();
+    mbar_arrive(bar_wconv);
+    uint8_t *ring = smem_al + 2 * w_bytes;
+    uint32_t stage = 0, phase = 0;
+    for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+      for (int kb = 0; kb < g.n_kb; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        if (!(g.dbg & 1)) split_block(ring + stage * kStage, TC_STAGE_BYTES, TC_STAGE_BYTES, ct, X3_CONV_THREADS);
+        fence_proxy_async_smem();
+        mbar_arrive(bar_conv + 8 * stage);
+        if (++stage == (uint32_t)g.n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..3: this CTA's two heads =====
+    uint32_t it = 0;
+    for (int64_t tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t row0 = tile * TC_BM + warp * 32;
+      const int64_t row = row0 + lane;
+      const bool in = row < g.M;
+      float *stg = s_stage[warp];
+      float st[2], ss[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tc_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * X3_BN + hh * 32, r);
+        float a_t = 0.f, a_s = 0.f;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r[j]) + s_bias[hh * 32 + j];
+          a_t = fmaf(v[j], s_at[hh * 32 + j], a_t);
+          a_s = fmaf(v[j], s_as[hh * 32 + j], a_s);
+        }
+        st[hh] = a_t;
+        ss[hh] = a_s;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st4(stg + lane * TC_EPI_LD + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), cc = (lane & 7) * 4;
+          if (row0 + rr < g.M && !(g.dbg & 4))
+            st4(g.C + (row0 + rr) * TC_BN + half * X3_BN + hh * 32 + cc, ld4(stg + rr * TC_EPI_LD + cc));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * acc);
+      if (in && g.S) {
+        *reinterpret_cast<float2 *>(g.S + row * 8 + half * 2) = make_float2(st[0], st[1]);
+        *reinterpret_cast<float2 *>(g.S + row * 8 + 4 + half * 2) = make_float2(ss[0], ss[1]);
+      }
+    }
+  }
+
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * X3_BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3xTF32, K <= 128: full-width version (one CTA per row tile, no pairs).  Measured on the pair kernel above
+// (gpurun_out/r4c: FNB_X3_DBG experiments at 215 k rows): the three N = 64 MMAs per K-step cost as much tensor time as
+// three N = 128 ones (~65 clocks each), converting every A block in both CTAs of a pair doubles that work, and only
+// 32 KB of distinct A bytes per SM are in flight.  Here
+//   * W lives in shared memory as [W_hi (128 rows) ; W_lo (128 rows)] per K-block, so ONE MMA with N = 256 yields
+//     A_hi W_hi^T (accumulator columns 0-127) and A_hi W_lo^T (columns 128-255), and a second one with N = 128 adds
+//     A_lo W_hi^T to columns 0-127: two instructions per K-step instead of six per pair; the epilogue adds the halves;
+//   * A never lands in shared memory raw: the eight converter warps load it from global memory into REGISTERS
+//     (16 bytes per thread and piece, two K-blocks per group ahead), split it there and store hi / lo straight into
+//     the 128-byte-swizzled operand slots -- the slots only decouple conversion from the MMAs, so two of them are
+//     enough and W_hi + W_lo (128 KB) fit beside them.
+// Both accumulator buffers together are the whole TMEM (2 x 256 columns).
+constexpr int X3R_SLOTS = 2;
+constexpr uint32_t kIdescTf32N256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((TC_BM >> 4) << 24);
+
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int X3R_DEPTH>
+__global__ void __launch_bounds__(X3_THREADS, 1)
+k_tc_proj3r(const float *__restrict__ A, int lda, const __grid_constant__ CUtensorMap tm_b, TcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * X3R_SLOTS + 2 + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[128], s_at[128], s_as[128];
+  __shared__ __align__(16) float s_stage[4][32 * TC_EPI_LD];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *smem_al = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  const uint32_t smem_base = smem_u32(smem_al);
+  constexpr uint32_t kWBlock = 2 * TC_STAGE_BYTES;             // [W_hi 16 KiB | W_lo 16 KiB] per K-block
+  constexpr uint32_t kSlot = 2 * TC_STAGE_BYTES;               // [A_hi | A_lo]
+  const uint32_t smem_w = smem_base;
+  const uint32_t w_total = (uint32_t)g.n_kb * kWBlock;
+  const uint32_t smem_a = smem_base + w_total;
+  const uint32_t bar_conv = smem_u32(&bars[0]);                          // [SLOTS] converters -> MMA
+  const uint32_t bar_empty = smem_u32(&bars[X3R_SLOTS]);                 // [SLOTS] MMA -> converters
+  const uint32_t bar_w = smem_u32(&bars[2 * X3R_SLOTS]);
+  const uint32_t bar_wconv = smem_u32(&bars[2 * X3R_SLOTS + 1]);
+  const uint32_t bar_acc_full = smem_u32(&bars[2 * X3R_SLOTS + 2]);      // [2]
+  const uint32_t bar_acc_empty = smem_u32(&bars[2 * X3R_SLOTS + 4]);     // [2]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < X3R_SLOTS; ++s) {
+      mbar_init(bar_conv + 8 * s, X3_CONV_THREADS / X3R_SLOTS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_w, 1);
+    mbar_init(bar_wconv, X3_CONV_THREADS);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();
+  for (int i = threadIdx.x; i < 128; i += X3_THREADS) {
+    const int hh = i >> 5, j = i & 31;
+    s_bias[i] = g.bias ? g.bias[i] : 0.f;
+    s_at[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_t + j] : 0.f;
+    s_as[i] = g.alpha ? g.alpha[hh * g.alpha_stride + g.off_s + j] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int64_t n_tiles = (g.M + TC_BM - 1) / TC_BM;
+
+  if (warp == 4) {
+    // ===== W loader (TMA): W_hi part of every K-block =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, (uint32_t)g.n_kb * TC_STAGE_BYTES);
+      for (int kb = 0; kb < g.n_kb; ++kb) tma_load_2d(smem_w + kb * kWBlock, &tm_b, bar_w, kb * TC_BK, 0);
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(bar_wconv, 0);
+      tc_fence_after();
+      uint32_t slot = 0, phase = 0;
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          mbar_wait(bar_conv + 8 * slot, phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_a + slot * kSlot, a_lo = a_hi + TC_STAGE_BYTES;
+          const uint32_t b = smem_w + kb * kWBlock;
+#pragma unroll
+          for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+            const uint32_t ko = k * UMMA_K * 4;
+            const uint64_t db = make_desc_sw128_kmajor(b + ko);
+            tc_mma_tf32(tmem_d, make_desc_sw128_kmajor(a_hi + ko), db, kIdescTf32N256, (kb | k) != 0);
+            tc_mma_tf32(tmem_d, make_desc_sw128_kmajor(a_lo + ko), db, kIdescTf32, 1);
+          }
+          tc_commit(bar_empty + 8 * slot);
+          if (++slot == X3R_SLOTS) { slot = 0; phase ^= 1; }
+        }
+        tc_commit(bar_acc_full + 8 * acc);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 6) {
+    // ===== converters: global -> registers -> (hi, lo) -> swizzled operand slots =====
+    const int ct = threadIdx.x - 192;
+    mbar_wait(bar_w, 0);
+    for (int kb = 0; kb < g.n_kb; ++kb)
+      split_block(smem_al + kb * kWBlock, TC_STAGE_BYTES, TC_STAGE_BYTES, ct, X3_CONV_THREADS);
+    fence_proxy_async_smem();
+    mbar_arrive(bar_wconv);
+    // Two groups of four warps, group = operand slot: group s converts K-blocks s, s + 2, ... of this CTA's (tile, kb)
+    // sequence.  fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, i.e. it also waits for the thread's
+    // outstanding global loads: with all eight warps on every block the prefetched loads of the next blocks were
+    // awaited at every fence and the tiles serialised on DRAM latency (r4d ncu: 22.7 us for 3 tiles per CTA, prefetch
+    // depth without effect).  Here the only loads a thread has in flight at its fence are those of its group's next
+    // block, issued a full group period (two block times) earlier.
+    // piece i of a K-block: row = i * 16 + gt / 8, 16-byte chunk c = gt % 8 (a warp reads four full 128-byte lines)
+    const int grp = ct >> 7, gt = ct & 127;
+    const int prow = gt >> 3, pc = gt & 7;
+    const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_blocks = my_tiles * g.n_kb;          // K-blocks of this CTA, in (tile, kb) order
+    const int64_t n_own = n_blocks > grp ? (n_blocks - grp + 1) / 2 : 0;
+    float4 buf[2][8];
+    int64_t f_tile = blockIdx.x;   // (tile, K-block) of this group's next fetch
+    int f_kb = grp;
+    while (f_kb >= g.n_kb) { f_kb -= g.n_kb; f_tile += gridDim.x; }
+    auto fetch = [&](float4 (&dst)[8]) {
+      const float *base = A + (f_tile * TC_BM + prow) * (int64_t)lda + f_kb * TC_BK + pc * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = f_tile * TC_BM + prow + i * 16;
+        dst[i] = row < g.M ? ldg_stream4(base + (int64_t)i * 16 * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      f_kb += 2;
+      while (f_kb >= g.n_kb) { f_kb -= g.n_kb; f_tile += gridDim.x; }
+    };
+    if (n_own > 0) fetch(buf[0]);
+    if (n_own > 1) fetch(buf[1]);
+    uint8_t *dst = smem_al + w_total + grp * kSlot;
+    for (int64_t j0 = 0; j0 < n_own; j0 += 2) {
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int64_t j = j0 + d;
+        if (j < n_own) {
+          mbar_wait(bar_empty + 8 * grp, (uint32_t)(j & 1) ^ 1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = prow + i * 16;
+            const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((pc ^ (row & 7)) << 4);
+            float4 hi, lo;
+            split4(buf[d][i], hi, lo);
+            *reinterpret_cast<float4 *>(dst + off) = hi;
+            *reinterpret_cast<float4 *>(dst + off + TC_STAGE_BYTES) = lo;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(bar_conv + 8 * grp);
+          if (j + 2 < n_own) fetch(buf[d]);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..3: (hi*hi + lo*hi) + hi*lo, bias, logit scalars =====
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t row0 = tile * TC_BM + warp * 32;
+      const int64_t row = row0 + lane;
+      const bool in = row < g.M;
+      float *stg = s_stage[warp];
+      float st[4], ss[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        uint32_t r[32], r2[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256 + hh * 32;
+        tc_ld_32x32(taddr, r);
+        tc_ld_32x32(taddr + 128, r2);
+        float a_t = 0.f, a_s = 0.f;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + s_bias[hh * 32 + j];
+          a_t = fmaf(v[j], s_at[hh * 32 + j], a_t);
+          a_s = fmaf(v[j], s_as[hh * 32 + j], a_s);
+        }
+        st[hh] = a_t;
+        ss[hh] = a_s;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st4(stg + lane * TC_EPI_LD + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), cc = (lane & 7) * 4;
+          if (row0 + rr < g.M) st4(g.C + (row0 + rr) * TC_BN + hh * 32 + cc, ld4(stg + rr * TC_EPI_LD + cc));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * acc);
+      if (in && g.S) {
+        st4(g.S + row * 8, make_float4(st[0], st[1], st[2], st[3]));
+        st4(g.S + row * 8 + 4, make_float4(ss[0], ss[1], ss[2], ss[3]));
+      }
+    }
+  }
+
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weight gradient dW[o,i] = sum_n dH[n,o] X[n,i] on the tensor cores.  Both operands are "MN-major" for the MMA
 // (the reduction index n is the slow index of the row-major inputs).  MN-major TF32 operands have exactly one legal
 // shared-memory layout, SWIZZLE_128B_BASE32B (128-byte rows swizzled at 32-byte granularity, atoms of 4 rows), which
@@ -401,6 +878,124 @@ k_tc_dw(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUten
   }
 }
 
+// 3xTF32 version of k_tc_dw: both operands stream, so every stage holds [dH | X] and, behind them, [dH_lo | X_lo];
+// converter warps 6-9 split a landed stage in place, the MMA warp issues lo*hi, hi*lo, hi*hi per K-step of 8 rows.
+__global__ void __launch_bounds__(X3_THREADS, 1)
+k_tc_dw3(const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUtensorMap tm_x, float *partials,
+         int64_t n_row_blocks, int64_t blocks_per_cta, int n_chunks, int n_stages, uint32_t tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * DW_MAX_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *smem_al = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  const uint32_t smem_base = smem_u32(smem_al);
+  const uint32_t half_bytes = TC_STAGE_BYTES + (uint32_t)n_chunks * 4096u;   // dH block + X block
+  const uint32_t stage_bytes = 2 * half_bytes;                               // ... and their lo parts
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_conv = smem_u32(&bars[DW_MAX_STAGES]);
+  const uint32_t bar_empty = smem_u32(&bars[2 * DW_MAX_STAGES]);
+  const uint32_t bar_done = smem_u32(&bars[3 * DW_MAX_STAGES]);
+  const int n_cols = n_chunks * 32;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, X3_CONV_THREADS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int64_t rb_begin = (int64_t)blockIdx.x * blocks_per_cta;
+  const int64_t rb_end = min(n_row_blocks, rb_begin + blocks_per_cta);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t rb = rb_begin; rb < rb_end; ++rb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        mbar_arrive_expect_tx(bar_full + 8 * stage, half_bytes);
+        const uint32_t a_addr = smem_base + stage * stage_bytes, b_addr = a_addr + TC_STAGE_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_2d(a_addr + c * 4096, &tm_dh, bar_full + 8 * stage, c * 32, (int)(rb * 32));
+        for (int c = 0; c < n_chunks; ++c) tma_load_2d(b_addr + c * 4096, &tm_x, bar_full + 8 * stage, c * 32, (int)(rb * 32));
+        if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32_mn(n_cols);
+      uint32_t stage = 0, phase = 0;
+      for (int64_t rb = rb_begin; rb < rb_end; ++rb) {
+        mbar_wait(bar_conv + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + stage * stage_bytes, b_hi = a_hi + TC_STAGE_BYTES;
+        const uint32_t a_lo = a_hi + half_bytes, b_lo = b_hi + half_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dah = make_desc_sw128_mnmajor(a_hi + k * 1024), dal = make_desc_sw128_mnmajor(a_lo + k * 1024);
+          const uint64_t dbh = make_desc_sw128_mnmajor(b_hi + k * 1024), dbl = make_desc_sw128_mnmajor(b_lo + k * 1024);
+          tc_mma_tf32(tmem_base, dal, dbh, idesc, (rb != rb_begin) || (k != 0));
+          tc_mma_tf32(tmem_base, dah, dbl, idesc, 1);
+          tc_mma_tf32(tmem_base, dah, dbh, idesc, 1);
+        }
+        tc_commit(bar_empty + 8 * stage);
+        if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(bar_done);
+    }
+    __syncwarp();
+  } else if (warp >= 6) {
+    const int ct = threadIdx.x - 192;
+    uint32_t stage = 0, phase = 0;
+    for (int64_t rb = rb_begin; rb < rb_end; ++rb) {
+      mbar_wait(bar_full + 8 * stage, phase);
+      split_block(smem_al + stage * stage_bytes, half_bytes, half_bytes, ct, X3_CONV_THREADS);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_conv + 8 * stage);
+      if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    float *stg = reinterpret_cast<float *>(smem_al) + warp * 32 * TC_EPI_LD;
+    float *rec0 = partials + ((int64_t)blockIdx.x * 128 + warp * 32) * n_cols;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t r[32];
+      tc_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, r);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        st4(stg + lane * TC_EPI_LD + 4 * q, make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), cc = (lane & 7) * 4;
+        st4(rec0 + (int64_t)rr * n_cols + c * 32 + cc, ld4(stg + rr * TC_EPI_LD + cc));
+      }
+    }
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // B^T for the input-gradient GEMM: Wt[i, o] = W[o, i] (128 x 128).
 __global__ void k_transpose_128(const float *__restrict__ W, float *__restrict__ Wt) {
   __shared__ float tile[32][33];
@@ -457,7 +1052,7 @@ int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int cols, int box
 // C[M,128] = A[M,K] @ B[128,K]^T (+bias) with optional fused S; returns FNB_ERR_MODE if the shape cannot take the
 // TMA path (K*4 not a multiple of 16 bytes, K > 256, unaligned pointers) so the caller can fall back to proj.cu.
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
-                       int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream) {
+                       int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream, int x3) {
   if (M <= 0) return 0;
   if ((K & 3) || K > TC_MAX_KB * TC_BK || !fnb_aligned16(A) || !fnb_aligned16(B) || !fnb_aligned16(C) ||
       (S && !fnb_aligned16(S)) || M >= (int64_t)INT32_MAX)
@@ -465,11 +1060,59 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
   CUtensorMap tm_a, tm_b;
   int rc = make_map(&tm_a, A, M, K, TC_BM);
   if (rc) return rc;
-  rc = make_map(&tm_b, B, TC_BN, K, TC_BN);
+  rc = make_map(&tm_b, B, TC_BN, K, x3 ? X3_BN : TC_BN);
   if (rc) return rc;
   TcArgs g;
   g.C = C; g.bias = bias; g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s;
   g.S = alpha ? S : nullptr; g.M = M; g.n_kb = (K + TC_BK - 1) / TC_BK;
+  g.dbg = 0;
+  if (x3) {
+    static const int dbg_env = getenv("FNB_X3_DBG") ? atoi(getenv("FNB_X3_DBG")) : 0;
+    g.dbg = dbg_env;
+    // [W_hi | W_lo] of this CTA's 64 columns + ring of [A_hi | A_lo] stages + alignment slack, next to ~20 KB static
+    constexpr size_t kDynMax3 = (size_t)206 * 1024;
+    const size_t w2 = (size_t)2 * g.n_kb * X3_W_BYTES;
+    g.n_stages = X3_MAX_STAGES;
+    while (g.n_stages > 1 && w2 + (size_t)g.n_stages * 2 * TC_STAGE_BYTES + 1024 > kDynMax3) --g.n_stages;
+    const size_t smem3 = w2 + (size_t)g.n_stages * 2 * TC_STAGE_BYTES + 1024;
+    if (smem3 > kDynMax3) return FNB_ERR_MODE;
+    static bool done3[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
+    if (!done3[dev]) {
+      const cudaError_t e = cudaFuncSetAttribute(k_tc_proj3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynMax3);
+      if (e != cudaSuccess) return (int)e;
+      done3[dev] = true;
+    }
+    const int64_t n_tiles3 = (M + TC_BM - 1) / TC_BM;
+    static const bool use_r = !(getenv("FNB_X3_PAIR") && atoi(getenv("FNB_X3_PAIR")));
+    if (use_r && g.n_kb <= 4 && (K & 31) == 0) {   // full-width register-staged kernel
+      constexpr size_t kDynR = (size_t)4 * 2 * TC_STAGE_BYTES + (size_t)X3R_SLOTS * 2 * TC_STAGE_BYTES + 1024;
+      static const int depth = getenv("FNB_X3_DEPTH") ? atoi(getenv("FNB_X3_DEPTH")) : 4;
+      void (*kern)(const float *, int, const CUtensorMap, TcArgs) =
+          depth <= 2 ? k_tc_proj3r<2> : depth == 3 ? k_tc_proj3r<3> : depth == 4 ? k_tc_proj3r<4> : depth == 5 ? k_tc_proj3r<5>
+                                                                                                            : k_tc_proj3r<6>;
+      static bool doneR[64] = {};
+      if (!doneR[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynR);
+        if (e != cudaSuccess) return (int)e;
+        doneR[dev] = true;
+      }
+      const size_t smemR = (size_t)g.n_kb * 2 * TC_STAGE_BYTES + (size_t)X3R_SLOTS * 2 * TC_STAGE_BYTES + 1024;
+      CUtensorMap tm_w;
+      rc = make_map(&tm_w, B, TC_BN, K, TC_BN);
+      if (rc) return rc;
+      const int gridR = (int)(n_tiles3 < kNumSMs ? n_tiles3 : kNumSMs);
+      if (cudaError_t le = fnb_launch(kern, dim3(gridR), dim3(X3_THREADS), smemR, stream, A, K, tm_w, g)) return (int)le;
+      FNB_CHECK_LAUNCH();
+      return 0;
+    }
+    const int pairs = (int)(n_tiles3 < kNumSMs / 2 ? n_tiles3 : kNumSMs / 2);
+    if (cudaError_t le = fnb_launch(k_tc_proj3, dim3(2 * pairs), dim3(X3_THREADS), smem3, stream, tm_a, tm_b, g)) return (int)le;
+    FNB_CHECK_LAUNCH();
+    return 0;
+  }
   // W (n_kb blocks) + the A ring + 1 KB alignment slack must fit next to ~21 KB of static shared memory
   constexpr size_t kDynMax = (size_t)204 * 1024;
   g.n_stages = TC_STAGES;
@@ -510,7 +1153,7 @@ int fnb_tc_transpose128_batched(const TransposeBatch &b, float *Wt_base, cudaStr
 // dW[128, k_out] = dH[n,128]^T @ X[n, x_cols] (TF32), x_cols a multiple of 32 up to 256 (columns >= k_out are padding and
 // are dropped by the second stage).  scratch must hold kNumSMs * 128 * x_cols floats of partials.
 int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols, int k_out, float *dW, float *scratch,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int x3) {
   if (n_rows <= 0 || !fnb_aligned16(dh) || !fnb_aligned16(x) || n_rows >= (int64_t)INT32_MAX || x_cols < 32 ||
       x_cols > 256 || (x_cols & 31) || k_out > x_cols || k_out <= 0)
     return FNB_ERR_MODE;
@@ -521,11 +1164,17 @@ int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols
   if (rc) return rc;
   const int n_chunks = x_cols / 32;
   const int64_t n_rb = (n_rows + 31) / 32;
-  const int64_t per = (n_rb + kNumSMs - 1) / kNumSMs;
+  // Every CTA leaves a 128 x x_cols partial (64 KiB at x_cols = 128) that the second stage reads back: a CTA should
+  // stream at least kDwMinBlocks row blocks (512 rows = 512 KiB of operands) so that the partials stay a small
+  // fraction of the traffic; the GEMM shares the GPU with the gather kernels of the other streams anyway.
+  constexpr int64_t kDwMinBlocks = 16;
+  int64_t per = (n_rb + kNumSMs - 1) / kNumSMs;
+  if (per < kDwMinBlocks) per = kDwMinBlocks;
   const int grid = (int)((n_rb + per - 1) / per);
-  const size_t stage_bytes = (size_t)TC_STAGE_BYTES + (size_t)n_chunks * 4096;
+  const size_t stage_bytes = ((size_t)TC_STAGE_BYTES + (size_t)n_chunks * 4096) * (x3 ? 2 : 1);
   int n_stages = (int)((200 * 1024) / stage_bytes);
   if (n_stages > DW_MAX_STAGES) n_stages = DW_MAX_STAGES;
+  if (n_stages < 1) return FNB_ERR_MODE;
   const size_t smem = (size_t)n_stages * stage_bytes + 1024;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < x_cols) tmem_cols <<= 1;
@@ -535,13 +1184,19 @@ int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return FNB_ERR_SIZE;
     if (!done[dev]) {
-      const cudaError_t e = cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024);
+      cudaError_t e = cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tc_dw3, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024);
       if (e != cudaSuccess) return (int)e;
       done[dev] = true;
     }
   }
-  if (cudaError_t le = fnb_launch(k_tc_dw, dim3(grid), dim3(TC_THREADS), smem, stream, tm_dh, tm_x, scratch, n_rb, per, n_chunks,
-                                  n_stages, tmem_cols))
+  if (x3) {
+    if (cudaError_t le = fnb_launch(k_tc_dw3, dim3(grid), dim3(X3_THREADS), smem, stream, tm_dh, tm_x, scratch, n_rb, per,
+                                    n_chunks, n_stages, tmem_cols))
+      return (int)le;
+  } else if (cudaError_t le = fnb_launch(k_tc_dw, dim3(grid), dim3(TC_THREADS), smem, stream, tm_dh, tm_x, scratch, n_rb, per,
+                                         n_chunks, n_stages, tmem_cols))
     return (int)le;
   FNB_CHECK_LAUNCH();
   // second stage: record [128][x_cols] -> dW [128][k_out]

@@ -15,7 +15,7 @@ import torch
 
 from . import _abi
 from ._abi import (EDGE_AFFINE1, EDGE_AFFINE6, EDGE_NONE, EDGE_TABLE,  # noqa: F401  (re-exported)
-                   PRECISION_FP32, PRECISION_TF32)
+                   PRECISION_FP32, PRECISION_TF32, PRECISION_TF32X3)
 
 D, H = 128, 4
 

@@ -138,25 +138,33 @@ class TrainerFineTune:
         return mean
 
     def _scores(self, model, loader, device):
+        """Targets and RAW model outputs (logits) of a loader, as the reference collects them (utils.py:466-476,
+        :519-531: ``predicted.append(pred)`` with ``pred = model(batch)``; ROC-AUC is rank based, so no sigmoid)."""
         model.eval()
         target, predicted = [], []
         with torch.no_grad():
             for batch in _batches(loader, device, model):
                 out = model(batch)
-                predicted.append(torch.sigmoid(out))
+                predicted.append(out)
                 target.append(batch["y"].view(out.shape))
         return torch.cat(target).cpu().numpy(), torch.cat(predicted).cpu().numpy()
 
+    @staticmethod
+    def _neg_mean_auc(target, predicted):
+        """-mean ROC-AUC over the label columns that hold at least one 1 and one 0 (utils.py:477-486, :532-542).
+        NEGATIVE because the callers minimise it (``early_stopping(val_loss, model)``, finetune_gat2.py:268-274)."""
+        from sklearn.metrics import roc_auc_score
+        rocs = []
+        for c in range(target.shape[1]):
+            if np.sum(target[:, c] == 1) > 0 and np.sum(target[:, c] == 0) > 0:
+                valid = target[:, c] > -0.5
+                rocs.append(roc_auc_score(target[valid, c], predicted[valid, c]))
+        return -(sum(rocs) / len(rocs))      # ZeroDivisionError without a scorable column, as upstream
+
     def validate_clsf_bce(self, model, loader, device):
-        """Negative mean ROC-AUC over the label columns that have both classes (lower is better)."""
-        return -self.test_clsf_bce(model, loader, device)[0]
+        return self._neg_mean_auc(*self._scores(model, loader, device))
 
     def test_clsf_bce(self, model, loader, device):
-        from sklearn.metrics import roc_auc_score
+        """Returns ``(-roc_auc, targets, raw outputs)`` exactly as the reference (utils.py:519-544)."""
         target, predicted = self._scores(model, loader, device)
-        aucs = []
-        for c in range(target.shape[1]):
-            valid = target[:, c] > -0.5
-            if valid.any() and len(np.unique(target[valid, c])) == 2:
-                aucs.append(roc_auc_score(target[valid, c], predicted[valid, c]))
-        return (float(np.mean(aucs)) if aucs else float("nan")), target, predicted
+        return self._neg_mean_auc(target, predicted), target, predicted

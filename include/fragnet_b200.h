@@ -45,6 +45,8 @@ extern "C" {
 /* arithmetic of the dense projections */
 #define FNB_PRECISION_FP32 0 /* FP32 FFMA: bit-for-bit comparable with the reference within 1e-5            */
 #define FNB_PRECISION_TF32 1 /* tcgen05 tensor cores, TF32 operands, FP32 accumulate (stated tolerance 2e-3) */
+#define FNB_PRECISION_TF32X3 2 /* tcgen05 tensor cores, 3xTF32 error-compensated split (hi*hi + hi*lo + lo*hi),
+                                  FP32 accumulate: FP32-grade results, within 1e-5 of the reference             */
 
 #define FNB_EDGE_NONE 0   /* no edge term                                              */
 #define FNB_EDGE_AFFINE1 1 /* bond graph: S_e[h] = attr[slot]*coef[h] + coef[4+h]       */

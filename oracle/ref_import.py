@@ -71,6 +71,43 @@ def load_lite():
     return _load("gat2_lite", "fragnet/model/gat/gat2_lite.py")
 
 
+def load_data():
+    """The reference's ``fragnet/dataset/data.py`` (``collate_fn``, ``collate_fn_pt``, ``get_incr_*``: data.py:11-113,
+    877-1032), unmodified.  Its module-scope imports of RDKit, PyG ``Data`` and ``.fragments`` (data.py:1-8) are only
+    used by the featurisation classes, never by the collate functions; they are satisfied with empty stand-ins for the
+    duration of the load."""
+    if not available():
+        raise FileNotFoundError(f"no reference checkout under {REFERENCE_ROOT}")
+    shims.install()
+    pkg = sys.modules.get(_PKG)
+    if pkg is None:
+        pkg = types.ModuleType(_PKG)
+        pkg.__path__ = []
+        sys.modules[_PKG] = pkg
+    stubs = {}
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        stubs[name] = m
+        return m
+    rd = stub("rdkit")
+    rd.Chem = stub("rdkit.Chem")
+    rd.Geometry = stub("rdkit.Geometry", Point3D=object)
+    stub("torch_geometric.data", Data=type("Data", (), {}))
+    stub(f"{_PKG}.fragments", FragmentedMol=object)
+    saved = {k: sys.modules.get(k) for k in stubs}
+    try:
+        sys.modules.update(stubs)
+        return _load("data", "fragnet/dataset/data.py")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
 @contextlib.contextmanager
 def quiet():
     """The reference layer prints on every forward (gat2.py:172); silence it."""

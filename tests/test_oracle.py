@@ -29,6 +29,23 @@ def test_collate_matches_reference_restatement():
             assert torch.equal(fast[k], slow[k]), k
 
 
+@needs_ref
+def test_collate_is_bit_equal_to_the_unmodified_reference_collate():
+    """Pins BOTH the product collate and its restatement to the reference's own ``collate_fn`` / ``collate_fn_pt``
+    (fragnet/dataset/data.py:877-1032, imported unmodified; RDKit / PyG are stubbed because only the featurisation
+    classes of that module use them)."""
+    ref = ref_import.load_data()
+    mols = _mols() + synth.make_dataset("unimol", 6, seed=8) + synth.make_dataset("stress", 2, seed=9)
+    for ours, theirs, restated in ((collate_fn, ref.collate_fn, False), (collate_fn_pt, ref.collate_fn_pt, True)):
+        for sel in (mols, mols[:1], mols[3:9], mols[::-1]):
+            got, want, port = ours(sel), theirs(sel), collate_oracle.collate(sel, restated)
+            assert list(got) == list(want) == list(port)
+            for k in want:
+                assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+                assert torch.equal(got[k], want[k]), k
+                assert torch.equal(port[k], want[k]), k
+
+
 def test_synthetic_graph_invariants():
     for shape in ("esol", "unimol", "stress"):
         for m in synth.make_dataset(shape, 4, seed=11):
