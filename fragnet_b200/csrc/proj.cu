@@ -331,7 +331,11 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
   if (!x || !W || !h) return FNB_ERR_NULL;
   if (S && !alpha) return FNB_ERR_NULL;
   if (!fnb_aligned16(h)) return FNB_ERR_ALIGN;
-  if (fnb_tc_precision(precision)) {
+  // 3xTF32 with K > 128 (the energy head's [G, 256] readout) and few rows: the FFMA kernel is as fast as the
+  // latency-bound tensor-core launch on <= 64 row tiles and exact FP32 (32 truncating accumulator additions at
+  // K = 256 left that prediction at 9e-6 of the reference, against 3e-6 here)
+  const bool small_wide = precision == FNB_PRECISION_TF32X3 && K > kD && n_rows <= 8192;
+  if (fnb_tc_precision(precision) && !small_wide) {
     const int rc = fnb_tc_proj_launch(x, W, b, n_rows, K, S ? alpha : nullptr, alpha_stride, off_t, off_s, h, S,
                                       (cudaStream_t)stream, precision == FNB_PRECISION_TF32X3);
     if (rc != FNB_ERR_MODE) return rc;   // shapes TMA cannot address (K*4 % 16 != 0) take the SIMT kernel below
