@@ -1,15 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the FragNet GAT2 hot path (BASELINE.json: molecules/s, fwd+bwd GAT2 message passing).
 
-Workload (``config.workload``): the reference's pretraining step -- ``FragNetPreTrain`` per
-``exps/pt/unimol_exp1s4/config.yaml`` (4 layers, 4 heads, emb 128, drop 0.2, Adam lr 1e-4, loss of
-``train/pretrain/pretrain_utils.py``) on UniMol-shaped synthetic molecules, per-GPU batch ``--batch``
-(default 1024, the per-GPU batch of BASELINE configs[3]; weak scaling).  A step = forward + backward +
-gradient all-reduce (N > 1) + Adam step on one batch; ``--rotate`` distinct pre-collated batches are cycled so
-the working set exceeds the 126 MB L2.
+Workload (``config.workload``, BASELINE configs[1] at the per-GPU batch of configs[3]): the reference's pretraining step
+-- ``FragNetPreTrain`` per ``exps/pt/unimol_exp1s4/config.yaml`` (4 layers, 4 heads, emb 128, drop 0.2, Adam lr 1e-4,
+loss of ``train/pretrain/pretrain_utils.py``) on UniMol-shaped synthetic molecules, per-GPU batch ``--batch`` (1024;
+weak scaling).  A step = on-device collate + forward + loss + backward + gradient all-reduce (N > 1) + Adam on one batch;
+``--rotate`` distinct pre-collated batches are cycled so the working set exceeds the 126 MB L2.
+
+``value`` is measured in the ``fp32`` precision mode -- the mode whose outputs are within 1e-5 of the reference (dense
+projections on tcgen05 tensor cores with the 3xTF32 split); ``value_tf32`` is the same step with single-TF32 products
+(stated tolerance 2e-3).  The JSON line also carries, from the same run: ``e2e`` (host batches in, loss out),
+``e2e_arena`` (molecule ids in), ``roofline`` (whole step + the four dominant kernels timed cold), ``cpu_baseline`` (the
+reference on the host cores) and ``extra`` (BASELINE configs[0], [2], [4]: ESOL finetuning on the CPU arm, inference
+screening at batch 4096, skewed-degree stress at batch 1024).
 
   python bench.py --gpus N --steps K --warmup W             (torchrun launches N ranks for N > 1)
-  python bench.py --impl reference ...                      CPU oracle port on the host cores, same metric
+  python bench.py --impl reference ...                      the reference itself on the host cores, same metric
 """
 from __future__ import annotations
 
@@ -31,14 +37,17 @@ sys.path.insert(0, ROOT)
 
 PT_KW = dict(num_layer=4, drop_ratio=0.2, num_heads=4, emb_dim=128, atom_features=167, frag_features=167,
              edge_features=17, fedge_in=6, fbond_edge_in=6)
+FT_KW = dict(n_classes=1, num_layer=4, drop_ratio=0.1, num_heads=4, emb_dim=128, h1=128, h2=1024, h3=1024, h4=512,
+             act="relu", fthead="FTHead3")          # exps/ft/esol/e1pt4.yaml: finetune.model
 LR = 1e-4
 METRIC = "molecules/s fwd+bwd GAT2 msg-passing (FragNetPreTrain step)"
+D, H = 128, 4
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="molecules per GPU per step")
@@ -46,27 +55,28 @@ def parse():
     ap.add_argument("--rotate", type=int, default=4, help="distinct batches cycled through")
     ap.add_argument("--pool", type=int, default=512, help="distinct synthetic molecules generated")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp32_simt"],
-                    help="arithmetic of the dense projections (everything else is fp32)")
+                    help="arithmetic of the dense projections for `value` (everything else is fp32)")
     ap.add_argument("--autograd", action="store_true",
                     help="drive the step through nn.Module / autograd / FlatAdam instead of the one-call fused step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--roofline-scale", type=int, default=4,
-                    help="also time the roofline kernel on a batch this many times larger (1 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[0]/[2]/[4] legs")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the second timed region (value_tf32)")
     return ap.parse_args()
 
 
-def make_batches(shape, batch, rotate, pool, seed):
+def make_batches(shape, batch, rotate, pool, seed, pretrain=True):
     """``rotate`` collated batches of ``batch`` molecules drawn (with replacement) from a pool of distinct
     synthetic molecules; deterministic per seed."""
     import random
 
     from fragnet_b200 import synth
-    from fragnet_b200.dataset.data import collate_fn_pt
-    mols = synth.make_dataset(shape, min(pool, batch * rotate), seed=seed)
+    from fragnet_b200.dataset.data import collate_fn, collate_fn_pt
+    mols = synth.make_dataset(shape, min(pool, batch * rotate), seed=seed, with_pretrain_targets=pretrain)
     rng = random.Random(seed)
-    return [collate_fn_pt([mols[rng.randrange(len(mols))] for _ in range(batch)]) for _ in range(rotate)]
+    col = collate_fn_pt if pretrain else collate_fn
+    return [col([mols[rng.randrange(len(mols))] for _ in range(batch)]) for _ in range(rotate)]
 
 
 def batch_counts(b):
@@ -77,7 +87,7 @@ def batch_counts(b):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (every 20 ms)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -87,8 +97,10 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            time.sleep(0.15)            # nvidia-smi needs a moment before its first sample
+            self.rows.clear()           # samples from before the timed region do not count
         except OSError:
             self.proc = None
 
@@ -99,7 +111,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+        time.sleep(0.03)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -120,38 +132,41 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def bond_fwd_bytes(N, E):
-    """Compulsory bytes of one training-mode bond-graph attention launch: reads h [N,128],
-    S [N,8], rowptr, col, row, cos(theta) per edge; writes the pre-activation rows, the ReLU(Dropout) rows, p [E,4]
-    and the atom graph's edge term [N,4].  (SURVEY 8d's B_att_fwd plus the fused epilogue outputs.)"""
-    reads = N * 128 * 4 + N * 8 * 4 + (N + 1) * 4 + 3 * E * 4
-    writes = 2 * N * 128 * 4 + E * 4 * 4 + N * 4 * 4
-    return reads + writes
+# Algorithmic bytes (compulsory traffic, every operand counted once per kernel, fp32 = 4 B,
+# int32 indices).  ``step_bytes`` is the contract's whole-step figure on the actual counts of a batch.
+def att_fwd_bytes(N, E, X, train=True):
+    return 2 * N * D * 4 + X + E * 4 + (N + 1) * 4 + (E * H * 4 if train else 0)
 
 
-def roofline_bond_fwd(batch_dev, peaks, iters=10, sets=8, traffic_note=None):
-    """Live CUDA-event timing of the dominant message-passing kernel -- the tiled bond-graph attention forward in its
-    training configuration (pre + post activation rows, saved p, fused consumer edge term) -- on the bench batch.
-    ``sets`` distinct input/output sets are cycled so that every launch streams operands that are not in L2
-    (sets x bytes per launch > 4 x the 126 MB L2); the average is taken over back-to-back launches between two
-    events on the launch stream."""
-    from fragnet_b200 import ops
-    b = batch_dev
-    dev = b["x_atoms"].device
-    Nb, Eb = b["node_features_bonds"].shape[0], b["edge_index_bonds_graph"].shape[1]
-    eb = b["edge_index_bonds_graph"]
-    g = ops.csr_build(eb[0].contiguous(), eb[1].contiguous(), Nb)
-    g.attr = ops.gather_rows(b["edge_attr_bonds"].reshape(-1, 1), g.eid, Eb)
-    alpha = torch.randn(4, 96, device=dev) * 0.1
-    nxt = torch.randn(4, 192, device=dev) * 0.1
-    We, be = torch.randn(32, 1, device=dev), torch.randn(32, device=dev)
-    hs = [torch.randn(Nb, 128, device=dev) for _ in range(sets)]
-    Ss = [ops.node_scalars(h, alpha, 96, 0, 64) for h in hs]
+def att_bwd_bytes(N, E, X, dX):
+    return 3 * N * D * 4 + E * H * 4 + 3 * E * 4 + 2 * (N + 1) * 4 + dX
 
-    def launch(i):
-        ops.gat_fwd_tiled(g, hs[i], Ss[i], ops.EDGE_AFFINE1, We=We, be=be, alpha_e=alpha[:, 32:], alpha_stride=96,
-                          post=(0.2, 1, 1, 1234, 0), next_alpha=nxt[:, 32:], next_alpha_stride=192)
 
+def step_bytes(c, n_layers=4, K0=(17, 167, 6), live_only=False):
+    """(fwd, fwd+bwd) bytes of the encoder for one batch with counts ``c`` (batch_counts).  ``live_only`` drops the
+    fragment-graph block and the pooling of the layers whose fragment output is overwritten unread (gat2.py:234; the
+    reference executes them, this library does not): the contract figure keeps them."""
+    Na, Ea, Eb, Nf, Ef, Efb, G = c["Na"], c["Ea"], c["Eb"], c["Nf"], c["Ef"], c["Efb"], c["G"]
+    Nb, Nfb = Ea, Ef
+    fwd = bwd = 0
+    for l in range(n_layers):
+        Kb, Ka, Kfb = K0 if l == 0 else (D, D, D)
+        gemm = (Nb * Kb + Nb * D + Na * Ka + Na * D + Nfb * Kfb + Nfb * D) * 4
+        blocks = [(Nb, Eb, Eb * 4, 0), (Na, Ea + Na, Ea * D * 4, Ea * D * 4), (Nfb, Efb, Efb * 24, 0)]
+        pool_f, pool_b = (Na + Nf) * D * 4 + Na * 4, (Na + Nf) * D * 4
+        if not live_only or l == n_layers - 1:
+            blocks.append((Nf, Ef, Ef * D * 4, Ef * D * 4))
+        else:
+            pool_f = pool_b = 0
+        fwd += gemm + pool_f + sum(att_fwd_bytes(N, E, X) for N, E, X, _ in blocks)
+        bwd += 2 * gemm + pool_b + sum(att_bwd_bytes(N, E, X, dX) for N, E, X, dX in blocks)
+    readout = (Na + Nf) * D * 4 + 2 * G * D * 4
+    return fwd + readout, fwd + bwd + 2 * readout
+
+
+def _cold_time(launch, sets, iters):
+    """Average microseconds per launch over back-to-back launches that cycle ``sets`` operand sets (no launch finds its
+    operands in L2), CUDA events on the launch stream."""
     for i in range(sets):
         launch(i)
     times = []
@@ -162,46 +177,118 @@ def roofline_bond_fwd(batch_dev, peaks, iters=10, sets=8, traffic_note=None):
             launch(i)
         e1.record()
         e1.synchronize()
-        times.append(e0.elapsed_time(e1) / sets)
-    ms = statistics.mean(times)
-    nbytes = bond_fwd_bytes(Nb, Eb)
+        times.append(e0.elapsed_time(e1) / sets * 1e3)
+    return statistics.mean(times)
+
+
+# Share of the summed kernel time of one fp32-mode step per kernel, and the DRAM traffic of one captured launch of each:
+# both come from the committed profiles of this state (scripts/summarize_launches.py, scripts/summarize_ncu_full.py
+# write profiles/r4_kernel_shares.json next to the markdown tables they are taken from).
+KERNEL_SHARE = {"source": "profiles/r4_launch_list.md"}
+NCU_TRAFFIC = {"source": "profiles/r4_ncu_full.md", "per_kernel": {}}
+try:
+    _p = os.path.join(ROOT, "profiles", "r4_kernel_shares.json")
+    if os.path.isfile(_p):
+        _d = json.load(open(_p))
+        KERNEL_SHARE.update(_d.get("share", {}))
+        NCU_TRAFFIC["per_kernel"] = _d.get("traffic", {})
+except (OSError, ValueError):
+    pass
+
+
+def roofline_kernels(batch_dev, peaks, iters=6, sets=8):
+    """Live, cold timings of the four dominant kernels on the bond graph of the bench batch (the bond graph is ~60 % of
+    the gathered rows of a step): attention forward in its training configuration, destination pass and source pass of
+    its backward (timed separately through an event recorded between the two launches), and the 3xTF32 projection."""
+    from fragnet_b200 import ops
+    b = batch_dev
+    dev = b["x_atoms"].device
+    Nb, Eb = b["node_features_bonds"].shape[0], b["edge_index_bonds_graph"].shape[1]
+    eb = b["edge_index_bonds_graph"]
+    g = ops.csr_build(eb[0].contiguous(), eb[1].contiguous(), Nb)
+    g.attr = ops.gather_rows(b["edge_attr_bonds"].reshape(-1, 1), g.eid, Eb)
+    alpha = torch.randn(4, 96, device=dev) * 0.1
+    nxt = torch.randn(4, 192, device=dev) * 0.1
+    We, be = torch.randn(32, 1, device=dev), torch.randn(32, device=dev)
+    W, bias = torch.randn(128, 128, device=dev) * 0.1, torch.randn(128, device=dev)
+    hs = [torch.randn(Nb, 128, device=dev) for _ in range(sets)]
+    gos = [torch.randn(Nb, 128, device=dev) for _ in range(sets)]
+    Ss = [ops.node_scalars(h, alpha, 96, 0, 64) for h in hs]
     peak = peaks.get("hbm_gbs")
-    achieved = nbytes / (ms * 1e-3) / 1e9
-    # practical ceiling at this problem size: a plain device copy moving the same number of bytes, timed the same way
-    # (arrays of a 1024-molecule batch are ~28 MB; launch + ramp-up keep even a copy well below the 1 GiB copy rate
-    # that MEASURED_PEAKS.json records)
-    n_copy = max(1, nbytes // 8)
+    out = []
+
+    def entry(name, us, nbytes, note, launches):
+        gbs = nbytes / us / 1e3
+        e = {"kernel": name, "us_per_launch": round(us, 2), "bytes_per_launch": int(nbytes), "achieved": round(gbs, 1),
+             "frac": round(gbs / peak, 4) if peak else None, "launches_per_step": launches,
+             "share_of_kernel_time": KERNEL_SHARE.get(name), "bytes_model": note,
+             "traffic": NCU_TRAFFIC["per_kernel"].get(name)}
+        out.append(e)
+        return e
+
+    # --- forward, training configuration (pre + post activation rows, saved p, consumer edge term)
+    def fwd(i):
+        return ops.gat_fwd_tiled(g, hs[i], Ss[i], ops.EDGE_AFFINE1, We=We, be=be, alpha_e=alpha[:, 32:], alpha_stride=96,
+                                 post=(0.2, 1, 1, 1234, 0), next_alpha=nxt[:, 32:], next_alpha_stride=192)
+    us = _cold_time(fwd, sets, iters)
+    contract = att_fwd_bytes(Nb, Eb, Eb * 4)
+    fused = Nb * 128 * 4 + Nb * 32 + (Nb + 1) * 4 + 3 * Eb * 4 + 2 * Nb * 128 * 4 + Eb * 16 + Nb * 16
+    e = entry("k_gat_fwd_tiled<AFFINE1>", us, fused,
+              "reads h, S, rowptr, col, row, cos; writes pre- and post-activation rows, p, consumer edge term "
+              "(section 8d B_att_fwd + the fused epilogue outputs)", 4)
+    e["bytes_contract"] = int(contract)
+    e["frac_contract"] = round(contract / us / 1e3 / peak, 4) if peak else None
+
+    # --- backward: destination pass | source pass
+    ps = [fwd(i)[2] for i in range(sets)]
+    d_alpha = torch.zeros(4, 96, device=dev)
+    bufs = [(torch.empty(Eb, 4, device=dev), torch.empty(Nb, 4, device=dev), torch.empty(Nb, 128, device=dev))
+            for _ in range(sets)]
+    mark = torch.cuda.Event(enable_timing=True)
+    mark.record()
+
+    def bwd(i, ev=None):
+        ops.gat_bwd_tiled(g, hs[i], gos[i], ps[i], ops.EDGE_AFFINE1, alpha, 96, 0, 32, 64, d_alpha, We=We, be=be,
+                          want_bias_grad=True, mark=ev, out=bufs[i])
+    for i in range(sets):
+        bwd(i)
+    t_dst, t_src = [], []
+    for _ in range(iters):
+        for i in range(sets):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            bwd(i, mark)
+            e1.record()
+            e1.synchronize()
+            t_dst.append(e0.elapsed_time(mark) * 1e3)
+            t_src.append(mark.elapsed_time(e1) * 1e3)
+    dst_b = 2 * Nb * D * 4 + 2 * Eb * H * 4 + Eb * 4 + (Nb + 1) * 4 + Nb * H * 4
+    src_b = 3 * Nb * D * 4 + 2 * Eb * H * 4 + 2 * Eb * 4 + (Nb + 1) * 4 + Nb * H * 4
+    entry("k_gat_bwd_dst_tiled<AFFINE1>", statistics.mean(t_dst), dst_b,
+          "reads h, g, p, rowptr, col; writes dz, dSt (in the step the FUSE variant also assembles g)", 4)
+    entry("k_gat_bwd_src_tiled", statistics.mean(t_src), src_b,
+          "reads g, own h row, p, dz, dSt, reverse CSR; writes dh (13 launches per step over the four graphs; this "
+          "is the bond graph's)", 13)
+    pair_contract = att_bwd_bytes(Nb, Eb, Eb * 4, 0)
+    pair_us = statistics.mean(t_dst) + statistics.mean(t_src)
+
+    # --- 3xTF32 projection (forward / dX)
+    def proj(i):
+        ops.proj_fwd(hs[i], W, bias, alpha, 96, 0, 64, precision=ops.PRECISION_TF32X3)
+    us = _cold_time(proj, sets, iters)
+    entry("k_tc_proj3r", us, (Nb * 128 + Nb * 128 + Nb * 8) * 4,
+          "reads x [N,128]; writes h [N,128] and the logit scalars S [N,8] (W resident in shared memory)", 24)
+    # a plain device copy of the forward kernel's byte count, timed the same way: what the memory system delivers at
+    # this problem size (launch ramp and tail included)
+    n_copy = max(1, fused // 8)
     srcs = [torch.empty(n_copy, dtype=torch.float32, device=dev) for _ in range(sets)]
     dsts = [torch.empty(n_copy, dtype=torch.float32, device=dev) for _ in range(sets)]
-    for i in range(sets):
-        dsts[i].copy_(srcs[i])
-    ctimes = []
-    for _ in range(iters):
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        for i in range(sets):
-            dsts[i].copy_(srcs[i])
-        e1.record()
-        e1.synchronize()
-        ctimes.append(e0.elapsed_time(e1) / sets)
-    copy_gbs = 2 * n_copy * 4 / (statistics.mean(ctimes) * 1e-3) / 1e9
-    out = {"bound": "hbm", "kernel": "k_gat_fwd_tiled<AFFINE1> (bond graph, training epilogue)",
-           "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-           "frac": round(achieved / peak, 4) if peak else None, "traffic": None, "bytes_per_launch": nbytes,
-           "us_per_launch": round(ms * 1e3, 2), "nodes": Nb, "edges": Eb,
-           "cache": f"{sets} operand sets cycled ({sets * nbytes / 1e6:.0f} MB > L2)",
-           "peak_source": peaks.get("source"),
-           "same_size_copy_gbs": round(copy_gbs, 1), "frac_of_same_size_copy": round(achieved / copy_gbs, 4)}
-    if traffic_note and Nb == traffic_note["nodes"]:
-        out["traffic"] = traffic_note["bytes"]
-        out["traffic_source"] = traffic_note["source"]
-    return out
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on bench batch 0
-# (profiles/r1q_ncu_full.md: 35.02 MB read + 13.73 MB written; the written rows mostly stay in the 126 MB L2 and are
-# evicted after the kernel, hence less than the algorithmic bytes)
-NCU_TRAFFIC = {"nodes": 53940, "bytes": 48750000, "source": "profiles/r1q_ncu_full.md (ncu --set full, batch 0 of the bench)"}
+    copy_us = _cold_time(lambda i: dsts[i].copy_(srcs[i]), sets, iters)
+    extra = {"bwd_pair_bytes_contract": int(pair_contract), "bwd_pair_us": round(pair_us, 2),
+             "bwd_pair_frac_contract": round(pair_contract / pair_us / 1e3 / peak, 4) if peak else None,
+             "same_size_copy_gbs": round(2 * n_copy * 4 / copy_us / 1e3, 1), "nodes": Nb, "edges": Eb,
+             "cache": f"{sets} operand sets cycled per kernel (> 126 MB L2)"}
+    return out, extra
 
 
 def load_peaks():
@@ -213,29 +300,104 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(shape, n_mols, steps, warmup, seed=0):
-    """Reference algorithm (oracle port) fwd+bwd+Adam on the host cores: molecules/s."""
-    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
-    from oracle import gat2_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(seed)
-    m = FragNetPreTrain(**PT_KW)
-    P = O.params_from_module(m)
-    live = [v for v in P.values() if v.requires_grad]
-    opt = torch.optim.Adam(live, lr=LR)
-    batches = make_batches(shape, n_mols, 2, 256, seed + 1)
+# CPU arm: the reference itself (oracle/_ref or the checkout, through oracle/shims.py) or, if neither is there, the port
+def _reference_modules():
+    from oracle import ref_import
+    if ref_import.available():
+        with ref_import.quiet():
+            ns = ref_import.load()
+        return ns, ("reference", f"unmodified reference modules ({ref_import.kind()}) + third-party shims")
+    return None, ("port", "oracle port (no reference build under oracle/_ref)")
+
+
+def _time_cpu_steps(one, batches, steps, warmup):
     times = []
     for i in range(warmup + steps):
-        b = batches[i % len(batches)]
         t0 = time.perf_counter()
-        opt.zero_grad()
-        loss = O.pretrain_loss(O.pretrain_forward(P, b, drop_ratio=PT_KW["drop_ratio"], training=True), b)
-        loss.backward()
-        loss.item()
-        opt.step()
+        one(batches[i % len(batches)])
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return n_mols / statistics.mean(times), statistics.mean(times)
+    return statistics.mean(times)
+
+
+def cpu_pretrain_rate(shape, n_mols, steps, warmup, seed=0):
+    """The reference's pretraining step (FragNetPreTrain.forward + the loss and update of Trainer.train,
+    pretrain_utils.py:9-31) on the host cores: (molecules/s, seconds per step, kind, description)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(seed)
+    ns, (kind, how) = _reference_modules()
+    batches = make_batches(shape, n_mols, 2, 256, seed + 1)
+    loss_fn = torch.nn.MSELoss()
+    if ns is not None:
+        from oracle import ref_import
+        model = ns.pretrain_heads.FragNetPreTrain(**PT_KW).train()
+        opt = torch.optim.Adam(model.parameters(), lr=LR)
+
+        def one(b):
+            opt.zero_grad()
+            with ref_import.quiet():          # the layer prints on every forward (gat2.py:172)
+                bl, ba, da, e = model(b)
+            # pretrain_utils.py:22-26 (the bond-length term is overwritten by the dihedral term)
+            loss_l = loss_fn(da, b["dh_angl"])
+            loss = loss_l + loss_fn(ba, b["bnd_angl"]) + loss_l + loss_fn(e.view(-1), b["y"])
+            loss.backward()
+            loss.item()
+            opt.step()
+    else:
+        from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+        from oracle import gat2_oracle as O
+        P = O.params_from_module(FragNetPreTrain(**PT_KW))
+        opt = torch.optim.Adam([v for v in P.values() if v.requires_grad], lr=LR)
+
+        def one(b):
+            opt.zero_grad()
+            loss = O.pretrain_loss(O.pretrain_forward(P, b, drop_ratio=PT_KW["drop_ratio"], training=True), b)
+            loss.backward()
+            loss.item()
+            opt.step()
+    sec = _time_cpu_steps(one, batches, steps, warmup)
+    return n_mols / sec, sec, kind, how
+
+
+def cpu_esol_finetune_rate(steps=5, warmup=1, batch=128):
+    """BASELINE configs[0]: FragNetFineTune per exps/ft/esol/e1pt4.yaml (FTHead3 128/1024/1024/512, drop 0.1), ESOL-shaped
+    molecules, batch 128, fwd + MSE + bwd + Adam on the host cores (train/utils.py:331-351)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    ns, (kind, how) = _reference_modules()
+    batches = make_batches("esol", batch, 2, 256, seed=7, pretrain=False)
+    loss_fn = torch.nn.MSELoss()
+    if ns is not None:
+        from oracle import ref_import
+        model = ns.gat2.FragNetFineTune(**FT_KW).train()
+        opt = torch.optim.Adam(model.parameters(), lr=LR)
+
+        def one(b):
+            opt.zero_grad()
+            with ref_import.quiet():
+                out = model(b)
+            loss = loss_fn(out.view(-1), b["y"])
+            loss.backward()
+            loss.item()
+            opt.step()
+    else:
+        from fragnet.model.gat.gat2 import FragNetFineTune
+        from oracle import gat2_oracle as O
+        P = O.params_from_module(FragNetFineTune(**FT_KW))
+        opt = torch.optim.Adam([v for v in P.values() if v.requires_grad], lr=LR)
+
+        def one(b):
+            opt.zero_grad()
+            loss = loss_fn(O.finetune_forward(P, b).view(-1), b["y"])
+            loss.backward()
+            loss.item()
+            opt.step()
+    sec = _time_cpu_steps(one, batches, steps, warmup)
+    return {"workload": "FragNetFineTune exps/ft/esol/e1pt4.yaml step (fwd + MSE + bwd + Adam), ESOL-shaped molecules, "
+                        f"batch {batch}, host cores (BASELINE configs[0])",
+            "value": round(batch / sec, 2), "unit": "molecules/s", "ms_per_step": round(sec * 1e3, 1),
+            "cores": os.cpu_count() or 1, "kind": kind, "how": how, "steps": steps, "warmup": warmup,
+            "batch0_counts": batch_counts(batches[0])}
 
 
 def workload_name(shape):
@@ -244,23 +406,24 @@ def workload_name(shape):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, on a bounded sample of
+    the workload (the full per-GPU batch when it fits the time budget)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     budget = 150.0 / max(1, args.steps + args.warmup)            # seconds per step
-    n_mols = int(max(32, min(512, 150 * budget)))
-    rate, sec = cpu_oracle_rate(args.shape, n_mols, args.steps, args.warmup)
+    n_mols = int(max(32, min(args.batch, 150 * budget)))
+    with contextlib.redirect_stdout(io.StringIO()):
+        rate, sec, kind, how = cpu_pretrain_rate(args.shape, n_mols, args.steps, args.warmup)
     cores = os.cpu_count() or 1
-    sample = f"{n_mols} {args.shape}-shaped molecules per step (fwd+bwd+Adam, train mode, drop 0.2)"
+    sample = f"{n_mols} {args.shape}-shaped molecules per step (fwd+bwd+Adam, train mode, drop 0.2); {how}"
     line = {"metric": METRIC, "value": round(rate, 2), "unit": "molecules/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
             "config": {"workload": workload_name(args.shape), "per_gpu_batch": args.batch,
-                       "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}",
-                       "sample_batch": n_mols},
-            "cpu_baseline": {"value": round(rate, 2), "unit": "molecules/s", "cores": cores, "kind": "port",
+                       "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}"},
+            "cpu_baseline": {"value": round(rate, 2), "unit": "molecules/s", "cores": cores, "kind": kind,
                              "sample": sample},
             "e2e": {"value": round(rate, 2), "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -271,25 +434,22 @@ def run_reference(args):
 def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="fp32", rank=0, world=1, dev=None,
               return_host=False, autograd_path=False):
     """The timed unit: ``step(batch_dict)`` = on-device collate + forward + loss + backward + gradient all-reduce
-    (world > 1) + Adam on one batch.  Returns (step, device batches[, pinned host batches])."""
+    (world > 1) + Adam on one batch.  Returns (step, device batches[, pinned host batches in the compact wire format])."""
     from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
     from fragnet_b200 import config, ops
+    from fragnet_b200.dataset.data import compact_batch
     from fragnet_b200.dist import FlatGradSync
     from fragnet_b200.train.optim import FlatAdam
     from fragnet_b200.train.pretrain_utils import pretrain_loss
     dev = dev or torch.device("cuda", torch.cuda.current_device())
     config.set_precision(precision)
-    if precision == "tf32":      # the nn.Linear heads (library GEMMs) follow the same precision switch
-        torch.backends.cuda.matmul.allow_tf32 = True
-        torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(1234)                      # identical initial weights on every rank
     model = FragNetPreTrain(**PT_KW).to(dev).train()
     loss_fn = torch.nn.MSELoss()
-    host_batches = make_batches(shape, batch, rotate, pool, seed=100 + rank)
-    for b in host_batches:
-        for k in b:
-            b[k] = b[k].pin_memory()
-    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
+    wide = make_batches(shape, batch, rotate, pool, seed=100 + rank)
+    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in wide]
+    # what a DataLoader with collate_fn_pt_compact + pin_memory hands over: uint8 one-hot matrices, int32 indices
+    host_batches = [compact_batch(b, pin=True) for b in wide] if return_host else None
     if autograd_path:
         # the unchanged reference loop: model(batch) -> loss -> backward -> (all-reduce) -> Adam, through nn.Module
         sync = FlatGradSync(model.parameters())
@@ -307,18 +467,119 @@ def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="fp32", 
             opt.step(sync.flat if world > 1 else None)
             return loss
     else:
-        # the same arithmetic as ONE library call per step (+ NCCL all-reduce + one Adam launch)
+        # the same arithmetic as ONE library call per step (+ gradient all-reduce + one Adam launch)
         from fragnet_b200.train.fused import FusedPretrainStep
         step = FusedPretrainStep(model, lr=LR).step
 
     return (step, dev_batches, host_batches) if return_host else (step, dev_batches)
 
 
+class Timer:
+    """K steps bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks."""
+
+    def __init__(self, dev, world, lib):
+        self.dev, self.world, self.lib = dev, world, lib
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def __call__(self, run_step, n_steps):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        l0 = self.lib.fnb_launch_count()
+        e0.record()
+        for i in range(n_steps):
+            run_step(i)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), self.lib.fnb_launch_count() - l0
+
+
+# ------------------------------------------------------------------------------------------------
+def extra_inference(dev, timed, world, rank, steps=24, warmup=3, batch=4096):
+    """BASELINE configs[2]: inference screening, batch 4096 per GPU, eval mode, the last layer's attention sums returned
+    (the arrangement of vizualize/model.py).  Resident: batches in HBM, outputs left on the device; e2e: the screening
+    pipeline on the packed arena -- molecule ids in, predictions + four attention tensors copied to pinned host memory."""
+    import numpy as np
+
+    from fragnet.vizualize.model import FragNetFineTuneViz
+    from fragnet_b200 import ops, synth
+    from fragnet_b200.dataset.arena import MoleculeArena
+    from fragnet_b200.screen import screen
+    torch.manual_seed(7)
+    viz = FragNetFineTuneViz(num_layer=4, drop_ratio=0.1, n_classes=1, edge_features=17).to(dev).eval()
+    pool = synth.make_dataset("unimol", 512, seed=300 + rank, with_pretrain_targets=False)
+    arena = MoleculeArena(pool, dev, pretrain=False)
+    rng = np.random.default_rng(300 + rank)
+    ids = [rng.integers(0, len(pool), size=batch) for _ in range(4)]
+    dev_batches = [{k: v.clone() for k, v in arena.batch(i).items()} for i in ids]
+    sink = [None]
+
+    def resident(i):
+        with torch.no_grad():
+            ops.clear_plan_cache()
+            sink[0] = viz(dev_batches[i % 4])
+    for i in range(warmup):
+        resident(i)
+    ms_res, _ = timed(resident, steps)
+    d2h = sum(int(t.numel()) * t.element_size() for t in sink[0])
+    all_ids = np.concatenate([ids[j % 4] for j in range(steps + warmup)])
+    state = {"n": 0}
+
+    def e2e(i):            # one timed call = the whole pipelined screen of (steps + warmup) batches
+        for _bid, outs in screen(viz, arena, batch_size=batch, ids=all_ids):
+            state["n"] += int(outs[0].shape[0])
+    for _ in screen(viz, arena, batch_size=batch, ids=all_ids[:2 * batch]):
+        pass
+    ms_e2e, _ = timed(e2e, 1)
+    assert state["n"] == all_ids.shape[0]
+    n_e2e = all_ids.shape[0]
+    out = {"workload": f"inference screening (BASELINE configs[2]): FragNetFineTuneViz eval, batch {batch} per GPU, "
+                       "prediction + last-layer attention sums of the four graphs returned, UniMol-shaped molecules",
+           "value": round(batch * steps * world / (ms_res * 1e-3), 1), "unit": "molecules/s",
+           "ms_per_batch": round(ms_res / steps, 3),
+           "e2e": {"value": round(n_e2e * world / (ms_e2e * 1e-3), 1), "unit": "molecules/s",
+                   "h2d_bytes_per_step": batch * 8, "d2h_bytes_per_step": d2h,
+                   "seconds_per_1M_molecules": round(1e6 / (n_e2e * world / (ms_e2e * 1e-3)), 3),
+                   "how": "fragnet_b200.screen on a MoleculeArena: molecule ids in; on-device batch assembly, forward and "
+                          "the pinned device-to-host copy of predictions + attention sums in flight together; every "
+                          "batch's results are on the host inside the timed region"},
+           "n_gpus": world, "steps": steps, "warmup": warmup, "precision": "fp32"}
+    del arena
+    return out
+
+
+def extra_stress(dev, timed, world, rank, steps=8, warmup=3, batch=1024):
+    """BASELINE configs[4]: skewed-degree stress (~100 atoms, ~20 fragments, 3 components, ~20 k fragment-connection
+    edges per molecule), per-GPU batch 1024, the same pretraining step."""
+    step, dev_batches = make_step(batch, "stress", rotate=2, pool=64, precision="fp32", rank=rank, world=world, dev=dev)
+    for i in range(warmup):
+        step(dev_batches[i % 2])
+    ms, launches = timed(lambda i: step(dev_batches[i % 2]), steps)
+    c = {k: int(v) for k, v in batch_counts(dev_batches[0]).items()}
+    _, all_b = step_bytes(c)
+    peak = load_peaks()["hbm_gbs"]
+    sec = ms * 1e-3 / steps
+    return {"workload": workload_name("stress") + f", per-GPU batch {batch} (BASELINE configs[4])",
+            "value": round(batch * world / sec, 1), "unit": "molecules/s", "ms_per_step": round(ms / steps, 3),
+            "n_gpus": world, "steps": steps, "warmup": warmup, "precision": "fp32", "batch0_counts": c,
+            "roofline_step": {"bytes_contract": int(all_b), "achieved": round(all_b / sec / 1e9, 1), "peak": peak,
+                              "frac": round(all_b / sec / 1e9 / peak, 4)},
+            "gpu_launches": int(launches)}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
 
-    from fragnet_b200 import _abi
+    from fragnet_b200 import _abi, config
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -333,25 +594,8 @@ def run_ours(args):
     lib = _abi.load()
     step, dev_batches, host_batches = make_step(args.batch, args.shape, args.rotate, args.pool, args.precision, rank,
                                                 world, dev, return_host=True, autograd_path=args.autograd)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(run_step, n_steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        l0 = lib.fnb_launch_count()
-        e0.record()
-        for i in range(n_steps):
-            run_step(i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms), lib.fnb_launch_count() - l0
+    timed = Timer(dev, world, lib)
+    barrier = timed.barrier
 
     # ---- kernel-resident throughput: inputs already in HBM
     for i in range(args.warmup):
@@ -364,21 +608,23 @@ def run_ours(args):
     mols = args.batch * world * args.steps
     value = mols / (ms_total * 1e-3)
 
+    # ---- the same step with single-TF32 products (stated tolerance 2e-3): value_tf32
+    tf32 = None
+    if not args.no_tf32 and args.precision == "fp32" and not args.autograd:
+        config.set_precision("tf32")
+        for i in range(max(3, args.warmup)):
+            step(dev_batches[i % args.rotate])
+        ms_tf, _ = timed(lambda i: step(dev_batches[i % args.rotate]), args.steps)
+        tf32 = {"value": round(mols / (ms_tf * 1e-3), 1), "ms_per_step": round(ms_tf / args.steps, 4)}
+        config.set_precision(args.precision)
+        step(dev_batches[0])
+
     # ---- end to end through the public API with HOST (pinned) batches: H2D + step + loss read back
     e2e = None
     if not args.no_e2e:
-        # what Trainer's fused path stages (DevicePrefetcher(hot_path_only=True)): every tensor of the batch dict except
-        # edge_attr / cnx_attr (never read by FragNet.forward, gat2.py:381-442) and the VALUES of x_frags (overwritten
-        # unread by the pooling, gat2.py:234)
-        h2d = sum(v.numel() * v.element_size() for k, v in host_batches[0].items()
-                  if k not in ("edge_attr", "cnx_attr", "x_frags"))
-
-        # public path: DevicePrefetcher (pinned host batches -> device on a copy stream, double buffered) feeding
-        # the step; every batch is copied inside the timed region and every step's loss is read back
-        from fragnet_b200.dataset.prefetch import DevicePrefetcher
-
+        from fragnet_b200.dataset.prefetch import DevicePrefetcher, staged_bytes
         from fragnet_b200.train.fused import LaggedScalars
-
+        h2d = staged_bytes(host_batches[0])
         reader = LaggedScalars(lag=1)     # three pinned floats, allocated once (cudaHostAlloc synchronises the device)
 
         def e2e_run(n):
@@ -412,7 +658,10 @@ def run_ours(args):
         ms_e2e, _ = timed(e2e_step, args.steps)
         e2e = {"value": round(mols / (ms_e2e * 1e-3), 1), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
-               "batch_dict_bytes": sum(v.numel() * v.element_size() for v in host_batches[0].values()),
+               "batch_dict_bytes": sum(v.numel() * v.element_size() for v in dev_batches[0].values()),
+               "staging": "pinned host batches in the compact wire format of collate_fn_pt_compact (one-hot feature "
+                          "matrices uint8, indices int32: exact) -> DevicePrefetcher(hot_path_only=True) copies the "
+                          "tensors FragNet.forward reads and widens them on the device (fnb_widen_batch)",
                "loss_read": "every step's loss is copied to pinned host memory behind its step and collected one step "
                             "later (after the next step has been enqueued); all reads inside the timed region"}
 
@@ -429,7 +678,6 @@ def run_ours(args):
         arena = MoleculeArena(pool, dev)
         rng = np.random.default_rng(100 + rank)
         id_lists = [rng.integers(0, len(pool), size=args.batch) for _ in range(args.rotate)]
-
         reader = LaggedScalars(lag=1)
 
         def arena_run(n):
@@ -464,33 +712,68 @@ def run_ours(args):
                              "assembly (fnb_arena_assemble), step, loss read back"}
         del arena
 
-    roofline = cpu = None
-    if rank == 0:
+    # ---- roofline legs use the bench batch: take them before the extras free it
+    roofline = None
+    counts = batch_counts(dev_batches[0])
+    if rank == 0 and not args.no_roofline:
         peaks = load_peaks()
-        if not args.no_roofline:
-            roofline = roofline_bond_fwd(dev_batches[0], peaks, traffic_note=NCU_TRAFFIC)
-            if args.roofline_scale > 1:      # the same kernel on a batch `roofline_scale` x larger (launch/ramp amortised)
-                big = make_batches(args.shape, args.batch * args.roofline_scale, 1, args.pool, seed=999)[0]
-                big = {k: v.to(dev) for k, v in big.items() if k in ("node_features_bonds", "edge_index_bonds_graph",
-                                                                    "edge_attr_bonds", "x_atoms")}
-                r2 = roofline_bond_fwd(big, peaks, sets=3)
-                roofline["at_larger_batch"] = {"per_gpu_batch": args.batch * args.roofline_scale,
-                                               **{k: r2[k] for k in ("achieved", "frac", "bytes_per_launch", "us_per_launch",
-                                                                     "nodes", "edges", "same_size_copy_gbs",
-                                                                     "frac_of_same_size_copy")}}
-                del big
+        peak = peaks["hbm_gbs"]
+        kernels, kextra = roofline_kernels(dev_batches[0], peaks)
+        _, all_b = step_bytes(counts)
+        _, live_b = step_bytes(counts, live_only=True)
+        sec = ms_total * 1e-3 / args.steps
+        step_r = {"bytes_contract": int(all_b), "bytes_live": int(live_b), "ms": round(sec * 1e3, 4),
+                  "achieved": round(all_b / sec / 1e9, 1), "peak": peak, "frac": round(all_b / sec / 1e9 / peak, 4),
+                  "frac_live": round(live_b / sec / 1e9 / peak, 4),
+                  "note": "encoder fwd+bwd bytes by SURVEY 8d on batch 0's counts (every block of every layer, as the "
+                          "reference executes them; `live` drops the fragment blocks / pooling whose output is "
+                          "overwritten unread and which this library skips); the heads, loss and Adam are in the time "
+                          "but not in the bytes"}
+        shares = [(k.get("share_of_kernel_time") or 0.0, i) for i, k in enumerate(kernels)]
+        top = kernels[max(shares)[1]] if any(s for s, _ in shares) else kernels[2]
+        roofline = {"bound": "hbm", "kernel": top["kernel"] + " (bond graph; largest share of the step's kernel time)",
+                    "achieved": top["achieved"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
+                    "traffic": top.get("traffic"), "bytes_per_launch": top["bytes_per_launch"],
+                    "us_per_launch": top["us_per_launch"], "peak_source": peaks.get("source"),
+                    "share_source": KERNEL_SHARE["source"], "traffic_source": NCU_TRAFFIC["source"],
+                    "step": step_r, "kernels": kernels, **kextra}
+
+    # ---- BASELINE configs[4] and [2] on every rank (weak scaling / replicas), configs[0] on rank 0's host cores
+    extra = {}
+    if not args.no_extras and not args.autograd:
+        del step, dev_batches
+        torch.cuda.empty_cache()
+        config.set_precision("fp32")
+        for name, fn in (("stress_b1024", extra_stress), ("infer_b4096", extra_inference)):
+            try:
+                extra[name] = fn(dev, timed, world, rank)
+            except Exception as ex:      # an extra leg must never take the headline down with it
+                if world > 1:
+                    raise                # (a rank that skips a collective would hang the others)
+                extra[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+            torch.cuda.empty_cache()
+
+    if rank == 0:
+        cpu = None
         if not args.no_cpu_baseline and world == 1:
             with contextlib.redirect_stdout(io.StringIO()):
-                rate, _ = cpu_oracle_rate(args.shape, 512, 10, 1)        # ~10-15 s of host work
-            cpu = {"value": round(rate, 2), "unit": "molecules/s", "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"512 {args.shape}-shaped molecules per step, 1 warm-up + 10 timed steps "
-                             "(fwd+bwd+Adam, train mode, all host threads)"}
-        counts = batch_counts(host_batches[0])
+                rate, _sec, kind, how = cpu_pretrain_rate(args.shape, 512, 8, 1)        # ~10-15 s of host work
+            cpu = {"value": round(rate, 2), "unit": "molecules/s", "cores": os.cpu_count() or 1, "kind": kind,
+                   "sample": f"512 {args.shape}-shaped molecules per step, 1 warm-up + 8 timed steps "
+                             f"(fwd+bwd+Adam, train mode, all host threads); {how}"}
+            if not args.no_extras:
+                try:
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        extra["esol_ft_cpu"] = cpu_esol_finetune_rate()
+                except Exception as ex:
+                    extra["esol_ft_cpu"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         line = {"metric": METRIC, "value": round(value, 1), "unit": "molecules/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32 (3xTF32 split tensor-core projections, f32-grade)", "fp32_simt": "f32",
-                          "tf32": "f32 (tf32-in/f32-acc tensor-core projections)"}[args.precision],
+                "dtype": {"fp32": "f32 (projections: 3xTF32 split on tcgen05, f32-grade; the 1e-5 parity mode)",
+                          "fp32_simt": "f32", "tf32": "f32 (tf32-in/f32-acc tensor-core projections)"}[args.precision],
+                "precision": args.precision,
+                "value_tf32": tf32["value"] if tf32 else None, "ms_per_step_tf32": tf32["ms_per_step"] if tf32 else None,
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.shape),
                            "per_gpu_batch": args.batch, "global_batch": args.batch * world,
@@ -499,7 +782,7 @@ def run_ours(args):
                            "driver": "nn.Module + autograd + FlatAdam" if args.autograd else
                                      "FusedPretrainStep (fnb_pretrain_step + fnb_adam_step)"},
                 "e2e": e2e, "e2e_arena": e2e_arena, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "extra": extra or None}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -41,8 +41,10 @@ SIGNATURES = {
     "fnb_dropout_relu_fwd": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _i32, _u64, _u64, _vp]),
     "fnb_dropout_relu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _i32, _vp]),
     "fnb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
+    "fnb_widen_batch": (C.c_int, [_vp, _i32, _vp]),
     "fnb_gat_fwd_tiled": (C.c_int, [_vp, _vp, _vp]),
     "fnb_gat_bwd_tiled": (C.c_int, [_vp, _vp, _vp]),
+    "fnb_gat_bwd_tiled_marked": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fnb_edge_table_bwd_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     "fnb_batch_plan_bytes": (_sz, [_vp]),
     "fnb_batch_plan_build": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
@@ -98,6 +100,11 @@ class CArenaJob(C.Structure):
                 ("mode", C.c_int32)]
 
 
+class CWidenJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("n", C.c_int64), ("mode", C.c_int32)]
+
+
+WIDEN_U8_F32, WIDEN_I32_I64, WIDEN_MAX_JOBS = 0, 1, 16
 ARENA_COPY32, ARENA_INDEX, ARENA_FILL = 0, 1, 2
 ARENA_MAX_KINDS, ARENA_MAX_JOBS = 24, 32
 ABI_VERSION = 6

@@ -12,6 +12,8 @@
 
 namespace {
 
+struct WidenJobs { fnb_widen_job j[FNB_WIDEN_MAX_JOBS]; };
+
 __global__ void __launch_bounds__(256) k_dropout_relu_fwd(const float *__restrict__ x, float *__restrict__ y, int64_t n,
                                                           float p, float scale, int relu, uint64_t seed,
                                                           uint64_t offset, int vec_ok) {
@@ -97,7 +99,64 @@ inline int ew_grid(int64_t n4) {
   return (int)b;
 }
 
+// Compact wire format of a batch dict -> the dtypes the reference's collate produces (fnb_widen_batch).
+// One launch for every tensor of the batch: blockIdx.y = job; 4 elements per thread and step.
+__global__ void __launch_bounds__(256) k_widen(WidenJobs jobs) {
+  pdl_wait();
+  const fnb_widen_job j = jobs.j[blockIdx.y];
+  const int64_t n4 = j.n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (j.mode == FNB_WIDEN_U8_F32) {
+    const uchar4 *src = reinterpret_cast<const uchar4 *>(j.src);
+    float4 *dst = reinterpret_cast<float4 *>(j.dst);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const uchar4 v = __ldg(src + i);
+      dst[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (j.n & 3)) {
+      const int64_t i = (n4 << 2) + threadIdx.x;
+      reinterpret_cast<float *>(j.dst)[i] = (float)reinterpret_cast<const uint8_t *>(j.src)[i];
+    }
+  } else {  // FNB_WIDEN_I32_I64
+    const int4 *src = reinterpret_cast<const int4 *>(j.src);
+    longlong2 *dst = reinterpret_cast<longlong2 *>(j.dst);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const int4 v = __ldg(src + i);
+      dst[2 * i] = make_longlong2((long long)v.x, (long long)v.y);
+      dst[2 * i + 1] = make_longlong2((long long)v.z, (long long)v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (j.n & 3)) {
+      const int64_t i = (n4 << 2) + threadIdx.x;
+      reinterpret_cast<int64_t *>(j.dst)[i] = (int64_t)reinterpret_cast<const int32_t *>(j.src)[i];
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int fnb_widen_batch(const fnb_widen_job *jobs, int n_jobs, void *stream) {
+  if (n_jobs < 0 || n_jobs > FNB_WIDEN_MAX_JOBS) return FNB_ERR_SIZE;
+  if (n_jobs == 0) return 0;
+  if (!jobs) return FNB_ERR_NULL;
+  WidenJobs w{};
+  int64_t most = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const fnb_widen_job &j = jobs[i];
+    if (j.n < 0) return FNB_ERR_SIZE;
+    if (j.mode != FNB_WIDEN_U8_F32 && j.mode != FNB_WIDEN_I32_I64) return FNB_ERR_MODE;
+    if (j.n > 0 && (!j.src || !j.dst)) return FNB_ERR_NULL;
+    if (!fnb_aligned16(j.src) || !fnb_aligned16(j.dst)) return FNB_ERR_ALIGN;
+    w.j[i] = j;
+    if (j.n > most) most = j.n;
+  }
+  if (most == 0) return 0;
+  int64_t blocks = ((most >> 2) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  if (cudaError_t le = fnb_launch(k_widen, dim3((unsigned)blocks, n_jobs), dim3(256), 0, (cudaStream_t)stream, w)) return (int)le;
+  FNB_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int fnb_dropout_relu_fwd(const float *x, float *y, int64_t n, float p, int training, int relu, uint64_t seed,
                                     uint64_t offset, void *stream) {

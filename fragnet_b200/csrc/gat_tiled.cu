@@ -1029,6 +1029,10 @@ extern "C" int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *b, 
   return fnb_gat_bwd_tiled_fused(g, b, nullptr, nullptr, nullptr, stream_);
 }
 
+extern "C" int fnb_gat_bwd_tiled_marked(const fnb_graph *g, const fnb_gat_bwd_args *b, void *between_passes, void *stream_) {
+  return fnb_gat_bwd_tiled_fused(g, b, nullptr, (cudaEvent_t)between_passes, nullptr, stream_);
+}
+
 int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *b, const FnbDstFuse *fz, cudaEvent_t after_dst,
                             cudaEvent_t before_src, void *stream_) {
   if (!graph_ok(g) || !b) return g && b ? FNB_ERR_SIZE : FNB_ERR_NULL;

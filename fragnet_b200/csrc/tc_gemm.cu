@@ -1099,6 +1099,13 @@ int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int cols, int box
   return r == CUDA_SUCCESS ? 0 : FNB_ERR_MODE;
 }
 
+// Persistent grid with the same number of tiles on every CTA: 203 tiles on 148 SMs are two rounds either way, and 102
+// CTAs with two tiles each leave 46 SMs to the kernels of the other streams (a GEMM CTA owns its SM's shared memory).
+int balanced_grid(int64_t n_tiles, int max_ctas) {
+  const int64_t per = (n_tiles + max_ctas - 1) / max_ctas;
+  return (int)((n_tiles + per - 1) / per);
+}
+
 }  // namespace
 
 // C[M,128] = A[M,K] @ B[128,K]^T (+bias) with optional fused S; returns FNB_ERR_MODE if the shape cannot take the
@@ -1154,12 +1161,12 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
       if (rc) return rc;
       rc = make_map(&tm_c, C, M, TC_BN, 32);       // store boxes: 32 columns x 32 rows, 128-byte swizzle
       if (rc) return rc;
-      const int gridR = (int)(n_tiles3 < kNumSMs ? n_tiles3 : kNumSMs);
+      const int gridR = balanced_grid(n_tiles3, kNumSMs);
       if (cudaError_t le = fnb_launch(kern, dim3(gridR), dim3(X3R_THREADS), smemR, stream, A, K, tm_w, tm_c, g)) return (int)le;
       FNB_CHECK_LAUNCH();
       return 0;
     }
-    const int pairs = (int)(n_tiles3 < kNumSMs / 2 ? n_tiles3 : kNumSMs / 2);
+    const int pairs = balanced_grid(n_tiles3, kNumSMs / 2);
     if (cudaError_t le = fnb_launch(k_tc_proj3, dim3(2 * pairs), dim3(X3_THREADS), smem3, stream, tm_a, tm_b, g)) return (int)le;
     FNB_CHECK_LAUNCH();
     return 0;
@@ -1182,7 +1189,7 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
     }
   }
   const int64_t n_tiles = (M + TC_BM - 1) / TC_BM;
-  const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  const int grid = balanced_grid(n_tiles, kNumSMs);
   if (cudaError_t le = fnb_launch(k_tc_proj, dim3(grid), dim3(TC_THREADS), smem, stream, tm_a, tm_b, g)) return (int)le;
   FNB_CHECK_LAUNCH();
   return 0;

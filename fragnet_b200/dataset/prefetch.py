@@ -8,13 +8,39 @@ the copies of the NEXT batches on a side stream from pinned memory while the cur
 
 Device memory comes from ``depth`` persistent slots of grow-only flat buffers (one per dtype), so the steady state
 performs no allocation and never touches the caching allocator from the copy stream.
+
+Batches in the compact wire format (``dataset.data.compact_batch``: uint8 feature matrices, int32 indices -- a third
+of the bytes) are widened on the device right behind their copy, on the copy stream, by one ``fnb_widen_batch`` launch:
+the consumer always sees ``collate_fn``'s dtypes and values.  Batches that already live on the device (an
+``ArenaLoader``) pass through untouched.
 """
 from __future__ import annotations
 
 import collections
+import ctypes as C
 from typing import Dict, Iterable, Iterator, List
 
 import torch
+
+from .. import _abi
+from .data import INDEX_KEYS, ONE_HOT_KEYS
+
+_UNREAD = ("edge_attr", "cnx_attr")
+
+
+def _wide_dtype(key: str, t: torch.Tensor):
+    """dtype the consumer expects for a (possibly narrowed) host tensor."""
+    if t.dtype == torch.uint8 and key in ONE_HOT_KEYS:
+        return torch.float32
+    if t.dtype == torch.int32 and key in INDEX_KEYS:
+        return torch.int64
+    return t.dtype
+
+
+def staged_bytes(host: Dict[str, torch.Tensor], hot_path_only: bool = True) -> int:
+    """Bytes ``DevicePrefetcher`` moves over PCIe for this host batch."""
+    return sum(v.numel() * v.element_size() for k, v in host.items()
+               if isinstance(v, torch.Tensor) and not (hot_path_only and (k in _UNREAD or k == "x_frags")))
 
 
 class _Slot:
@@ -26,27 +52,36 @@ class _Slot:
         self.free_event = None          # recorded on the compute stream once the consumer has moved on
 
     def views(self, host: Dict[str, torch.Tensor]):
-        """(views, grew): device views shaped like the tensors of ``host``; ``grew`` if a buffer was (re)allocated."""
+        """(wire views, consumer views, grew): device views shaped like the tensors of ``host`` in their wire dtype and
+        in the dtype the consumer expects (the same view where nothing has to be widened)."""
         grew = False
         need: Dict[torch.dtype, int] = collections.defaultdict(int)
-        for v in host.values():
+        pad = lambda n: (n + 63) // 64 * 64
+        for k, v in host.items():
             if isinstance(v, torch.Tensor):
-                need[v.dtype] += (v.numel() + 63) // 64 * 64
+                need[v.dtype] += pad(v.numel())
+                if _wide_dtype(k, v) != v.dtype:
+                    need[_wide_dtype(k, v)] += pad(v.numel())
         for dt, n in need.items():
             buf = self.buffers.get(dt)
             if buf is None or buf.numel() < n:
                 self.buffers[dt] = torch.empty(int(n * 1.25) + 64, dtype=dt, device=self.device)
                 grew = True
         used: Dict[torch.dtype, int] = collections.defaultdict(int)
-        out = {}
+
+        def take(dt, shape, n):
+            o = used[dt]
+            used[dt] = o + pad(n)
+            return self.buffers[dt][o:o + n].view(shape)
+        wire, out = {}, {}
         for k, v in host.items():
             if isinstance(v, torch.Tensor):
-                o = used[v.dtype]
-                out[k] = self.buffers[v.dtype][o:o + v.numel()].view(v.shape)
-                used[v.dtype] = o + (v.numel() + 63) // 64 * 64
+                wire[k] = take(v.dtype, v.shape, v.numel())
+                wd = _wide_dtype(k, v)
+                out[k] = wire[k] if wd == v.dtype else take(wd, v.shape, v.numel())
             else:
                 out[k] = v
-        return out, grew
+        return wire, out, grew
 
 
 class DevicePrefetcher:
@@ -68,32 +103,42 @@ class DevicePrefetcher:
         self._copy_stream = torch.cuda.Stream(self.device)
         self._slots: List[_Slot] = [_Slot(self.device) for _ in range(self.depth + 1)]
 
-    _UNREAD = ("edge_attr", "cnx_attr")
-
     def _stage(self, host: Dict[str, torch.Tensor], slot: _Slot):
+        if all(v.is_cuda for v in host.values() if isinstance(v, torch.Tensor)):
+            return host, None, None, None                # already on the device (ArenaLoader): nothing to stage
         shape_only = None
         if self.hot_path_only:
-            host = {k: v for k, v in host.items() if k not in self._UNREAD}
+            host = {k: v for k, v in host.items() if k not in _UNREAD}
             if isinstance(host.get("x_frags"), torch.Tensor):
                 shape_only = host.pop("x_frags")
         dev, ev, pinned, slot = self._stage_tensors(host, slot)
         if shape_only is not None:
-            dev["x_frags"] = torch.empty(shape_only.shape, dtype=shape_only.dtype, device="meta")
+            dev["x_frags"] = torch.empty(shape_only.shape, dtype=torch.float32, device="meta")
         return dev, ev, pinned, slot
 
     def _stage_tensors(self, host: Dict[str, torch.Tensor], slot: _Slot):
         pinned = {k: (v if (not isinstance(v, torch.Tensor) or v.is_cuda or v.is_pinned()) else v.pin_memory())
                   for k, v in host.items()}
-        dev, grew = slot.views(pinned)                   # (re)allocation, if any, happens on the current stream
+        wire, dev, grew = slot.views(pinned)             # (re)allocation, if any, happens on the current stream
         cs = self._copy_stream
         if slot.free_event is not None:
             cs.wait_event(slot.free_event)               # the previous tenant of this slot has been consumed
         if grew:
             cs.wait_stream(torch.cuda.current_stream(self.device))   # stream-ordered reuse of freed memory
+        jobs = []
         with torch.cuda.stream(cs):
             for k, v in pinned.items():
                 if isinstance(v, torch.Tensor):
-                    dev[k].copy_(v, non_blocking=True)
+                    if v.is_cuda:
+                        cs.wait_stream(torch.cuda.current_stream(self.device))   # its producer runs on the consumer's stream
+                    wire[k].copy_(v, non_blocking=True)
+                    if wire[k] is not dev[k] and v.numel():
+                        jobs.append((wire[k], dev[k], _abi.WIDEN_U8_F32 if v.dtype == torch.uint8 else _abi.WIDEN_I32_I64))
+            for c in range(0, len(jobs), _abi.WIDEN_MAX_JOBS):
+                chunk = jobs[c:c + _abi.WIDEN_MAX_JOBS]
+                arr = (_abi.CWidenJob * len(chunk))(*[_abi.CWidenJob(s.data_ptr(), d.data_ptr(), s.numel(), m)
+                                                      for s, d, m in chunk])
+                _abi.check(_abi.load().fnb_widen_batch(arr, len(chunk), C.c_void_p(cs.cuda_stream)), "widen_batch")
             ev = torch.cuda.Event()
             ev.record(cs)
         return dev, ev, pinned, slot                     # pinned host tensors stay alive until the copy was waited for
@@ -119,6 +164,7 @@ class DevicePrefetcher:
             if not queue:
                 return
             dev, ev, _pinned, slot = queue.popleft()
-            cur.wait_event(ev)
+            if ev is not None:
+                cur.wait_event(ev)
             last = slot
             yield dev

@@ -461,13 +461,17 @@ def gat_fwd_tiled(g: GraphCSR, h, S, mode, *, table=None, We=None, be=None, alph
 
 
 def gat_bwd_tiled(g: GraphCSR, h, dout, p, mode, alpha, alpha_stride, off_t, off_e, off_s, d_alpha, *, We=None,
-                  be=None, want_bias_grad=False):
+                  be=None, want_bias_grad=False, mark=None, out=None):
     """``fnb_gat_bwd_tiled`` (destination pass + source pass).  Writes the off_t / off_s (and, for the affine modes,
-    off_e) slices of ``d_alpha``.  Returns (dh, dz, d_bias | None, dWe | None, dbe | None)."""
+    off_e) slices of ``d_alpha``.  Returns (dh, dz, d_bias | None, dWe | None, dbe | None).  ``mark``: a created
+    ``torch.cuda.Event`` recorded between the two passes; ``out``: (dz, dSt, dh) buffers to reuse."""
     dev = h.device
-    dz = torch.empty((g.n_edges, H), dtype=torch.float32, device=dev)
-    dSt = torch.empty((g.n_nodes, H), dtype=torch.float32, device=dev)
-    dh = torch.empty((g.n_nodes, D), dtype=torch.float32, device=dev)
+    if out is not None:
+        dz, dSt, dh = out
+    else:
+        dz = torch.empty((g.n_edges, H), dtype=torch.float32, device=dev)
+        dSt = torch.empty((g.n_nodes, H), dtype=torch.float32, device=dev)
+        dh = torch.empty((g.n_nodes, D), dtype=torch.float32, device=dev)
     db = torch.empty(D, dtype=torch.float32, device=dev) if want_bias_grad else None
     affine = mode in (EDGE_AFFINE1, EDGE_AFFINE6)
     dWe = torch.empty_like(We) if affine else None
@@ -475,7 +479,11 @@ def gat_bwd_tiled(g: GraphCSR, h, dout, p, mode, alpha, alpha_stride, off_t, off
     args = _abi.CGatBwdArgs(_ptr(h), _ptr(dout), _ptr(p), mode, _ptr(We), _ptr(be), _ptr(alpha), alpha_stride, off_t,
                             off_e, off_s, _ptr(dz), _ptr(dSt), _ptr(dh), _ptr(d_alpha), _ptr(db), _ptr(dWe), _ptr(dbe),
                             _ptr(scratch(dev)))
-    _abi.check(_lib().fnb_gat_bwd_tiled(C.byref(g.cstruct()), C.byref(args), _stream()), "gat_bwd_tiled")
+    if mark is not None:
+        _abi.check(_lib().fnb_gat_bwd_tiled_marked(C.byref(g.cstruct()), C.byref(args), C.c_void_p(mark.cuda_event),
+                                                   _stream()), "gat_bwd_tiled_marked")
+    else:
+        _abi.check(_lib().fnb_gat_bwd_tiled(C.byref(g.cstruct()), C.byref(args), _stream()), "gat_bwd_tiled")
     return dh, dz, db, dWe, dbe
 
 

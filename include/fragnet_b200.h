@@ -228,6 +228,9 @@ typedef struct fnb_gat_bwd_args {
 int fnb_gat_fwd_tiled(const fnb_graph *g, const fnb_gat_fwd_args *args, void *stream);
 /* destination pass then source pass (two launches) */
 int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *args, void *stream);
+/* Same two launches with `between_passes` (a cudaEvent_t of the caller, may be NULL) recorded on `stream` after the
+ * destination pass: lets a caller time the two passes separately (bench.py's roofline.kernels). */
+int fnb_gat_bwd_tiled_marked(const fnb_graph *g, const fnb_gat_bwd_args *args, void *between_passes, void *stream);
 /* g_feat[e,:] = g_base[e,:] (if given) + dy[e,:]*(y[e,:]>0)*post_scale (if given) + sum_h dz[slot_of_eid[e],h]*alpha_e[h,:];
  * d_alpha[h, off_e:off_e+128] = sum_e dz[slot_of_eid[e],h] * feat[e,:] */
 int fnb_edge_table_bwd_fused(const fnb_graph *g, const float *dz, const float *feat, const float *alpha,
@@ -361,6 +364,22 @@ int fnb_dropout_relu_fwd(const float *x, float *y, int64_t n, float p, int train
 /* dx = dy * (y > 0) / (1-p)   (valid for the fused ReLU form; y is the forward output) */
 int fnb_dropout_relu_bwd(const float *dy, const float *y, float *dx, int64_t n, float p,
                          int training, void *stream);
+
+/* ---- compact wire format of a batch dict (host -> device staging, dataset/prefetch.py) ----------------------------
+ * collate_fn (fragnet/dataset/data.py:877-948) emits one-hot / small-integer feature matrices as fp32 and every index
+ * as int64: 32 MB per 1 024-molecule batch on the wire for 11 MB of information.  The compact format ships those
+ * matrices as uint8 and the indices as int32; one launch widens every tensor of a batch into the dtypes the reference
+ * produces (exact: the host side verifies the round trip before it narrows). */
+#define FNB_WIDEN_U8_F32 0  /* uint8 -> float32 */
+#define FNB_WIDEN_I32_I64 1 /* int32 -> int64   */
+#define FNB_WIDEN_MAX_JOBS 16
+typedef struct fnb_widen_job {
+  const void *src; /* n elements, 16-byte aligned */
+  void *dst;       /* n elements of the wide type, 16-byte aligned */
+  int64_t n;
+  int mode;        /* FNB_WIDEN_* */
+} fnb_widen_job;
+int fnb_widen_batch(const fnb_widen_job *jobs, int n_jobs, void *stream);
 
 /* ---- optimizer step over one flat parameter buffer (the trainer's torch.optim.Adam, pretrain_gat2.py:165) -------
  * torch.optim.Adam's update (no amsgrad) on n contiguous fp32 elements in ONE launch; step counts from 1. */

@@ -1,12 +1,14 @@
-"""Load the UNMODIFIED reference modules with the shims injected.  TEST INFRASTRUCTURE.
+"""Load the UNMODIFIED reference modules with the shims injected.  TEST / BENCH INFRASTRUCTURE.
 
-Only usable where a reference checkout exists (``$FRAGNET_REFERENCE`` or ``/root/reference``);
-that is the build container, never the GPU box.  Used to (1) validate ``gat2_oracle`` and
-(2) generate the golden fixtures under ``tests/golden/``.
+Sources: the reference checkout (``$FRAGNET_REFERENCE`` or ``/root/reference``, build container only) or the
+bytecode ``oracle/build_ref.py`` compiled from it into ``oracle/_ref`` (git-ignored build output that travels to the GPU
+box; no reference source is copied).  Used to (1) validate ``gat2_oracle``, (2) generate the golden fixtures under ``tests/golden/`` and (3) time
+the reference itself on the host cores (``bench.py --impl reference``).
 """
 from __future__ import annotations
 
 import contextlib
+import importlib.machinery
 import importlib.util
 import io
 import os
@@ -15,19 +17,49 @@ import types
 
 from . import shims
 
-REFERENCE_ROOT = os.environ.get("FRAGNET_REFERENCE", "/root/reference")
 _PKG = "_fragnet_reference"      # private package name so it never shadows the product's ``fragnet``
+_PROBE = "fragnet/model/gat/gat2.py"
+
+
+def _find_root() -> str:
+    """The reference checkout (build container) or, failing that, ``oracle/_ref`` -- the bytecode ``oracle/build_ref.py``
+    compiled from it (what travels to the GPU box)."""
+    checkout = os.environ.get("FRAGNET_REFERENCE", "/root/reference")
+    if os.path.isfile(os.path.join(checkout, _PROBE)):
+        return checkout
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_root()
+
+
+def _module_file(relpath: str):
+    """Source file of the checkout, or the compiled module under oracle/_ref (``<relpath>c``)."""
+    src = os.path.join(REFERENCE_ROOT, relpath)
+    if os.path.isfile(src):
+        return src
+    return src + "c" if os.path.isfile(src + "c") else None
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "fragnet/model/gat/gat2.py"))
+    return _module_file(_PROBE) is not None
+
+
+def kind() -> str:
+    """"checkout" (sources under /root/reference) or "compiled" (bytecode under oracle/_ref)."""
+    f = _module_file(_PROBE)
+    return "none" if f is None else ("compiled" if f.endswith(".pyc") else "checkout")
 
 
 def _load(modname: str, relpath: str):
     full = f"{_PKG}.{modname}"
     if full in sys.modules:
         return sys.modules[full]
-    spec = importlib.util.spec_from_file_location(full, os.path.join(REFERENCE_ROOT, relpath))
+    path = _module_file(relpath)
+    if path is None:
+        raise FileNotFoundError(f"{relpath} not found under {REFERENCE_ROOT}")
+    loader = importlib.machinery.SourcelessFileLoader(full, path) if path.endswith(".pyc") else None
+    spec = importlib.util.spec_from_file_location(full, path, loader=loader)
     mod = importlib.util.module_from_spec(spec)
     sys.modules[full] = mod
     spec.loader.exec_module(mod)
@@ -69,6 +101,14 @@ def load_lite():
         pkg.__path__ = []
         sys.modules[_PKG] = pkg
     return _load("gat2_lite", "fragnet/model/gat/gat2_lite.py")
+
+
+def load_trainer():
+    """The reference's ``fragnet/train/pretrain/pretrain_utils.py`` (``Trainer``: the step loop and loss of
+    pretrain_utils.py:9-31), unmodified."""
+    if not available():
+        raise FileNotFoundError(f"no reference sources under {REFERENCE_ROOT}")
+    return _load("pretrain_utils", "fragnet/train/pretrain/pretrain_utils.py")
 
 
 def load_data():

@@ -106,3 +106,30 @@ def test_model_on_arena_batch_is_bitwise_the_collated_batch():
     b = m({k: v.cuda() for k, v in collate_fn_pt([ds[int(i)] for i in ids]).items()})
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_prefetcher_widens_the_compact_wire_format_bit_exactly():
+    """Compact host batches (uint8 feature matrices, int32 indices) arrive on the device with collate_fn_pt's dtypes and
+    values; device-resident batches pass through untouched; ragged element counts exercise the kernel's tail."""
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt, compact_batch
+    from fragnet_b200.dataset.prefetch import DevicePrefetcher, staged_bytes
+    ds = synth.make_dataset("unimol", 37, seed=13) + [synth.handmade("ion_pair")]
+    wide = [collate_fn_pt(ds[i:i + n]) for i, n in ((0, 7), (7, 30), (37, 1), (3, 5))]
+    narrow = [compact_batch(b, pin=True) for b in wide]
+    assert staged_bytes(narrow[1]) < 0.45 * staged_bytes(wide[1])
+    for hot in (False, True):
+        got = list(DevicePrefetcher(iter(narrow), "cuda", depth=2, hot_path_only=hot))
+        assert len(got) == len(wide)
+        for g, w in zip(got, wide):
+            torch.cuda.synchronize()
+            for k, v in w.items():
+                if hot and k in ("edge_attr", "cnx_attr"):
+                    assert k not in g
+                elif hot and k == "x_frags":
+                    assert g[k].device.type == "meta" and g[k].shape == v.shape and g[k].dtype == v.dtype
+                else:
+                    assert g[k].dtype == v.dtype and torch.equal(g[k].cpu(), v), k
+    dev = [{k: v.cuda() for k, v in b.items()} for b in wide[:2]]
+    through = list(DevicePrefetcher(iter(dev), "cuda"))
+    assert all(t[k] is d[k] for t, d in zip(through, dev) for k in d)
