@@ -42,6 +42,8 @@ SIGNATURES = {
     "fnb_dropout_relu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _i32, _vp]),
     "fnb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
     "fnb_widen_batch": (C.c_int, [_vp, _i32, _vp]),
+    "fnb_allreduce_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, C.c_uint32, _vp,
+                                          _vp]),
     "fnb_gat_fwd_tiled": (C.c_int, [_vp, _vp, _vp]),
     "fnb_gat_bwd_tiled": (C.c_int, [_vp, _vp, _vp]),
     "fnb_gat_bwd_tiled_marked": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -98,6 +100,10 @@ class CArenaKind(C.Structure):
 class CArenaJob(C.Structure):
     _fields_ = [("src", _vp), ("dst", _vp), ("kind", C.c_int32), ("offset_kind", C.c_int32), ("width", C.c_int32),
                 ("mode", C.c_int32)]
+
+
+class CPeerSet(C.Structure):
+    _fields_ = [("grads", _vp * 8), ("flags", _vp * 8), ("world", C.c_int32), ("rank", C.c_int32)]
 
 
 class CWidenJob(C.Structure):

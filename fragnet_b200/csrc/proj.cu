@@ -339,7 +339,7 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
     const int rc = fnb_tc_proj_launch(x, W, b, n_rows, K, S ? alpha : nullptr, alpha_stride, off_t, off_s, h, S,
                                       (cudaStream_t)stream, precision == FNB_PRECISION_TF32X3);
     if (rc != FNB_ERR_MODE) return rc;   // shapes TMA cannot address (K*4 % 16 != 0) take the SIMT kernel below
-  } else if (precision != FNB_PRECISION_FP32) {
+  } else if (precision != FNB_PRECISION_FP32 && !fnb_tc_precision(precision)) {
     return FNB_ERR_MODE;
   }
   if (rowsparse_shape(K) && K <= kProjBwdMaxK) {

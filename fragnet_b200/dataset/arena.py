@@ -291,6 +291,7 @@ class ArenaLoader:
                  generator: Optional[torch.Generator] = None, rank: int = 0, world: int = 1):
         self.arena, self.batch_size, self.shuffle, self.drop_last = arena, int(batch_size), shuffle, drop_last
         self.generator, self.rank, self.world = generator, int(rank), int(world)
+        self.dataset = arena         # the loops divide by len(loader.dataset) (pretrain_utils.py:31, utils.py:351)
 
     def __len__(self) -> int:
         return len(epoch_batches(len(self.arena), self.batch_size, False, self.drop_last, None, self.rank, self.world))

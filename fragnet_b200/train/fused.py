@@ -54,7 +54,9 @@ class FusedPretrainStep:
             raise ValueError("FusedPretrainStep needs fp32 parameters on one CUDA device")
         self.live = live
         self.flat_p, p_views = _flat_views(live, dev)
-        self.flat_g, g_views = _flat_views(live, dev)
+        self._peers = None
+        g_store = self._symmetric_gradient_buffer(live, dev, group)
+        self.flat_g, g_views = _flat_views(live, dev, storage=g_store)
         with torch.no_grad():
             torch._foreach_copy_(p_views, [p.data for p in live])
             for p, v, g in zip(live, p_views, g_views):
@@ -63,6 +65,11 @@ class FusedPretrainStep:
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.t = 0
+        self._p_views = p_views
+        if self.world_size > 1:
+            # DDP / Fabric broadcast rank 0's parameters at wrap time (finetune_gat2_pl.py:230): differently seeded
+            # ranks, or a checkpoint loaded on one rank only, must not diverge silently
+            dist.broadcast(self.flat_p, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         grad_of: Dict[int, torch.Tensor] = {id(p): g for p, g in zip(live, g_views)}
         # ---- C structs (built once: parameter storage never moves afterwards)
         self._layers = (_abi.CLayerParams * n_layers)()
@@ -93,6 +100,70 @@ class FusedPretrainStep:
         self.n_layers = n_layers
 
     # ------------------------------------------------------------------------------------------
+    def _symmetric_gradient_buffer(self, live, dev, group):
+        """World > 1: the flat gradient buffer is allocated in symmetric memory (peer-mapped over NVLink at rendezvous)
+        so that ``fnb_allreduce_adam_step`` can read every rank's gradients directly -- exchange, mean and Adam are then
+        one kernel instead of ncclAllReduce + scale + Adam.  Returns the storage tensor, or None (single rank, no NVLink
+        peer access, ``FNB_FUSED_ALLREDUCE=0``): ``step`` then uses ``dist.all_reduce`` + ``fnb_adam_step``."""
+        import os
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+            return None
+        w = dist.get_world_size(group)
+        if os.environ.get("FNB_FUSED_ALLREDUCE", "1") == "0" or w > 8 or dist.get_backend(group) != "nccl":
+            return None
+        from .optim import ALIGN
+        total = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for p in live)
+        try:
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            g = symm.empty(total, dtype=torch.float32, device=dev)
+            flags = symm.empty(2 * w, dtype=torch.int32, device=dev)
+            g.zero_()
+            flags.zero_()
+            hg, hf = symm.rendezvous(g, pg), symm.rendezvous(flags, pg)
+            ps = _abi.CPeerSet()
+            for r in range(w):
+                ps.grads[r], ps.flags[r] = hg.buffer_ptrs[r], hf.buffer_ptrs[r]
+            ps.world, ps.rank = w, hg.rank
+            ok = torch.ones(1, device=dev)
+        except Exception as ex:          # no P2P between these devices, or an older torch: NCCL path
+            import warnings
+            warnings.warn(f"fragnet_b200: symmetric-memory gradient exchange unavailable ({type(ex).__name__}: {ex}); "
+                          "using ncclAllReduce", RuntimeWarning)
+            g, ok = None, torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)       # all ranks take the same path (zeroed flags visible)
+        if float(ok) < 1.0 or g is None:
+            return None
+        self._peers, self._flags, self._epoch = ps, flags, 0
+        self._done = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._symm_keep = (hg, hf)
+        return g
+
+    def bound_to_model(self) -> bool:
+        """True while every live parameter still is its view of the flat buffer (``model.to()``, ``.cpu()`` or a
+        re-assigned ``p.data`` break the binding; the caller then has to fall back to the generic loop)."""
+        return all(p.data_ptr() == v.data_ptr() and p.device == v.device for p, v in zip(self.live, self._p_views))
+
+    def attach_optimizer(self, optimizer) -> None:
+        """Keep a caller-owned ``torch.optim.Adam`` truthful: its ``state`` entries of the live parameters become VIEWS
+        of this object's moment buffers plus a shared step counter, so ``optimizer.state_dict()`` checkpoints the real
+        state; moments already present in ``optimizer.state`` (a resumed run) are adopted first."""
+        from .optim import flat_views
+        _, m_views = flat_views(self.live, self.dev, storage=self.exp_avg)
+        _, v_views = flat_views(self.live, self.dev, storage=self.exp_avg_sq)
+        steps = [int(optimizer.state[p]["step"]) for p in self.live if p in optimizer.state and "step" in optimizer.state[p]]
+        with torch.no_grad():
+            for p, m, v in zip(self.live, m_views, v_views):
+                st = optimizer.state.get(p)
+                if st and "exp_avg" in st:
+                    m.copy_(st["exp_avg"])
+                    v.copy_(st["exp_avg_sq"])
+        if steps:
+            self.t = max(steps)
+        self._opt_step = torch.tensor(float(self.t))
+        for p, m, v in zip(self.live, m_views, v_views):
+            optimizer.state[p] = {"step": self._opt_step, "exp_avg": m, "exp_avg_sq": v}
+
     @property
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
@@ -168,13 +239,25 @@ class FusedPretrainStep:
         """collate + forward + loss + backward (+ all-reduce) + Adam on one batch dict; returns the loss."""
         loss, _ = self._run(batch, backward=True)
         w = self.world_size
+        self.t += 1
+        if w > 1 and self._peers is not None:
+            # gradient exchange + mean + Adam in one kernel over NVLink peer memory (csrc/dist.cu)
+            self._epoch += 1
+            _abi.check(ops._lib().fnb_allreduce_adam_step(
+                C.byref(self._peers), ops._p(self.flat_p), ops._p(self.exp_avg), ops._p(self.exp_avg_sq),
+                self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t,
+                self._epoch & 0xFFFFFFFF, ops._p(self._done), ops._stream()), "allreduce_adam_step")
+            if getattr(self, "_opt_step", None) is not None:
+                self._opt_step.fill_(float(self.t))
+            return loss
         if w > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
             self.flat_g.mul_(1.0 / w)
-        self.t += 1
         _abi.check(ops._lib().fnb_adam_step(ops._p(self.flat_p), ops._p(self.flat_g), ops._p(self.exp_avg),
                                             ops._p(self.exp_avg_sq), self.flat_p.numel(), self.lr, self.betas[0],
                                             self.betas[1], self.eps, self.weight_decay, self.t, ops._stream()), "adam_step")
+        if getattr(self, "_opt_step", None) is not None:
+            self._opt_step.fill_(float(self.t))
         return loss
 
     def forward_backward(self, batch) -> torch.Tensor:

@@ -20,13 +20,16 @@ from .. import _abi
 ALIGN = 64     # floats: every tensor of a flat buffer starts on a 256-byte boundary (TMA operands need 16 bytes)
 
 
-def flat_views(params, device, dtype=torch.float32):
-    """One zero-filled flat buffer with an aligned slot per tensor of ``params``; returns (flat, views)."""
+def flat_views(params, device, dtype=torch.float32, storage=None):
+    """One zero-filled flat buffer with an aligned slot per tensor of ``params``; returns (flat, views).  ``storage``:
+    an existing flat buffer of that layout to take the views of instead of allocating one."""
     offs, total = [], 0
     for p in params:
         offs.append(total)
         total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
-    flat = torch.zeros(total, dtype=dtype, device=device)
+    if storage is not None and storage.numel() != total:
+        raise ValueError("flat_views: storage does not match the layout of params")
+    flat = storage if storage is not None else torch.zeros(total, dtype=dtype, device=device)
     return flat, [flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
 
 

@@ -37,14 +37,16 @@ def _plain_adam(optimizer) -> bool:
         return False
     g = optimizer.param_groups[0]
     return not (g.get("amsgrad") or g.get("maximize") or g.get("capturable") or g.get("differentiable")
-                or g.get("decoupled_weight_decay")) and len(optimizer.state) == 0
+                or g.get("decoupled_weight_decay"))
 
 
 class Trainer:
     def __init__(self, loss_fn=None, fused: bool = True):
         self.loss_fn = loss_fn
         self.fused = fused
-        self._fused_steps = {}       # (id(model), id(optimizer)) -> FusedPretrainStep
+        # FusedPretrainStep per (model, optimizer), held through weak references: an id() can be recycled after garbage
+        # collection, a dead weakref cannot be mistaken for a new object
+        self._fused_steps = []       # [(weakref(model), weakref(optimizer) | None, FusedPretrainStep | None)]
 
     # ---- fused path -----------------------------------------------------------------------------
     def _fused_for(self, model, optimizer, device):
@@ -53,9 +55,21 @@ class Trainer:
             return None
         if not (isinstance(self.loss_fn, torch.nn.MSELoss) and self.loss_fn.reduction == "mean"):
             return None
-        key = (id(model), id(optimizer))
-        if key in self._fused_steps:
-            return self._fused_steps[key]
+        if not torch.is_tensor(next(model.parameters(), None)):
+            return None
+        self._fused_steps = [e for e in self._fused_steps if e[0]() is not None and (e[1] is None or e[1]() is not None)]
+        for wm, wo, fs in self._fused_steps:
+            if wm() is model and (wo() if wo is not None else None) is optimizer:
+                if fs is not None and not fs.bound_to_model():
+                    # the parameters were moved or re-assigned (model.to(), .cpu(), p.data = ...): the flat buffers no
+                    # longer are the model -- hand this pair to the generic loop for good rather than train an orphan
+                    import warnings
+                    warnings.warn("fragnet_b200: the model's parameters were moved after the fused pretraining step was "
+                                  "built; falling back to the generic training loop", RuntimeWarning)
+                    self._fused_steps = [e for e in self._fused_steps if e[2] is not fs]
+                    self._fused_steps.append((wm, wo, None))
+                    return None
+                return fs
         from ..model.gat.pretrain_heads import FragNetPreTrain
         from .fused import FusedPretrainStep
         ok = isinstance(model, FragNetPreTrain) and model.head._library_shapes() and \
@@ -65,7 +79,12 @@ class Trainer:
             g = optimizer.param_groups[0] if optimizer is not None else {}
             fs = FusedPretrainStep(model, lr=g.get("lr", 1e-3), betas=g.get("betas", (0.9, 0.999)),
                                    eps=g.get("eps", 1e-8), weight_decay=g.get("weight_decay", 0.0))
-        self._fused_steps[key] = fs
+            if optimizer is not None:
+                # the caller's optimizer stays the owner of the state: its entries become views of the fused buffers
+                # (optimizer.state_dict() checkpoints them; moments loaded before the first step are adopted)
+                fs.attach_optimizer(optimizer)
+        import weakref
+        self._fused_steps.append((weakref.ref(model), weakref.ref(optimizer) if optimizer is not None else None, fs))
         return fs
 
     @staticmethod
@@ -95,7 +114,8 @@ class Trainer:
         fs = self._fused_for(model, optimizer, device)
         if fs is not None:
             def launch(batch):
-                fs.lr = float(optimizer.param_groups[0]["lr"])       # LR schedulers keep working
+                g = optimizer.param_groups[0]                        # LR schedulers / edited hyper-parameters keep working
+                fs.lr, fs.betas, fs.eps, fs.weight_decay = float(g["lr"]), g["betas"], float(g["eps"]), float(g["weight_decay"])
                 return fs.step(batch)
             return self._run_pipelined(loader, device, launch) / len(loader.dataset)
         total = 0.0
@@ -111,7 +131,7 @@ class Trainer:
 
     def validate(self, loader, model, device):
         model.eval()
-        fs = next((v for (mid, _), v in self._fused_steps.items() if mid == id(model) and v is not None), None)
+        fs = next((f for wm, _, f in self._fused_steps if wm() is model and f is not None and f.bound_to_model()), None)
         if fs is None:
             fs = self._fused_for(model, None, device)
         if fs is not None:

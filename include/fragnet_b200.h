@@ -386,6 +386,23 @@ int fnb_widen_batch(const fnb_widen_job *jobs, int n_jobs, void *stream);
 int fnb_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, void *stream);
 
+/* ---- data-parallel step: gradient exchange fused with the optimizer (dist.cu) ---------------------------------------
+ * Replaces ncclAllReduce(grad) + grad *= 1/W + Adam (Fabric DDP semantics, finetune_gat2_pl.py:230) by ONE kernel that
+ * reads every rank's gradient buffer through NVLink peer mappings, averages in rank order (bitwise identical parameters
+ * on every rank, run-to-run deterministic) and updates the local parameters.  grads[r] / flags[r]: rank r's gradient
+ * buffer (n floats) and flag row (2*world uint32, zero before first use) as mapped in THIS process (symmetric memory);
+ * epoch: a counter that grows by one per call, the same on every rank; done_counter: one device-local uint32, zero
+ * before first use.  Every rank must call it once per step. */
+#define FNB_MAX_PEERS 8
+typedef struct fnb_peer_set {
+  const void *grads[FNB_MAX_PEERS];
+  void *flags[FNB_MAX_PEERS];
+  int world, rank;
+} fnb_peer_set;
+int fnb_allreduce_adam_step(const fnb_peer_set *peers, float *param, float *exp_avg, float *exp_avg_sq, int64_t n,
+                            float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                            uint32_t epoch, void *done_counter, void *stream);
+
 /* ---- pretraining heads + loss (heads.cu) -------------------------------------------------------------------------
  * PretrainTask.forward (fragnet/model/gat/pretrain_heads.py:64-102) behind one call per direction: bond-length,
  * bond-angle, dihedral heads (Linear 128-64, ReLU, 64-32, ReLU, 32-1; the bond-length head first reduces

@@ -5,8 +5,9 @@ lie under the reference checkout, so that the reference itself can be timed on t
 INFRASTRUCTURE.
 
 The reference is pure Python, so its build product is CPython bytecode: every module the path needs
-is compiled with ``py_compile`` straight from the checkout into ``oracle/_ref/<same relative path>.pyc`` (git-ignored
-like any built artefact, shipped with the gpurun snapshot; no reference source is copied into the repo) next to a
+is compiled with ``py_compile`` straight from the checkout into ``oracle/_ref/<same relative path>.bin`` (CPython's
+.pyc format under a neutral suffix -- snapshot tools commonly drop ``*.pyc``; git-ignored like any built artefact,
+shipped with the gpurun snapshot; no reference source is copied into the repo) next to a
 manifest with the SHA-256 of the source each one was compiled from and the interpreter's bytecode magic.
 ``oracle/ref_import.py`` loads them through the same third-party shims as the checkout.
 Run here, where the checkout exists:  python oracle/build_ref.py
@@ -36,7 +37,7 @@ def build(reference_root: str = os.environ.get("FRAGNET_REFERENCE", "/root/refer
         raise FileNotFoundError(f"no reference checkout under {reference_root}")
     manifest = {}
     for rel in MODULES:
-        src, dst = os.path.join(reference_root, rel), os.path.join(DEST, rel + "c")
+        src, dst = os.path.join(reference_root, rel), os.path.join(DEST, rel + ".bin")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, dfile=rel, doraise=True)
         manifest[rel] = hashlib.sha256(open(src, "rb").read()).hexdigest()

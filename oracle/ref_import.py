@@ -34,11 +34,11 @@ REFERENCE_ROOT = _find_root()
 
 
 def _module_file(relpath: str):
-    """Source file of the checkout, or the compiled module under oracle/_ref (``<relpath>c``)."""
+    """Source file of the checkout, or the compiled module under oracle/_ref (``<relpath>.bin``, .pyc format)."""
     src = os.path.join(REFERENCE_ROOT, relpath)
     if os.path.isfile(src):
         return src
-    return src + "c" if os.path.isfile(src + "c") else None
+    return src + ".bin" if os.path.isfile(src + ".bin") else None
 
 
 def available() -> bool:
@@ -48,7 +48,7 @@ def available() -> bool:
 def kind() -> str:
     """"checkout" (sources under /root/reference) or "compiled" (bytecode under oracle/_ref)."""
     f = _module_file(_PROBE)
-    return "none" if f is None else ("compiled" if f.endswith(".pyc") else "checkout")
+    return "none" if f is None else ("compiled" if f.endswith(".bin") else "checkout")
 
 
 def _load(modname: str, relpath: str):
@@ -58,7 +58,7 @@ def _load(modname: str, relpath: str):
     path = _module_file(relpath)
     if path is None:
         raise FileNotFoundError(f"{relpath} not found under {REFERENCE_ROOT}")
-    loader = importlib.machinery.SourcelessFileLoader(full, path) if path.endswith(".pyc") else None
+    loader = importlib.machinery.SourcelessFileLoader(full, path) if path.endswith(".bin") else None
     spec = importlib.util.spec_from_file_location(full, path, loader=loader)
     mod = importlib.util.module_from_spec(spec)
     sys.modules[full] = mod

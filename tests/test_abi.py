@@ -68,7 +68,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
              ("fnb_mlp3_grads", A.CMlp3), ("fnb_pretrain_head_params", A.CPretrainHeadParams),
              ("fnb_pretrain_head_grads", A.CPretrainHeadParams), ("fnb_pretrain_head_io", A.CPretrainHeadIO),
              ("fnb_mse_term", A.CMseTerm), ("fnb_pretrain_step_args", A.CPretrainStepArgs),
-             ("fnb_arena_kind", A.CArenaKind), ("fnb_arena_job", A.CArenaJob), ("fnb_widen_job", A.CWidenJob)]
+             ("fnb_arena_kind", A.CArenaKind), ("fnb_arena_job", A.CArenaJob), ("fnb_widen_job", A.CWidenJob), ("fnb_peer_set", A.CPeerSet)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fragnet_b200.h"', 'int main(void){']
     for cname, cls in pairs:
         lines.append(f'printf("{cname} %zu", sizeof({cname}));')

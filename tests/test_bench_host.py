@@ -79,7 +79,7 @@ def test_compiled_reference_build_loads(tmp_path, monkeypatch):
     if ref_import.kind() != "checkout":
         pytest.skip("needs the reference checkout")
     dest = build_ref.build()
-    assert os.path.isfile(os.path.join(dest, "fragnet/model/gat/gat2.pyc"))
+    assert os.path.isfile(os.path.join(dest, "fragnet/model/gat/gat2.py.bin"))
     assert not any(f.endswith(".py") for _, _, fs in os.walk(dest) for f in fs)      # no reference source is copied
     import subprocess
     code = ("import sys; sys.path.insert(0, %r); from oracle import ref_import as r; "

@@ -119,9 +119,9 @@ def test_prefetcher_widens_the_compact_wire_format_bit_exactly():
     narrow = [compact_batch(b, pin=True) for b in wide]
     assert staged_bytes(narrow[1]) < 0.45 * staged_bytes(wide[1])
     for hot in (False, True):
-        got = list(DevicePrefetcher(iter(narrow), "cuda", depth=2, hot_path_only=hot))
-        assert len(got) == len(wide)
-        for g, w in zip(got, wide):
+        n_seen = 0
+        for g, w in zip(DevicePrefetcher(iter(narrow), "cuda", depth=2, hot_path_only=hot), wide):
+            n_seen += 1          # (a yielded batch is only valid until `depth` further ones have been requested)
             torch.cuda.synchronize()
             for k, v in w.items():
                 if hot and k in ("edge_attr", "cnx_attr"):
@@ -130,6 +130,7 @@ def test_prefetcher_widens_the_compact_wire_format_bit_exactly():
                     assert g[k].device.type == "meta" and g[k].shape == v.shape and g[k].dtype == v.dtype
                 else:
                     assert g[k].dtype == v.dtype and torch.equal(g[k].cpu(), v), k
+        assert n_seen == len(wide)
     dev = [{k: v.cuda() for k, v in b.items()} for b in wide[:2]]
     through = list(DevicePrefetcher(iter(dev), "cuda"))
     assert all(t[k] is d[k] for t, d in zip(through, dev) for k in d)

@@ -286,3 +286,52 @@ def test_trainer_fused_path_equals_generic_loop():
     assert max(rel_err(p, p2[k]) for k, p in m1.named_parameters()) <= 5e-4
     v1, v2 = t1.validate(loader, m1, "cuda"), t2.validate(loader, m2, "cuda")
     assert abs(v1 - v2) <= 1e-5 * abs(v2)
+
+
+def test_trainer_keeps_the_callers_optimizer_truthful_and_survives_moves():
+    """The fused path must not hide the optimizer state: ``optimizer.state`` holds views of the fused moment
+    buffers and the step count, a state dict saved from it resumes into a fresh trainer with identical results, an
+    ArenaLoader can drive ``train`` (its ``dataset`` gives the divisor), and moving the model afterwards falls back to
+    the generic loop instead of training an orphaned buffer."""
+    import copy
+    import warnings
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet.train.pretrain.pretrain_utils import Trainer
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.arena import ArenaLoader, MoleculeArena
+    mols = synth.make_dataset("unimol", 32, seed=19)
+    arena = MoleculeArena(mols, "cuda")
+    loader = ArenaLoader(arena, batch_size=16)
+    assert len(loader.dataset) == 32
+    torch.manual_seed(6)
+    m1 = FragNetPreTrain(num_layer=2, drop_ratio=0.0, edge_features=17).cuda()
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3)
+    t1 = Trainer(torch.nn.MSELoss())
+    t1.train(m1, loader, o1, "cuda")
+    fs = t1._fused_for(m1, o1, "cuda")
+    assert fs is not None and fs.t == 2
+    live = [p for p in m1.parameters() if p in o1.state]
+    assert len(live) == len(fs.live) and all(int(o1.state[p]["step"]) == 2 for p in live)
+    assert all(o1.state[p]["exp_avg"].data_ptr() >= fs.exp_avg.data_ptr() for p in live)
+    assert float(sum(o1.state[p]["exp_avg_sq"].sum() for p in live)) > 0
+    # checkpoint -> fresh model / optimizer / trainer -> one more epoch == continuing the original
+    ck_m, ck_o = copy.deepcopy(m1.state_dict()), copy.deepcopy(o1.state_dict())
+    m2 = FragNetPreTrain(num_layer=2, drop_ratio=0.0, edge_features=17).cuda()
+    m2.load_state_dict(ck_m)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    o2.load_state_dict(ck_o)
+    t2 = Trainer(torch.nn.MSELoss())
+    l1 = t1.train(m1, loader, o1, "cuda")
+    l2 = t2.train(m2, loader, o2, "cuda")
+    assert t2._fused_for(m2, o2, "cuda").t == 4
+    assert l1 == l2
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    # a moved model: the binding check trips, the generic loop takes over (and still trains)
+    m1.cpu()
+    m1.cuda()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        l3 = t1.train(m1, loader, o1, "cuda")
+    assert any("falling back" in str(x.message) for x in w) and l3 == l3
+    assert t1._fused_for(m1, o1, "cuda") is None
