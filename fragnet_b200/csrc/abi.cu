@@ -46,8 +46,10 @@ int fnb_aux_streams(FnbAux *out) {
       const bool prio = e && e[0] == '1' && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess;
       if (cudaStreamCreateWithPriority(&a.astream, cudaStreamNonBlocking, prio ? greatest : 0) != cudaSuccess) return 1;
     }
-    cudaEvent_t *evs[11] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.done2[0], &a.done2[1], &a.wjoin,
-                            &a.a_fork, &a.a_dz, &a.a_table, &a.a_join};
+    if (cudaStreamCreateWithFlags(&a.estream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    cudaEvent_t *evs[16] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.done2[0], &a.done2[1], &a.wjoin,
+                            &a.a_fork, &a.a_dz, &a.a_table, &a.a_join, &a.plan_fwd, &a.e_ready, &a.e_done[0],
+                            &a.e_done[1], &a.e_join};
     for (cudaEvent_t *e : evs)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return 1;
     aux[dev] = a;

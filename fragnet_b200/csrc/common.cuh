@@ -280,6 +280,9 @@ struct FnbAux {
   cudaEvent_t ready[2], done[2], done2[2], wjoin;   // done / done2: even / odd layers (dh is double-buffered)
   cudaStream_t astream;      // atom-graph chain (it only meets the bond chain at the edge-term kernels)
   cudaEvent_t a_fork, a_dz, a_table, a_join;
+  cudaEvent_t plan_fwd;      // forward half of the batch plan is complete (plan.cu)
+  cudaStream_t estream;      // head-vector gradients of the 128-wide edge terms (nobody's input: off every chain)
+  cudaEvent_t e_ready, e_done[2], e_join;
 };
 int fnb_aux_streams(FnbAux *out);
 
@@ -301,7 +304,9 @@ int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *args, co
 
 int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts *opts, const fnb_layer_params *layers,
                              const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
-                             void *stream, cudaEvent_t plan_ready);
+                             void *stream, cudaEvent_t plan_ready, cudaEvent_t plan_complete);
+int fnb_batch_plan_build_impl(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out,
+                              void *stream, cudaEvent_t forward_ready);
 int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
                                      const fnb_pretrain_head_io *io, int precision, void *workspace,
                                      size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,

@@ -125,13 +125,14 @@ size_t layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_l
 
 struct BwdBufs {
   float *g_bond, *dz_b, *dSt_b, *dh_b, *dh_b2, *dx_bond;   // dh: one buffer per layer parity, so that a layer's
-  float *g_atom, *dz_a, *dSt_a, *dh_a, *dh_a2, *dx_atom;   // source pass never waits for the weight-gradient GEMM above it
+  float *g_atom, *dz_a, *dz_a2, *dSt_a, *dh_a, *dh_a2, *dx_atom;   // source pass never waits for the weight-gradient GEMM above it
   float *g_fbond, *dz_fb, *dSt_fb, *dh_fb, *dx_fbond;
   float *g_frag, *dz_f, *dSt_f, *d_hf;
   float *Wt;   // [n_layers][3][128*128] transposed K=128 projection weights
   float *scratch2;   // scratch of the fragment-connection chain when it runs on the auxiliary stream
   float *scratch3;   // scratch of the weight-gradient stream
   float *scratch4;   // scratch of the atom-graph stream
+  float *scratch5;   // scratch of the edge-term stream
 };
 
 size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *base, BwdBufs *out) {
@@ -140,7 +141,8 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   BwdBufs b{};
   b.g_bond = a.take<float>(z.Nb * kD); b.dz_b = a.take<float>(z.Eb * 4); b.dSt_b = a.take<float>(z.Nb * 4);
   b.dh_b = a.take<float>(z.Nb * kD); b.dh_b2 = a.take<float>(z.Nb * kD); b.dx_bond = a.take<float>(z.Nb * kD);
-  b.g_atom = a.take<float>(z.Na * kD); b.dz_a = a.take<float>(z.Ea * 4); b.dSt_a = a.take<float>(z.Na * 4);
+  b.g_atom = a.take<float>(z.Na * kD); b.dz_a = a.take<float>(z.Ea * 4); b.dz_a2 = a.take<float>(z.Ea * 4);
+  b.dSt_a = a.take<float>(z.Na * 4);
   b.dh_a = a.take<float>(z.Na * kD); b.dh_a2 = a.take<float>(z.Na * kD); b.dx_atom = a.take<float>(z.Na * kD);
   b.g_fbond = a.take<float>(z.Nfb * kD); b.dz_fb = a.take<float>(z.Efb * 4); b.dSt_fb = a.take<float>(z.Nfb * 4);
   b.dh_fb = a.take<float>(z.Nfb * kD); b.dx_fbond = a.take<float>(z.Nfb * kD);
@@ -150,6 +152,7 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   b.scratch2 = a.take<float>(kScratchFloats);
   b.scratch3 = a.take<float>(kScratchFloats);
   b.scratch4 = a.take<float>(kScratchFloats);
+  b.scratch5 = a.take<float>(kScratchFloats);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -276,7 +279,7 @@ extern "C" uint64_t fnb_encoder_rng_span(const fnb_batch_plan *plan, const fnb_e
 extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
                                    const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
                                    void *stream_) {
-  return fnb_encoder_forward_impl(plan, o, L, io, workspace, workspace_bytes, scratch, stream_, nullptr);
+  return fnb_encoder_forward_impl(plan, o, L, io, workspace, workspace_bytes, scratch, stream_, nullptr, nullptr);
 }
 
 // plan_ready: optional event after which the ARRAYS of `plan` are complete (its sizes and pointers are valid at call
@@ -285,7 +288,7 @@ extern "C" int fnb_encoder_forward(const fnb_batch_plan *plan, const fnb_encoder
 // waits for the event.
 int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts *o, const fnb_layer_params *L,
                              const fnb_encoder_io *io, void *workspace, size_t workspace_bytes, void *scratch,
-                             void *stream_, cudaEvent_t plan_ready) {
+                             void *stream_, cudaEvent_t plan_ready, cudaEvent_t plan_complete) {
   RC(check_common(plan, o, L, io));
   if (!workspace || !scratch) return FNB_ERR_NULL;
   LayerBufs B[16];
@@ -391,6 +394,8 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
       f.next_alpha_e = P.a + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_atom;
       if (plan_ready && l == 0) RC((int)cudaStreamWaitEvent(stream, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->bond, &f, stream_));
+      // everything later on this stream (pooling, readout, the backward) may read the rest of the plan
+      if (plan_complete && l == 0) RC((int)cudaStreamWaitEvent(stream, plan_complete, 0));
       if (P.bond_mask_rows && P.n_bond_mask_rows > 0) {
         k_zero_rows<<<(int)((P.n_bond_mask_rows * 32 + 255) / 256), 256, 0, stream>>>(pre_bond, y_bond, b.se_atom,
                                                                                     P.bond_mask_rows, P.n_bond_mask_rows);
@@ -409,6 +414,7 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
       f.mask_lo = P.atom_mask >= 0 ? P.atom_mask : -1; f.mask_hi = P.atom_mask >= 0 ? P.atom_mask + 1 : -1;
       if (plan_ready && l == 0 && two) RC((int)cudaStreamWaitEvent(sA, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->atom, &f, sA_));
+      if (plan_complete && l == 0 && two) RC((int)cudaStreamWaitEvent(sA, plan_complete, 0));
       if (P.atom_mask_list && P.n_atom_mask > 0) {
         k_zero_rows<<<(int)((P.n_atom_mask * 32 + 255) / 256), 256, 0, sA>>>(pre_atom, y_atom, nullptr, P.atom_mask_list,
                                                                            P.n_atom_mask);
@@ -430,6 +436,7 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
       if (frag) { f.next_alpha_e = P.f + A_E; f.next_alpha_stride = A_STRIDE; f.next_Se = b.se_frag; }
       if (plan_ready && l == 0 && two) RC((int)cudaStreamWaitEvent(sB, plan_ready, 0));
       RC(fnb_gat_fwd_tiled(&plan->fbond, &f, sB_));
+      if (plan_complete && l == 0 && two) RC((int)cudaStreamWaitEvent(sB, plan_complete, 0));
       if (P.fbond_mask_rows && P.n_fbond_mask_rows > 0) {
         k_zero_rows<<<(int)((P.n_fbond_mask_rows * 32 + 255) / 256), 256, 0, sB>>>(
             pre_fbond, y_fbond, frag ? b.se_frag : nullptr, P.fbond_mask_rows, P.n_fbond_mask_rows);
@@ -560,6 +567,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
   void *sA_ = (void *)sA;
   void *scratchA = two ? (void *)W.scratch4 : scratch;
   bool a_forked = false, a_table_pending = false;
+  bool e_used = false, e_pending[2] = {false, false};
 
   // gradients arriving at the four outputs of the current layer (post-activation copies in post_act mode)
   const float *dy_atom = io->g_atoms, *dy_bond = io->g_bond, *dy_fbond = io->g_fbond, *dy_frag = io->g_frags;
@@ -581,6 +589,11 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     const bool need_dx = l > 0;
     const int par = l & 1;
     float *dh_a = par ? W.dh_a2 : W.dh_a, *dh_b = par ? W.dh_b2 : W.dh_b;
+    // dz of the atom graph is double-buffered by layer parity like dh: its last reader, the edge-term kernel that forms
+    // d a[:, edge slice], runs on the weight-gradient stream -- on the atom chain it sat between this layer's dX GEMM
+    // and the next layer's destination pass, whose dz the bond chain (the critical path) waits for (~40 us per layer,
+    // gpurun_out/r4l_device_profile.log)
+    float *dz_a = par ? W.dz_a2 : W.dz_a;
 
     // ---- fragment graph block (only where it ran and a gradient arrives)
     const float *d_hf = nullptr;
@@ -649,9 +662,13 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         }
         fnb_gat_bwd_args a{};
         a.h = b.ha; a.dout = W.g_atom; a.p_saved = b.p_a; a.edge_mode = FNB_EDGE_TABLE; a.alpha = P.a;
-        a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = W.dz_a; a.dSt = W.dSt_a;
+        a.alpha_stride = A_STRIDE; a.off_t = A_T; a.off_e = A_E; a.off_s = A_S; a.dz = dz_a; a.dSt = W.dSt_a;
         a.dh = dh_a; a.d_alpha = D.a; a.d_bias = D.ba; a.scratch = scratchA;
         RC(w_wait(0, par, sA));
+        if (two && e_pending[par]) {      // the edge-term kernel two layers up has read this parity's dz buffer
+          RC((int)cudaStreamWaitEvent(sA, aux.e_done[par], 0));
+          e_pending[par] = false;
+        }
         // the bond graph's destination pass (caller's stream) only needs dz of this graph: the event sits between the
         // two launches
         FnbDstFuse fza{};     // ReLU(Dropout) backward of dy_atom + pooling backward of the fragment gradient
@@ -666,12 +683,27 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
           RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), dh_a, z.Na, P.K_atom, dx, o->precision, scratchA, sA_));
           RC(fnb_proj_bwd_dw(xa, dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchW, sW_));
         }
-        // bond features were this graph's edge vectors (gat2.py:203-208): the head-vector gradient of that term stays
-        // on the atom chain, behind the dX GEMM the next layer waits for; the row gradient is assembled inside the
-        // bond graph's destination pass
-        RC(fnb_edge_table_bwd_fused(&plan->atom, W.dz_a, pre_bond, P.a, A_STRIDE, A_E, nullptr, nullptr, nullptr, scale,
-                                    nullptr, D.a, scratchA, sA_));
         RC(w_end(0, par));
+        // bond features were this graph's edge vectors (gat2.py:203-208): the head-vector gradient of that term is
+        // nobody's input.  On the atom chain it delayed the next layer's dz (which the bond chain, the critical path,
+        // waits for) by ~40 us per layer; behind the weight-gradient GEMMs it piled up at the end of the pass
+        // (gpurun_out/r4l, r4m): it gets a stream of its own and this parity's dz buffer to itself until e_done[par].
+        // The row gradient is assembled inside the bond graph's destination pass.
+        if (two) {
+          RC((int)cudaEventRecord(aux.e_ready, sA));
+          RC((int)cudaStreamWaitEvent(aux.estream, aux.e_ready, 0));
+          if (!e_used) {
+            RC((int)cudaMemsetAsync(W.scratch5, 0, kScratchCounters * sizeof(float), aux.estream));
+            e_used = true;
+          }
+          RC(fnb_edge_table_bwd_fused(&plan->atom, dz_a, pre_bond, P.a, A_STRIDE, A_E, nullptr, nullptr, nullptr, scale,
+                                      nullptr, D.a, W.scratch5, (void *)aux.estream));
+          RC((int)cudaEventRecord(aux.e_done[par], aux.estream));
+          e_pending[par] = true;
+        } else {
+          RC(fnb_edge_table_bwd_fused(&plan->atom, dz_a, pre_bond, P.a, A_STRIDE, A_E, nullptr, nullptr, nullptr, scale,
+                                      nullptr, D.a, scratchA, sA_));
+        }
         dy_atom = need_dx ? W.dx_atom : nullptr;
       } else {
         RC((int)cudaMemsetAsync(D.a, 0, 4 * A_STRIDE * 4, stream));
@@ -689,7 +721,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         // incoming gradient = edge term of the atom graph (dz_a) + ReLU(Dropout) backward of dy_bond, assembled by
         // the destination pass; the atom chain may overwrite dz_a once that launch is done
         FnbDstFuse fz{};
-        fz.dz_up = have ? W.dz_a : nullptr; fz.slot_of_eid = plan->atom.slot_of_eid; fz.alpha_up = P.a + A_E;
+        fz.dz_up = have ? dz_a : nullptr; fz.slot_of_eid = plan->atom.slot_of_eid; fz.alpha_up = P.a + A_E;
         fz.alpha_up_stride = A_STRIDE; fz.g_base = y_bond ? nullptr : dy_bond; fz.dy = y_bond ? dy_bond : nullptr;
         fz.y = y_bond && dy_bond ? y_bond : nullptr; fz.scale = scale;
         // (the weight-gradient GEMM two layers above read this dh buffer: only the source pass has to wait for it)
@@ -730,6 +762,10 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
   }
   for (int i = 0; i < 2; ++i)
     for (int p2 = 0; p2 < 2; ++p2) RC(w_wait(i, p2, stream));
+  if (two && e_used) {
+    RC((int)cudaEventRecord(aux.e_join, aux.estream));
+    RC((int)cudaStreamWaitEvent(stream, aux.e_join, 0));
+  }
   // input dropout backward (gat2.py:396) when the caller wants d x_atoms: same RNG stream as the forward
   if (o->need_dx_atoms && io->dx_atoms && input_dropout(o)) {
     const RngPlan ph = rng_plan(plan, o, L);

@@ -377,6 +377,15 @@ extern "C" size_t fnb_batch_plan_bytes(const fnb_batch_inputs *in) {
 
 extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out,
                                     void *stream_) {
+  return fnb_batch_plan_build_impl(in, arena, arena_bytes, out, stream_, nullptr);
+}
+
+// forward_ready (optional): recorded once everything the FORWARD attention kernels read is complete -- destination-
+// sorted CSRs, slot-ordered edge attributes, the pooling CSR.  The reverse CSRs, the tile ranges and the int32 /
+// per-molecule arrays (backward, readout) follow; a step's first attention kernel starts ~20 us earlier by waiting
+// for this event instead of for the whole plan.
+int fnb_batch_plan_build_impl(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out,
+                              void *stream_, cudaEvent_t forward_ready) {
   if (!in || !out || !arena) return FNB_ERR_NULL;
   if (!inputs_ok(in)) return FNB_ERR_SIZE;
   if (in->n_bonds > 0 && !in->edge_index) return FNB_ERR_NULL;
@@ -453,6 +462,10 @@ extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, siz
                                   stream, a))
     return (int)le;
   FNB_CHECK_LAUNCH();
+  if (forward_ready) {
+    err = cudaEventRecord(forward_ready, stream);
+    if (err != cudaSuccess) return (int)err;
+  }
   if (z.e_total > 0) {
     if (cudaError_t le = fnb_launch(k_plan_rank_reverse, dim3(grid_for(z.e_total)), dim3(256), 0, stream, a)) return (int)le;
     FNB_CHECK_LAUNCH();

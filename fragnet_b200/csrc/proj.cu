@@ -322,6 +322,92 @@ __global__ void k_edge_coef_bwd(const float *__restrict__ We, const float *__res
   }
 }
 
+// Small-M linear layer: C[M, Nc] = A[M, Kd] @ op(B) (+ bias) for a few thousand rows at most (the energy head:
+// one row per molecule, [G, 256] x [256 -> 128] forward and [G, 128] x [128 -> 256] input gradient).  k_gemm tiles 64
+// rows per CTA: 16 CTAs at G = 1024 and 45 us of pure latency on the critical path between the encoder's forward and
+// backward (gpurun_out/r4j_device_profile.log).  Here a CTA owns LR_ROWS = 8 rows (128 CTAs at G = 1024), a thread owns
+// output columns t, t + 128, ... for all 8 rows: the A rows sit in shared memory (broadcast reads), every thread
+// streams its own part of B once.  Exact FP32 (FFMA, k ascending).
+constexpr int LR_ROWS = 8, LR_THREADS = 128, LR_MAXK = 256, LR_MAXC = 2;   // Nc <= LR_MAXC * LR_THREADS
+
+template <bool TRANS_B>
+__global__ void __launch_bounds__(LR_THREADS) k_linear_rows(GemmArgs g) {
+  pdl_wait();
+  __shared__ __align__(16) float sA[LR_ROWS][LR_MAXK];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * LR_ROWS;
+  for (int i = tid; i < LR_ROWS * g.Kd; i += LR_THREADS) {
+    const int r = i / g.Kd, k = i - r * g.Kd;
+    sA[r][k] = (m0 + r < g.M) ? __ldg(g.A + (m0 + r) * g.lda + k) : 0.f;
+  }
+  __syncthreads();
+  float acc[LR_MAXC][LR_ROWS];
+#pragma unroll
+  for (int c = 0; c < LR_MAXC; ++c)
+#pragma unroll
+    for (int r = 0; r < LR_ROWS; ++r) acc[c][r] = 0.f;
+  if (TRANS_B) {            // B = nn.Linear weight [Nc, Kd]: the thread reads its row(s) of B, 16 bytes at a time
+#pragma unroll
+    for (int c = 0; c < LR_MAXC; ++c) {
+      const int n = tid + c * LR_THREADS;
+      if (n >= g.Nc) break;
+      const float *brow = g.B + (int64_t)n * g.ldb;
+      for (int k0 = 0; k0 < g.Kd; k0 += 32) {        // 8 independent 16-byte loads in flight (Kd is a multiple of 32 here)
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = (k0 + 4 * u < g.Kd) ? ldg4(brow + k0 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + 4 * u;
+          if (k >= g.Kd) break;
+#pragma unroll
+          for (int r = 0; r < LR_ROWS; ++r) {
+            const float4 a = ld4(&sA[r][k]);
+            acc[c][r] = fmaf(a.x, w[u].x, acc[c][r]);
+            acc[c][r] = fmaf(a.y, w[u].y, acc[c][r]);
+            acc[c][r] = fmaf(a.z, w[u].z, acc[c][r]);
+            acc[c][r] = fmaf(a.w, w[u].w, acc[c][r]);
+          }
+        }
+      }
+    }
+  } else {                  // B [Kd, Nc]: coalesced reads of B's rows
+    for (int k0 = 0; k0 < g.Kd; k0 += 8) {             // 16 independent loads in flight per thread
+      float w[8][LR_MAXC];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int c = 0; c < LR_MAXC; ++c) {
+          const int n = tid + c * LR_THREADS;
+          w[u][c] = (n < g.Nc && k0 + u < g.Kd) ? __ldg(g.B + (int64_t)(k0 + u) * g.ldb + n) : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int r = 0; r < LR_ROWS; ++r) {
+          const float a = sA[r][(k0 + u) & (LR_MAXK - 1)];
+#pragma unroll
+          for (int c = 0; c < LR_MAXC; ++c) acc[c][r] = fmaf(a, w[u][c], acc[c][r]);
+        }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < LR_MAXC; ++c) {
+    const int n = tid + c * LR_THREADS;
+    if (n >= g.Nc) break;
+    const float b = g.bias ? __ldg(g.bias + n) : 0.f;
+#pragma unroll
+    for (int r = 0; r < LR_ROWS; ++r)
+      if (m0 + r < g.M) g.C[(m0 + r) * g.ldc + n] = acc[c][r] + b;
+  }
+}
+
+// Shapes k_linear_rows takes: few rows, K a multiple of 32 up to 256, at most 256 output columns, 16-byte aligned rows.
+bool linear_rows_shape(int64_t M, int Kd, int Nc, const float *A, int lda, const float *B, int ldb, bool trans_b) {
+  return M > 0 && M <= 8192 && Kd <= LR_MAXK && (Kd & 31) == 0 && Nc <= LR_MAXC * LR_THREADS && fnb_aligned16(A) &&
+         (lda & 3) == 0 && (!trans_b || (fnb_aligned16(B) && (ldb & 3) == 0));
+}
+
 }  // namespace
 
 extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int64_t n_rows, int K, const float *alpha,
@@ -364,6 +450,13 @@ extern "C" int fnb_proj_fwd(const float *x, const float *W, const float *b, int6
   GemmArgs g;
   g.A = x; g.lda = K; g.B = W; g.ldb = K; g.C = h; g.ldc = kD; g.M = n_rows; g.Kd = K; g.Nc = kD; g.bias = b;
   g.alpha = alpha; g.alpha_stride = alpha_stride; g.off_t = off_t; g.off_s = off_s; g.S = S;
+  if (!S && K > kD && linear_rows_shape(n_rows, K, kD, x, K, W, K, true)) {
+    if (cudaError_t le = fnb_launch(k_linear_rows<true>, dim3((unsigned)((n_rows + LR_ROWS - 1) / LR_ROWS)), dim3(LR_THREADS), 0,
+                                    (cudaStream_t)stream, g))
+      return (int)le;
+    FNB_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 grid((unsigned)((n_rows + BM - 1) / BM), 1);
   if (cudaError_t le = fnb_launch(k_gemm<true, true>, grid, dim3(kGemmThreads), 0, (cudaStream_t)stream, g)) return (int)le;
   FNB_CHECK_LAUNCH();
@@ -402,6 +495,13 @@ int fnb_proj_bwd_dx(const float *W, const float *Wt_pre, const float *dh, int64_
   GemmArgs g;
   g.A = dh; g.lda = kD; g.B = W; g.ldb = K; g.C = dx; g.ldc = K; g.M = n_rows; g.Kd = kD; g.Nc = K; g.bias = nullptr;
   g.alpha = nullptr; g.alpha_stride = 0; g.off_t = 0; g.off_s = 0; g.S = nullptr;
+  if (linear_rows_shape(n_rows, kD, K, dh, kD, W, K, false)) {
+    if (cudaError_t le = fnb_launch(k_linear_rows<false>, dim3((unsigned)((n_rows + LR_ROWS - 1) / LR_ROWS)), dim3(LR_THREADS), 0,
+                                    stream, g))
+      return (int)le;
+    FNB_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 grid((unsigned)((n_rows + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
   if (cudaError_t le = fnb_launch(k_gemm<false, false>, grid, dim3(kGemmThreads), 0, stream, g)) return (int)le;
   FNB_CHECK_LAUNCH();

@@ -7,6 +7,8 @@
 // ~3 us each.  Everything lives in one caller-provided workspace whose layout is a pure function of the batch sizes.
 // The optimizer update (fnb_adam_step over the flat parameter buffer) and, with several GPUs, the gradient
 // all-reduce stay separate calls so that NCCL can sit between them.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -126,14 +128,18 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   fnb_batch_plan plan{};
   FnbAux aux{};
   const bool two = fnb_aux_streams(&aux) == 0;
-  cudaEvent_t plan_ready = nullptr;
+  cudaEvent_t plan_ready = nullptr, plan_complete = nullptr;
   if (two) {
     cudaStream_t s = (cudaStream_t)stream;
     RC((int)cudaEventRecord(aux.ready[1], s));               // the batch tensors are complete on the caller's stream
     RC((int)cudaStreamWaitEvent(aux.wstream, aux.ready[1], 0));
-    RC(fnb_batch_plan_build(in, B.plan_arena, B.plan_bytes, &plan, (void *)aux.wstream));
+    RC(fnb_batch_plan_build_impl(in, B.plan_arena, B.plan_bytes, &plan, (void *)aux.wstream, aux.plan_fwd));
     RC((int)cudaEventRecord(aux.wjoin, aux.wstream));
-    plan_ready = aux.wjoin;
+    // forward CSRs: what the first attention kernels wait for (the experimental staged forward, FNB_STAGE=1, also reads
+    // the tile ranges: it waits for the whole plan)
+    static const bool staged = getenv("FNB_STAGE") && getenv("FNB_STAGE")[0] == '1';
+    plan_ready = staged ? aux.wjoin : aux.plan_fwd;
+    plan_complete = aux.wjoin;       // + reverse CSRs, per-molecule arrays: waited for behind those kernels
   } else {
     RC(fnb_batch_plan_build(in, B.plan_arena, B.plan_bytes, &plan, stream));
   }
@@ -142,7 +148,7 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   fnb_encoder_io eio{};
   eio.x_atoms = a->x_atoms; eio.x_bond = a->x_bond; eio.x_fbond = a->x_fbond;
   eio.out_atoms = B.out_atoms; eio.out_frags = B.out_frags; eio.out_bond = B.out_bond; eio.out_fbond = B.out_fbond;
-  RC(fnb_encoder_forward_impl(&plan, &o, a->layers, &eio, B.enc_ws, B.enc_bytes, scratch, stream, plan_ready));
+  RC(fnb_encoder_forward_impl(&plan, &o, a->layers, &eio, B.enc_ws, B.enc_bytes, scratch, stream, plan_ready, plan_complete));
   // ---- heads (PretrainTask.forward, pretrain_heads.py:64-102)
   fnb_pretrain_head_io hio{};
   hio.x_atoms = B.out_atoms; hio.x_frags = B.out_frags; hio.edge_feat = B.out_bond; hio.edge_index = in->edge_index;

@@ -514,25 +514,27 @@ def segment_gather(g, g_stride, seg_of, n_rows, base=None):
     return dx
 
 
-_rng_offset = 0
+def _take_rng(n_counters: int) -> int:
+    """Dropout masks are a function of (torch's seed, a counter).  The counter is the Philox offset of torch's own CUDA
+    generator of the current device -- the stream torch's dropout kernels draw from -- advanced by what a call
+    consumes: ``torch.manual_seed`` therefore restarts it, and re-seeding reproduces the masks exactly as it does for
+    ``nn.Dropout``."""
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    off = int(gen.get_offset())
+    gen.set_offset(off + (int(n_counters) + 3) // 4 * 4)        # torch keeps the offset a multiple of 4
+    return off
 
 
 def next_rng(n_elems: int):
     """(seed, offset) for one dropout call; the offset stream advances by the number of RNG
     counters the call consumes, so no two calls of a run share random numbers."""
-    global _rng_offset
-    off = _rng_offset
-    _rng_offset += (n_elems + 3) // 4
-    return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, off
+    return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, _take_rng((n_elems + 3) // 4)
 
 
 def reserve_rng(n_counters: int) -> int:
     """First counter of a block of ``n_counters`` RNG counters (whole-encoder calls reserve all their dropout sites
     at once: ``fnb_encoder_rng_span``)."""
-    global _rng_offset
-    off = _rng_offset
-    _rng_offset += int(n_counters)
-    return off
+    return _take_rng(n_counters)
 
 
 def dropout_relu_fwd(x, p: float, training: bool, relu: bool, seed: int, offset: int):

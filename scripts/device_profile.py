@@ -42,6 +42,22 @@ def main():
         t1 = e.time_range.end
         t_first = t0 if t_first is None else min(t_first, t0)
         t_last = t1 if t_last is None else max(t_last, t1)
+    if os.environ.get("FNB_STREAMS_SEQ"):   # last step, in start order, with the CUDA stream of every kernel (kineto)
+        try:
+            kev = [e for e in prof.profiler.kineto_results.events()
+                   if "cuda" in str(e.device_type()).lower() and e.duration_ns() > 0]
+            kev.sort(key=lambda e: e.start_ns())
+            per = len(kev) // steps
+            last = kev[-per:]
+            t0 = last[0].start_ns()
+            ids = {}
+            print("# start_us  dur_us  stream  kernel   (last step)")
+            for e in last:
+                sid = ids.setdefault(e.device_resource_id(), len(ids))
+                nm = e.name().replace("(anonymous namespace)::", "").replace("void ", "")
+                print(f"{(e.start_ns() - t0) / 1e3:9.1f} {e.duration_ns() / 1e3:7.1f}   s{sid}   {nm[:70]}")
+        except Exception as ex:      # kineto internals differ between torch versions: the summary below still prints
+            print("# stream timeline unavailable:", ex)
     if os.environ.get("FNB_SEQ"):      # launch sequence of the last profiled step, in start order
         evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
                      key=lambda e: e.time_range.start)

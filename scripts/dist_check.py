@@ -50,6 +50,7 @@ def main():
         err = float((f1.flat_p - f2.flat_p).abs().max() / f2.flat_p.abs().max())
         assert err < 2e-5, (i, err)
         assert torch.isfinite(l1) and abs(float(l1) - float(l2)) <= 1e-4 * abs(float(l2)) + 1e-6, (float(l1), float(l2))
+    # with dropout: the same seed gives the twins the same masks (the counter restarts with torch.manual_seed)
     # timing
     big = [{k: v.to(dev) for k, v in b.items()} for b in bench.make_batches("unimol", 1024, 2, 256, seed=70 + rank)]
     out = {}
