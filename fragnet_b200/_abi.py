@@ -191,7 +191,8 @@ class CEncoderOpts(C.Structure):
 class CEncoderIO(C.Structure):
     _fields_ = [(n, _vp) for n in ("x_atoms", "x_bond", "x_fbond", "out_atoms", "out_frags", "out_bond", "out_fbond",
                                    "attn_atoms", "attn_frags", "attn_bonds", "attn_fbonds", "g_atoms", "g_frags",
-                                   "g_bond", "g_fbond", "dx_atoms", "dx_bond", "dx_fbond")]
+                                   "g_bond", "g_fbond", "dx_atoms", "dx_bond", "dx_fbond", "frag_table",
+                                   "d_frag_table")]
 
 
 MLP3_FIELDS = ("W0", "b0", "W1", "b1", "W2", "b2")

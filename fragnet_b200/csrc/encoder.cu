@@ -228,6 +228,14 @@ __global__ void k_zero_rows(float *__restrict__ a, float *__restrict__ b, float 
   }
 }
 
+// out[e, 0:4] = src[index[e], 0:4]: gradient of an external edge table (slot order -> edge-id order).
+__global__ void __launch_bounds__(256) k_gather_rows4(const float *__restrict__ src, const int *__restrict__ index,
+                                                       float *__restrict__ out, int64_t n) {
+  pdl_wait();
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < n) st4(out + e * 4, ldg4(src + (int64_t)__ldg(index + e) * 4));
+}
+
 #define RC(expr)            \
   do {                      \
     const int rc__ = (expr); \
@@ -449,7 +457,8 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
       RC(fnb_segment_sum(plan->pool_rowptr, plan->pool_col, z.Nf, pre_atom, b.hf, kD, P.f, A_STRIDE, A_T, A_S, b.Sf,
                          stream_));
       fnb_gat_fwd_args f{};
-      f.h = b.hf; f.S = b.Sf; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = b.se_frag; f.out = pre_frag; f.y = y_frag;
+      f.h = b.hf; f.S = b.Sf; f.edge_mode = FNB_EDGE_TABLE; f.edge_table = io->frag_table ? io->frag_table : b.se_frag;
+      f.out = pre_frag; f.y = y_frag;
       f.post = post_of(o, ph.frag[l]); f.p_saved = want_p ? b.p_f : nullptr; f.mask_lo = f.mask_hi = -1;
       RC(fnb_gat_fwd_tiled(&plan->frag, &f, stream_));
     }
@@ -606,16 +615,27 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
       a.dh = W.d_hf; a.d_alpha = D.f; a.d_bias = nullptr; a.scratch = scratch;
       FnbDstFuse fz{};      // ReLU(Dropout) backward of dy_frag inside the destination pass
       fz.dy = dy_frag; fz.y = y_frag; fz.scale = scale;
+      // external edge term (gat2_edge): nothing in here writes the edge slice of d f -- it flows back through
+      // d_frag_table on the caller's side -- so the whole tensor starts from zero
+      if (io->frag_table) RC((int)cudaMemsetAsync(D.f, 0, 4 * A_STRIDE * sizeof(float), stream));
       RC(fnb_gat_bwd_tiled_fused(&plan->frag, &a, &fz, nullptr, nullptr, stream_));
+      if (io->frag_table && io->d_frag_table && plan->frag.n_real_edges > 0) {
+        const int64_t n = plan->frag.n_real_edges;
+        if (cudaError_t le = fnb_launch(k_gather_rows4, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, W.dz_f,
+                                        plan->frag.slot_of_eid, io->d_frag_table, n))
+          return (int)le;
+        FNB_CHECK_LAUNCH();
+      }
       d_hf = W.d_hf;
     }
+    const bool frag_feeds_fbond = frag_bwd && !io->frag_table;   // gat2: the fragment graph's edges ARE the fbond rows
     // ---- fragment-connection graph block
     {
       RC(fork());
       // incoming gradient = ReLU(Dropout) backward of dy_fbond + (last layer) the fragment graph's edge term
       // sum_h dz_f alpha_e, assembled inside the destination pass; d f[:, edge slice] by the edge-table kernel
-      const bool have = frag_bwd || dy_fbond != nullptr;
-      if (frag_bwd)
+      const bool have = frag_feeds_fbond || dy_fbond != nullptr;
+      if (frag_feeds_fbond)
         RC(fnb_edge_table_bwd_fused(&plan->frag, W.dz_f, pre_fbond, P.f, A_STRIDE, A_E, nullptr, nullptr, nullptr, scale,
                                     nullptr, D.f, scratchB, sB_));
       if (have) {
@@ -625,7 +645,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         a.dz = W.dz_fb; a.dSt = W.dSt_fb; a.dh = W.dh_fb; a.d_alpha = D.f_a_b; a.d_bias = D.bfb; a.dWe = D.We_fb;
         a.dbe = D.be_fb; a.scratch = scratchB;
         FnbDstFuse fz{};
-        fz.dz_up = frag_bwd ? W.dz_f : nullptr; fz.slot_of_eid = plan->frag.slot_of_eid; fz.alpha_up = P.f + A_E;
+        fz.dz_up = frag_feeds_fbond ? W.dz_f : nullptr; fz.slot_of_eid = plan->frag.slot_of_eid; fz.alpha_up = P.f + A_E;
         fz.alpha_up_stride = A_STRIDE; fz.dy = dy_fbond; fz.y = dy_fbond ? y_fbond : nullptr; fz.scale = scale;
         RC(fnb_gat_bwd_tiled_fused(&plan->fbond, &a, &fz, nullptr, nullptr, sB_));
         float *dx = need_dx ? W.dx_fbond : (o->need_dx_fbond ? io->dx_fbond : nullptr);

@@ -328,6 +328,12 @@ typedef struct fnb_encoder_io {
   /* backward only */
   const float *g_atoms, *g_frags, *g_bond, *g_fbond; /* gradients of the four outputs; NULL = zero */
   float *dx_atoms, *dx_bond, *dx_fbond;              /* gradients of the layer-0 inputs (see need_dx_*) */
+  /* gat2_edge (fragnet/model/gat/gat2_edge.py:139-160): the fragment graph's edge term comes from the connection
+   * attributes, <cnx_attr_transform(cnx_attr[e]), f_e[h]>, not from fragment-connection features.  frag_table: that
+   * term per real edge, [Ef,4] in edge-id order, read by the layer that runs the fragment block instead of the table
+   * the fragment-connection block would emit (NULL = gat2 behaviour); d_frag_table (backward): its gradient. */
+  const float *frag_table;
+  float *d_frag_table;
 } fnb_encoder_io;
 
 size_t fnb_encoder_workspace_bytes(const fnb_batch_plan *plan, const fnb_encoder_opts *opts,
