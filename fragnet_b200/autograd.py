@@ -39,6 +39,8 @@ class EncoderConfig:
     training: bool = False
     precision: int = 0
     grad_enabled: bool = True           # torch.is_grad_enabled() at the call site (it is always off inside forward)
+    frag_table: bool = False            # gat2_edge: the LAST tensor passed to EncoderFn is the fragment graph's edge
+                                        # term [Ef,4] (edge-id order), used instead of the fragment-connection block's
     _keep: list = field(default_factory=list, repr=False)   # tensors the C structs point into
 
 
@@ -91,9 +93,12 @@ class EncoderFn(torch.autograd.Function):
         f32 = ops._f32c
         x_atoms, x_bond, x_fbond = f32(x_atoms), f32(x_bond), f32(x_fbond)
         params = [f32(t) for t in params]
+        frag_table = params.pop() if cfg.frag_table else None
         dev = x_atoms.device
         n_layers = len(cfg.layers)
         assert len(params) == n_layers * N_PARAMS
+        if frag_table is not None and tuple(frag_table.shape) != (plan.frag.n_real, ops.H):
+            raise ValueError(f"EncoderFn: frag_table must be [{plan.frag.n_real}, {ops.H}], got {tuple(frag_table.shape)}")
         need_grad = cfg.grad_enabled and any(ctx.needs_input_grad)
         if need_grad and _has_mask(cfg):
             raise NotImplementedError(
@@ -122,6 +127,7 @@ class EncoderFn(torch.autograd.Function):
         pt = ops._ptr
         io = _abi.CEncoderIO(pt(x_atoms), pt(x_bond), pt(x_fbond), pt(out_atoms), pt(out_frags), pt(out_bond),
                              pt(out_fbond), pt(attn[0]), pt(attn[1]), pt(attn[2]), pt(attn[3]))
+        io.frag_table = pt(frag_table)
         _abi.check(lib.fnb_encoder_forward(C.byref(cplan), C.byref(opts), layers, C.byref(io), pt(ws), ws_bytes,
                                            pt(ops.scratch(dev)), ops._stream()), "encoder_forward")
         if out_frags is None:
@@ -135,13 +141,16 @@ class EncoderFn(torch.autograd.Function):
         if need_grad:
             ctx.set_materialize_grads(False)
             ctx.plan, ctx.cfg, ctx.opts, ctx.ws = plan, cfg, opts, ws
-            ctx.save_for_backward(x_atoms, x_bond, x_fbond, *params, out_atoms, out_frags, out_bond, out_fbond)
+            ctx.has_table = frag_table is not None
+            ctx.save_for_backward(x_atoms, x_bond, x_fbond, *params, out_atoms, out_frags, out_bond, out_fbond,
+                                  *([frag_table] if frag_table is not None else []))
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, g_atoms, g_frags, g_bond, g_fbond, *_attn_grads):
         plan, cfg, opts, ws = ctx.plan, ctx.cfg, ctx.opts, ctx.ws
-        saved = ctx.saved_tensors
+        saved = list(ctx.saved_tensors)
+        frag_table = saved.pop() if ctx.has_table else None
         x_atoms, x_bond, x_fbond = saved[:3]
         params = list(saved[3:-4])
         out_atoms, out_frags, out_bond, out_fbond = saved[-4:]
@@ -169,6 +178,12 @@ class EncoderFn(torch.autograd.Function):
         io = _abi.CEncoderIO(pt(x_atoms), pt(x_bond), pt(x_fbond), pt(out_atoms), pt(out_frags) if run_frag_last else None,
                              pt(out_bond), pt(out_fbond), None, None, None, None, pt(g_atoms),
                              pt(g_frags) if run_frag_last else None, pt(g_bond), pt(g_fbond), pt(dx[0]), pt(dx[1]), pt(dx[2]))
+        d_table = None
+        if frag_table is not None:
+            io.frag_table = pt(frag_table)
+            # zero where no gradient reaches the fragment block (its backward does not run then)
+            d_table = torch.zeros_like(frag_table)
+            io.d_frag_table = pt(d_table)
         _abi.check(lib.fnb_encoder_backward(C.byref(cplan), C.byref(opts), layers, grads, C.byref(io), pt(ws), ws.numel(),
                                             pt(bws), bws_bytes, pt(ops.scratch(dev)), ops._stream()), "encoder_backward")
         out = []
@@ -177,6 +192,8 @@ class EncoderFn(torch.autograd.Function):
                 k = l * N_PARAMS + j
                 dead = j == _F_INDEX and not (sw.run_frag_block and g_frags is not None and l == len(cfg.layers) - 1)
                 out.append(views[k] if needs[5 + k] and not dead else None)
+        if frag_table is not None:
+            out.append(d_table if needs[5 + len(params)] else None)
         return (None, None, dx[0], dx[1], dx[2], *out)
 
 

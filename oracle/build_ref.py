@@ -27,6 +27,7 @@ MODULES = [
     "fragnet/model/gat/gat2.py",                  # FragNetLayerA, FragNet, FragNetFineTune, FTHead*
     "fragnet/model/gat/pretrain_heads.py",        # PretrainTask, FragNetPreTrain
     "fragnet/model/gat/gat2_lite.py",
+    "fragnet/model/gat/gat2_edge.py",
     "fragnet/train/pretrain/pretrain_utils.py",   # Trainer.train: the pretraining step loop and loss
     "fragnet/dataset/data.py",                    # collate_fn / collate_fn_pt
 ]

@@ -228,6 +228,53 @@ def lite_finetune_forward(P: Params, batch, num_layer: int = 4, num_heads: int =
     return fthead_forward(P, readout(x_atoms, x_frags, batch), fthead, act, drop_ratio, training)
 
 
+def edge_layer_forward(P: Params, prefix: str, num_heads: int, x_atoms, edge_index, edge_attr, frag_index, x_frags,
+                       atom_to_frag_ids, x_bond_nodes, edge_index_bonds_graph, edge_attr_bond_graph, cnx_attr):
+    """``gat2_edge.FragNetLayerA.forward`` (gat2_edge.py:62-175): bond-graph block, atom-graph block with self loops,
+    pooling, and the fragment-graph block whose edge vectors are ``cnx_attr_transform(cnx_attr)`` (:152-158).  Returns
+    ``(x_atoms_new, x_frags_new, new_bond, attn_atoms, attn_frags, attn_bonds)`` (:172-173)."""
+    p = lambda n: P[prefix + n]
+    H = num_heads
+    tgt, src = edge_index_bonds_graph[0], edge_index_bonds_graph[1]                      # :75
+    ea = F.linear(edge_attr_bond_graph, p("edge_attr_bond_embed.weight"), p("edge_attr_bond_embed.bias"))
+    hb = F.linear(x_bond_nodes, p("projection_b.weight"), p("projection_b.bias")).view(x_bond_nodes.size(0), H, -1)
+    new_bond, attn_bonds = attention_block(hb, tgt, src, ea, p("a_b"))
+    ei_loops, _ = add_self_loops(edge_index)                                              # :107-112
+    e_full = torch.cat((new_bond, torch.zeros(x_atoms.size(0), new_bond.size(1), dtype=new_bond.dtype)), dim=0)
+    src, tgt = ei_loops[0], ei_loops[1]
+    ha = F.linear(x_atoms, p("projection_a.weight"), p("projection_a.bias")).view(x_atoms.size(0), H, -1)
+    x_atoms_new, attn_atoms = attention_block(ha, tgt, src, e_full, p("a"))
+    pooled = scatter_add(x_atoms_new, atom_to_frag_ids, dim=0)                            # :139
+    src, tgt = frag_index[0], frag_index[1]                                               # :145
+    hf = pooled.view(pooled.size(0), H, -1)
+    cnx = F.linear(cnx_attr, p("cnx_attr_transform.weight"), p("cnx_attr_transform.bias"))
+    x_frags_new, attn_frags = attention_block(hf, tgt, src, cnx, p("f"))
+    return x_atoms_new, x_frags_new, new_bond, attn_atoms, attn_frags, attn_bonds
+
+
+def edge_fragnet_forward(P: Params, batch, num_layer: int, num_heads: int = 4, drop_ratio: float = 0.0,
+                         training: bool = False, prefix: str = "pretrain."):
+    """``gat2_edge.FragNet.forward`` (gat2_edge.py:198-239)."""
+    drop = lambda t: F.dropout(t, drop_ratio, training)
+    post = lambda t: F.relu(drop(t))
+    x_atoms, x_frags = drop(batch["x_atoms"]), drop(batch["x_frags"])
+    edge_feat, bond_nodes = batch["edge_attr"], batch["node_features_bonds"]
+    for li in range(num_layer):
+        out = edge_layer_forward(P, f"{prefix}layers.{li}.", num_heads, x_atoms, batch["edge_index"], edge_feat,
+                                 batch["frag_index"], x_frags, batch["atom_to_frag_ids"], bond_nodes,
+                                 batch["edge_index_bonds_graph"], batch["edge_attr_bonds"], batch["cnx_attr"])
+        x_atoms, x_frags, edge_feat = post(out[0]), post(out[1]), post(out[2])
+        bond_nodes = edge_feat
+    return x_atoms, x_frags, edge_feat
+
+
+def edge_finetune_forward(P: Params, batch, num_layer: int = 4, num_heads: int = 4, drop_ratio: float = 0.0,
+                          training: bool = False, fthead: str = "FTHead3", act: str = "relu"):
+    """``gat2_edge.FragNetFineTune.forward`` (gat2_edge.py:550-561)."""
+    x_atoms, x_frags, _ = edge_fragnet_forward(P, batch, num_layer, num_heads, drop_ratio, training)
+    return fthead_forward(P, readout(x_atoms, x_frags, batch), fthead, act, drop_ratio, training)
+
+
 def _mlp_stack(P: Params, name: str, x: torch.Tensor, L: int, act_first: bool) -> torch.Tensor:
     if act_first:                       # bond-length head: activation BEFORE each linear (pretrain_heads.py:72-74)
         for l in range(L + 1):

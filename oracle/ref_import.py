@@ -103,6 +103,22 @@ def load_lite():
     return _load("gat2_lite", "fragnet/model/gat/gat2_lite.py")
 
 
+def load_edge():
+    """The reference's ``gat2_edge`` module.  Its flat ``from pretrain_heads import PretrainTask`` (gat2_edge.py:327, a
+    stale sys.path-relative import) is satisfied by the ``pretrain_heads`` module loaded above, for the duration of the
+    load only."""
+    ns = load()
+    saved = sys.modules.get("pretrain_heads")
+    try:
+        sys.modules["pretrain_heads"] = ns.pretrain_heads
+        return _load("gat2_edge", "fragnet/model/gat/gat2_edge.py")
+    finally:
+        if saved is None:
+            sys.modules.pop("pretrain_heads", None)
+        else:
+            sys.modules["pretrain_heads"] = saved
+
+
 def load_trainer():
     """The reference's ``fragnet/train/pretrain/pretrain_utils.py`` (``Trainer``: the step loop and loss of
     pretrain_utils.py:9-31), unmodified."""
