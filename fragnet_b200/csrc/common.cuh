@@ -320,6 +320,7 @@ int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb
 // x3 != 0: 3xTF32 (error-compensated, FP32-grade) instead of one TF32 product.
 int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_t M, int K, const float *alpha,
                        int alpha_stride, int off_t, int off_s, float *C, float *S, cudaStream_t stream, int x3);
+void fnb_tc_set_cta_cap(int cap);   // CTA cap of this thread's next projection launches (0 = none)
 int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream);
 // Up to 16 [128,128] matrices transposed by one launch: Wt_base + i * 128 * 128 = Ws[i]^T.
 struct TransposeBatch { const float *W[16]; int count; };

@@ -1099,14 +1099,24 @@ int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int cols, int box
   return r == CUDA_SUCCESS ? 0 : FNB_ERR_MODE;
 }
 
+// CTA cap for the projection launches of the calling thread (0 = none): the encoder programs set it around the GEMMs of
+// their side chains (atom / fragment-connection graphs), see fnb_tc_set_cta_cap.
+thread_local int t_cta_cap = 0;
+
 // Persistent grid with the same number of tiles on every CTA: 203 tiles on 148 SMs are two rounds either way, and 102
 // CTAs with two tiles each leave 46 SMs to the kernels of the other streams (a GEMM CTA owns its SM's shared memory).
 int balanced_grid(int64_t n_tiles, int max_ctas) {
+  if (t_cta_cap > 0 && t_cta_cap < max_ctas) max_ctas = t_cta_cap;
   const int64_t per = (n_tiles + max_ctas - 1) / max_ctas;
   return (int)((n_tiles + per - 1) / per);
 }
 
 }  // namespace
+
+// A tcgen05 GEMM CTA owns its SM's shared memory: while a 148-CTA projection runs, the gather kernels of the other
+// streams cannot start anywhere.  GEMMs that nothing on the critical path waits for (side chains) are therefore capped
+// to a fraction of the SMs: they take longer, the bond chain keeps the rest of the GPU.
+void fnb_tc_set_cta_cap(int cap) { t_cta_cap = cap; }
 
 // C[M,128] = A[M,K] @ B[128,K]^T (+bias) with optional fused S; returns FNB_ERR_MODE if the shape cannot take the
 // TMA path (K*4 not a multiple of 16 bytes, K > 256, unaligned pointers) so the caller can fall back to proj.cu.
@@ -1226,7 +1236,9 @@ int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols
   // stream at least kDwMinBlocks row blocks (512 rows = 512 KiB of operands) so that the partials stay a small
   // fraction of the traffic; the GEMM shares the GPU with the gather kernels of the other streams anyway.
   constexpr int64_t kDwMinBlocks = 16;
-  int64_t per = (n_rb + kNumSMs - 1) / kNumSMs;
+  static const int dw_cap = getenv("FNB_DW_MAX_CTAS") ? atoi(getenv("FNB_DW_MAX_CTAS")) : kNumSMs;
+  const int cap = dw_cap > 0 && dw_cap < kNumSMs ? dw_cap : kNumSMs;
+  int64_t per = (n_rb + cap - 1) / cap;
   if (per < kDwMinBlocks) per = kDwMinBlocks;
   const int grid = (int)((n_rb + per - 1) / per);
   const size_t stage_bytes = ((size_t)TC_STAGE_BYTES + (size_t)n_chunks * 4096) * (x3 ? 2 : 1);

@@ -147,3 +147,31 @@ def test_stress_shape_batch_independence():
         head = m({k: v.cuda() for k, v in collate_fn(pool[:3]).items()})
         tail = m({k: v.cuda() for k, v in collate_fn(pool[-2:]).items()})
     assert rel_err(full[:3], head) <= FP32_REL_TOL and rel_err(full[-2:], tail) <= FP32_REL_TOL
+
+
+def test_forward_parity_with_the_oracle_at_the_bench_batch_size():
+    """BASELINE's per-GPU batch (1 024 UniMol-shaped molecules, the batch bench.py times): the CUDA forward of the
+    pretraining model in eval mode against the CPU oracle on the very same batch -- every prediction tensor, the loss and
+    the four encoder outputs within 1e-5 (the oracle needs a few seconds per forward at this size, so this runs once)."""
+    import bench
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet_b200.train.pretrain_utils import pretrain_loss
+    from oracle import gat2_oracle as O
+    hb = bench.make_batches("unimol", 1024, 1, 512, seed=100)[0]
+    torch.manual_seed(1234)
+    m = FragNetPreTrain(**bench.PT_KW).eval()
+    P = O.params_from_module(m, requires_grad=False)
+    m = m.cuda()
+    b = {k: v.cuda() for k, v in hb.items()}
+    with torch.no_grad():
+        preds = m(b)
+        enc = m.pretrain(b)
+        loss = pretrain_loss(torch.nn.MSELoss(), preds, b)
+        want_enc = O.fragnet_forward(P, hb, bench.PT_KW["num_layer"])
+        want = O.pretrain_heads_forward(P, want_enc[0], want_enc[1], want_enc[2], hb)
+        want_loss = O.pretrain_loss(want, hb)
+    for name, a, r in zip(("bond_length", "bond_angle", "dihedral", "energy"), preds, want):
+        assert a.shape == r.shape and rel_err(a, r) <= FP32_REL_TOL, (name, rel_err(a, r))
+    for name, a, r in zip(("x_atoms", "x_frags", "edge_features", "fedge_features"), enc, want_enc):
+        assert rel_err(a, r) <= FP32_REL_TOL, (name, rel_err(a, r))
+    assert rel_err(loss, want_loss) <= FP32_REL_TOL
