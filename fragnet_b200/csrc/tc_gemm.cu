@@ -14,8 +14,21 @@
 // thread, so the per-head dot products of the fused epilogue need no shuffles), warp 4 TMA producer (one lane),
 // warp 5 TMEM allocator + MMA issuer (one lane).
 //
-// Numerics: TF32 operands (10-bit mantissa) with FP32 accumulation -- more accurate than the bf16-in/fp32-acc the
-// north star allows for the projections; the strict-FP32 path (proj.cu) remains the parity reference.
+// Numerics, two modes (FNB_PRECISION_*):
+//  * TF32 (k_tc_proj / k_tc_proj_pair / k_tc_dw): one TF32 product per K-step (10-bit mantissa, FP32 accumulate) --
+//    more accurate than the bf16-in/fp32-acc the north star allows, but 1e-3-class, not 1e-5.
+//  * TF32X3 (k_tc_proj3r / k_tc_proj3 / k_tc_dw3), the library default: each fp32 operand is split on the fly into
+//    hi = rna_tf32(x) and lo = rna_tf32(x - hi), and the product is hi*hi + hi*lo + lo*hi (the dropped lo*lo term is
+//    2^-22 relative).  A is loaded to registers, split by converter warps and written to the swizzled operand layout
+//    (two converter groups alternate so that one group's proxy fence never waits for the other's loads); W is split
+//    once per CTA and stacked [W_hi; W_lo] so that ONE N=256 MMA forms A_hi*W_hi and A_hi*W_lo.  tcgen05 accumulates
+//    with truncation, which biases a long accumulation chain downwards; therefore hi*hi goes to its own TMEM
+//    accumulator and the (2^-11 smaller) cross terms to a second one, summed in the epilogue.  Measured error vs an
+//    fp64 product: <= 4e-6 relative to the row norm at K = 256 (tests/test_gpu_tc.py), against 1e-3 for single TF32.
+//    TF32 MMAs from shared memory are operand-bandwidth bound (an N=64 MMA costs what an N=128 one does), so the
+//    split costs ~1.5x the MMA time of the single product, hidden under the A stream for K <= 128.
+//  The strict-FP32 FFMA path (proj.cu) remains as the arithmetic cross-check and serves the small wide shapes
+//  (K > 128 with <= 8192 rows) where a 128-row tile would leave most SMs idle.
 #include <cuda.h>
 
 #include <cstdlib>
