@@ -63,3 +63,26 @@ bool fnb_pdl_enabled() {
   static const bool on = [] { const char *e = getenv("FNB_PDL"); return !(e && e[0] == '0'); }();
   return on;
 }
+
+// FNB_STAGE=1: bulk-copy (TMA) staging of the gathered source rows in the attention forward (measured slower than the
+// gather path on B200, profiles/r1h_kbench_stage*.log); the plan computes the tile ranges it needs only then.
+bool fnb_use_staging() {
+  static const bool on = [] { const char *e = getenv("FNB_STAGE"); return e && e[0] == '1'; }();
+  return on;
+}
+
+// One-kernel attention backward for graphs with a component table (gat_tiled.cu: k_gat_bwd_fused).  Opt-in
+// (FNB_FUSED_BWD=1 or fnb_debug_set_fused_bwd(1)): measured no faster than the two-pass kernels on B200 in any of the
+// three forms tried (gpurun_out/r5c..r5f_fused_bwd_bench.log); the batch plan builds the
+// component tables only while it is on.
+static int g_fused_bwd = -1;
+bool fnb_fused_bwd_enabled() {
+  int v = __atomic_load_n(&g_fused_bwd, __ATOMIC_RELAXED);
+  if (v < 0) {
+    const char *e = getenv("FNB_FUSED_BWD");
+    v = e && e[0] == '1';
+    __atomic_store_n(&g_fused_bwd, v, __ATOMIC_RELAXED);
+  }
+  return v != 0;
+}
+extern "C" void fnb_debug_set_fused_bwd(int on) { __atomic_store_n(&g_fused_bwd, on ? 1 : 0, __ATOMIC_RELAXED); }

@@ -86,6 +86,8 @@ __device__ __forceinline__ void pdl_wait() {
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool fnb_pdl_enabled();
+bool fnb_use_staging();
+bool fnb_fused_bwd_enabled();   // FNB_FUSED_BWD=0 or fnb_debug_set_fused_bwd(0): two-pass attention backward only
 template <class... KArgs, class... Args>
 inline cudaError_t fnb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args... args) {
@@ -298,6 +300,7 @@ struct FnbDstFuse {
   float scale;
   const float *pool;         // [n_seg,128] gradient of sum-pooled rows to hand back to their members, or NULL
   const int *seg_of;         // [N]
+  int skip_dz;               // nobody reads args->dz after this call: the one-kernel backward keeps it in shared memory
 };
 int fnb_gat_bwd_tiled_fused(const fnb_graph *g, const fnb_gat_bwd_args *args, const FnbDstFuse *fuse,
                             cudaEvent_t after_dst, cudaEvent_t before_src, void *stream);

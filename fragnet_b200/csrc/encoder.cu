@@ -665,6 +665,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         FnbDstFuse fz{};
         fz.dz_up = frag_feeds_fbond ? W.dz_f : nullptr; fz.slot_of_eid = plan->frag.slot_of_eid; fz.alpha_up = P.f + A_E;
         fz.alpha_up_stride = A_STRIDE; fz.dy = dy_fbond; fz.y = dy_fbond ? y_fbond : nullptr; fz.scale = scale;
+        fz.skip_dz = 1;   // dz of this graph has no consumer
         RC(fnb_gat_bwd_tiled_fused(&plan->fbond, &a, &fz, nullptr, nullptr, sB_));
         float *dx = need_dx ? W.dx_fbond : (o->need_dx_fbond ? io->dx_fbond : nullptr);
         if (l == 0 && b.k_pad[2] && !dx)
@@ -768,6 +769,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         fz.dz_up = have ? dz_a : nullptr; fz.slot_of_eid = plan->atom.slot_of_eid; fz.alpha_up = P.a + A_E;
         fz.alpha_up_stride = A_STRIDE; fz.g_base = y_bond ? nullptr : dy_bond; fz.dy = y_bond ? dy_bond : nullptr;
         fz.y = y_bond && dy_bond ? y_bond : nullptr; fz.scale = scale;
+        fz.skip_dz = 1;   // dz of this graph has no consumer
         // (the weight-gradient GEMM two layers above read this dh buffer: only the source pass has to wait for it)
         const bool wait_w = two && w_pending[1][par];
         w_pending[1][par] = false;

@@ -251,6 +251,14 @@ class LayerPlan:
         return self._view(self.c.status, 1)
 
     @property
+    def comp_open(self):
+        """int32[4] (bond, atom, fbond, frag): 0 = the graph's molecules are closed, tile-sized components, so its
+        attention backward runs as one kernel (gat_tiled.cu: k_gat_bwd_fused); None without batch vectors."""
+        if not self.c.bond.comp_open:
+            return None
+        return self._view(self.c.bond.comp_open, 4)
+
+    @property
     def readout(self) -> Optional[ReadoutPlan]:
         if not self.c.mol_atom_ptr:
             return None

@@ -39,7 +39,7 @@ extern "C" {
 
 #define FNB_D 128 /* embedding width  */
 #define FNB_H 4   /* attention heads  */
-#define FNB_ABI_VERSION 6
+#define FNB_ABI_VERSION 7
 
 /* edge-term modes of the fused attention kernels */
 /* arithmetic of the dense projections */
@@ -186,7 +186,18 @@ typedef struct fnb_graph {
    * likewise bounds the DESTINATIONS met by 64 consecutive sources in the reverse CSR.  NULL = always gather. */
   const int32_t *tile_range, *rtile_range;
   const float *edge_attr; /* slot-ordered attributes: [E] (bond graph), [E,6] (fragment-connection graph), else NULL */
+  /* Optional component table (fnb_batch_plan_build with batch vectors while fnb_debug_set_fused_bwd(1)): nodes [comp_ptr[c], comp_ptr[c+1]) are the
+   * nodes of molecule c.  comp_open is a device word the plan writes: 0 = every component is CLOSED (no edge of the
+   * graph leaves it, in either direction) and fits one tile of the fused attention backward (FNB_FUSED_NODES nodes,
+   * FNB_FUSED_SLOTS edge slots), so destination and source pass run as ONE kernel with the tile's gradient rows in
+   * shared memory; non-zero = the two-pass kernels run instead.  comp_ptr == NULL: unknown, two passes. */
+  const int32_t *comp_ptr;    /* [n_comps + 1]; n_comps may exceed the molecule count (trailing empty components) */
+  int64_t n_comps;
+  const int32_t *comp_bucket; /* [ceil(n_nodes / 8) + 1]: first component whose first node is >= 8 k */
+  const int32_t *comp_open;
 } fnb_graph;
+#define FNB_FUSED_NODES 128
+#define FNB_FUSED_SLOTS 896
 
 typedef struct fnb_post_act { /* y = ReLU(Dropout_p(out)); RNG counter of element i is offset + i/4 */
   float p;
@@ -231,6 +242,10 @@ int fnb_gat_bwd_tiled(const fnb_graph *g, const fnb_gat_bwd_args *args, void *st
 /* Same two launches with `between_passes` (a cudaEvent_t of the caller, may be NULL) recorded on `stream` after the
  * destination pass: lets a caller time the two passes separately (bench.py's roofline.kernels). */
 int fnb_gat_bwd_tiled_marked(const fnb_graph *g, const fnb_gat_bwd_args *args, void *between_passes, void *stream);
+/* Opt-in (also FNB_FUSED_BWD=1 in the environment; default 0): plans built while it is 1 carry component tables and
+ * their attention backward runs as one kernel.  Measured no faster than the two passes on B200;
+ * kept for graphs / parts where it may pay, and exercised by the tests. */
+void fnb_debug_set_fused_bwd(int on);
 /* g_feat[e,:] = g_base[e,:] (if given) + dy[e,:]*(y[e,:]>0)*post_scale (if given) + sum_h dz[slot_of_eid[e],h]*alpha_e[h,:];
  * d_alpha[h, off_e:off_e+128] = sum_e dz[slot_of_eid[e],h] * feat[e,:] */
 int fnb_edge_table_bwd_fused(const fnb_graph *g, const float *dz, const float *feat, const float *alpha,
