@@ -85,3 +85,34 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         got = [int(x) for x in line.split()[1:]]
         want = [C.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
         assert got == want, cname
+
+
+def test_fragnet_shim_falls_through_to_a_reference_checkout(tmp_path):
+    """The ``fragnet`` shim serves the hot path; with the reference further down sys.path, modules and names outside
+    it are the reference's own (pretrain_gat2.py:4-12 imports ``fragnet.dataset.dataset.load_data_parts`` and
+    ``FragNetPreTrainMasked`` next to the classes the shim replaces)."""
+    import os
+    import subprocess
+    import sys
+    ref = tmp_path / "ref"
+    (ref / "fragnet" / "dataset").mkdir(parents=True)
+    (ref / "fragnet" / "model" / "gat").mkdir(parents=True)
+    (ref / "fragnet" / "dataset" / "dataset.py").write_text("def load_data_parts():\n    return 'reference'\n")
+    (ref / "fragnet" / "model" / "gat" / "pretrain_heads.py").write_text(
+        "from fragnet.model.gat.gat2 import FragNet\n\n\nclass FragNetPreTrainMasked:\n    encoder = FragNet\n\n\n"
+        "class FragNetPreTrain:\n    shadowed = True\n")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "from fragnet.dataset.dataset import load_data_parts\n"
+        "from fragnet.model.gat.pretrain_heads import FragNetPreTrain, FragNetPreTrainMasked\n"
+        "import fragnet_b200.model.gat.pretrain_heads as ours, fragnet_b200.model.gat.gat2 as g\n"
+        "assert load_data_parts() == 'reference'\n"
+        "assert FragNetPreTrain is ours.FragNetPreTrain and not hasattr(FragNetPreTrain, 'shadowed')\n"
+        "assert FragNetPreTrainMasked.encoder is g.FragNet\n"
+        "import fragnet.model.gat.pretrain_heads as shim\n"
+        "try:\n    shim.Nope\n    raise SystemExit('no AttributeError')\n"
+        "except AttributeError as e:\n    assert 'hot path' in str(e)\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([repo, str(ref)]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
