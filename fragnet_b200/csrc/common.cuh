@@ -285,6 +285,8 @@ struct FnbAux {
   cudaEvent_t plan_fwd;      // forward half of the batch plan is complete (plan.cu)
   cudaStream_t estream;      // head-vector gradients of the 128-wide edge terms (nobody's input: off every chain)
   cudaEvent_t e_ready, e_done[2], e_join;
+  cudaStream_t hstream;      // energy head (~1e3 rows, latency-bound): off the fragment-connection chain's stream
+  cudaEvent_t h_done;
 };
 int fnb_aux_streams(FnbAux *out);
 

@@ -20,6 +20,8 @@
 //     from shared memory; the backward tail recomputes the hidden layer, and reduces the parameter gradients of the
 //     tail (dW1 [MID,IN], db1, dW2, db2, db0) over the rows of its tile out of shared memory into per-CTA records.
 // Parameter-gradient sums are fixed-order two-stage reductions: run-to-run deterministic, no atomics.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -69,7 +71,10 @@ size_t fwd_layout(int64_t Na, int64_t Ea, int64_t G, char *base, FwdBufs *out) {
 }
 
 // ---- backward workspace -----------------------------------------------------------------------------------------------
-constexpr int kTailCtasMax = kNumSMs;
+// Tail kernels run 3 CTAs of 128 threads per SM (444 slots); a tile is 128 rows.  At 148 CTAs per head the 422 tiles of
+// the dihedral head were 3 rounds on some CTAs while a third of the slots idled; 222 per head make it 2 rounds
+// (k_mlp_tail_bwd2: 54 -> 40 us at batch 1 024).
+constexpr int kTailCtasMax = kNumSMs * 3 / 2;
 __host__ __device__ constexpr int rec_floats(int IN, int MID) { return (MID * IN + MID + MID + 1 + IN + 3) & ~3; }
 constexpr int kRecSmall = rec_floats(64, 32);    // 2180
 constexpr int kRecWide = rec_floats(128, 64);    // 8452
@@ -673,6 +678,260 @@ __global__ void __launch_bounds__(128, 3) k_mlp_tail_bwd2(TailJobs J) {
   }
 }
 
+// ---- the energy head of a training step as ONE kernel -------------------------------------------------------------
+// pretrain_heads.py:93-102 for G ~ 1e3 molecules is six latency-bound launches in a chain (two readout sums, first
+// layer, tail forward+backward, input gradient, readout backward) that the encoder backward has to wait for: 165 us in
+// the step (gpurun_out/r5k_device_profile.log) for 70 MFLOP.  Here a CTA takes 8 molecules through the whole chain in
+// shared memory: readout (written out for the weight-gradient GEMM of the first layer) -> h0 = W0 readout + b0 ->
+// tail forward, loss share, tail backward -> dh0 (written out, same GEMM) -> d_readout = dh0 W0 (atom half written out
+// for the caller's gather, fragment half scattered to the molecule's fragment rows here) and the per-CTA record of the
+// tail's parameter gradients in k_mlp_tail_bwd's layout.  Exact FP32, fixed summation order.
+struct EnergyArgs {
+  const int *atom_ptr, *frag_ptr;             // [G + 1] molecule boundaries
+  const float *x_atoms, *x_frags;             // [Na,128], [Nf,128]
+  const float *W0, *b0, *W1, *b1, *W2, *b2;   // fc head: [128,256] [128] [64,128] [64] [64] [1]
+  const float *target;                        // [G]
+  float loss_coef;
+  int G;
+  float *readout, *dh0, *d_readout, *g_frags, *rec;
+};
+constexpr int EH_ROWS = 8, EH_THREADS = 256, EH_IN0 = 2 * kD, EH_H = kD, EH_MID = 64;
+constexpr size_t kEnergySmem =
+    sizeof(float) * ((size_t)2 * EH_H * EH_MID + EH_ROWS * EH_IN0 + 2 * EH_ROWS * EH_H + 2 * EH_ROWS * EH_H +
+                     3 * EH_ROWS * EH_MID + 2 * EH_MID + 4 * EH_ROWS);
+
+__global__ void __launch_bounds__(EH_THREADS) k_energy_head_fused(EnergyArgs a) {
+  constexpr int REC = rec_floats(EH_H, EH_MID);
+  extern __shared__ __align__(16) float smem[];
+  float *sW1 = smem;                          // [MID][H]   W1[i][k]
+  float *sW1t = sW1 + EH_MID * EH_H;          // [H][MID]   W1t[k][i]
+  float *sA = sW1t + EH_MID * EH_H;           // [ROWS][256] readout, later d_readout
+  float *sH = sA + EH_ROWS * EH_IN0;          // [ROWS][128] h0 (pre-activation)
+  float *sD0 = sH + EH_ROWS * EH_H;           // [ROWS][128] dh0
+  float *sP = sD0 + EH_ROWS * EH_H;           // [2][ROWS][128] K-halves of h0
+  float *sH1 = sP + 2 * EH_ROWS * EH_H;       // [ROWS][MID] hidden pre-activation
+  float *sD1 = sH1 + EH_ROWS * EH_MID;        // [ROWS][MID]
+  float *sH1g = sD1 + EH_ROWS * EH_MID;       // [ROWS][MID] g * ReLU(hidden)
+  float *sb1 = sH1g + EH_ROWS * EH_MID;       // [MID] b1, [MID] W2
+  float *sG = sb1 + 2 * EH_MID;               // [ROWS] g, [ROWS] loss share, [2 * ROWS] spare
+  const int tid = threadIdx.x;
+  for (int i = tid; i < EH_MID * EH_H; i += EH_THREADS) {   // parameters: before the dependency wait
+    const float w = __ldg(a.W1 + i);      // i = unit * H + k
+    sW1[i] = w;
+    sW1t[(i & (EH_H - 1)) * EH_MID + (i >> 7)] = w;
+  }
+  if (tid < EH_MID) {
+    sb1[tid] = __ldg(a.b1 + tid);
+    sb1[EH_MID + tid] = __ldg(a.W2 + tid);
+  }
+  const float b2 = __ldg(a.b2);
+  pdl_wait();
+  const int oj = tid >> 2, ok0 = (tid & 3) * 4;   // dW1 ownership as in k_mlp_tail_bwd: row oj, columns ok0 + 16 q .. +3
+  float wacc[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) wacc[q] = 0.f;
+  float vacc = 0.f, b0acc = 0.f, b2acc = 0.f, lossacc = 0.f;
+  const int n_tiles = (a.G + EH_ROWS - 1) / EH_ROWS;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int g0 = tile * EH_ROWS, rows = min(EH_ROWS, a.G - g0);
+    __syncthreads();
+    // ---- readout (pretrain_heads.py:93-96): [sum of atom rows | sum of fragment rows]; one warp per molecule, a lane
+    // owns 4 columns, 8 row loads in flight (a thread per column walking 8 molecules in turn was 50 dependent round
+    // trips: half of the kernel's time)
+    {
+      const int m = tid >> 5, lane = tid & 31;
+      float4 sum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      if (m < rows) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int *ptr = half ? a.frag_ptr : a.atom_ptr;
+          const float *x = (half ? a.x_frags : a.x_atoms) + lane * 4;
+          const int b = __ldg(ptr + g0 + m), e = __ldg(ptr + g0 + m + 1);
+          float4 s_ = make_float4(0.f, 0.f, 0.f, 0.f);
+          int r = b;
+          for (; r + 8 <= e; r += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ldg4(x + (int64_t)(r + u) * kD);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s_.x += v[u].x; s_.y += v[u].y; s_.z += v[u].z; s_.w += v[u].w; }
+          }
+          for (; r < e; ++r) {
+            const float4 v = ldg4(x + (int64_t)r * kD);
+            s_.x += v.x; s_.y += v.y; s_.z += v.z; s_.w += v.w;
+          }
+          sum[half] = s_;
+          st4(a.readout + (int64_t)(g0 + m) * EH_IN0 + half * kD + lane * 4, s_);
+        }
+      }
+      st4(sA + m * EH_IN0 + lane * 4, sum[0]);
+      st4(sA + m * EH_IN0 + kD + lane * 4, sum[1]);
+    }
+    __syncthreads();
+    // ---- h0 = readout W0^T + b0: thread = (output j, K-half), 8 molecules each
+    {
+      const int j = tid & 127, kh = tid >> 7;
+      float acc[EH_ROWS];
+#pragma unroll
+      for (int m = 0; m < EH_ROWS; ++m) acc[m] = 0.f;
+      const float *wrow = a.W0 + (int64_t)j * EH_IN0 + kh * kD;
+      for (int k0 = 0; k0 < kD; k0 += 32) {
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = ldg4(wrow + k0 + 4 * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int m = 0; m < EH_ROWS; ++m) {
+            const float4 av = ld4(sA + m * EH_IN0 + kh * kD + k0 + 4 * u);
+            acc[m] = fmaf(av.x, w[u].x, acc[m]);
+            acc[m] = fmaf(av.y, w[u].y, acc[m]);
+            acc[m] = fmaf(av.z, w[u].z, acc[m]);
+            acc[m] = fmaf(av.w, w[u].w, acc[m]);
+          }
+      }
+#pragma unroll
+      for (int m = 0; m < EH_ROWS; ++m) sP[(kh * EH_ROWS + m) * EH_H + j] = acc[m];
+    }
+    __syncthreads();
+    for (int i = tid; i < EH_ROWS * EH_H; i += EH_THREADS)
+      sH[i] = (sP[i] + sP[EH_ROWS * EH_H + i]) + __ldg(a.b0 + (i & (EH_H - 1)));
+    __syncthreads();
+    // ---- hidden layer: thread = (unit i, molecule pair)
+    {
+      const int i = tid & 63, mp = tid >> 6;
+      float acc0 = sb1[i], acc1 = sb1[i];
+      const float *h0a = sH + (2 * mp) * EH_H, *h0b = h0a + EH_H;
+#pragma unroll 4
+      for (int k = 0; k < EH_H; ++k) {
+        const float w = sW1t[k * EH_MID + i];
+        acc0 = fmaf(fmaxf(h0a[k], 0.f), w, acc0);
+        acc1 = fmaf(fmaxf(h0b[k], 0.f), w, acc1);
+      }
+      sH1[(2 * mp) * EH_MID + i] = acc0;
+      sH1[(2 * mp + 1) * EH_MID + i] = acc1;
+    }
+    __syncthreads();
+    // ---- prediction, loss share, gradient of the prediction
+    if (tid < EH_ROWS) {
+      float o = b2;
+      for (int i = 0; i < EH_MID; ++i) o = fmaf(fmaxf(sH1[tid * EH_MID + i], 0.f), sb1[EH_MID + i], o);
+      const float diff = tid < rows ? o - __ldg(a.target + g0 + tid) : 0.f;
+      sG[tid] = 2.f * a.loss_coef * diff;
+      sG[EH_ROWS + tid] = a.loss_coef * diff * diff;
+    }
+    __syncthreads();
+    {
+      const int i = tid & 63, mp = tid >> 6;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int m = 2 * mp + d;
+        const float pre = sH1[m * EH_MID + i], g = sG[m];
+        sD1[m * EH_MID + i] = pre > 0.f ? g * sb1[EH_MID + i] : 0.f;
+        sH1g[m * EH_MID + i] = g * fmaxf(pre, 0.f);
+      }
+    }
+    __syncthreads();
+    // ---- dh0: thread = (column k, molecule quad)
+    {
+      const int k = tid & 127, mh = tid >> 7;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int i = 0; i < EH_MID; ++i) {
+        const float w = sW1[i * EH_H + k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = fmaf(sD1[(4 * mh + q) * EH_MID + i], w, acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = 4 * mh + q;
+        const float v = sH[m * EH_H + k] > 0.f ? acc[q] : 0.f;
+        sD0[m * EH_H + k] = v;
+        if (m < rows) a.dh0[(int64_t)(g0 + m) * kD + k] = v;
+      }
+    }
+    __syncthreads();
+    // ---- parameter-gradient partials of the tail (registers, summed over the CTA's tiles)
+    for (int m = 0; m < EH_ROWS; ++m) {
+      const float d = sD1[m * EH_MID + oj];
+      const float *hp = sH + m * EH_H + ok0;
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 hv = ld4(hp + q4 * 16);
+        wacc[q4 * 4 + 0] = fmaf(d, fmaxf(hv.x, 0.f), wacc[q4 * 4 + 0]);
+        wacc[q4 * 4 + 1] = fmaf(d, fmaxf(hv.y, 0.f), wacc[q4 * 4 + 1]);
+        wacc[q4 * 4 + 2] = fmaf(d, fmaxf(hv.z, 0.f), wacc[q4 * 4 + 2]);
+        wacc[q4 * 4 + 3] = fmaf(d, fmaxf(hv.w, 0.f), wacc[q4 * 4 + 3]);
+      }
+      if ((tid & 3) == 0) vacc += d;
+      else if ((tid & 3) == 1) vacc += sH1g[m * EH_MID + oj];
+      if (tid < EH_H) b0acc += sD0[m * EH_H + tid];
+      if (tid == 0) {
+        b2acc += sG[m];
+        lossacc += sG[EH_ROWS + m];
+      }
+    }
+    // ---- d_readout = dh0 W0: thread = column c of the 256, 8 molecules
+    {
+      const int c = tid;
+      float acc[EH_ROWS];
+#pragma unroll
+      for (int m = 0; m < EH_ROWS; ++m) acc[m] = 0.f;
+      for (int j0 = 0; j0 < EH_H; j0 += 32) {
+        float w[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) w[u] = __ldg(a.W0 + (int64_t)(j0 + u) * EH_IN0 + c);
+#pragma unroll
+        for (int u = 0; u < 32; ++u)
+#pragma unroll
+          for (int m = 0; m < EH_ROWS; ++m) acc[m] = fmaf(sD0[m * EH_H + j0 + u], w[u], acc[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < EH_ROWS; ++m) {
+        sA[m * EH_IN0 + c] = acc[m];    // (the readout was last read two barriers ago)
+        if (m < rows) a.d_readout[(int64_t)(g0 + m) * EH_IN0 + c] = acc[m];
+      }
+    }
+    __syncthreads();
+    // ---- readout backward of the fragments: every fragment row receives its molecule's gradient
+    {
+      const int c = tid & 127, sub = tid >> 7;
+      for (int m = 0; m < rows; ++m) {
+        const int fb = __ldg(a.frag_ptr + g0 + m), fe = __ldg(a.frag_ptr + g0 + m + 1);
+        const float v = sA[m * EH_IN0 + kD + c];
+        for (int f = fb + sub; f < fe; f += 2) a.g_frags[(int64_t)f * kD + c] = v;
+      }
+    }
+  }
+  // ---- CTA record: [dW1 MID*H][db1 MID][dW2 MID][db2 1][db0 H][loss]  (k_mlp_tail_bwd<128, 64>'s layout)
+  pdl_launch_dependents();
+  float *rec = a.rec + (size_t)blockIdx.x * REC;
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4)
+    st4(rec + oj * EH_H + ok0 + q4 * 16, make_float4(wacc[q4 * 4], wacc[q4 * 4 + 1], wacc[q4 * 4 + 2], wacc[q4 * 4 + 3]));
+  if ((tid & 3) == 0) rec[EH_MID * EH_H + oj] = vacc;
+  if ((tid & 3) == 1) rec[EH_MID * EH_H + EH_MID + oj] = vacc;
+  if (tid == 0) {
+    rec[EH_MID * EH_H + 2 * EH_MID] = b2acc;
+    rec[EH_MID * EH_H + 2 * EH_MID + 1 + EH_H] = lossacc;
+  }
+  if (tid < EH_H) rec[EH_MID * EH_H + 2 * EH_MID + 1 + tid] = b0acc;
+}
+
+// FNB_ENERGY_EARLY=1 (measurement switch): fork the energy stream at the head of the forward program instead of at the
+// head of the backward program.  Earlier looks better on paper (everything the kernel reads is complete there) and
+// measured worse, 1.312 vs 1.299 ms per step on the same box (gpurun_out/r5n): its 128 CTAs then hold their SMs when
+// the per-atom / per-bond tail kernel -- the critical path -- launches, which gets one CTA per SM instead of three.
+bool energy_fork_early() {
+  static const bool on = [] { const char *e = getenv("FNB_ENERGY_EARLY"); return e && e[0] == '1'; }();
+  return on;
+}
+
+bool energy_fused_enabled() {
+  static const bool on = [] { const char *e = getenv("FNB_ENERGY_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int IN, int MID, int ROWS>
 constexpr size_t tail_bwd_smem() {
   return sizeof(float) * ((size_t)IN * MID + 2 * (size_t)ROWS * (IN + 4) + 2 * (size_t)ROWS * (MID + 1) + ROWS);
@@ -799,6 +1058,18 @@ int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool want_bl = io->bond_length != nullptr && Ea > 0 && !skip_tails;
 
+  // ---- energy head: ~1e3 rows, latency-bound kernels on an auxiliary stream underneath the per-atom / per-bond heads.
+  // Training step with the fused energy kernel: that kernel is launched by the backward program (see energy_fork_early
+  // for the variant that forks the stream here).
+  FnbAux aux{};
+  const bool two = fnb_aux_streams(&aux) == 0;
+  cudaStream_t sB = two ? aux.hstream : stream;
+  void *sB_ = (void *)sB;
+  const bool energy_in_backward = skip_tails && energy_fused_enabled();
+  if (two && G > 0 && energy_in_backward && energy_fork_early()) {
+    RC((int)cudaEventRecord(aux.fork, stream));
+    RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
+  }
   {  // padded / split operands (one launch)
     PackJobs p{};
     p.W0[0] = P->ba.W0; p.b0[0] = P->ba.b0; p.Wpad[0] = B.W0pad_ba; p.WpadT[0] = B.W0padT_ba; p.bpad[0] = B.b0pad_ba;
@@ -810,13 +1081,8 @@ int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb
     if (cudaError_t le = fnb_launch(k_head_pack, dim3(16, want_bl ? 6 : 2), dim3(256), 0, stream, p)) return (int)le;
     FNB_CHECK_LAUNCH();
   }
-  // ---- energy head (graph readout pretrain_heads.py:93-96, first layer, tail): ~1e3 rows, latency-bound kernels that
-  // run on the auxiliary stream underneath the per-atom / per-bond heads
-  FnbAux aux{};
-  const bool two = fnb_aux_streams(&aux) == 0;
-  cudaStream_t sB = two ? aux.stream : stream;
-  void *sB_ = (void *)sB;
-  if (G > 0) {
+  // ---- energy head (graph readout pretrain_heads.py:93-96, first layer, tail)
+  if (G > 0 && !energy_in_backward) {
     if (two) {
       RC((int)cudaEventRecord(aux.fork, stream));
       RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
@@ -867,7 +1133,10 @@ int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb
       FNB_CHECK_LAUNCH();
     }
   }
-  if (two && G > 0) {
+  // skip_tails: the caller (fnb_pretrain_step) runs the backward program next on the same streams; the energy chain
+  // stays on its stream (the backward continues it there and joins once, before the readout gradient) instead of
+  // making the per-atom / per-bond tails wait ~40 us for a 1 024-row GEMM (gpurun_out/r4n_device_profile.log)
+  if (two && G > 0 && !skip_tails) {
     RC((int)cudaEventRecord(aux.join, sB));
     RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
   }
@@ -875,8 +1144,8 @@ int fnb_pretrain_heads_forward_impl(const fnb_pretrain_head_params *P, const fnb
 }
 
 // defer_join != 0: the weight gradients still running on the auxiliary streams are NOT joined into the caller's
-// stream at return (fnb_pretrain_step joins them through the encoder backward that follows, which ends by waiting for
-// those in-order streams).
+// stream at return: fnb_pretrain_step joins the weight-gradient stream through the encoder backward that follows
+// (which ends by waiting for that in-order stream) and the energy head's stream through aux.h_done.
 int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
                                      const fnb_pretrain_head_io *io, int precision, void *workspace,
                                      size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
@@ -902,7 +1171,7 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
 
   FnbAux aux{};
   const bool two = fnb_aux_streams(&aux) == 0;
-  cudaStream_t sB = two ? aux.stream : stream;
+  cudaStream_t sB = two ? aux.hstream : stream;
   void *sB_ = (void *)sB;
   void *scratchB = two ? (void *)W.scratch2 : scratch;
   int ctas_ba = 0, ctas_da = 0, ctas_fc = 0;
@@ -918,17 +1187,34 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
       e = cudaFuncSetAttribute(k_mlp_tail_bwd<128, 64, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)tail_bwd_smem<128, 64, 32>());
       if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(k_energy_head_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEnergySmem);
+      if (e != cudaSuccess) return (int)e;
       done[dev] = true;
     }
   }
   // ---- energy head on the auxiliary stream (its ~1e3-row kernels are latency-bound and hide under the other heads):
   // tail, dX / dW of its first layer, readout backward of the fragments
   if (G > 0) {
+    const bool one_kernel = fused && energy_fused_enabled();
     if (two) {
-      RC((int)cudaEventRecord(aux.fork, stream));
-      RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
+      if (!one_kernel || !energy_fork_early()) {
+        RC((int)cudaEventRecord(aux.fork, stream));
+        RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
+      }
       RC((int)cudaMemsetAsync(W.scratch2, 0, kScratchCounters * sizeof(float), sB));
     }
+    if (one_kernel) {
+      // training step: readout, first layer, tail forward + loss + backward, input gradient and the fragments' readout
+      // backward in one kernel (the forward program skipped the energy head)
+      EnergyArgs e{};
+      e.atom_ptr = io->mol_atom_ptr; e.frag_ptr = io->mol_frag_ptr; e.x_atoms = io->x_atoms; e.x_frags = io->x_frags;
+      e.W0 = P->fc.W0; e.b0 = P->fc.b0; e.W1 = P->fc.W1; e.b1 = P->fc.b1; e.W2 = P->fc.W2; e.b2 = P->fc.b2;
+      e.target = fused[2].target; e.loss_coef = fused[2].weight / (float)G; e.G = (int)G;
+      e.readout = B.readout; e.dh0 = W.dh0_fc; e.d_readout = W.d_readout; e.g_frags = io->g_frags; e.rec = W.rec_fc;
+      ctas_fc = tail_grid(G, EH_ROWS);
+      if (cudaError_t le = fnb_launch(k_energy_head_fused, dim3(ctas_fc), dim3(EH_THREADS), kEnergySmem, sB, e)) return (int)le;
+      FNB_CHECK_LAUNCH();
+    } else {
     TailJobs F{};
     F.n = 1;
     ctas_fc = tail_grid(G, 32);
@@ -942,11 +1228,13 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
     // input gradient first: the atoms' gradient on the caller's stream waits for d_readout, nothing waits for dW
     RC(fnb_proj_bwd_dx(P->fc.W0, nullptr, W.dh0_fc, G, 2 * kD, W.d_readout, precision, scratchB, sB_));
     RC(fnb_segment_gather(W.d_readout + kD, 2 * kD, io->frag_batch32, Nf, nullptr, io->g_frags, sB_));
+    }
     if (two) RC((int)cudaEventRecord(aux.join, sB));
     RC(fnb_proj_bwd_dw(B.readout, W.dh0_fc, G, 2 * kD, D->fc.W0, nullptr, precision, scratchB, sB_));
-    if (two) RC((int)cudaEventRecord(aux.wjoin, sB));
+    if (two) RC((int)cudaEventRecord(defer_join ? aux.h_done : aux.wjoin, sB));
   } else {
     RC((int)cudaMemsetAsync(D->fc.W0, 0, sizeof(float) * kD * 2 * kD, stream));
+    if (two && defer_join) RC((int)cudaEventRecord(aux.h_done, stream));
   }
   // ---- tails of the per-atom / per-bond heads: dh0 + per-CTA records of their tail gradients
   {
@@ -996,7 +1284,6 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
     cp.add(W.dWpad_da, 1, 0, 0, 64 * kD, D->da.W0);
     RC(cp.launch(sW));
   }
-  if (two) RC((int)cudaEventRecord(aux.done[0], sW));
   if (G > 0) {
     if (two) RC((int)cudaStreamWaitEvent(stream, aux.join, 0));
     // readout backward (pretrain_heads.py:93-96): every atom receives its molecule's gradient row on top of the
@@ -1013,12 +1300,16 @@ int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fn
     sb.add(W.rec_da, ctas_da, kRecSmall, 64 * 32 + 2 * 32 + 1 + 64, 1, W.loss_parts + 1);
     sb.add(W.rec_fc, ctas_fc, kRecWide, 128 * 64 + 2 * 64 + 1 + 128, 1, W.loss_parts + 2);
   }
-  RC(sb.launch(stream));
+  // (on the weight-gradient stream: the encoder backward that follows on the caller's stream needs none of this; the
+  // tails' records are complete at aux.ready[0], which that stream has waited for, the energy head's at aux.join)
+  if (two && G > 0) RC((int)cudaStreamWaitEvent(sW, aux.join, 0));
+  RC(sb.launch(sW));
   if (fused) {
-    if (cudaError_t le = fnb_launch(k_loss_total, dim3(1), dim3(32), 0, stream, (const float *)W.loss_parts, 3, loss_out))
+    if (cudaError_t le = fnb_launch(k_loss_total, dim3(1), dim3(32), 0, sW, (const float *)W.loss_parts, 3, loss_out))
       return (int)le;
     FNB_CHECK_LAUNCH();
   }
+  if (two) RC((int)cudaEventRecord(aux.done[0], sW));
   if (two && !defer_join) {
     if (G > 0) RC((int)cudaStreamWaitEvent(stream, aux.wjoin, 0));   // energy head's first-layer weight gradient
     RC((int)cudaStreamWaitEvent(stream, aux.done[0], 0));            // first-layer weight gradients of the other heads

@@ -181,5 +181,6 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   eio.g_atoms = B.g_atoms; eio.g_frags = B.g_frags; eio.g_bond = B.g_edge; eio.g_fbond = nullptr;
   RC(fnb_encoder_backward(&plan, &o, a->layers, a->layer_grads, &eio, B.enc_ws, B.enc_bytes, B.enc_bws, B.enc_bws_bytes,
                           scratch, stream));
+  if (two) RC((int)cudaStreamWaitEvent((cudaStream_t)stream, aux.h_done, 0));   // energy head's first-layer weight gradient
   return 0;
 }
