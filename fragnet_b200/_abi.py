@@ -64,6 +64,7 @@ SIGNATURES = {
     "fnb_pretrain_step_workspace_bytes": (_sz, [_vp]),
     "fnb_pretrain_step_rng_span": (_u64, [_vp]),
     "fnb_pretrain_step": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "fnb_pretrain_plan_prefetch": (C.c_int, [_vp, _vp, _sz, _vp]),
     "fnb_arena_workspace_bytes": (_sz, [_i64, _i32]),
     "fnb_arena_assemble": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _sz, _vp, _vp]),
 }
@@ -115,7 +116,7 @@ class CWidenJob(C.Structure):
 WIDEN_U8_F32, WIDEN_I32_I64, WIDEN_MAX_JOBS = 0, 1, 16
 ARENA_COPY32, ARENA_INDEX, ARENA_FILL = 0, 1, 2
 ARENA_MAX_KINDS, ARENA_MAX_JOBS = 24, 32
-ABI_VERSION = 7
+ABI_VERSION = 8
 EDGE_NONE, EDGE_AFFINE1, EDGE_AFFINE6, EDGE_TABLE = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_TF32, PRECISION_TF32X3 = 0, 1, 2
 
@@ -226,4 +227,4 @@ class CPretrainStepArgs(C.Structure):
                [("n_layers", _i32), ("layers", _vp), ("layer_grads", _vp), ("heads", _vp), ("head_grads", _vp),
                 ("drop_p", _f32), ("training", _i32), ("seed", _u64), ("offset", _u64), ("precision", _i32),
                 ("backward", _i32)] + \
-               [(n, _vp) for n in ("loss", "bond_length", "bond_angle", "dihedral", "energy")]
+               [(n, _vp) for n in ("loss", "bond_length", "bond_angle", "dihedral", "energy", "plan_arena")]

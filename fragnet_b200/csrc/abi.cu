@@ -56,6 +56,9 @@ int fnb_aux_streams(FnbAux *out) {
       if (cudaStreamCreateWithPriority(&a.hstream, cudaStreamNonBlocking, prio ? greatest : 0) != cudaSuccess) return 1;
     }
     if (cudaEventCreateWithFlags(&a.h_done, cudaEventDisableTiming) != cudaSuccess) return 1;
+    if (cudaStreamCreateWithFlags(&a.pstream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    for (cudaEvent_t *e : {&a.p_fwd, &a.p_done, &a.step_begin})
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return 1;
     cudaEvent_t *evs[16] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.done2[0], &a.done2[1], &a.wjoin,
                             &a.a_fork, &a.a_dz, &a.a_table, &a.a_join, &a.plan_fwd, &a.e_ready, &a.e_done[0],
                             &a.e_done[1], &a.e_join};

@@ -287,6 +287,8 @@ struct FnbAux {
   cudaEvent_t e_ready, e_done[2], e_join;
   cudaStream_t hstream;      // energy head (~1e3 rows, latency-bound): off the fragment-connection chain's stream
   cudaEvent_t h_done;
+  cudaStream_t pstream;      // batch plan of the NEXT step (fnb_pretrain_plan_prefetch)
+  cudaEvent_t p_fwd, p_done, step_begin;
 };
 int fnb_aux_streams(FnbAux *out);
 
@@ -312,6 +314,8 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
                              void *stream, cudaEvent_t plan_ready, cudaEvent_t plan_complete);
 int fnb_batch_plan_build_impl(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out,
                               void *stream, cudaEvent_t forward_ready);
+// The plan struct of an arena that fnb_batch_plan_build filled (or is filling) for `in`: pointers only, no launch.
+int fnb_batch_plan_view(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out);
 int fnb_pretrain_heads_backward_impl(const fnb_pretrain_head_params *P, const fnb_pretrain_head_grads *D,
                                      const fnb_pretrain_head_io *io, int precision, void *workspace,
                                      size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,

@@ -450,11 +450,48 @@ inline int grid_for(int64_t n) {
   return (int)g;
 }
 
+// The plan struct over a laid-out arena (pure function of the inputs' sizes and the two build options).
+void fill_plan(const fnb_batch_inputs *in, const PlanLayout &L, const Sz &z, bool staging, bool comps, fnb_batch_plan *out) {
+  const int n_real[PG] = {(int)in->n_bond_edges, (int)in->n_bonds, (int)in->n_fbond_edges, (int)in->n_fbond_nodes,
+                          (int)in->n_atoms};
+  int *comp_ptr[4] = {L.bond_ptr, L.atom_ptr, L.fbond_ptr, L.frag_ptr};
+  fnb_graph *gs[4] = {&out->bond, &out->atom, &out->fbond, &out->frag};
+  for (int i = 0; i < 4; ++i) {
+    fnb_graph &g = *gs[i];
+    g.n_nodes = z.n_nodes[i]; g.n_edges = z.n_total[i]; g.n_real_edges = n_real[i];
+    g.rowptr = L.rowptr[i]; g.col = L.col[i]; g.row = L.row[i]; g.eid = L.eid[i]; g.slot_of_eid = L.slot_of_eid[i];
+    g.rrowptr = L.rrowptr[i]; g.rslot = L.rslot[i]; g.rdst = L.rdst[i]; g.edge_attr = nullptr;
+    g.tile_range = staging ? L.tile_range[i] : nullptr; g.rtile_range = staging ? L.rtile_range[i] : nullptr;
+    g.comp_ptr = comps ? comp_ptr[i] : nullptr; g.n_comps = comps ? in->n_graphs : 0;
+    g.comp_bucket = comps ? L.comp_bucket[i] : nullptr;
+    g.comp_open = comps ? L.status + 8 + i : nullptr;
+  }
+  out->bond.edge_attr = L.attr_bond;
+  out->fbond.edge_attr = L.attr_fbond;
+  out->pool_rowptr = L.rowptr[4]; out->pool_col = L.col[4]; out->a2f = L.a2f32;
+  out->n_atoms = in->n_atoms; out->n_frags = in->n_frags;
+  out->mol_atom_ptr = in->batch ? L.atom_ptr : nullptr; out->mol_frag_ptr = in->batch ? L.frag_ptr : nullptr;
+  out->batch32 = in->batch ? L.batch32 : nullptr; out->frag_batch32 = in->batch ? L.frag_batch32 : nullptr;
+  out->n_graphs = in->batch ? in->n_graphs : 0;
+  out->status = L.status;
+}
+
 }  // namespace
 
 extern "C" size_t fnb_batch_plan_bytes(const fnb_batch_inputs *in) {
   if (!inputs_ok(in)) return 0;
   return plan_layout(in, nullptr).total;
+}
+
+int fnb_batch_plan_view(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out) {
+  if (!in || !out || !arena) return FNB_ERR_NULL;
+  if (!inputs_ok(in)) return FNB_ERR_SIZE;
+  if (reinterpret_cast<uintptr_t>(arena) & 255u) return FNB_ERR_ALIGN;
+  const PlanLayout L = plan_layout(in, (char *)arena);
+  if (L.total > arena_bytes) return FNB_ERR_WORKSPACE;
+  const bool comps = in->batch != nullptr && in->n_graphs > 0 && fnb_fused_bwd_enabled();
+  fill_plan(in, L, sizes(in), fnb_use_staging(), comps, out);
+  return 0;
 }
 
 extern "C" int fnb_batch_plan_build(const fnb_batch_inputs *in, void *arena, size_t arena_bytes, fnb_batch_plan *out,
@@ -600,24 +637,6 @@ int fnb_batch_plan_build_impl(const fnb_batch_inputs *in, void *arena, size_t ar
     FNB_CHECK_LAUNCH();
   }
 
-  fnb_graph *gs[4] = {&out->bond, &out->atom, &out->fbond, &out->frag};
-  for (int i = 0; i < 4; ++i) {
-    fnb_graph &g = *gs[i];
-    g.n_nodes = z.n_nodes[i]; g.n_edges = z.n_total[i]; g.n_real_edges = n_real[i];
-    g.rowptr = L.rowptr[i]; g.col = L.col[i]; g.row = L.row[i]; g.eid = L.eid[i]; g.slot_of_eid = L.slot_of_eid[i];
-    g.rrowptr = L.rrowptr[i]; g.rslot = L.rslot[i]; g.rdst = L.rdst[i]; g.edge_attr = nullptr;
-    g.tile_range = staging ? L.tile_range[i] : nullptr; g.rtile_range = staging ? L.rtile_range[i] : nullptr;
-    g.comp_ptr = comps ? comp_ptr[i] : nullptr; g.n_comps = comps ? in->n_graphs : 0;
-    g.comp_bucket = comps ? L.comp_bucket[i] : nullptr;
-    g.comp_open = comps ? L.status + 8 + i : nullptr;
-  }
-  out->bond.edge_attr = L.attr_bond;
-  out->fbond.edge_attr = L.attr_fbond;
-  out->pool_rowptr = L.rowptr[4]; out->pool_col = L.col[4]; out->a2f = L.a2f32;
-  out->n_atoms = in->n_atoms; out->n_frags = in->n_frags;
-  out->mol_atom_ptr = in->batch ? L.atom_ptr : nullptr; out->mol_frag_ptr = in->batch ? L.frag_ptr : nullptr;
-  out->batch32 = in->batch ? L.batch32 : nullptr; out->frag_batch32 = in->batch ? L.frag_batch32 : nullptr;
-  out->n_graphs = in->batch ? in->n_graphs : 0;
-  out->status = L.status;
+  fill_plan(in, L, z, staging, comps, out);
   return 0;
 }

@@ -129,7 +129,12 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   FnbAux aux{};
   const bool two = fnb_aux_streams(&aux) == 0;
   cudaEvent_t plan_ready = nullptr, plan_complete = nullptr;
-  if (two) {
+  if (two && a->plan_arena) {
+    // collated ahead of this step by fnb_pretrain_plan_prefetch (on its own stream, underneath the previous step)
+    RC(fnb_batch_plan_view(in, const_cast<void *>(a->plan_arena), fnb_batch_plan_bytes(in), &plan));
+    plan_ready = aux.p_fwd;
+    plan_complete = aux.p_done;
+  } else if (two) {
     cudaStream_t s = (cudaStream_t)stream;
     RC((int)cudaEventRecord(aux.ready[1], s));               // the batch tensors are complete on the caller's stream
     RC((int)cudaStreamWaitEvent(aux.wstream, aux.ready[1], 0));
@@ -149,6 +154,9 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   eio.x_atoms = a->x_atoms; eio.x_bond = a->x_bond; eio.x_fbond = a->x_fbond;
   eio.out_atoms = B.out_atoms; eio.out_frags = B.out_frags; eio.out_bond = B.out_bond; eio.out_fbond = B.out_fbond;
   RC(fnb_encoder_forward_impl(&plan, &o, a->layers, &eio, B.enc_ws, B.enc_bytes, scratch, stream, plan_ready, plan_complete));
+  // the collate of the next batch (fnb_pretrain_plan_prefetch) starts here: underneath the heads, where one or two
+  // kernels are in flight, rather than underneath the forward, whose chains it slowed (gpurun_out/r5q)
+  if (two) RC((int)cudaEventRecord(aux.step_begin, (cudaStream_t)stream));
   // ---- heads (PretrainTask.forward, pretrain_heads.py:64-102)
   fnb_pretrain_head_io hio{};
   hio.x_atoms = B.out_atoms; hio.x_frags = B.out_frags; hio.edge_feat = B.out_bond; hio.edge_index = in->edge_index;
@@ -184,3 +192,21 @@ extern "C" int fnb_pretrain_step(const fnb_pretrain_step_args *a, void *workspac
   if (two) RC((int)cudaStreamWaitEvent((cudaStream_t)stream, aux.h_done, 0));   // energy head's first-layer weight gradient
   return 0;
 }
+
+extern "C" int fnb_pretrain_plan_prefetch(const fnb_batch_inputs *next, void *arena, size_t arena_bytes, void *batch_ready) {
+  if (!next || !arena) return FNB_ERR_NULL;
+  if (!next->batch || !next->frag_batch) return FNB_ERR_SIZE;
+  FnbAux aux{};
+  if (fnb_aux_streams(&aux) != 0) return FNB_ERR_MODE;
+  // Starts once the encoder forward of the step launched last is complete (aux.step_begin is recorded there): by then
+  // the arena's previous tenant -- the step before that one, two arenas alternate -- is long finished.  The staged
+  // forward (FNB_STAGE=1) waits for the whole plan, which this path does not distinguish: not supported together.
+  if (fnb_use_staging()) return FNB_ERR_MODE;
+  RC((int)cudaStreamWaitEvent(aux.pstream, aux.step_begin, 0));
+  if (batch_ready) RC((int)cudaStreamWaitEvent(aux.pstream, (cudaEvent_t)batch_ready, 0));
+  fnb_batch_plan plan{};
+  RC(fnb_batch_plan_build_impl(next, arena, arena_bytes, &plan, (void *)aux.pstream, aux.p_fwd));
+  RC((int)cudaEventRecord(aux.p_done, aux.pstream));
+  return 0;
+}
+

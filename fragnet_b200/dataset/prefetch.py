@@ -102,6 +102,7 @@ class DevicePrefetcher:
             raise ValueError("DevicePrefetcher stages batches onto a CUDA device")
         self._copy_stream = torch.cuda.Stream(self.device)
         self._slots: List[_Slot] = [_Slot(self.device) for _ in range(self.depth + 1)]
+        self.last_event = None          # CUDA event after which the tensors of the batch yielded last are complete
 
     def _stage(self, host: Dict[str, torch.Tensor], slot: _Slot):
         if all(v.is_cuda for v in host.values() if isinstance(v, torch.Tensor)):
@@ -166,5 +167,9 @@ class DevicePrefetcher:
             dev, ev, _pinned, slot = queue.popleft()
             if ev is not None:
                 cur.wait_event(ev)
+            else:                                        # produced on the consumer's stream (ArenaLoader)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+            self.last_event = ev                         # (for consumers that touch the batch from another stream)
             last = slot
             yield dev

@@ -98,6 +98,11 @@ class FusedPretrainStep:
         self._loss = torch.zeros(8, dtype=torch.float32, device=dev)      # ring of loss scalars
         self._loss_i = 0
         self.n_layers = n_layers
+        # collate of the next batch underneath the running step (prefetch_plan): two alternating plan arenas
+        self._plan_arenas: List[Optional[torch.Tensor]] = [None, None]
+        self._plan_parity = 0
+        self._prefetched = None          # (key of the batch inputs, arena, tensors kept alive)
+        self.plan_hits = 0               # steps that found their plan prefetched
 
     # ------------------------------------------------------------------------------------------
     def _symmetric_gradient_buffer(self, live, dev, group):
@@ -220,7 +225,65 @@ class FusedPretrainStep:
             preds = (new(nb), new(na), new(nb), new(g))
             a.bond_length, a.bond_angle, a.dihedral, a.energy = (pt(t) for t in preds)
         keep = (ei, fi, a2f, eb, efb, bv, fbv, cos, a6, xa, xb, xfb, t_ba, t_dh, y)
+        pre, self._prefetched = self._prefetched, None       # one prefetch serves one step
+        if pre is not None and pre[0] == self._plan_key(a.batch):
+            a.plan_arena = pre[1].data_ptr()       # collated ahead of this step (see prefetch_plan)
+            self.plan_hits += 1
         return a, loss, preds, keep
+
+    # ---- collate of the next batch underneath the running step -------------------------------------------------------
+    _PLAN_TENSORS = ("edge_index", "frag_index", "atom_to_frag_ids", "edge_index_bonds_graph", "edge_index_fbonds",
+                     "batch", "frag_batch")
+
+    @staticmethod
+    def _plan_key(inp: "_abi.CBatchInputs"):
+        return tuple(getattr(inp, n) for n, _ in _abi.CBatchInputs._fields_)
+
+    def prefetch_plan(self, next_batch, ready_event: Optional["torch.cuda.Event"] = None) -> bool:
+        """Queue the on-device collate (``fnb_batch_plan_build``) of the batch the NEXT ``step`` call will get, on a
+        library stream underneath the step that is running -- the plan depends on nothing but the batch's index tensors,
+        and without it the first attention kernel of a step waits ~50 us for nine small launches that compete with the
+        layer-0 GEMMs for SMs.  ``ready_event``: recorded once the tensors of ``next_batch`` are complete (a
+        ``DevicePrefetcher`` slot still being copied); None if they already are.  Only batches that need no dtype /
+        device conversion qualify (returns False otherwise: the step then collates by itself, as always).  The tensors
+        must not be modified until that step has been launched."""
+        self._prefetched = None
+        dev = self.dev
+        for k in self._PLAN_TENSORS:
+            t = next_batch.get(k)
+            if not isinstance(t, torch.Tensor) or t.device != dev or t.dtype != torch.int64 or not t.is_contiguous():
+                return False
+        for k in ("edge_attr_bonds", "edge_attr_fbonds"):
+            t = next_batch.get(k)
+            if not isinstance(t, torch.Tensor) or t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                return False
+        b = next_batch
+        na, nf = b["x_atoms"].shape[0], b["x_frags"].shape[0]
+        nb, nfb, g = b["edge_index"].shape[1], b["frag_index"].shape[1], b["y"].numel()
+        pt = ops._ptr
+        inp = _abi.CBatchInputs(pt(b["edge_index"]), pt(b["frag_index"]), pt(b["atom_to_frag_ids"]),
+                                pt(b["edge_index_bonds_graph"]), pt(b["edge_index_fbonds"]), pt(b["batch"]),
+                                pt(b["frag_batch"]), pt(b["edge_attr_bonds"]), pt(b["edge_attr_fbonds"]),
+                                na, nf, nb, b["edge_index_bonds_graph"].shape[1], nfb, b["edge_index_fbonds"].shape[1], g)
+        lib = ops._lib()
+        need = lib.fnb_batch_plan_bytes(C.byref(inp))
+        if need == 0:
+            return False
+        self._plan_parity ^= 1
+        arena = self._plan_arenas[self._plan_parity]
+        if arena is None or arena.numel() < need:
+            # (re)allocation: the block may have been freed by work still running on the compute stream, and the collate
+            # writes it from another stream -- rare (first steps, a larger batch), so simply wait
+            torch.cuda.current_stream(dev).synchronize()
+            arena = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=dev)
+            self._plan_arenas[self._plan_parity] = arena
+        ev = C.c_void_p(ready_event.cuda_event) if ready_event is not None else None
+        rc = lib.fnb_pretrain_plan_prefetch(C.byref(inp), ops._ptr(arena), arena.numel(), ev)
+        if rc != 0:
+            return False                 # single-stream mode: the step collates by itself
+        keep = tuple(b[k] for k in self._PLAN_TENSORS) + (b["edge_attr_bonds"], b["edge_attr_fbonds"])
+        self._prefetched = (self._plan_key(inp), arena, keep)
+        return True
 
     def _run(self, batch, backward: bool, want_preds: bool = False):
         lib = ops._lib()
@@ -235,8 +298,16 @@ class FusedPretrainStep:
         del keep        # stream-ordered allocator: safe to release once the launches are queued on this stream
         return loss, preds
 
-    def step(self, batch) -> torch.Tensor:
-        """collate + forward + loss + backward (+ all-reduce) + Adam on one batch dict; returns the loss."""
+    def step(self, batch, next_batch=None, next_ready=None) -> torch.Tensor:
+        """collate + forward + loss + backward (+ all-reduce) + Adam on one batch dict; returns the loss.
+        ``next_batch`` (optional): the batch of the following call, whose collate is then queued underneath this step
+        (``prefetch_plan``); ``next_ready``: the CUDA event after which its tensors are complete, if they are not yet."""
+        loss = self._step(batch)
+        if next_batch is not None:
+            self.prefetch_plan(next_batch, next_ready)
+        return loss
+
+    def _step(self, batch) -> torch.Tensor:
         loss, _ = self._run(batch, backward=True)
         w = self.world_size
         self.t += 1

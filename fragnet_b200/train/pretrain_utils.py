@@ -88,7 +88,7 @@ class Trainer:
         return fs
 
     @staticmethod
-    def _run_pipelined(loader, device, launch):
+    def _run_pipelined(loader, device, launch, prefetch=None):
         """``launch(batch) -> loss tensor`` per batch; the next batches are staged while the GPU works and every
         loss is read back (the reference's ``loss.item()`` per step), one step behind the launches so that the GPU
         never waits for the host.  The sum runs in step order over the same fp32 values: identical to the reference's
@@ -96,12 +96,15 @@ class Trainer:
         from ..dataset.prefetch import DevicePrefetcher
         from .fused import LaggedScalars
         # this path only runs the drop-in FragNetPreTrain: tensors the GAT2 path never reads stay on the host
-        feed = iter(DevicePrefetcher(loader, device, depth=2, hot_path_only=True))
+        staged = DevicePrefetcher(loader, device, depth=2, hot_path_only=True)
+        feed = iter(staged)
         reader = LaggedScalars(lag=1)
         total, batch = 0.0, next(feed, None)
         while batch is not None:
             loss = launch(batch)
             batch = next(feed, None)
+            if batch is not None and prefetch is not None:
+                prefetch(batch, staged.last_event)       # its on-device collate runs underneath the step just launched
             for v in reader.push(loss):
                 total += v
         for v in reader.drain():
@@ -117,7 +120,7 @@ class Trainer:
                 g = optimizer.param_groups[0]                        # LR schedulers / edited hyper-parameters keep working
                 fs.lr, fs.betas, fs.eps, fs.weight_decay = float(g["lr"]), g["betas"], float(g["eps"]), float(g["weight_decay"])
                 return fs.step(batch)
-            return self._run_pipelined(loader, device, launch) / len(loader.dataset)
+            return self._run_pipelined(loader, device, launch, fs.prefetch_plan) / len(loader.dataset)
         total = 0.0
         for batch in loader:
             for k in batch:
@@ -135,7 +138,7 @@ class Trainer:
         if fs is None:
             fs = self._fused_for(model, None, device)
         if fs is not None:
-            return self._run_pipelined(loader, device, fs.evaluate) / len(loader.dataset)
+            return self._run_pipelined(loader, device, fs.evaluate, fs.prefetch_plan) / len(loader.dataset)
         total = 0.0
         with torch.no_grad():
             for batch in loader:

@@ -39,7 +39,7 @@ extern "C" {
 
 #define FNB_D 128 /* embedding width  */
 #define FNB_H 4   /* attention heads  */
-#define FNB_ABI_VERSION 7
+#define FNB_ABI_VERSION 8
 
 /* edge-term modes of the fused attention kernels */
 /* arithmetic of the dense projections */
@@ -502,12 +502,23 @@ typedef struct fnb_pretrain_step_args {
   int backward;                                   /* 0: forward + loss only (validation) */
   float *loss;                                    /* device scalar */
   float *bond_length, *bond_angle, *dihedral, *energy; /* optional prediction outputs; bond_length NULL = head skipped */
+  const void *plan_arena;                         /* NULL, or the arena fnb_pretrain_plan_prefetch() filled for exactly this
+                                                     `batch` (same pointers and sizes): the step skips its own collate */
 } fnb_pretrain_step_args;
 size_t fnb_pretrain_step_workspace_bytes(const fnb_pretrain_step_args *args);
 uint64_t fnb_pretrain_step_rng_span(const fnb_pretrain_step_args *args);
 /* workspace: 256-byte aligned, fnb_pretrain_step_workspace_bytes() bytes. */
 int fnb_pretrain_step(const fnb_pretrain_step_args *args, void *workspace, size_t workspace_bytes, void *scratch,
                       void *stream);
+/* On-device collate of the NEXT batch ahead of its step, on a library stream, underneath the step that is running: a
+ * training loop knows its next batch (DataLoader prefetch), and the plan depends on nothing but the batch's index
+ * tensors.  arena: fnb_batch_plan_bytes(next) bytes, 256-byte aligned, not the arena of the plan the running step uses
+ * (alternate between two).  batch_ready: a cudaEvent_t after which the tensors of `next` are complete, or NULL if they
+ * already are.  The build starts once the encoder forward of the step launched last is complete (underneath its heads
+ * and backward), i.e. after the last user of this arena when two arenas alternate.  The next fnb_pretrain_step takes the
+ * result through args->plan_arena.  Returns FNB_ERR_MODE
+ * when the library runs single-stream (FNB_STREAMS=1): nothing was queued, build inside the step as usual. */
+int fnb_pretrain_plan_prefetch(const fnb_batch_inputs *next, void *arena, size_t arena_bytes, void *batch_ready);
 
 /* ---- device-side batch assembly from a packed dataset arena (arena.cu) ---------------------------
  * Replaces, for a dataset resident in device memory, collate_fn / collate_fn_pt (fragnet/dataset/data.py:877-948,

@@ -241,6 +241,43 @@ def test_fused_step_equals_autograd_path_and_torch_adam():
     assert rel_err(loss_e, pretrain_loss(torch.nn.MSELoss(), ref, b)) <= 1e-6
 
 
+def test_plan_prefetch_gives_bitwise_the_same_training_run():
+    """The on-device collate of the next batch queued underneath the running step (FusedPretrainStep.prefetch_plan,
+    fnb_pretrain_plan_prefetch) is the same plan as the one a step builds for itself: losses and parameters of a
+    run over alternating batches are bitwise equal with and without it; a batch the prefetch was not made for (or one
+    that needs a dtype conversion) falls back to the in-step collate."""
+    import copy
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    from fragnet_b200.train.fused import FusedPretrainStep
+    m1, m2, b0 = _pretrain_pair(9, num_layer=3, drop=0.1)
+    hb = collate_fn_pt(synth.make_dataset("unimol", 23, seed=77) + [synth.handmade("two_frag")])
+    b1 = {k: v.cuda() for k, v in hb.items()}
+    batches = [b0, b1, b0, b1, b1, b0]
+    runs = []
+    for model, use in ((m1, True), (m2, False)):
+        torch.manual_seed(5)
+        fused = FusedPretrainStep(model, lr=1e-3)
+        losses = []
+        for i, b in enumerate(batches):
+            nxt = batches[i + 1] if use and i + 1 < len(batches) else None
+            if use and i == 3:
+                nxt = b0                       # a wrong guess: the next step gets b1 and must collate by itself
+            losses.append(fused.step(b, next_batch=nxt))
+        runs.append(([float(x) for x in losses], {k: v.clone() for k, v in model.state_dict().items()}, fused.plan_hits))
+    assert runs[0][2] == 4 and runs[1][2] == 0       # steps 1, 2, 3 and 5 found their plan; step 4 was guessed wrong
+    assert runs[0][0] == runs[1][0]
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+    # a batch with int32 indices would need a conversion: no prefetch, the step still works
+    fused = FusedPretrainStep(m1, lr=1e-3)
+    narrow = dict(b0)
+    narrow["edge_index"] = b0["edge_index"].to(torch.int32)
+    assert fused.prefetch_plan(narrow) is False
+    m1.eval()
+    assert float(fused.evaluate(narrow)) == float(fused.evaluate(b0))
+
+
 def test_fused_step_dropout_training_is_seeded_and_finite():
     from fragnet_b200 import ops
     from fragnet_b200.train.fused import FusedPretrainStep
