@@ -198,11 +198,24 @@ struct PadJobs {
   int64_t rows[6];
   int K[6], k_pad[6];
   int n;
+  // job `drop_job` (or -1): nn.Dropout (gat2.py:396) applied on the way -- element i of the UNPADDED matrix draws the
+  // same bit as in k_dropout_relu_fwd (counter offset + i / 4, position i % 4), so the two forms are interchangeable
+  int drop_job;
+  float drop_scale;
+  uint32_t drop_threshold;
+  uint64_t seed, offset;
 };
+__device__ __forceinline__ float dropped(const PadJobs &j, float v, int64_t i) {
+  const uint2 r = dropout_bits(j.seed, j.offset + (uint64_t)(i >> 2));
+  const uint32_t w = (i & 2) ? r.y : r.x;
+  const uint32_t bits = (i & 1) ? (w >> 16) : (w & 0xffffu);
+  return bits >= j.drop_threshold ? v * j.drop_scale : 0.f;
+}
 __global__ void __launch_bounds__(256) k_pad_cols(PadJobs j) {
   pdl_wait();
   const int job = blockIdx.y;
   const int K = j.K[job], kp = j.k_pad[job];
+  const bool drop = job == j.drop_job;
   const int64_t total = j.rows[job] * (kp >> 2);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (kp >> 2);
@@ -213,6 +226,13 @@ __global__ void __launch_bounds__(256) k_pad_cols(PadJobs j) {
     v.y = c + 1 < K ? __ldg(sp + 1) : 0.f;
     v.z = c + 2 < K ? __ldg(sp + 2) : 0.f;
     v.w = c + 3 < K ? __ldg(sp + 3) : 0.f;
+    if (drop) {
+      const int64_t e = r * K + c;
+      if (c < K) v.x = dropped(j, v.x, e);
+      if (c + 1 < K) v.y = dropped(j, v.y, e + 1);
+      if (c + 2 < K) v.z = dropped(j, v.z, e + 2);
+      if (c + 3 < K) v.w = dropped(j, v.w, e + 3);
+    }
     st4(j.dst[job] + r * kp + c, v);
   }
 }
@@ -319,12 +339,17 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
   const bool keep = o->save_for_backward != 0;
 
   const float *xa = io->x_atoms, *xb = io->x_bond, *xfb = io->x_fbond;
-  if (input_dropout(o)) {  // nn.Dropout on the raw atom features, gat2.py:396
+  // nn.Dropout on the raw atom features (gat2.py:396).  When layer 0 takes the padded operands anyway and nobody asks
+  // for d x_atoms (whose backward reads the dropped copy), the padding kernel applies it on the way: one launch and one
+  // pass over x_atoms fewer at the very head of the step.
+  const bool drop_in_pad = input_dropout(o) && B[0].k_pad[1] != 0 && !o->need_dx_atoms;
+  if (input_dropout(o) && !drop_in_pad) {
     RC(fnb_dropout_relu_fwd(xa, B[0].xa0, z.Na * (int64_t)L[0].K_atom, o->drop_p, 1, 0, o->seed, ph.input, stream_));
     xa = B[0].xa0;
   }
   {  // layer-0 operands padded for the tensor-core path (one launch for inputs and weights)
     PadJobs pj{};
+    pj.drop_job = -1;
     const float *xs[3] = {xb, xa, xfb}, *ws[3] = {L[0].Wb, L[0].Wa, L[0].Wfb};
     const int ks[3] = {L[0].K_bond, L[0].K_atom, L[0].K_fbond};
     const int64_t ns[3] = {z.Nb, z.Na, z.Nfb};
@@ -336,6 +361,12 @@ int fnb_encoder_forward_impl(const fnb_batch_plan *plan, const fnb_encoder_opts 
         float *dst[2] = {B[0].x_pad[j], B[0].W_pad[j]};
         for (int t = 0; t < 2; ++t) {
           const int k = pj.n++;
+          if (j == 1 && t == 0 && drop_in_pad) {
+            pj.drop_job = k;
+            pj.drop_scale = 1.f / (1.f - o->drop_p);
+            pj.drop_threshold = (uint32_t)(o->drop_p * 65536.0f + 0.5f);
+            pj.seed = o->seed; pj.offset = ph.input;
+          }
           pj.src[k] = src[t]; pj.dst[k] = dst[t]; pj.rows[k] = rows[t]; pj.K[k] = ks[j]; pj.k_pad[k] = B[0].k_pad[j];
           if (rows[t] * (B[0].k_pad[j] >> 2) > most) most = rows[t] * (B[0].k_pad[j] >> 2);
         }

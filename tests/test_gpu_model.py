@@ -344,3 +344,23 @@ def test_one_kernel_backward_falls_back_on_unsorted_edges():
         lib.fnb_debug_set_fused_bwd(0)
         ops.clear_plan_cache()
     _assert_grads([(k, p.grad, P[k].grad) for k, p in m.named_parameters() if p.grad is not None])
+
+
+def test_input_dropout_fused_into_padding_draws_the_same_mask():
+    """nn.Dropout on x_atoms (gat2.py:396) is applied by the layer-0 padding kernel unless d x_atoms is wanted, in which
+    case the standalone kernel runs: same counters, same bits -- bitwise the same forward either way."""
+    from fragnet.model.gat.gat2 import FragNetFineTune
+    from fragnet_b200 import ops
+    b = _to(_batch("esol", 20, 12, pretrain=False), "cuda")
+    torch.manual_seed(3)
+    m = FragNetFineTune(n_classes=1, num_layer=2, drop_ratio=0.3, h1=32, h2=32, h3=32, h4=32, act="relu").cuda().train()
+    outs = []
+    for want_dx in (False, True):
+        torch.manual_seed(99)
+        ops.clear_plan_cache()
+        x = dict(b)
+        x["x_atoms"] = b["x_atoms"].clone().requires_grad_(want_dx)
+        outs.append(m.pretrain(x))
+    for a, c in zip(outs[0], outs[1]):
+        if isinstance(a, torch.Tensor):
+            assert torch.equal(a, c)
