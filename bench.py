@@ -658,8 +658,11 @@ def run_ours(args):
                     assert state["read"] == n and state["sum"] == state["sum"]
             return one
 
-        warm = e2e_run(min(3, args.warmup))
-        for i in range(min(3, args.warmup)):
+        # (the first pinned-memory transfers of a fresh process run slower for some tens of milliseconds: the host-fed legs
+        # warm up for at least 24 steps, whatever --warmup says for the resident leg)
+        n_warm = max(24, args.warmup)
+        warm = e2e_run(n_warm)
+        for i in range(n_warm):
             warm(i)
         barrier()
         run = None
@@ -706,8 +709,9 @@ def run_ours(args):
                     assert state["read"] == n
             return one
 
-        warm = arena_run(min(3, args.warmup))
-        for i in range(min(3, args.warmup)):
+        n_warm = max(24, args.warmup)
+        warm = arena_run(n_warm)
+        for i in range(n_warm):
             warm(i)
         barrier()
         run_a = None

@@ -57,6 +57,7 @@ int fnb_aux_streams(FnbAux *out) {
     }
     if (cudaEventCreateWithFlags(&a.h_done, cudaEventDisableTiming) != cudaSuccess) return 1;
     if (cudaStreamCreateWithFlags(&a.pstream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    if (cudaStreamCreateWithFlags(&a.wstream2, cudaStreamNonBlocking) != cudaSuccess) return 1;
     for (cudaEvent_t *e : {&a.p_fwd, &a.p_done, &a.step_begin})
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return 1;
     cudaEvent_t *evs[16] = {&a.ready[0], &a.ready[1], &a.done[0], &a.done[1], &a.done2[0], &a.done2[1], &a.wjoin,

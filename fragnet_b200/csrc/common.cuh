@@ -279,6 +279,8 @@ struct FnbAux {
   cudaStream_t stream;       // independent chains (fragment-connection graph, energy head)
   cudaEvent_t fork, join;
   cudaStream_t wstream;      // weight-gradient GEMMs: nothing downstream waits for them until the end of the pass
+  cudaStream_t wstream2;     // ... of the atom chain (encoder backward): the last bond-graph GEMM of a step, whose operand
+                             // arrives last, then does not queue behind the atom chain's (20 us of the step's tail)
   cudaEvent_t ready[2], done[2], done2[2], wjoin;   // done / done2: even / odd layers (dh is double-buffered)
   cudaStream_t astream;      // atom-graph chain (it only meets the bond chain at the edge-term kernels)
   cudaEvent_t a_fork, a_dz, a_table, a_join;
@@ -332,7 +334,9 @@ int fnb_tc_proj_launch(const float *A, const float *B, const float *bias, int64_
 void fnb_tc_set_cta_cap(int cap);   // CTA cap of this thread's next projection launches (0 = none)
 int fnb_tc_transpose128_launch(const float *W, float *Wt, cudaStream_t stream);
 // Up to 16 [128,128] matrices transposed by one launch: Wt_base + i * 128 * 128 = Ws[i]^T.
-struct TransposeBatch { const float *W[16]; int count; };
+// zero[0..n_zero): scratch buffers whose arrival counters (first kScratchCounters floats) the launch clears on the way --
+// the backward program's side streams then need no memset of their own between their fork and their first kernel.
+struct TransposeBatch { const float *W[16]; int count; float *zero[6]; int n_zero; };
 int fnb_tc_transpose128_batched(const TransposeBatch &b, float *Wt_base, cudaStream_t stream);
 int fnb_proj_bwd_impl(const float *x, const float *W, const float *Wt_pre, const float *dh, int64_t n_rows, int K,
                       float *dx, float *dW, float *db, int precision, void *scratch, void *stream);

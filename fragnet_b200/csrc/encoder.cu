@@ -135,6 +135,7 @@ struct BwdBufs {
   float *scratch3;   // scratch of the weight-gradient stream
   float *scratch4;   // scratch of the atom-graph stream
   float *scratch5;   // scratch of the edge-term stream
+  float *scratch6;   // scratch of the atom chain's weight-gradient stream
 };
 
 size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *base, BwdBufs *out) {
@@ -155,6 +156,7 @@ size_t bwd_layout(const fnb_batch_plan *plan, const fnb_encoder_opts *o, char *b
   b.scratch3 = a.take<float>(kScratchFloats);
   b.scratch4 = a.take<float>(kScratchFloats);
   b.scratch5 = a.take<float>(kScratchFloats);
+  b.scratch6 = a.take<float>(kScratchFloats);
   if (out) *out = b;
   return (a.off + 255) & ~(size_t)255;
 }
@@ -539,6 +541,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
   const Sizes z = sizes_of(plan);
   cudaStream_t stream = (cudaStream_t)stream_;
   const float scale = (o->post_act && o->training && o->drop_p > 0.f) ? 1.f / (1.f - o->drop_p) : 1.f;
+  bool counters_cleared = false;
   const bool tf32 = fnb_tc_precision(o->precision);
   const int x3 = o->precision == FNB_PRECISION_TF32X3;
 
@@ -562,6 +565,12 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
       TransposeBatch tb{};
       tb.count = nm - c < 16 ? nm - c : 16;
       for (int i = 0; i < tb.count; ++i) tb.W[i] = mats[c + i];
+      if (c == 0) {   // the side streams' arrival counters, cleared here instead of by a memset behind every fork
+        tb.zero[0] = W.scratch2; tb.zero[1] = W.scratch3; tb.zero[2] = W.scratch4; tb.zero[3] = W.scratch5;
+        tb.zero[4] = W.scratch6;
+        tb.n_zero = 5;
+        counters_cleared = true;
+      }
       RC(fnb_tc_transpose128_batched(tb, W.Wt + (size_t)c * kD * kD, stream));
     }
   }
@@ -581,7 +590,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
     if (two && !forked) {
       RC((int)cudaEventRecord(aux.fork, stream));
       RC((int)cudaStreamWaitEvent(sB, aux.fork, 0));
-      RC((int)cudaMemsetAsync(W.scratch2, 0, kScratchCounters * sizeof(float), sB));
+      if (!counters_cleared) RC((int)cudaMemsetAsync(W.scratch2, 0, kScratchCounters * sizeof(float), sB));
       forked = true;
     }
     return 0;
@@ -589,24 +598,24 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
 
   // Weight gradients of the atom / bond projections: nothing waits for them before the end of the pass, so they run
   // on a third stream; the caller's stream only waits before it overwrites the dh buffer such a GEMM is reading.
-  cudaStream_t sW = two ? aux.wstream : stream;
-  void *sW_ = (void *)sW;
-  void *scratchW = two ? (void *)W.scratch3 : scratch;
-  bool w_used = false, w_pending[2][2] = {{false, false}, {false, false}};   // [graph][layer parity]
+  // (one stream per chain: graph 0 = atom, 1 = bond)
+  cudaStream_t sWs[2] = {two ? aux.wstream2 : stream, two ? aux.wstream : stream};
+  void *scratchWs[2] = {two ? (void *)W.scratch6 : scratch, two ? (void *)W.scratch3 : scratch};
+  bool w_used[2] = {false, false}, w_pending[2][2] = {{false, false}, {false, false}};   // [graph][layer parity]
   auto done_ev = [&](int i, int par) { return par ? aux.done2[i] : aux.done[i]; };
   auto w_begin = [&](int i, cudaStream_t producer) -> int {   // dh of graph i (0 atom, 1 bond) is complete on `producer`
     if (!two) return 0;
     RC((int)cudaEventRecord(aux.ready[i], producer));
-    RC((int)cudaStreamWaitEvent(sW, aux.ready[i], 0));
-    if (!w_used) {
-      RC((int)cudaMemsetAsync(W.scratch3, 0, kScratchCounters * sizeof(float), sW));
-      w_used = true;
+    RC((int)cudaStreamWaitEvent(sWs[i], aux.ready[i], 0));
+    if (!w_used[i]) {
+      if (!counters_cleared) RC((int)cudaMemsetAsync(scratchWs[i], 0, kScratchCounters * sizeof(float), sWs[i]));
+      w_used[i] = true;
     }
     return 0;
   };
   auto w_end = [&](int i, int par) -> int {
     if (!two) return 0;
-    RC((int)cudaEventRecord(done_ev(i, par), sW));
+    RC((int)cudaEventRecord(done_ev(i, par), sWs[i]));
     w_pending[i][par] = true;
     return 0;
   };
@@ -726,7 +735,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         if (two && !a_forked) {   // the caller's gradients and the fragment block's pooled gradient are visible to sA
           RC((int)cudaEventRecord(aux.a_fork, stream));
           RC((int)cudaStreamWaitEvent(sA, aux.a_fork, 0));
-          RC((int)cudaMemsetAsync(W.scratch4, 0, kScratchCounters * sizeof(float), sA));
+          if (!counters_cleared) RC((int)cudaMemsetAsync(W.scratch4, 0, kScratchCounters * sizeof(float), sA));
           a_forked = true;
         }
         if (two && a_table_pending) {   // the edge-term kernel of the layer above has consumed dz of the atom graph
@@ -751,13 +760,13 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         RC(w_begin(0, sA));
         float *dx = need_dx ? W.dx_atom : (o->need_dx_atoms ? io->dx_atoms : nullptr);
         if (l == 0 && b.k_pad[1] && !dx) {
-          RC(fnb_tc_dw_launch(dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchW), sW, x3));
+          RC(fnb_tc_dw_launch(dh_a, b.x_pad[1], z.Na, b.k_pad[1], P.K_atom, D.Wa, scratch_body(scratchWs[0]), sWs[0], x3));
         } else {
           {
             SideCap cap(two);
             RC(fnb_proj_bwd_dx(P.Wa, wt_of(l, 1), dh_a, z.Na, P.K_atom, dx, o->precision, scratchA, sA_));
           }
-          RC(fnb_proj_bwd_dw(xa, dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchW, sW_));
+          RC(fnb_proj_bwd_dw(xa, dh_a, z.Na, P.K_atom, D.Wa, nullptr, o->precision, scratchWs[0], (void *)sWs[0]));
         }
         RC(w_end(0, par));
         // bond features were this graph's edge vectors (gat2.py:203-208): the head-vector gradient of that term is
@@ -769,7 +778,7 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
           RC((int)cudaEventRecord(aux.e_ready, sA));
           RC((int)cudaStreamWaitEvent(aux.estream, aux.e_ready, 0));
           if (!e_used) {
-            RC((int)cudaMemsetAsync(W.scratch5, 0, kScratchCounters * sizeof(float), aux.estream));
+            if (!counters_cleared) RC((int)cudaMemsetAsync(W.scratch5, 0, kScratchCounters * sizeof(float), aux.estream));
             e_used = true;
           }
           RC(fnb_edge_table_bwd_fused(&plan->atom, dz_a, pre_bond, P.a, A_STRIDE, A_E, nullptr, nullptr, nullptr, scale,
@@ -810,10 +819,10 @@ extern "C" int fnb_encoder_backward(const fnb_batch_plan *plan, const fnb_encode
         RC(w_begin(1, stream));
         float *dx = need_dx ? W.dx_bond : (o->need_dx_bond ? io->dx_bond : nullptr);
         if (l == 0 && b.k_pad[0] && !dx) {
-          RC(fnb_tc_dw_launch(dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchW), sW, x3));
+          RC(fnb_tc_dw_launch(dh_b, b.x_pad[0], z.Nb, b.k_pad[0], P.K_bond, D.Wb, scratch_body(scratchWs[1]), sWs[1], x3));
         } else {
           RC(fnb_proj_bwd_dx(P.Wb, wt_of(l, 0), dh_b, z.Nb, P.K_bond, dx, o->precision, scratch, stream_));
-          RC(fnb_proj_bwd_dw(xb, dh_b, z.Nb, P.K_bond, D.Wb, nullptr, o->precision, scratchW, sW_));
+          RC(fnb_proj_bwd_dw(xb, dh_b, z.Nb, P.K_bond, D.Wb, nullptr, o->precision, scratchWs[1], (void *)sWs[1]));
         }
         RC(w_end(1, par));
         dy_bond = need_dx ? W.dx_bond : nullptr;

@@ -1073,6 +1073,11 @@ __global__ void k_transpose_128(const float *__restrict__ W, float *__restrict__
 __global__ void k_transpose_128_batched(TransposeBatch b, float *__restrict__ Wt_base) {
   pdl_wait();
   __shared__ float tile[32][33];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    if (t < kScratchCounters)
+      for (int q = 0; q < b.n_zero; ++q) b.zero[q][t] = 0.f;
+  }
   const float *W = b.W[blockIdx.z];
   float *Wt = Wt_base + (size_t)blockIdx.z * 128 * 128;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
