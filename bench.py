@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[0]/[2]/[4] legs")
+    ap.add_argument("--pack", action="store_true",
+                    help="host batches packed into one pinned buffer (one copy per batch; measured no faster: r5x)")
+    ap.add_argument("--no-arena", action="store_true", help="skip the arena-fed leg")
     ap.add_argument("--no-plan-prefetch", action="store_true",
                     help="collate every batch at the head of its own step instead of underneath the previous one")
     ap.add_argument("--no-tf32", action="store_true", help="skip the second timed region (value_tf32)")
@@ -434,12 +437,12 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="fp32", rank=0, world=1, dev=None,
-              return_host=False, autograd_path=False):
+              return_host=False, autograd_path=False, pack=False):
     """The timed unit: ``step(batch_dict)`` = on-device collate + forward + loss + backward + gradient all-reduce
     (world > 1) + Adam on one batch.  Returns (step, device batches[, pinned host batches in the compact wire format])."""
     from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
     from fragnet_b200 import config, ops
-    from fragnet_b200.dataset.data import compact_batch
+    from fragnet_b200.dataset.data import compact_batch, pack_batch
     from fragnet_b200.dist import FlatGradSync
     from fragnet_b200.train.optim import FlatAdam
     from fragnet_b200.train.pretrain_utils import pretrain_loss
@@ -451,7 +454,9 @@ def make_step(batch=1024, shape="unimol", rotate=4, pool=512, precision="fp32", 
     wide = make_batches(shape, batch, rotate, pool, seed=100 + rank)
     dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in wide]
     # what a DataLoader with collate_fn_pt_compact + pin_memory hands over: uint8 one-hot matrices, int32 indices
-    host_batches = [compact_batch(b, pin=True) for b in wide] if return_host else None
+    # (pack: collate_fn_pt_packed, the tensors of the hot path as views of one pinned buffer per batch)
+    host_batches = [(pack_batch(compact_batch(b), pin=True) if pack else compact_batch(b, pin=True)) for b in wide] \
+        if return_host else None
     if autograd_path:
         # the unchanged reference loop: model(batch) -> loss -> backward -> (all-reduce) -> Adam, through nn.Module
         sync = FlatGradSync(model.parameters())
@@ -595,7 +600,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _abi.load()
     step, dev_batches, host_batches = make_step(args.batch, args.shape, args.rotate, args.pool, args.precision, rank,
-                                                world, dev, return_host=True, autograd_path=args.autograd)
+                                                world, dev, return_host=True, autograd_path=args.autograd, pack=args.pack)
     timed = Timer(dev, world, lib)
     barrier = timed.barrier
     # a training loop knows its next batch: its on-device collate is queued underneath the running step
@@ -677,15 +682,16 @@ def run_ours(args):
                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
                "batch_dict_bytes": sum(v.numel() * v.element_size() for v in dev_batches[0].values()),
                "staging": "pinned host batches in the compact wire format of collate_fn_pt_compact (one-hot feature "
-                          "matrices uint8, indices int32: exact) -> DevicePrefetcher(hot_path_only=True) copies the "
-                          "tensors FragNet.forward reads and widens them on the device (fnb_widen_batch)",
+                          "matrices uint8, indices int32: exact" + ("; packed into one buffer per batch" if args.pack else "")
+                          + ") -> DevicePrefetcher(hot_path_only=True) copies the tensors FragNet.forward reads and "
+                          "widens them on the device (fnb_widen_batch)",
                "loss_read": "every step's loss is copied to pinned host memory behind its step and collected one step "
                             "later (after the next step has been enqueued); all reads inside the timed region"}
 
     # ---- the same loop fed by the device-resident packed arena: the per-step host -> device traffic
     # is the list of molecule ids; the batch dict is assembled on the device inside the timed region
     e2e_arena = None
-    if not args.no_e2e and not args.autograd:
+    if not args.no_e2e and not args.autograd and not args.no_arena:
         import numpy as np
 
         from fragnet_b200 import synth

@@ -51,6 +51,36 @@ class _Slot:
         self.buffers: Dict[torch.dtype, torch.Tensor] = {}
         self.free_event = None          # recorded on the compute stream once the consumer has moved on
 
+    def packed_views(self, blob: torch.Tensor, layout, widen):
+        """Device mirror of a ``PackedBatch`` buffer: (device blob, wire views, consumer views, grew).  ``widen`` maps a
+        key to the dtype the consumer expects where it differs from the wire dtype."""
+        grew = False
+        pad = lambda n: (n + 63) // 64 * 64
+        need: Dict[object, int] = collections.defaultdict(int)
+        need["blob"] = blob.numel()
+        for key, dtype, shape, off, nbytes in layout:
+            if key in widen:
+                need[widen[key]] += pad(nbytes // torch.empty((), dtype=dtype).element_size())
+        for dt, n in need.items():
+            buf = self.buffers.get(dt)
+            if buf is None or buf.numel() < n:
+                self.buffers[dt] = torch.empty(int(n * 1.25) + 64, dtype=torch.uint8 if dt == "blob" else dt,
+                                               device=self.device)
+                grew = True
+        dev_blob = self.buffers["blob"][:blob.numel()]
+        used: Dict[object, int] = collections.defaultdict(int)
+        wire, out = {}, {}
+        for key, dtype, shape, off, nbytes in layout:
+            wire[key] = dev_blob[off:off + nbytes].view(dtype).view(shape)
+            if key in widen:
+                n = wire[key].numel()
+                o = used[widen[key]]
+                used[widen[key]] = o + pad(n)
+                out[key] = self.buffers[widen[key]][o:o + n].view(shape)
+            else:
+                out[key] = wire[key]
+        return dev_blob, wire, out, grew
+
     def views(self, host: Dict[str, torch.Tensor]):
         """(wire views, consumer views, grew): device views shaped like the tensors of ``host`` in their wire dtype and
         in the dtype the consumer expects (the same view where nothing has to be widened)."""
@@ -109,7 +139,11 @@ class DevicePrefetcher:
             return host, None, None, None                # already on the device (ArenaLoader): nothing to stage
         shape_only = None
         if self.hot_path_only:
-            host = {k: v for k, v in host.items() if k not in _UNREAD}
+            kept = {k: v for k, v in host.items() if k not in _UNREAD}
+            if getattr(host, "blob", None) is not None:      # a PackedBatch stays one (its buffer holds the hot path only)
+                kept = type(host)(kept)
+                kept.blob, kept.layout = host.blob, host.layout
+            host = kept
             if isinstance(host.get("x_frags"), torch.Tensor):
                 shape_only = host.pop("x_frags")
         dev, ev, pinned, slot = self._stage_tensors(host, slot)
@@ -117,7 +151,39 @@ class DevicePrefetcher:
             dev["x_frags"] = torch.empty(shape_only.shape, dtype=torch.float32, device="meta")
         return dev, ev, pinned, slot
 
+    def _stage_packed(self, host, slot: _Slot):
+        """A ``PackedBatch`` (dataset.data.pack_batch): the tensors of the hot path travel as ONE copy of its buffer."""
+        packed = host if host.blob.is_pinned() else host.pin_memory()
+        blob, layout = packed.blob, packed.layout
+        in_blob = {k for k, *_ in layout}
+        widen = {k: _wide_dtype(k, packed[k]) for k in in_blob if _wide_dtype(k, packed[k]) != packed[k].dtype}
+        dev_blob, wire, dev, grew = slot.packed_views(blob, layout, widen)
+        rest = {k: v for k, v in packed.items() if k not in in_blob}     # tensors outside the buffer, non-tensor entries
+        cs = self._copy_stream
+        if slot.free_event is not None:
+            cs.wait_event(slot.free_event)
+        if grew:
+            cs.wait_stream(torch.cuda.current_stream(self.device))
+        keep = [packed]
+        with torch.cuda.stream(cs):
+            dev_blob.copy_(blob, non_blocking=True)
+            jobs = [(wire[k], dev[k], _abi.WIDEN_U8_F32 if wire[k].dtype == torch.uint8 else _abi.WIDEN_I32_I64)
+                    for k in widen if wire[k].numel()]
+            for c in range(0, len(jobs), _abi.WIDEN_MAX_JOBS):
+                chunk = jobs[c:c + _abi.WIDEN_MAX_JOBS]
+                arr = (_abi.CWidenJob * len(chunk))(*[_abi.CWidenJob(s.data_ptr(), d.data_ptr(), s.numel(), m)
+                                                      for s, d, m in chunk])
+                _abi.check(_abi.load().fnb_widen_batch(arr, len(chunk), C.c_void_p(cs.cuda_stream)), "widen_batch")
+            dev.update(rest)                   # non-tensor entries (every host tensor is inside the buffer here)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return dev, ev, keep, slot
+
     def _stage_tensors(self, host: Dict[str, torch.Tensor], slot: _Slot):
+        if getattr(host, "blob", None) is not None:
+            inside = {k for k, *_ in host.layout}
+            if not any(isinstance(v, torch.Tensor) and not v.is_cuda for k, v in host.items() if k not in inside):
+                return self._stage_packed(host, slot)    # (otherwise: tensor by tensor, like any other dict)
         pinned = {k: (v if (not isinstance(v, torch.Tensor) or v.is_cuda or v.is_pinned()) else v.pin_memory())
                   for k, v in host.items()}
         wire, dev, grew = slot.views(pinned)             # (re)allocation, if any, happens on the current stream

@@ -51,6 +51,24 @@ def test_compact_batch_is_exact_and_a_third_of_the_bytes():
     assert kept["x_atoms"].dtype == torch.float32 and kept["edge_index"].dtype == torch.int64
 
 
+def test_packed_batch_is_the_same_dict_over_one_buffer():
+    import pickle
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import PACK_SKIP, PackedBatch, collate_fn_pt, collate_fn_pt_packed, compact_batch
+    mols = synth.make_dataset("unimol", 16, seed=2) + [synth.handmade("ion_pair")]
+    narrow, packed = compact_batch(collate_fn_pt(mols)), collate_fn_pt_packed(mols)
+    assert isinstance(packed, PackedBatch) and list(packed) == list(narrow)
+    lo, hi = packed.blob.data_ptr(), packed.blob.data_ptr() + packed.blob.numel()
+    for k, v in narrow.items():
+        assert packed[k].dtype == v.dtype and torch.equal(packed[k], v), k
+        inside = lo <= packed[k].data_ptr() < hi
+        assert inside == (k not in PACK_SKIP) or v.numel() == 0, k
+    assert all(off % 64 == 0 for _, _, _, off, _ in packed.layout)
+    again = pickle.loads(pickle.dumps(packed))            # what a DataLoader worker hands over
+    assert isinstance(again, PackedBatch) and again.layout == packed.layout and torch.equal(again.blob, packed.blob)
+    assert packed.pin_memory is not None and PackedBatch(narrow).pin_memory() is not None   # (no buffer: returns itself)
+
+
 def test_reference_arm_runs_the_unmodified_reference():
     """``bench.py --impl reference`` / ``cpu_baseline``: kind "reference" wherever the reference modules are available
     (checkout here, oracle/_ref bytecode on the GPU box), and its loss equals the oracle port's on the same batch."""

@@ -112,15 +112,21 @@ def test_prefetcher_widens_the_compact_wire_format_bit_exactly():
     """Compact host batches (uint8 feature matrices, int32 indices) arrive on the device with collate_fn_pt's dtypes and
     values; device-resident batches pass through untouched; ragged element counts exercise the kernel's tail."""
     from fragnet_b200 import synth
-    from fragnet_b200.dataset.data import collate_fn_pt, compact_batch
+    from fragnet_b200.dataset.data import collate_fn_pt, compact_batch, pack_batch
     from fragnet_b200.dataset.prefetch import DevicePrefetcher, staged_bytes
     ds = synth.make_dataset("unimol", 37, seed=13) + [synth.handmade("ion_pair")]
     wide = [collate_fn_pt(ds[i:i + n]) for i, n in ((0, 7), (7, 30), (37, 1), (3, 5))]
     narrow = [compact_batch(b, pin=True) for b in wide]
     assert staged_bytes(narrow[1]) < 0.45 * staged_bytes(wide[1])
-    for hot in (False, True):
+    # packed: the same tensors as views of one pinned buffer per batch -> one copy per batch (hot-path mode), the
+    # tensor-by-tensor path when the unread tensors are wanted too; wide (unnarrowed) batches pack as well
+    packed = [pack_batch(b, pin=True) for b in narrow]
+    assert all(p.blob.is_pinned() and p["x_atoms"].data_ptr() >= p.blob.data_ptr() for p in packed)
+    packed_wide = [pack_batch(b).pin_memory() for b in wide]
+    assert all(p.blob.is_pinned() for p in packed_wide)
+    for hot, feed in ((False, narrow), (True, narrow), (True, packed), (False, packed), (True, packed_wide)):
         n_seen = 0
-        for g, w in zip(DevicePrefetcher(iter(narrow), "cuda", depth=2, hot_path_only=hot), wide):
+        for g, w in zip(DevicePrefetcher(iter(feed), "cuda", depth=2, hot_path_only=hot), wide):
             n_seen += 1          # (a yielded batch is only valid until `depth` further ones have been requested)
             torch.cuda.synchronize()
             for k, v in w.items():
