@@ -704,11 +704,14 @@ def run_ours(args):
         reader = LaggedScalars(lag=1)
 
         def arena_run(n):
-            state = {"b": arena.batch(id_lists[0]), "read": 0}
+            state = {"b": arena.batch_overlapped(id_lists[0]), "read": 0}
 
             def one(i):
                 loss = step(state["b"])
-                state["b"] = arena.batch(id_lists[(i + 1) % args.rotate])   # assembled behind step i on the same stream
+                # assembled on a side stream underneath step i, its collate queued behind it
+                state["b"] = arena.batch_overlapped(id_lists[(i + 1) % args.rotate])
+                if prefetch is not None:
+                    prefetch(state["b"], arena.last_event)
                 vals = reader.push(loss) + (reader.drain() if i == n - 1 else [])
                 state["read"] += len(vals)
                 if i == n - 1:

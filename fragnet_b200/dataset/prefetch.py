@@ -136,7 +136,8 @@ class DevicePrefetcher:
 
     def _stage(self, host: Dict[str, torch.Tensor], slot: _Slot):
         if all(v.is_cuda for v in host.values() if isinstance(v, torch.Tensor)):
-            return host, None, None, None                # already on the device (ArenaLoader): nothing to stage
+            # already on the device (ArenaLoader): nothing to stage; an overlapped assembly brings its own event
+            return host, getattr(host, "ready_event", None), None, None
         shape_only = None
         if self.hot_path_only:
             kept = {k: v for k, v in host.items() if k not in _UNREAD}

@@ -356,6 +356,8 @@ class LaggedScalars:
         n = self.lag + 2
         self._host = torch.empty(n, dtype=torch.float32).pin_memory()
         self._events = [torch.cuda.Event() for _ in range(n)]
+        self._ready = [torch.cuda.Event() for _ in range(n)]
+        self._side: Optional[torch.cuda.Stream] = None
         self._pending = collections.deque()
         self._count = 0
 
@@ -370,8 +372,18 @@ class LaggedScalars:
     def push(self, value: torch.Tensor) -> List[float]:
         s = self._count % len(self._events)
         self._count += 1
-        self._host[s:s + 1].copy_(value.detach().reshape(1), non_blocking=True)
-        self._events[s].record(torch.cuda.current_stream(value.device))
+        # the copy runs on a side stream behind the step: in the compute stream the 4-byte DMA would sit between this
+        # step's last kernel and the next step's first one (~10 us per step, gpurun_out/r5x)
+        cur = torch.cuda.current_stream(value.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(value.device)
+        src = value.detach().reshape(1)
+        self._ready[s].record(cur)
+        self._side.wait_event(self._ready[s])
+        with torch.cuda.stream(self._side):
+            self._host[s:s + 1].copy_(src, non_blocking=True)
+        src.record_stream(self._side)
+        self._events[s].record(self._side)
         self._pending.append(s)
         return self._collect(self.lag)
 

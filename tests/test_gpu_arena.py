@@ -140,3 +140,32 @@ def test_prefetcher_widens_the_compact_wire_format_bit_exactly():
     dev = [{k: v.cuda() for k, v in b.items()} for b in wide[:2]]
     through = list(DevicePrefetcher(iter(dev), "cuda"))
     assert all(t[k] is d[k] for t, d in zip(through, dev) for k in d)
+
+
+def test_overlapped_assembly_and_prefetched_collate_train_bitwise_the_same():
+    """ArenaLoader(overlap=True) assembles every batch on a side stream underneath the step in flight and the trainer
+    queues its collate there too: the batches and a two-epoch training run are bitwise those of the in-stream loader."""
+    import copy
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet_b200.dataset.arena import ArenaLoader, DeviceBatch, MoleculeArena
+    from fragnet_b200.dataset.data import collate_fn_pt
+    from fragnet_b200.train.pretrain_utils import Trainer
+    ds = _dataset(57, seed=9)
+    arena = MoleculeArena(ds, "cuda")
+    for b, got in enumerate(ArenaLoader(arena, batch_size=8, overlap=True)):
+        assert isinstance(got, DeviceBatch) and got.ready_event is not None
+        _same(got, collate_fn_pt(ds[b * 8:(b + 1) * 8]))
+    torch.manual_seed(4)
+    m0 = FragNetPreTrain(num_layer=2, drop_ratio=0.1, edge_features=17).cuda()
+    runs = []
+    for overlap in (True, False):
+        m = copy.deepcopy(m0)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        tr = Trainer(torch.nn.MSELoss())
+        torch.manual_seed(8)
+        losses = [tr.train(m, ArenaLoader(MoleculeArena(ds, "cuda"), batch_size=10, overlap=overlap), opt, "cuda")
+                  for _ in range(2)]
+        runs.append((losses, {k: v.clone() for k, v in m.state_dict().items()}))
+    assert runs[0][0] == runs[1][0]
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
