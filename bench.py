@@ -188,11 +188,11 @@ def _cold_time(launch, sets, iters):
 
 # Share of the summed kernel time of one fp32-mode step per kernel, and the DRAM traffic of one captured launch of each:
 # both come from the committed profiles of this state (scripts/summarize_launches.py, scripts/summarize_ncu_full.py
-# write profiles/r4_kernel_shares.json next to the markdown tables they are taken from).
-KERNEL_SHARE = {"source": "profiles/r4_launch_list.md"}
-NCU_TRAFFIC = {"source": "profiles/r4_ncu_full.md", "per_kernel": {}}
+# write profiles/r5_kernel_shares.json next to the markdown tables they are taken from).
+KERNEL_SHARE = {"source": "profiles/r5_launch_list.md"}
+NCU_TRAFFIC = {"source": "profiles/r5_ncu_full.md", "per_kernel": {}}
 try:
-    _p = os.path.join(ROOT, "profiles", "r4_kernel_shares.json")
+    _p = os.path.join(ROOT, "profiles", "r5_kernel_shares.json")
     if os.path.isfile(_p):
         _d = json.load(open(_p))
         KERNEL_SHARE.update(_d.get("share", {}))
