@@ -1262,6 +1262,12 @@ int fnb_tc_dw_launch(const float *dh, const float *x, int64_t n_rows, int x_cols
   const size_t stage_bytes = ((size_t)TC_STAGE_BYTES + (size_t)n_chunks * 4096) * (x3 ? 2 : 1);
   int n_stages = (int)((200 * 1024) / stage_bytes);
   if (n_stages > DW_MAX_STAGES) n_stages = DW_MAX_STAGES;
+  {
+    // FNB_DW_STAGES (measurement switch): fewer stages = less shared memory, so that gather CTAs of the other streams
+    // can share the SM with a weight-gradient CTA
+    static const int cap = [] { const char *e = getenv("FNB_DW_STAGES"); return e ? atoi(e) : 0; }();
+    if (cap > 0 && n_stages > cap) n_stages = cap;
+  }
   if (n_stages < 1) return FNB_ERR_MODE;
   const size_t smem = (size_t)n_stages * stage_bytes + 1024;
   uint32_t tmem_cols = 32;
