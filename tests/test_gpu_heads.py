@@ -241,6 +241,37 @@ def test_fused_step_equals_autograd_path_and_torch_adam():
     assert rel_err(loss_e, pretrain_loss(torch.nn.MSELoss(), ref, b)) <= 1e-6
 
 
+@pytest.mark.parametrize("kinds", [("two_frag",), ("ion_pair", "two_atom", "single_frag"), None])
+def test_fused_step_on_tiny_and_ragged_batches(kinds):
+    """One molecule, three molecules, nine molecules (a partial 8-molecule tile of the fused energy-head kernel): loss and
+    gradients of the one-call step against the autograd path."""
+    import copy
+    from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
+    from fragnet_b200 import synth
+    from fragnet_b200.dataset.data import collate_fn_pt
+    from fragnet_b200.train.fused import FusedPretrainStep
+    from fragnet_b200.train.pretrain_utils import pretrain_loss
+    mols = [synth.handmade(k) for k in kinds] if kinds else synth.make_dataset("esol", 9, seed=31)
+    hb = collate_fn_pt(mols)
+    gen = torch.Generator().manual_seed(3)
+    for k in ("bnd_angl", "dh_angl"):
+        hb[k] = torch.randn(hb[k].shape, generator=gen)
+    hb["y"] = torch.randn(hb["y"].shape, generator=gen)
+    b = {k: v.cuda() for k, v in hb.items()}
+    torch.manual_seed(17)
+    m1 = FragNetPreTrain(num_layer=2, drop_ratio=0.0, edge_features=17).cuda().train()
+    m2 = copy.deepcopy(m1)
+    loss1 = FusedPretrainStep(m1, lr=1e-3).forward_backward(b)
+    loss2 = pretrain_loss(torch.nn.MSELoss(), m2(b), b)
+    loss2.backward()
+    assert rel_err(loss1, loss2) <= 1e-6
+    g1 = {k: p.grad for k, p in m1.named_parameters() if p.grad is not None}
+    g2 = {k: p.grad for k, p in m2.named_parameters() if p.grad is not None}
+    assert set(g1) == set(g2)
+    bad = {k: v for k, v in grad_errs([(k, g1[k], g2[k]) for k in g2]).items() if v > 1e-5}
+    assert not bad, bad
+
+
 def test_plan_prefetch_gives_bitwise_the_same_training_run():
     """The on-device collate of the next batch queued underneath the running step (FusedPretrainStep.prefetch_plan,
     fnb_pretrain_plan_prefetch) is the same plan as the one a step builds for itself: losses and parameters of a
