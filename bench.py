@@ -410,6 +410,14 @@ def workload_name(shape):
     return f"FragNetPreTrain exps/pt/unimol_exp1s4 step (4 layers, 4 heads, emb 128, drop 0.2, Adam), {shape}-shaped molecules"
 
 
+def bench_config(args, world):
+    """``config`` of the JSON line -- the same dict in both arms (the driver compares them)."""
+    return {"workload": workload_name(args.shape), "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+            "parallelism": f"dp{world}",
+            "cache": f"GPU arm: {args.rotate} distinct batches rotated, fwd+bwd working set > 126 MB L2, CSR plans rebuilt "
+                     "every step; CPU arm: a bounded sample of the same workload per step (see cpu_baseline.sample)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, all host threads, on a bounded sample of
     the workload (the full per-GPU batch when it fits the time budget)."""
@@ -426,8 +434,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": workload_name(args.shape), "per_gpu_batch": args.batch,
-                       "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}"},
+            "config": bench_config(args, args.gpus),
             "cpu_baseline": {"value": round(rate, 2), "unit": "molecules/s", "cores": cores, "kind": kind,
                              "sample": sample},
             "e2e": {"value": round(rate, 2), "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -802,13 +809,12 @@ def run_ours(args):
                 "precision": args.precision,
                 "value_tf32": tf32["value"] if tf32 else None, "ms_per_step_tf32": tf32["ms_per_step"] if tf32 else None,
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.shape),
-                           "per_gpu_batch": args.batch, "global_batch": args.batch * world,
-                           "parallelism": f"dp{world}", "batch0_counts": counts,
-                           "cache": f"{args.rotate} distinct batches rotated; fwd+bwd working set > 126 MB L2; CSR plans rebuilt every step"
-                                    + (" (the collate of batch i+1 is queued underneath step i)" if prefetch is not None else ""),
-                           "driver": "nn.Module + autograd + FlatAdam" if args.autograd else
-                                     "FusedPretrainStep (fnb_pretrain_step + fnb_adam_step)"},
+                "config": bench_config(args, world),
+                "run": {"batch0_counts": counts,
+                        "collate": "on the device, every step" + (" (the collate of batch i+1 is queued underneath step i, "
+                                   "as a prefetching loader allows)" if prefetch is not None else ""),
+                        "driver": "nn.Module + autograd + FlatAdam" if args.autograd else
+                                  "FusedPretrainStep (fnb_pretrain_step + fnb_adam_step)"},
                 "e2e": e2e, "e2e_arena": e2e_arena, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "extra": extra or None}
         print(json.dumps(line))
