@@ -672,19 +672,16 @@ def run_ours(args):
 
         # (the first pinned-memory transfers of a fresh process run slower for some tens of milliseconds: the host-fed legs
         # warm up for at least 24 steps, whatever --warmup says for the resident leg)
+        # One epoch-like run: the same DevicePrefetcher feeds the warm-up steps and the timed steps.  (A prefetcher
+        # created inside the timed region allocates its device slots there; depending on the state of the caching
+        # allocator that is a cudaMalloc / cudaFree round -- a 100-300 ms device-synchronising stall that showed up as
+        # 1.45-2.3 ms per step in one run out of three, gpurun_out/r5w..r6b -- which an epoch of thousands of steps pays once.)
         n_warm = max(24, args.warmup)
-        warm = e2e_run(n_warm)
+        run = e2e_run(n_warm + args.steps)
         for i in range(n_warm):
-            warm(i)
-        barrier()
-        run = None
-
-        def e2e_step(i):                          # the prefetcher is created INSIDE the timed region (first step)
-            nonlocal run
-            if run is None:
-                run = e2e_run(args.steps)
             run(i)
-        ms_e2e, _ = timed(e2e_step, args.steps)
+        barrier()
+        ms_e2e, _ = timed(lambda i: run(n_warm + i), args.steps)
         e2e = {"value": round(mols / (ms_e2e * 1e-3), 1), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
                "batch_dict_bytes": sum(v.numel() * v.element_size() for v in dev_batches[0].values()),
@@ -726,18 +723,11 @@ def run_ours(args):
             return one
 
         n_warm = max(24, args.warmup)
-        warm = arena_run(n_warm)
+        run_a = arena_run(n_warm + args.steps)
         for i in range(n_warm):
-            warm(i)
-        barrier()
-        run_a = None
-
-        def arena_step(i):
-            nonlocal run_a
-            if run_a is None:
-                run_a = arena_run(args.steps)
             run_a(i)
-        ms_a, _ = timed(arena_step, args.steps)
+        barrier()
+        ms_a, _ = timed(lambda i: run_a(n_warm + i), args.steps)
         e2e_arena = {"value": round(mols / (ms_a * 1e-3), 1), "unit": "molecules/s",
                      "h2d_bytes_per_step": int(args.batch * 8), "d2h_bytes_per_step": 4,
                      "ms_per_step": round(ms_a / args.steps, 3),

@@ -130,9 +130,30 @@ class DevicePrefetcher:
         self.hot_path_only = bool(hot_path_only)
         if self.device.type != "cuda":
             raise ValueError("DevicePrefetcher stages batches onto a CUDA device")
-        self._copy_stream = torch.cuda.Stream(self.device)
-        self._slots: List[_Slot] = [_Slot(self.device) for _ in range(self.depth + 1)]
+        # copy stream and staging slots are recycled across prefetchers of a device (a training loop makes one per
+        # epoch, plus one per validation pass): a new set of slots is ~150 MB of cudaMalloc, i.e. a device-synchronising
+        # stall of 100-300 ms whenever the caching allocator has to make room
+        key = (self.device.type, torch.cuda.current_device() if self.device.index is None else self.device.index, self.depth)
+        pooled = DevicePrefetcher._pool.get(key)
+        if pooled:
+            self._copy_stream, self._slots = pooled.pop()
+        else:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._slots = [_Slot(self.device) for _ in range(self.depth + 1)]
+        self._pool_key = key
         self.last_event = None          # CUDA event after which the tensors of the batch yielded last are complete
+
+    _pool: Dict[tuple, list] = {}
+
+    def _release(self):
+        """Hand stream and slots to the next prefetcher of this device (their last consumer is ordered by ``free_event``)."""
+        if self._slots is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            for s in self._slots:
+                s.free_event = ev
+            DevicePrefetcher._pool.setdefault(self._pool_key, []).append((self._copy_stream, self._slots))
+            self._slots = None
 
     def _stage(self, host: Dict[str, torch.Tensor], slot: _Slot):
         if all(v.is_cuda for v in host.values() if isinstance(v, torch.Tensor)):
@@ -212,6 +233,14 @@ class DevicePrefetcher:
         return dev, ev, pinned, slot                     # pinned host tensors stay alive until the copy was waited for
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
+        if self._slots is None:
+            raise RuntimeError("DevicePrefetcher: a prefetcher iterates once (make a new one per epoch)")
+        try:
+            yield from self._iterate()
+        finally:
+            self._release()
+
+    def _iterate(self) -> Iterator[Dict[str, torch.Tensor]]:
         it = iter(self.batches)
         queue = collections.deque()
         done, n_staged, last = False, 0, None
