@@ -49,7 +49,10 @@ def screen(model, arena: MoleculeArena, batch_size: int = 4096, ids: Optional[Se
     if not chunks:
         return
     copy_stream = torch.cuda.Stream(dev)
-    slots = [None] * (depth + 1)           # pinned host buffers per slot
+    # pinned host buffers per slot, kept on the arena across calls (a screening service calls this per request; every
+    # fresh set is a round of cudaHostAlloc)
+    cache = arena.__dict__.setdefault("_screen_slots", {})
+    slots = cache.setdefault(depth, [None] * (depth + 1))
     pending = []                           # (ids, host tensors, event)
     was_training = model.training
     model.eval()
