@@ -410,6 +410,11 @@ def workload_name(shape):
     return f"FragNetPreTrain exps/pt/unimol_exp1s4 step (4 layers, 4 heads, emb 128, drop 0.2, Adam), {shape}-shaped molecules"
 
 
+# Steps between the launch of a step and the host's read of its loss in the host-fed legs (every loss is read inside the
+# timed region either way).  FNB_BENCH_LAG overrides for measurements.
+LOSS_LAG = int(os.environ.get("FNB_BENCH_LAG", "1"))
+
+
 def bench_config(args, world):
     """``config`` of the JSON line -- the same dict in both arms (the driver compares them)."""
     return {"workload": workload_name(args.shape), "per_gpu_batch": args.batch, "global_batch": args.batch * world,
@@ -649,7 +654,7 @@ def run_ours(args):
         from fragnet_b200.dataset.prefetch import DevicePrefetcher, staged_bytes
         from fragnet_b200.train.fused import LaggedScalars
         h2d = staged_bytes(host_batches[0])
-        reader = LaggedScalars(lag=1)     # three pinned floats, allocated once (cudaHostAlloc synchronises the device)
+        reader = LaggedScalars(lag=LOSS_LAG)     # pinned floats, allocated once (cudaHostAlloc synchronises the device)
 
         def e2e_run(n):
             staged = DevicePrefetcher((host_batches[i % args.rotate] for i in range(n)), dev, depth=2, hot_path_only=True)
@@ -705,7 +710,7 @@ def run_ours(args):
         arena = MoleculeArena(pool, dev)
         rng = np.random.default_rng(100 + rank)
         id_lists = [rng.integers(0, len(pool), size=args.batch) for _ in range(args.rotate)]
-        reader = LaggedScalars(lag=1)
+        reader = LaggedScalars(lag=LOSS_LAG)
 
         def arena_run(n):
             state = {"b": arena.batch_overlapped(id_lists[0]), "read": 0}
