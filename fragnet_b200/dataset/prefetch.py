@@ -133,17 +133,20 @@ class DevicePrefetcher:
         # copy stream and staging slots are recycled across prefetchers of a device (a training loop makes one per
         # epoch, plus one per validation pass): a new set of slots is ~150 MB of cudaMalloc, i.e. a device-synchronising
         # stall of 100-300 ms whenever the caching allocator has to make room
-        key = (self.device.type, torch.cuda.current_device() if self.device.index is None else self.device.index, self.depth)
-        pooled = DevicePrefetcher._pool.get(key)
+        self._pool_key = (self.device.type, torch.cuda.current_device() if self.device.index is None else self.device.index,
+                          self.depth)
+        self._copy_stream, self._slots = None, None      # taken from the pool for the duration of one iteration
+        self.last_event = None          # CUDA event after which the tensors of the batch yielded last are complete
+
+    _pool: Dict[tuple, list] = {}
+
+    def _acquire(self):
+        pooled = DevicePrefetcher._pool.get(self._pool_key)
         if pooled:
             self._copy_stream, self._slots = pooled.pop()
         else:
             self._copy_stream = torch.cuda.Stream(self.device)
             self._slots = [_Slot(self.device) for _ in range(self.depth + 1)]
-        self._pool_key = key
-        self.last_event = None          # CUDA event after which the tensors of the batch yielded last are complete
-
-    _pool: Dict[tuple, list] = {}
 
     def _release(self):
         """Hand stream and slots to the next prefetcher of this device (their last consumer is ordered by ``free_event``)."""
@@ -233,8 +236,9 @@ class DevicePrefetcher:
         return dev, ev, pinned, slot                     # pinned host tensors stay alive until the copy was waited for
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
-        if self._slots is None:
-            raise RuntimeError("DevicePrefetcher: a prefetcher iterates once (make a new one per epoch)")
+        if self._slots is not None:
+            raise RuntimeError("DevicePrefetcher: one iteration at a time")
+        self._acquire()
         try:
             yield from self._iterate()
         finally:

@@ -100,7 +100,7 @@ class FusedPretrainStep:
         self.n_layers = n_layers
         # collate of the next batch underneath the running step (prefetch_plan): two alternating plan arenas
         self._plan_arenas: List[Optional[torch.Tensor]] = [None, None]
-        self._plan_parity = 0
+        self._step_parity: Optional[int] = None     # arena the step launched last reads, if it found its plan prefetched
         self._prefetched = None          # (key of the batch inputs, arena, tensors kept alive)
         self.plan_hits = 0               # steps that found their plan prefetched
 
@@ -226,8 +226,10 @@ class FusedPretrainStep:
             a.bond_length, a.bond_angle, a.dihedral, a.energy = (pt(t) for t in preds)
         keep = (ei, fi, a2f, eb, efb, bv, fbv, cos, a6, xa, xb, xfb, t_ba, t_dh, y)
         pre, self._prefetched = self._prefetched, None       # one prefetch serves one step
+        self._step_parity = None
         if pre is not None and pre[0] == self._plan_key(a.batch):
             a.plan_arena = pre[1].data_ptr()       # collated ahead of this step (see prefetch_plan)
+            self._step_parity = pre[3]             # ... and this arena is now in use until the step has run
             self.plan_hits += 1
         return a, loss, preds, keep
 
@@ -269,20 +271,22 @@ class FusedPretrainStep:
         need = lib.fnb_batch_plan_bytes(C.byref(inp))
         if need == 0:
             return False
-        self._plan_parity ^= 1
-        arena = self._plan_arenas[self._plan_parity]
+        # never the arena the step launched last reads (its backward still needs the plan); a second prefetch before the
+        # next step simply replaces the first
+        parity = 0 if self._step_parity is None else 1 - self._step_parity
+        arena = self._plan_arenas[parity]
         if arena is None or arena.numel() < need:
             # (re)allocation: the block may have been freed by work still running on the compute stream, and the collate
             # writes it from another stream -- rare (first steps, a larger batch), so simply wait
             torch.cuda.current_stream(dev).synchronize()
             arena = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=dev)
-            self._plan_arenas[self._plan_parity] = arena
+            self._plan_arenas[parity] = arena
         ev = C.c_void_p(ready_event.cuda_event) if ready_event is not None else None
         rc = lib.fnb_pretrain_plan_prefetch(C.byref(inp), ops._ptr(arena), arena.numel(), ev)
         if rc != 0:
             return False                 # single-stream mode: the step collates by itself
         keep = tuple(b[k] for k in self._PLAN_TENSORS) + (b["edge_attr_bonds"], b["edge_attr_fbonds"])
-        self._prefetched = (self._plan_key(inp), arena, keep)
+        self._prefetched = (self._plan_key(inp), arena, keep, parity)
         return True
 
     def _run(self, batch, backward: bool, want_preds: bool = False):

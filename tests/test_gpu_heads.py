@@ -300,6 +300,17 @@ def test_plan_prefetch_gives_bitwise_the_same_training_run():
     assert runs[0][0] == runs[1][0]
     for k in runs[0][1]:
         assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+    # two prefetches in a row (the second replaces the first, never the arena of the step in flight), then the step
+    fused = FusedPretrainStep(m1, lr=1e-3)
+    fused.step(b0, next_batch=b1)
+    fused.step(b1)                                  # reads the prefetched arena
+    assert fused.prefetch_plan(b0) and fused.prefetch_plan(b1) and fused.prefetch_plan(b0)
+    hits = fused.plan_hits
+    m1.eval()
+    l_pre = float(fused.evaluate(b0))
+    assert fused.plan_hits == hits + 1
+    assert l_pre == float(fused.evaluate(b0))       # the same loss from a plan built inside the call
+    m1.train()
     # a batch with int32 indices would need a conversion: no prefetch, the step still works
     fused = FusedPretrainStep(m1, lr=1e-3)
     narrow = dict(b0)
