@@ -36,6 +36,8 @@ class FlatGradSync:
         """Find the parameters that received a gradient (a property of the model, not of the batch; checked to
         agree across ranks) and lay out the flat buffer."""
         self.live = [p for p in self.all_params if p.grad is not None]
+        if not self.live:
+            raise RuntimeError("FlatGradSync: no parameter has a gradient yet -- call backward() before sync()")
         if self.world_size > 1:
             n = torch.tensor([len(self.live), sum(p.numel() for p in self.live)], dtype=torch.int64,
                              device=self.live[0].device)

@@ -64,6 +64,12 @@ def test_flat_grad_sync_equals_mean_of_rank_grads(tmp_path):
     assert got["dead.weight"] is None and got["dead.bias"] is None
 
 
+def test_flat_grad_sync_without_gradients_says_so():
+    from fragnet_b200.dist import FlatGradSync
+    with pytest.raises(RuntimeError, match="no parameter has a gradient"):
+        FlatGradSync(_Toy().parameters()).sync()
+
+
 def test_epoch_batches_shard_every_step_over_the_ranks():
     """Host-side batch schedule of ArenaLoader: world 1 = DataLoader semantics; world W = disjoint equal slices of
     every global batch, the same number of steps on every rank, identical shuffles from identical generators."""
