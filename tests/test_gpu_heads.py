@@ -320,6 +320,34 @@ def test_plan_prefetch_gives_bitwise_the_same_training_run():
     assert float(fused.evaluate(narrow)) == float(fused.evaluate(b0))
 
 
+def test_plan_prefetch_in_single_stream_mode_is_declined():
+    """FNB_STREAMS=1 (everything on the caller's stream): fnb_pretrain_plan_prefetch queues nothing and says so, the
+    step collates by itself and trains to the same losses (a fresh process: the stream mode is read once)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys\n"
+        "sys.path.insert(0, 'tests')\n"
+        "from test_gpu_heads import _pretrain_pair\n"
+        "from fragnet_b200.train.fused import FusedPretrainStep\n"
+        "m1, m2, b = _pretrain_pair(21, num_layer=2, drop=0.0)\n"
+        "f = FusedPretrainStep(m1, lr=1e-3)\n"
+        "ok = f.prefetch_plan(b)\n"
+        "losses = [float(f.step(b, next_batch=b)) for _ in range(3)]\n"
+        "print('RESULT', ok, f.plan_hits, ' '.join(repr(x) for x in losses))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for streams in ("1", "0"):
+        env = dict(os.environ, FNB_STREAMS=streams, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split())
+    assert outs[0][1] == "False" and outs[0][2] == "0"          # single stream: declined, no hits
+    assert outs[1][1] == "True" and outs[1][2] == "3"           # default: every step found its plan
+    assert outs[0][3:] == outs[1][3:]                           # and the same training run either way
+
+
 def test_fused_step_dropout_training_is_seeded_and_finite():
     from fragnet_b200 import ops
     from fragnet_b200.train.fused import FusedPretrainStep
