@@ -241,10 +241,12 @@ def test_fused_step_equals_autograd_path_and_torch_adam():
     assert rel_err(loss_e, pretrain_loss(torch.nn.MSELoss(), ref, b)) <= 1e-6
 
 
-@pytest.mark.parametrize("kinds", [("two_frag",), ("ion_pair", "two_atom", "single_frag"), None])
+@pytest.mark.parametrize("kinds", [("two_frag",), ("ion_pair", "two_atom", "single_frag"), None,
+                                   ("two_atom", "ion_pair", "two_frag", "single_frag") * 500])
 def test_fused_step_on_tiny_and_ragged_batches(kinds):
-    """One molecule, three molecules, nine molecules (a partial 8-molecule tile of the fused energy-head kernel): loss and
-    gradients of the one-call step against the autograd path."""
+    """One molecule, three molecules, nine molecules (a partial 8-molecule tile of the fused energy-head kernel), 2 000
+    molecules (250 tiles on 222 CTAs: more than one tile per CTA): loss and gradients of the one-call step against the
+    autograd path."""
     import copy
     from fragnet.model.gat.gat2_pretrain import FragNetPreTrain
     from fragnet_b200 import synth
